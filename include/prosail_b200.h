@@ -1,0 +1,173 @@
+/* prosail_b200.h -- C ABI of libprosail_b200.so: batched PROSPECT-5/D -> LSM -> 4SAIL -> band means on B200 (sm_100a).
+ *
+ * The reference (ibaris/pyrism 0.0.5) is pure Python and has no FFI layer; its boundary for this path is the
+ * constructor surface  pyrism.PROSPECT(...) / pyrism.LSM(...) / pyrism.SAIL(...) / pyrism.VolScatt(...).coef(...)
+ * in pyrism/models/models.py.  Each entry point below names the reference interface it replaces.  The Python
+ * drop-in classes in pyrism_b200/models.py bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes and small POD structs; no C++/torch types cross the boundary.
+ *   - return 0 on success, > 0 a cudaError_t, < 0 a PROSAIL_E_* code; prosail_last_error() gives the text
+ *     (thread-local).  Nothing throws across the ABI.
+ *   - on_host = 0: every data pointer is a DEVICE pointer on the handle's device, the call is asynchronous and
+ *     ordered on `stream` (a cudaStream_t, NULL = the handle's own stream); the caller owns all buffers.
+ *     on_host = 1: every data pointer is a HOST pointer; the library slices the work, overlaps H2D copies,
+ *     kernels and D2H copies on two internal streams and returns when the results are in host memory.
+ *   - angles are radians, already normalised as the reference's Kernel does (core/_core.py:136-146: negative
+ *     zenith -> abs value and raa += pi).
+ *   - spectra have PROSAIL_NBANDS = 2101 values (400..2500 nm); `pitch` is the row stride in elements
+ *     (>= 2101; 2112 gives 128-byte aligned rows).
+ *   - a handle is bound to one device; calls on one handle must not overlap in time (use one handle per
+ *     host thread / stream).
+ */
+#ifndef PROSAIL_B200_H
+#define PROSAIL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PROSAIL_NBANDS 2101
+#define PROSAIL_NLIDF 18
+#define PROSAIL_MAX_WINDOWS 64
+
+/* error codes (negative) */
+#define PROSAIL_E_ARG (-1)      /* bad argument */
+#define PROSAIL_E_STATE (-2)    /* tables / windows not set */
+#define PROSAIL_E_NOGPU (-3)    /* no usable CUDA device: there is NO CPU fallback */
+
+/* PROSPECT versions (reference: version='5' | 'D', models.py:915) */
+#define PROSAIL_VERSION_5 0
+#define PROSAIL_VERSION_D 1
+/* LIDF types (reference: lidf_type='campbell' | 'verhoef', models.py:560-565) */
+#define PROSAIL_LIDF_CAMPBELL 0
+#define PROSAIL_LIDF_VERHOEF 1
+
+/* output planes: index into prosail_out_t.plane[] and bit index of mean_mask */
+enum {
+    PROSAIL_O_RSOT = 0, /* BRF  = SAIL.BRF.ref  (models.py:575, rsot :726) */
+    PROSAIL_O_RDDT,     /* BHR  = SAIL.BHR.ref  (rddt :721) */
+    PROSAIL_O_RSDT,     /* DHR  = SAIL.DHR.ref  (rsdt :722) */
+    PROSAIL_O_RDOT,     /* HDR  = SAIL.HDR.ref  (rdot :723) */
+    PROSAIL_O_RSO,      /* SAIL.canopy.BRF (rso :710) */
+    PROSAIL_O_RDD,      /* SAIL.canopy.BHR */
+    PROSAIL_O_TDD,      /* SAIL.canopy.BHT */
+    PROSAIL_O_RSD,      /* SAIL.canopy.DHR */
+    PROSAIL_O_TSD,      /* SAIL.canopy.DHT */
+    PROSAIL_O_RDO,      /* SAIL.canopy.HDR */
+    PROSAIL_O_TDO,      /* SAIL.canopy.HDT */
+    PROSAIL_O_KE,       /* SAIL.ke = m (models.py:601-602) */
+    PROSAIL_O_LEAF_R,   /* PROSPECT.ks (leaf reflectance, models.py:1065) */
+    PROSAIL_O_LEAF_T,   /* PROSPECT.kt (leaf transmittance, models.py:1064) */
+    PROSAIL_O_RHO,      /* LSM.ref (soil reflectance, models.py:1917) */
+    PROSAIL_NOUT
+};
+
+typedef struct prosail_handle prosail_handle_t;
+
+/* PROSPECT(N, Cab, Cxc, Cbr, Cw, Cm, Can) parameter arrays, models.py:900.  Can may be NULL for version '5'. */
+typedef struct prosail_leaf {
+    const double *N, *Cab, *Cxc, *Cbr, *Cw, *Cm, *Can; /* [n] each */
+} prosail_leaf_t;
+
+/* LSM(reflectance, moisture), models.py:1908 */
+typedef struct prosail_soil {
+    const double *reflectance, *moisture; /* [n] each */
+} prosail_soil_t;
+
+/* SAIL(iza, vza, raa, ..., lai, hotspot, lidf_type, a, b), models.py:528-529 */
+typedef struct prosail_canopy {
+    int lidf_type;                               /* PROSAIL_LIDF_* */
+    const double *lidf_a, *lidf_b;               /* [n]; lidf_b may be NULL for campbell */
+    const double *lai, *hotspot;                 /* [n] */
+    int n_geom;                                  /* geometries per parameter set (G >= 1) */
+    int geom_per_sample;                         /* 0: iza/vza/raa are [n_geom], shared; 1: [n], n_geom must be 1 */
+    const double *iza, *vza, *raa;               /* radians */
+} prosail_canopy_t;
+
+/* results; item index = sample * n_geom + geometry */
+typedef struct prosail_out {
+    double* plane[PROSAIL_NOUT]; /* spectra [n_items][pitch]; NULL = not wanted */
+    long long pitch;
+    unsigned mean_mask;          /* planes whose window means are wanted (bit = plane index) */
+    double* means;               /* [n_items][popcount(mean_mask)][n_windows], planes in bit order */
+    double* geom;                /* optional [n_items][8]: VolScatt ks, ko, bf, Fs, Ft, tss, too, tsstoo */
+    int windows_only;            /* 1: evaluate only the wavelengths inside some window (planes must be NULL) */
+} prosail_out_t;
+
+/* ---- lifetime --------------------------------------------------------------------------------------- */
+/* Replaces the import-time global `lib = get_data_*()` (models.py:16-19): create a handle on `device`. */
+int prosail_create(int device, prosail_handle_t** out);
+void prosail_destroy(prosail_handle_t* h);
+const char* prosail_last_error(void);
+const char* prosail_version(void);
+
+/* Upload one coefficient set.  Replaces PROSPECT.__set_coef (models.py:923-947) + library.py:43-64.
+ * K* are the float32 tables [2101]; Kan may be NULL (version '5': zeros, models.py:935);
+ * talf/t12/t21 are the per-band interface transmissivities in float64, computed by the host exactly as
+ * PROSPECT.__calctav / __refl_trans_one_layer do (models.py:961-998, 1011-1015) for the chosen alpha. */
+int prosail_set_leaf_tables(prosail_handle_t* h, int version, const float* Kab, const float* Kxc, const float* Kbr,
+                            const float* Kw, const float* Km, const float* Kan, const double* talf, const double* t12,
+                            const double* t21);
+/* Soil spectra rsoil1/rsoil2 (library.py:57), float32 [2101]. */
+int prosail_set_soil_tables(prosail_handle_t* h, const float* rsoil1, const float* rsoil2);
+/* Inclusive wavelength windows [lo_nm, hi_nm] for the band means.  Replaces the hard-coded L8/ASTER windows of
+ * SAIL.__store_L8/__store_aster (models.py:801-809, 836-841) and PROSPECT/LSM.select (models.py:1197-1225). */
+int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm);
+
+/* ---- the hot path ------------------------------------------------------------------------------------ */
+/* pyrism.PROSPECT(...) for n parameter sets (models.py:900-921): ks -> out ks, kt -> out kt ([n][pitch]).
+ * means_f32 (optional) = float32 window means of (ks, kt, ka, ke, om), [n][5][n_windows]  (models.py:1071-1195). */
+int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, double* ks, double* kt,
+                         long long pitch, float* means_f32, int on_host, void* stream);
+
+/* pyrism.LSM(reflectance, moisture) for n parameter sets (models.py:1908-1920): rho [n][pitch];
+ * means_f32 (optional) [n][1][n_windows] float32 (models.py:1918-2006). */
+int prosail_soil_f64(prosail_handle_t* h, long long n, const prosail_soil_t* soil, double* rho, long long pitch,
+                     float* means_f32, int on_host, void* stream);
+
+/* pyrism.VolScatt(iza, vza, raa).coef(lidf_type, a, b) + LIDF.campbell/verhoef (models.py:82-175, 283-392),
+ * plus the direct transmittances/hotspot terms of SAIL.__calc (models.py:664-702) when lai/hotspot are given.
+ * geom [n_items][8] (see prosail_out_t.geom); lidf (optional) [n][18]. */
+int prosail_volscatt_f64(prosail_handle_t* h, long long n, const prosail_canopy_t* canopy, double* geom, double* lidf,
+                         int on_host, void* stream);
+
+/* pyrism.SAIL(...) for n parameter sets x n_geom geometries (models.py:528-729) with leaf and soil spectra
+ * supplied as arrays: ks, kt, rho are [n][pitch_*] or a single spectrum broadcast to all sets (pitch_* = 0). */
+int prosail_sail_f64(prosail_handle_t* h, long long n, const double* ks, long long pitch_ks, const double* kt,
+                     long long pitch_kt, const double* rho, long long pitch_rho, const prosail_canopy_t* canopy,
+                     const prosail_out_t* out, int on_host, void* stream);
+
+/* Fused PROSPECT -> LSM -> SAIL (examples/prospect_sail.py:9-28 per parameter set) without materialising the leaf
+ * and soil spectra in HBM: the LUT-production kernel. */
+int prosail_prosail_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_soil_t* soil,
+                        const prosail_canopy_t* canopy, const prosail_out_t* out, int on_host, void* stream);
+
+/* ---- memory / stream helpers (so that a host without torch/cupy can drive the device API) -------------- */
+int prosail_dev_alloc(prosail_handle_t* h, long long bytes, void** out);
+int prosail_dev_free(prosail_handle_t* h, void* p);
+int prosail_host_alloc(long long bytes, void** out); /* pinned */
+int prosail_host_free(void* p);
+int prosail_memcpy_h2d(prosail_handle_t* h, void* dst, const void* src, long long bytes, void* stream);
+int prosail_memcpy_d2h(prosail_handle_t* h, void* dst, const void* src, long long bytes, void* stream);
+int prosail_sync(prosail_handle_t* h, void* stream);
+/* CUDA-event timer on `stream` (NULL = handle stream): begin/end bracket device work, end returns milliseconds. */
+int prosail_timer_begin(prosail_handle_t* h, void* stream);
+int prosail_timer_end(prosail_handle_t* h, void* stream, float* ms);
+/* number of kernel launches issued through this handle so far */
+long long prosail_launch_count(prosail_handle_t* h);
+/* name, SM count, HBM bytes of the handle's device */
+int prosail_device_info(prosail_handle_t* h, char* name, int name_len, int* sm_count, long long* mem_bytes);
+
+/* ---- calibration / self-test -------------------------------------------------------------------------- */
+/* FP64 roofline denominator: sustained DFMA throughput of the device (TFLOP/s, FMA = 2 flops), measured with a
+ * register-resident FMA kernel for about `millis` milliseconds. */
+int prosail_measure_fp64_peak(prosail_handle_t* h, int millis, double* tflops);
+/* evaluates one fp64 primitive of the kernels on device arrays (op: 0 rcp, 1 sqrt, 2 exp(x<=0), 3 log2, 4 exp2,
+ * 5 tau(k) = (1-k)e^-k + k^2 E1(k)); used by the GPU unit tests. */
+int prosail_test_math(prosail_handle_t* h, int op, long long n, const double* in, double* out, int on_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROSAIL_B200_H */

@@ -1,0 +1,755 @@
+// C ABI of libprosail_b200.so (see include/prosail_b200.h).  Host-side orchestration only: validation,
+// constant upload, workspace management, slab pipelining, kernel launches.  All arithmetic of the hot
+// path lives in prosail_kernels.cuh; there is no CPU implementation in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/prosail_b200.h"
+#include "prosail_kernels.cuh"
+
+using namespace pb;
+
+static_assert((int)PROSAIL_NOUT == (int)NOUT, "plane enums out of sync");
+static_assert(PROSAIL_MAX_WINDOWS == MAX_WINDOWS, "window limit out of sync");
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail((int)e_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail((int)e, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Work {            // per-stream scratch
+    DevBuf srec, grec, partial;
+    DevBuf in;           // host mode: parameter slices
+    DevBuf out;          // host mode: output planes / means / geom of one slab
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void release() { srec.release(); grec.release(); partial.release(); in.release(); out.release(); }
+};
+
+struct prosail_handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    double* d_bandc[2] = {nullptr, nullptr};
+    bool have_leaf[2] = {false, false};
+    bool have_soil = false;
+    double* d_tables = nullptr;
+    WindowMap* d_win = nullptr;
+    WindowMap h_win;
+    bool have_win = false;
+    Work work;           // device mode (caller's stream)
+    Work slot[2];        // host mode pipeline
+    long long launches = 0;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static int popcount(unsigned v) { return __builtin_popcount(v); }
+
+// ------------------------------------------------------------------------------------------------
+// job description shared by all entry points
+// ------------------------------------------------------------------------------------------------
+struct Job {
+    int mode = MODE_PROSAIL;
+    int version = 0;
+    long long n = 0;
+    bool has_leaf = false, has_soil = false, has_canopy = false;
+    prosail_leaf_t leaf{};
+    prosail_soil_t soil{};
+    prosail_canopy_t can{};
+    const double *in_r = nullptr, *in_t = nullptr, *in_rho = nullptr;
+    long long pr = 0, pt = 0, prho = 0;
+    double* plane[NOUT] = {};
+    long long pitch = NB;
+    unsigned mean_mask = 0;
+    int nmean = 0;
+    double* means = nullptr;
+    float* means_f32 = nullptr;
+    double* geom = nullptr;
+    double* lidf = nullptr;
+    int windows_only = 0;
+    int f32_means = 0;
+    int G() const { return has_canopy ? can.n_geom : 1; }
+};
+
+static int validate(const prosail_handle* h, const Job& j) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    if (j.n < 0) return fail(PROSAIL_E_ARG, "negative number of parameter sets");
+    if (j.pitch < NB) return fail(PROSAIL_E_ARG, "pitch %lld < %d", j.pitch, NB);
+    if (j.has_leaf) {
+        if (j.version != 0 && j.version != 1) return fail(PROSAIL_E_ARG, "version must be PROSAIL_VERSION_5 or PROSAIL_VERSION_D");
+        if (!h->have_leaf[j.version]) return fail(PROSAIL_E_STATE, "leaf tables for this PROSPECT version were not set");
+        const prosail_leaf_t& l = j.leaf;
+        if (!l.N || !l.Cab || !l.Cxc || !l.Cbr || !l.Cw || !l.Cm) return fail(PROSAIL_E_ARG, "null leaf parameter array");
+        if (j.version == 1 && !l.Can) return fail(PROSAIL_E_ARG, "PROSPECT-D needs the Can array");
+    }
+    if (j.has_soil) {
+        if (!h->have_soil) return fail(PROSAIL_E_STATE, "soil tables were not set");
+        if (!j.soil.reflectance || !j.soil.moisture) return fail(PROSAIL_E_ARG, "null soil parameter array");
+    }
+    if (j.has_canopy) {
+        const prosail_canopy_t& c = j.can;
+        if (c.lidf_type != 0 && c.lidf_type != 1) return fail(PROSAIL_E_ARG, "lidf_type must be PROSAIL_LIDF_CAMPBELL or PROSAIL_LIDF_VERHOEF");
+        if (c.n_geom < 1) return fail(PROSAIL_E_ARG, "n_geom must be >= 1");
+        if (c.geom_per_sample && c.n_geom != 1) return fail(PROSAIL_E_ARG, "geom_per_sample needs n_geom == 1");
+        if (!c.lidf_a || !c.lai || !c.hotspot || !c.iza || !c.vza || !c.raa) return fail(PROSAIL_E_ARG, "null canopy parameter array");
+        if (c.lidf_type == 1 && !c.lidf_b) return fail(PROSAIL_E_ARG, "verhoef LIDF needs lidf_b");
+    }
+    if (j.mode == MODE_SAIL && (!j.in_r || !j.in_t || !j.in_rho)) return fail(PROSAIL_E_ARG, "null ks / kt / rho_surface array");
+    if (j.mean_mask) {
+        if (!h->have_win) return fail(PROSAIL_E_STATE, "band-mean windows were not set");
+        if (!j.means && !j.means_f32) return fail(PROSAIL_E_ARG, "mean_mask set but no means buffer");
+    }
+    if (j.windows_only) {
+        for (int i = 0; i < NOUT; ++i)
+            if (j.plane[i]) return fail(PROSAIL_E_ARG, "windows_only excludes full-spectrum output planes");
+        if (!j.mean_mask) return fail(PROSAIL_E_ARG, "windows_only without mean_mask does nothing");
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side execution of a job whose pointers are all device pointers
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+static int launch_bands(prosail_handle* h, const SailArgs& a, int band_ctas, cudaStream_t st) {
+    const size_t smem = sizeof(SailSmem);
+    CK(cudaFuncSetAttribute(k_bands<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
+    // persistent-style grid: about 3 resident CTAs per SM (launch bound), split over the band CTAs
+    long long ychunks = std::max<long long>(1, (3LL * h->sm_count + band_ctas - 1) / band_ctas);
+    ychunks = std::min(ychunks, nchunks);
+    dim3 grid((unsigned)band_ctas, (unsigned)ychunks);
+    k_bands<MODE><<<grid, CTA_THREADS, smem, st>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st) {
+    const int G = j.G();
+    const long long nitems_total = j.n * G;
+    if (nitems_total == 0) return 0;
+    const int nw = h->have_win ? h->h_win.nwindows : 0;
+    const int nt = h->have_win ? h->h_win.ntotal : 0;
+    // slab = bounded workspace
+    long long cap_items = 1LL << 20;
+    if (j.nmean > 0) cap_items = std::min<long long>(cap_items, std::max<long long>(4096, (1LL << 30) / ((long long)j.nmean * std::max(nt, 1) * 8)));
+    const long long slab_samples = std::max<long long>(1, cap_items / G);
+
+    for (long long s0 = 0; s0 < j.n; s0 += slab_samples) {
+        const long long ns = std::min(slab_samples, j.n - s0);
+        const long long ni = ns * G, i0 = s0 * G;
+        int rc;
+        if ((rc = w.srec.reserve((size_t)ns * REC * 8))) return rc;
+        if ((rc = w.grec.reserve((size_t)std::max<long long>(ni, 1) * REC * 8))) return rc;
+        if (j.nmean > 0 && (rc = w.partial.reserve((size_t)ni * j.nmean * nt * 8))) return rc;
+
+        PrologueArgs p{};
+        p.nsamples = ns;
+        p.G = G;
+        p.geom_per_sample = j.has_canopy ? j.can.geom_per_sample : 0;
+        p.lidf_type = j.has_canopy ? j.can.lidf_type : 0;
+        p.has_leaf = j.has_leaf; p.has_soil = j.has_soil; p.has_canopy = j.has_canopy;
+        if (j.has_leaf) {
+            p.N = j.leaf.N + s0; p.Cab = j.leaf.Cab + s0; p.Cxc = j.leaf.Cxc + s0; p.Cbr = j.leaf.Cbr + s0;
+            p.Cw = j.leaf.Cw + s0; p.Cm = j.leaf.Cm + s0; p.Can = (j.version == 1 && j.leaf.Can) ? j.leaf.Can + s0 : nullptr;
+        }
+        if (j.has_soil) { p.soil_refl = j.soil.reflectance + s0; p.soil_moist = j.soil.moisture + s0; }
+        if (j.has_canopy) {
+            p.lai = j.can.lai + s0; p.hot = j.can.hotspot + s0; p.lidf_a = j.can.lidf_a + s0;
+            p.lidf_b = j.can.lidf_b ? j.can.lidf_b + s0 : nullptr;
+            const long long go = j.can.geom_per_sample ? s0 : 0;
+            p.iza = j.can.iza + go; p.vza = j.can.vza + go; p.raa = j.can.raa + go;
+        }
+        p.srec = (double*)w.srec.p;
+        p.grec = (double*)w.grec.p;
+        p.geom_out = j.geom ? j.geom + i0 * 8 : nullptr;
+        p.lidf_out = j.lidf ? j.lidf + s0 * PROSAIL_NLIDF : nullptr;
+        {
+            const long long threads = ni * 32;
+            const unsigned blocks = (unsigned)((threads + 127) / 128);
+            k_prologue<<<blocks, 128, 0, st>>>(p);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
+        if (j.mode < 0) continue;   // volscatt-only job
+
+        SailArgs a{};
+        a.bandc = h->d_bandc[j.has_leaf ? j.version : 0];
+        a.tables = h->d_tables;
+        a.win = h->d_win;
+        a.srec = (const double*)w.srec.p;
+        a.grec = (const double*)w.grec.p;
+        a.nitems = ni;
+        a.G = G;
+        if (j.mode == MODE_SAIL) {
+            a.in_r = j.in_r + s0 * j.pr; a.in_t = j.in_t + s0 * j.pt; a.in_rho = j.in_rho + s0 * j.prho;
+            a.in_pitch_r = j.pr; a.in_pitch_t = j.pt; a.in_pitch_rho = j.prho;
+        }
+        for (int i = 0; i < NOUT; ++i) a.out[i] = j.plane[i] ? j.plane[i] + i0 * j.pitch : nullptr;
+        a.out_pitch = j.pitch;
+        a.mean_mask = j.mean_mask;
+        a.partial = (double*)w.partial.p;
+        a.nmean = j.nmean;
+        a.only_active_tiles = j.windows_only;
+        a.f32_means = j.f32_means;
+        const int band_ctas = j.windows_only ? (h->h_win.ntiles_active + WARPS_PER_CTA - 1) / WARPS_PER_CTA : BAND_CTAS;
+        if (band_ctas > 0) {
+            switch (j.mode) {
+                case MODE_PROSAIL: rc = launch_bands<MODE_PROSAIL>(h, a, band_ctas, st); break;
+                case MODE_SAIL: rc = launch_bands<MODE_SAIL>(h, a, band_ctas, st); break;
+                case MODE_PROSPECT: rc = launch_bands<MODE_PROSPECT>(h, a, band_ctas, st); break;
+                default: rc = launch_bands<MODE_SOIL>(h, a, band_ctas, st); break;
+            }
+            if (rc) return rc;
+        }
+        if (j.nmean > 0) {
+            const long long rows = ni * j.nmean, total = rows * nw;
+            const unsigned blocks = (unsigned)((total + 255) / 256);
+            k_finalize_means<<<blocks, 256, 0, st>>>(h->d_win, (const double*)w.partial.p, rows,
+                                                     j.means ? j.means + i0 * j.nmean * nw : nullptr,
+                                                     j.means_f32 ? j.means_f32 + i0 * j.nmean * nw : nullptr);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer execution: slabs, two slots, H2D -> kernels -> D2H overlapped
+// ------------------------------------------------------------------------------------------------
+struct Carver {          // carve typed sub-buffers out of one device allocation
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base((char*)p) {}
+    template <class T>
+    T* take(size_t count) {
+        T* r = (T*)(base + off);
+        off += (count * sizeof(T) + 255) & ~(size_t)255;
+        return r;
+    }
+};
+
+static int run_host(prosail_handle* h, const Job& j) {
+    const int G = j.G();
+    const int nw = h->have_win ? h->h_win.nwindows : 0;
+    int nplanes = 0;
+    for (int i = 0; i < NOUT; ++i) nplanes += j.plane[i] ? 1 : 0;
+    const size_t out_per_item = (size_t)nplanes * j.pitch * 8 + (size_t)j.nmean * nw * 8 + 64 + 256;
+    size_t in_per_sample = 16 * 8 + (j.mode == MODE_SAIL ? (size_t)(j.pr + j.pt + j.prho) * 8 : 0) + PROSAIL_NLIDF * 8;
+    const size_t per_sample = out_per_item * G + in_per_sample;
+    long long slab = std::max<long long>(1, (long long)((256ull << 20) / per_sample));
+    slab = std::min<long long>(slab, std::max<long long>(1, (j.n + 1) / 2));      // at least two slabs to overlap copies
+    if (j.n <= 64) slab = std::max<long long>(slab, j.n);
+
+    long long idx = 0;
+    for (long long s0 = 0; s0 < j.n; s0 += slab, ++idx) {
+        Work& w = h->slot[idx & 1];
+        cudaStream_t st = w.stream;
+        const long long ns = std::min(slab, j.n - s0), ni = ns * G, i0 = s0 * G;
+        CK(cudaEventSynchronize(w.done));       // the slot's previous D2H has finished
+        int rc;
+        // ---- inputs ----
+        size_t in_bytes = 20 * (((size_t)ns * 8 + 255) & ~(size_t)255) + 3 * ((((size_t)G) * 8 + 255) & ~(size_t)255) + 4096;
+        if (j.mode == MODE_SAIL)
+            for (long long p : {j.pr, j.pt, j.prho}) in_bytes += (((size_t)(p ? ns * p : NB) * 8 + 255) & ~(size_t)255);
+        if ((rc = w.in.reserve(in_bytes))) return rc;
+        Carver ci(w.in.p);
+        Job d = j;
+        d.n = ns;
+        auto up = [&](const double* src, size_t count, const double** dst) -> int {
+            if (!src) { *dst = nullptr; return 0; }
+            double* p = ci.take<double>(count);
+            CK(cudaMemcpyAsync(p, src, count * 8, cudaMemcpyHostToDevice, st));
+            *dst = p;
+            return 0;
+        };
+        if (j.has_leaf) {
+            if ((rc = up(j.leaf.N + s0, ns, &d.leaf.N)) || (rc = up(j.leaf.Cab + s0, ns, &d.leaf.Cab)) ||
+                (rc = up(j.leaf.Cxc + s0, ns, &d.leaf.Cxc)) || (rc = up(j.leaf.Cbr + s0, ns, &d.leaf.Cbr)) ||
+                (rc = up(j.leaf.Cw + s0, ns, &d.leaf.Cw)) || (rc = up(j.leaf.Cm + s0, ns, &d.leaf.Cm)) ||
+                (rc = up(j.leaf.Can ? j.leaf.Can + s0 : nullptr, ns, &d.leaf.Can)))
+                return rc;
+        }
+        if (j.has_soil) {
+            if ((rc = up(j.soil.reflectance + s0, ns, &d.soil.reflectance)) || (rc = up(j.soil.moisture + s0, ns, &d.soil.moisture))) return rc;
+        }
+        if (j.has_canopy) {
+            if ((rc = up(j.can.lidf_a + s0, ns, &d.can.lidf_a)) || (rc = up(j.can.lidf_b ? j.can.lidf_b + s0 : nullptr, ns, &d.can.lidf_b)) ||
+                (rc = up(j.can.lai + s0, ns, &d.can.lai)) || (rc = up(j.can.hotspot + s0, ns, &d.can.hotspot)))
+                return rc;
+            const long long go = j.can.geom_per_sample ? s0 : 0;
+            const size_t gc = j.can.geom_per_sample ? (size_t)ns : (size_t)G;
+            if ((rc = up(j.can.iza + go, gc, &d.can.iza)) || (rc = up(j.can.vza + go, gc, &d.can.vza)) || (rc = up(j.can.raa + go, gc, &d.can.raa))) return rc;
+        }
+        if (j.mode == MODE_SAIL) {
+            auto upspec = [&](const double* src, long long pitch, const double** dst) -> int {
+                return pitch == 0 ? up(src, (size_t)NB, dst) : up(src + s0 * pitch, (size_t)ns * pitch, dst);
+            };
+            if ((rc = upspec(j.in_r, j.pr, &d.in_r)) || (rc = upspec(j.in_t, j.pt, &d.in_t)) || (rc = upspec(j.in_rho, j.prho, &d.in_rho))) return rc;
+        }
+        // ---- outputs ----
+        if ((rc = w.out.reserve(out_per_item * (size_t)ni + (size_t)ns * PROSAIL_NLIDF * 8 + 8192))) return rc;
+        Carver co(w.out.p);
+        for (int i = 0; i < NOUT; ++i) d.plane[i] = j.plane[i] ? co.take<double>((size_t)ni * j.pitch) : nullptr;
+        d.means = j.means ? co.take<double>((size_t)ni * j.nmean * nw) : nullptr;
+        d.means_f32 = j.means_f32 ? co.take<float>((size_t)ni * j.nmean * nw) : nullptr;
+        d.geom = j.geom ? co.take<double>((size_t)ni * 8) : nullptr;
+        d.lidf = j.lidf ? co.take<double>((size_t)ns * PROSAIL_NLIDF) : nullptr;
+
+        if ((rc = run_device(h, d, w, st))) return rc;
+
+        for (int i = 0; i < NOUT; ++i)
+            if (j.plane[i]) CK(cudaMemcpyAsync(j.plane[i] + i0 * j.pitch, d.plane[i], (size_t)ni * j.pitch * 8, cudaMemcpyDeviceToHost, st));
+        if (j.means) CK(cudaMemcpyAsync(j.means + i0 * j.nmean * nw, d.means, (size_t)ni * j.nmean * nw * 8, cudaMemcpyDeviceToHost, st));
+        if (j.means_f32) CK(cudaMemcpyAsync(j.means_f32 + i0 * j.nmean * nw, d.means_f32, (size_t)ni * j.nmean * nw * 4, cudaMemcpyDeviceToHost, st));
+        if (j.geom) CK(cudaMemcpyAsync(j.geom + i0 * 8, d.geom, (size_t)ni * 8 * 8, cudaMemcpyDeviceToHost, st));
+        if (j.lidf) CK(cudaMemcpyAsync(j.lidf + s0 * PROSAIL_NLIDF, d.lidf, (size_t)ns * PROSAIL_NLIDF * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(w.done, st));
+    }
+    CK(cudaStreamSynchronize(h->slot[0].stream));
+    CK(cudaStreamSynchronize(h->slot[1].stream));
+    return 0;
+}
+
+static int run(prosail_handle* h, Job& j, int on_host, void* stream) {
+    j.nmean = popcount(j.mean_mask);
+    if (j.mode == MODE_PROSPECT && j.mean_mask) j.nmean = 5;     // ks, kt, ka, ke, om
+    int rc = validate(h, j);
+    if (rc) return rc;
+    DeviceGuard guard(h->device);
+    if (on_host) return run_host(h, j);
+    return run_device(h, j, h->work, stream ? (cudaStream_t)stream : h->stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exported functions
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* prosail_last_error(void) { return g_err.c_str(); }
+const char* prosail_version(void) { return "pyrism_b200 0.1.0 (sm_100a)"; }
+
+int prosail_create(int device, prosail_handle_t** out) {
+    if (!out) return fail(PROSAIL_E_ARG, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(PROSAIL_E_NOGPU, "no CUDA device available (%s); pyrism_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(PROSAIL_E_ARG, "device %d out of range (0..%d)", device, count - 1);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(PROSAIL_E_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    prosail_handle* h = new prosail_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->t0));
+    CK(cudaEventCreate(&h->t1));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaStreamCreateWithFlags(&h->slot[i].stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming));
+        CK(cudaEventRecord(h->slot[i].done, h->slot[i].stream));
+        CK(cudaMalloc(&h->d_bandc[i], sizeof(double) * NCONST * NBP));
+        CK(cudaMemset(h->d_bandc[i], 0, sizeof(double) * NCONST * NBP));
+    }
+    // math tables image
+    {
+        std::vector<double> img(sizeof(MathTables) / 8);
+        MathTables* mt = reinterpret_cast<MathTables*>(img.data());
+        memcpy(mt->tau, h_tau_table, sizeof(mt->tau));
+        memcpy(mt->exp2t, h_exp2_table, sizeof(mt->exp2t));
+        memcpy(mt->logt, h_log_table, sizeof(mt->logt));
+        CK(cudaMalloc(&h->d_tables, sizeof(MathTables)));
+        CK(cudaMemcpy(h->d_tables, img.data(), sizeof(MathTables), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMalloc(&h->d_win, sizeof(WindowMap)));
+    CK(cudaMemset(h->d_win, 0, sizeof(WindowMap)));
+    memset(&h->h_win, 0, sizeof(WindowMap));
+    *out = h;
+    return 0;
+}
+
+void prosail_destroy(prosail_handle_t* h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    h->work.release();
+    for (int i = 0; i < 2; ++i) {
+        h->slot[i].release();
+        if (h->slot[i].stream) cudaStreamDestroy(h->slot[i].stream);
+        if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
+        if (h->d_bandc[i]) cudaFree(h->d_bandc[i]);
+    }
+    if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_win) cudaFree(h->d_win);
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int prosail_set_leaf_tables(prosail_handle_t* h, int version, const float* Kab, const float* Kxc, const float* Kbr, const float* Kw,
+                            const float* Km, const float* Kan, const double* talf, const double* t12, const double* t21) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    if (version != 0 && version != 1) return fail(PROSAIL_E_ARG, "version must be 0 ('5') or 1 ('D')");
+    if (!Kab || !Kxc || !Kbr || !Kw || !Km || !talf || !t12 || !t21) return fail(PROSAIL_E_ARG, "null table pointer");
+    DeviceGuard guard(h->device);
+    std::vector<double> img((size_t)9 * NBP, 0.0);
+    const float* src[6] = {Kab, Kxc, Kan, Kbr, Kw, Km};
+    const int plane[6] = {C_KAB, C_KXC, C_KAN, C_KBR, C_KW, C_KM};
+    for (int p = 0; p < 6; ++p)
+        for (int i = 0; i < NB; ++i) img[(size_t)plane[p] * NBP + i] = src[p] ? (double)src[p][i] : 0.0;   // float32 -> float64 is exact
+    for (int i = 0; i < NB; ++i) {
+        img[(size_t)C_TALF * NBP + i] = talf[i];
+        img[(size_t)C_T12 * NBP + i] = t12[i];
+        img[(size_t)C_T21 * NBP + i] = t21[i];
+    }
+    for (int i = NB; i < NBP; ++i) {   // padding lanes: benign constants (band 2100 replicated) so that they never trap
+        for (int p = 0; p < 9; ++p) img[(size_t)p * NBP + i] = img[(size_t)p * NBP + NB - 1];
+    }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h->d_bandc[version], img.data(), img.size() * 8, cudaMemcpyHostToDevice));
+    h->have_leaf[version] = true;
+    return 0;
+}
+
+int prosail_set_soil_tables(prosail_handle_t* h, const float* rsoil1, const float* rsoil2) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    if (!rsoil1 || !rsoil2) return fail(PROSAIL_E_ARG, "null table pointer");
+    DeviceGuard guard(h->device);
+    std::vector<double> img((size_t)2 * NBP, 0.0);
+    for (int i = 0; i < NBP; ++i) {
+        const int k = std::min(i, NB - 1);
+        img[i] = (double)rsoil1[k];
+        img[(size_t)NBP + i] = (double)rsoil2[k];
+    }
+    CK(cudaDeviceSynchronize());
+    for (int v = 0; v < 2; ++v) CK(cudaMemcpy(h->d_bandc[v] + (size_t)C_RS1 * NBP, img.data(), img.size() * 8, cudaMemcpyHostToDevice));
+    h->have_soil = true;
+    return 0;
+}
+
+int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    if (n_windows < 1 || n_windows > MAX_WINDOWS) return fail(PROSAIL_E_ARG, "n_windows must be in 1..%d", MAX_WINDOWS);
+    if (!lo_nm || !hi_nm) return fail(PROSAIL_E_ARG, "null window array");
+    WindowMap m;
+    memset(&m, 0, sizeof m);
+    m.nwindows = n_windows;
+    bool touched[NTILES] = {};
+    int slot = 0;
+    for (int w = 0; w < n_windows; ++w) {
+        const int lo = std::max(lo_nm[w], 400) - 400, hi = std::min(hi_nm[w], 2500) - 400;   // band indices, inclusive
+        if (lo > hi) return fail(PROSAIL_E_ARG, "window %d [%d, %d] nm selects no wavelength in 400..2500", w, lo_nm[w], hi_nm[w]);
+        m.wstart[w] = slot;
+        m.wcount[w] = hi - lo + 1;
+        for (int t = lo / 32; t <= hi / 32; ++t) {
+            if (m.nslots[t] >= MAX_TILE_SLOTS) return fail(PROSAIL_E_ARG, "more than %d windows overlap wavelengths %d..%d nm", MAX_TILE_SLOTS, 400 + t * 32, 431 + t * 32);
+            if (slot >= MAX_SLOTS) return fail(PROSAIL_E_ARG, "too many window segments (> %d)", MAX_SLOTS);
+            unsigned mask = 0;
+            for (int l = 0; l < 32; ++l) {
+                const int b = t * 32 + l;
+                if (b >= lo && b <= hi) mask |= 1u << l;
+            }
+            m.mask[t][m.nslots[t]] = mask;
+            m.slot[t][m.nslots[t]] = slot++;
+            m.nslots[t]++;
+            touched[t] = true;
+        }
+    }
+    m.wstart[n_windows] = slot;
+    m.ntotal = slot;
+    for (int t = 0; t < NTILES; ++t)
+        if (touched[t]) m.active_tile[m.ntiles_active++] = t;
+    DeviceGuard guard(h->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h->d_win, &m, sizeof m, cudaMemcpyHostToDevice));
+    h->h_win = m;
+    h->have_win = true;
+    return 0;
+}
+
+int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, double* ks, double* kt,
+                         long long pitch, float* means_f32, int on_host, void* stream) {
+    if (!leaf) return fail(PROSAIL_E_ARG, "null leaf struct");
+    Job j;
+    j.mode = MODE_PROSPECT;
+    j.version = version;
+    j.n = n;
+    j.has_leaf = true;
+    j.leaf = *leaf;
+    j.plane[O_LEAF_R] = ks;
+    j.plane[O_LEAF_T] = kt;
+    j.pitch = pitch;
+    if (means_f32) {
+        j.mean_mask = (1u << O_LEAF_R) | (1u << O_LEAF_T) | (1u << O_RSOT);   // + ka, ke, om
+        j.means_f32 = means_f32;
+        j.f32_means = 1;
+    }
+    return run(h, j, on_host, stream);
+}
+
+int prosail_soil_f64(prosail_handle_t* h, long long n, const prosail_soil_t* soil, double* rho, long long pitch, float* means_f32,
+                     int on_host, void* stream) {
+    if (!soil) return fail(PROSAIL_E_ARG, "null soil struct");
+    Job j;
+    j.mode = MODE_SOIL;
+    j.n = n;
+    j.has_soil = true;
+    j.soil = *soil;
+    j.plane[O_RHO] = rho;
+    j.pitch = pitch;
+    if (means_f32) {
+        j.mean_mask = 1u << O_RHO;
+        j.means_f32 = means_f32;
+        j.f32_means = 1;
+    }
+    return run(h, j, on_host, stream);
+}
+
+int prosail_volscatt_f64(prosail_handle_t* h, long long n, const prosail_canopy_t* canopy, double* geom, double* lidf, int on_host,
+                         void* stream) {
+    if (!canopy) return fail(PROSAIL_E_ARG, "null canopy struct");
+    if (!geom) return fail(PROSAIL_E_ARG, "null geom output");
+    Job j;
+    j.mode = -1;
+    j.n = n;
+    j.has_canopy = true;
+    j.can = *canopy;
+    j.geom = geom;
+    j.lidf = lidf;
+    return run(h, j, on_host, stream);
+}
+
+static void copy_out(Job& j, const prosail_out_t* out) {
+    for (int i = 0; i < NOUT; ++i) j.plane[i] = out->plane[i];
+    j.pitch = out->pitch;
+    j.mean_mask = out->mean_mask;
+    j.means = out->means;
+    j.geom = out->geom;
+    j.windows_only = out->windows_only;
+}
+
+int prosail_sail_f64(prosail_handle_t* h, long long n, const double* ks, long long pitch_ks, const double* kt, long long pitch_kt,
+                     const double* rho, long long pitch_rho, const prosail_canopy_t* canopy, const prosail_out_t* out, int on_host,
+                     void* stream) {
+    if (!canopy || !out) return fail(PROSAIL_E_ARG, "null canopy / out struct");
+    for (long long p : {pitch_ks, pitch_kt, pitch_rho})
+        if (p != 0 && p < NB) return fail(PROSAIL_E_ARG, "input pitch must be 0 (broadcast) or >= %d", NB);
+    Job j;
+    j.mode = MODE_SAIL;
+    j.n = n;
+    j.has_canopy = true;
+    j.can = *canopy;
+    j.in_r = ks; j.pr = pitch_ks;
+    j.in_t = kt; j.pt = pitch_kt;
+    j.in_rho = rho; j.prho = pitch_rho;
+    copy_out(j, out);
+    if (j.mean_mask & ((1u << O_LEAF_R) | (1u << O_LEAF_T) | (1u << O_RHO))) return fail(PROSAIL_E_ARG, "means of input spectra are not provided by prosail_sail_f64");
+    return run(h, j, on_host, stream);
+}
+
+int prosail_prosail_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_soil_t* soil,
+                        const prosail_canopy_t* canopy, const prosail_out_t* out, int on_host, void* stream) {
+    if (!leaf || !soil || !canopy || !out) return fail(PROSAIL_E_ARG, "null leaf / soil / canopy / out struct");
+    Job j;
+    j.mode = MODE_PROSAIL;
+    j.version = version;
+    j.n = n;
+    j.has_leaf = j.has_soil = j.has_canopy = true;
+    j.leaf = *leaf;
+    j.soil = *soil;
+    j.can = *canopy;
+    copy_out(j, out);
+    return run(h, j, on_host, stream);
+}
+
+// ---- helpers ----
+int prosail_dev_alloc(prosail_handle_t* h, long long bytes, void** out) {
+    if (!h || !out || bytes < 0) return fail(PROSAIL_E_ARG, "bad argument");
+    DeviceGuard guard(h->device);
+    CK(cudaMalloc(out, (size_t)std::max<long long>(bytes, 1)));
+    return 0;
+}
+int prosail_dev_free(prosail_handle_t* h, void* p) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    DeviceGuard guard(h->device);
+    CK(cudaFree(p));
+    return 0;
+}
+int prosail_host_alloc(long long bytes, void** out) {
+    if (!out || bytes < 0) return fail(PROSAIL_E_ARG, "bad argument");
+    CK(cudaHostAlloc(out, (size_t)std::max<long long>(bytes, 1), cudaHostAllocPortable));
+    return 0;
+}
+int prosail_host_free(void* p) {
+    CK(cudaFreeHost(p));
+    return 0;
+}
+int prosail_memcpy_h2d(prosail_handle_t* h, void* dst, const void* src, long long bytes, void* stream) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    DeviceGuard guard(h->device);
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, stream ? (cudaStream_t)stream : h->stream));
+    return 0;
+}
+int prosail_memcpy_d2h(prosail_handle_t* h, void* dst, const void* src, long long bytes, void* stream) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    DeviceGuard guard(h->device);
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, stream ? (cudaStream_t)stream : h->stream));
+    return 0;
+}
+int prosail_sync(prosail_handle_t* h, void* stream) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    DeviceGuard guard(h->device);
+    CK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : h->stream));
+    return 0;
+}
+int prosail_timer_begin(prosail_handle_t* h, void* stream) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    DeviceGuard guard(h->device);
+    CK(cudaEventRecord(h->t0, stream ? (cudaStream_t)stream : h->stream));
+    return 0;
+}
+int prosail_timer_end(prosail_handle_t* h, void* stream, float* ms) {
+    if (!h || !ms) return fail(PROSAIL_E_ARG, "bad argument");
+    DeviceGuard guard(h->device);
+    CK(cudaEventRecord(h->t1, stream ? (cudaStream_t)stream : h->stream));
+    CK(cudaEventSynchronize(h->t1));
+    CK(cudaEventElapsedTime(ms, h->t0, h->t1));
+    return 0;
+}
+long long prosail_launch_count(prosail_handle_t* h) { return h ? h->launches : 0; }
+
+int prosail_device_info(prosail_handle_t* h, char* name, int name_len, int* sm_count, long long* mem_bytes) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (mem_bytes) *mem_bytes = (long long)prop.totalGlobalMem;
+    return 0;
+}
+
+int prosail_measure_fp64_peak(prosail_handle_t* h, int millis, double* tflops) {
+    if (!h || !tflops) return fail(PROSAIL_E_ARG, "bad argument");
+    DeviceGuard guard(h->device);
+    double* sink = nullptr;
+    CK(cudaMalloc(&sink, 8));
+    const int blocks = h->sm_count * 8, threads = 256;
+    auto once = [&](int iters, float* ms) -> int {
+        CK(cudaEventRecord(h->t0, h->stream));
+        k_dfma_peak<<<blocks, threads, 0, h->stream>>>(iters, sink);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->t1, h->stream));
+        CK(cudaEventSynchronize(h->t1));
+        CK(cudaEventElapsedTime(ms, h->t0, h->t1));
+        return 0;
+    };
+    float ms = 0.f;
+    int rc;
+    if ((rc = once(2000, &ms))) return rc;          // warm-up + calibration
+    if ((rc = once(2000, &ms))) return rc;
+    int iters = (int)std::min(4.0e6, std::max(2000.0, 2000.0 * (double)std::max(millis, 1) / std::max(ms, 1e-3f)));
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        if ((rc = once(iters, &ms))) return rc;
+        const double flops = (double)blocks * threads * (double)iters * 32.0 * 2.0;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaFree(sink);
+    *tflops = best;
+    return 0;
+}
+
+int prosail_test_math(prosail_handle_t* h, int op, long long n, const double* in, double* out, int on_host) {
+    if (!h || !in || !out || n < 0) return fail(PROSAIL_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    DeviceGuard guard(h->device);
+    const double* din = in;
+    double* dout = out;
+    DevBuf bi, bo;
+    if (on_host) {
+        int rc;
+        if ((rc = bi.reserve((size_t)n * 8)) || (rc = bo.reserve((size_t)n * 8))) return rc;
+        CK(cudaMemcpyAsync(bi.p, in, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+        din = (const double*)bi.p;
+        dout = (double*)bo.p;
+    }
+    k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(op, n, din, dout, h->d_tables);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (on_host) {
+        CK(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        bi.release();
+        bo.release();
+    }
+    return 0;
+}
+
+}  // extern "C"

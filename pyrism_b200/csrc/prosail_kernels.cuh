@@ -1,0 +1,684 @@
+// sm_100a kernels for the batched PROSPECT-5/D -> 4SAIL -> band-mean path.
+//
+// Mapping (all kernels): one THREAD owns one wavelength and keeps that band's constants
+// (6-7 specific absorption coefficients, 3 interface transmissivities, 2 soil spectra) in registers;
+// a WARP owns 32 consecutive bands (66 warp tiles cover 2101 bands, 99.5% lane efficiency) and walks
+// over the work items (parameter set x geometry).  Per-item scalars come from 128-byte records that
+// the prologue kernel packs and that each CTA stages into shared memory with bulk async copies
+// (cp.async.bulk + mbarrier, double buffered), so the inner loop touches HBM only for the coalesced
+// 256-byte-per-warp stores of the output spectra.
+//
+// Reference (ibaris/pyrism 0.0.5, pyrism/models/models.py) lines are cited at each step.
+#pragma once
+#include "math64.cuh"
+
+namespace pb {
+
+constexpr int NB = 2101;          // wavelengths 400..2500 nm
+constexpr int NTILES = 66;        // 32-band warp tiles
+constexpr int NBP = NTILES * 32;  // padded band count (2112)
+constexpr int WARPS_PER_CTA = 6;  // 66 = 11 x 6
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int BAND_CTAS = NTILES / WARPS_PER_CTA;   // 11
+constexpr int CHUNK = 32;         // work items per shared-memory stage
+constexpr int REC = 16;           // doubles per record (128 B)
+constexpr int MAX_TILE_SLOTS = 8; // windows that may overlap one 32-band tile
+constexpr int MAX_WINDOWS = 64;
+constexpr int MAX_SLOTS = 256;
+
+// planes of the per-band constant array  double[NCONST][NBP]
+enum { C_KAB = 0, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RS1, C_RS2, NCONST };
+
+// sample record (per parameter set)
+enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DDB, S_DDF, S_NEGLAI, S_LAI, S_NOCANOPY, S_THR };
+// geometry record (per parameter set x geometry)
+enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_BF, G_SUMINT, G_ALF };
+
+// output planes (bit index in out_mask / mean_mask)
+enum { O_RSOT = 0, O_RDDT, O_RSDT, O_RDOT, O_RSO, O_RDD, O_TDD, O_RSD, O_TSD, O_RDO, O_TDO, O_KE, O_LEAF_R, O_LEAF_T, O_RHO, NOUT };
+
+struct WindowMap {                       // which band-mean windows touch which warp tile
+    int nslots[NTILES];
+    unsigned mask[NTILES][MAX_TILE_SLOTS];   // lanes of the tile inside the window
+    int slot[NTILES][MAX_TILE_SLOTS];        // global slot id (window-major)
+    int wstart[MAX_WINDOWS + 1];             // slots of window w: [wstart[w], wstart[w+1])
+    int wcount[MAX_WINDOWS];                 // number of bands in window w
+    int nwindows, ntotal;
+    int ntiles_active;                       // tiles touched by at least one window
+    int active_tile[NTILES];
+};
+
+struct SailArgs {
+    const double* bandc;       // [NCONST][NBP]
+    const double* tables;      // MathTables image in global memory
+    const WindowMap* win;      // band-mean window map (global memory, read uniformly)
+    const double* srec;        // [nsamples][REC]
+    const double* grec;        // [nitems][REC]
+    long long nitems;
+    int G;                     // geometries per sample (item = s*G + g)
+    // SAIL-only mode: leaf / soil spectra from memory, row pitch in elements (0 = one spectrum for all samples)
+    const double* in_r; const double* in_t; const double* in_rho;
+    long long in_pitch_r, in_pitch_t, in_pitch_rho;
+    double* out[NOUT];         // output planes [nitems][pitch] (NULL = not requested)
+    long long out_pitch;
+    unsigned mean_mask;        // planes whose band means are accumulated
+    double* partial;           // [nitems][nmean][ntotal slots]
+    int nmean;
+    int only_active_tiles;     // 1: visit only tiles touched by a window (band-mean-only LUTs)
+    int f32_means;             // 1: round values to float before averaging (PROSPECT/LSM convention, models.py:1071)
+};
+
+
+// ---------------------------------------------------------------------------------------------
+// bulk-async staging helpers (mbarrier + cp.async.bulk, CTA scope)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n"
+        " bra WAIT_%=;\n"
+        "DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct alignas(128) Stage {
+    double s[CHUNK * REC];   // sample records spanned by the chunk
+    double g[CHUNK * REC];   // geometry records of the chunk
+};
+
+struct alignas(128) SailSmem {
+    MathTables mt;
+    Stage stage[2];
+    uint64_t bar[2];
+};
+
+// issue the two bulk copies of one chunk (called by one thread)
+__device__ __forceinline__ void stage_issue(const SailArgs& a, Stage* st, uint64_t* bar, long long chunk) {
+    const long long i0 = chunk * CHUNK;
+    const long long i1 = min(i0 + (long long)CHUNK, a.nitems);
+    const long long s0 = i0 / a.G, s1 = (i1 - 1) / a.G;
+    const uint32_t gbytes = (uint32_t)(i1 - i0) * REC * 8u;
+    const uint32_t sbytes = (uint32_t)(s1 - s0 + 1) * REC * 8u;
+    mbar_expect_tx(bar, gbytes + sbytes);
+    bulk_g2s(st->g, a.grec + i0 * REC, gbytes, bar);
+    bulk_g2s(st->s, a.srec + s0 * REC, sbytes, bar);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-band device functions
+// ---------------------------------------------------------------------------------------------
+struct BandConst {
+    double kab, kxc, kan, kbr, kw, km;      // specific absorption coefficients
+    double talf, ralf, t12, r12, t21, r21;  // interface terms (models.py:1011-1016)
+    double rs1, rs2;                        // soil spectra
+};
+
+// PROSPECT for one band and one parameter set: leaf reflectance (ks) and transmittance (kt).
+// models.py:949-959 (kall, tau), 1019-1025 (one layer), 1043-1068 (Stokes, N layers).
+__device__ __forceinline__ void leaf_optics(const BandConst& c, const double* __restrict__ s, const MathTables& mt,
+                                            double& refl, double& tran) {
+    // kall = sum_i C_i K_i / N ; the division by N is folded into the record (C_i / N)      :950-951
+    double kall = s[S_CAB] * c.kab;
+    kall = fma(s[S_CXC], c.kxc, kall);
+    kall = fma(s[S_CAN], c.kan, kall);
+    kall = fma(s[S_CBR], c.kbr, kall);
+    kall = fma(s[S_CW], c.kw, kall);
+    kall = fma(s[S_CM], c.km, kall);
+    const double tau = tau_plate(kall, mt.tau);                                               // :953-957
+    // one layer                                                                              :1019-1025
+    const double x = c.r21 * tau;
+    const double inv = rcp(fma(-x, x, 1.0));
+    const double tt = tau * c.t21 * inv;
+    const double Ta = c.talf * tt;
+    const double t = c.t12 * tt;
+    const double Ra = fma(x, Ta, c.ralf);
+    const double r = fma(x, t, c.r12);
+    // Stokes: D^2 = (1+r+t)(1+r-t)(1-r+t)(1-r-t)                                             :1043
+    const double p = 1.0 + r, q = 1.0 - r;
+    const double P12 = (p + t) * (p - t);
+    const double P34 = (q + t) * (q - t);
+    const double D = sqrt_pos(P12 * P34);
+    const double A = fma(-2.0, r, P12);            // 1 + r^2 - t^2
+    const double hD = 0.5 * D;
+    const double al = fma(0.5, A, hD);             // a * r   (a of :1046)
+    const double be = fma(-0.5, A, 1.0 + hD);      // b * t   (b of :1047), using 1 - r^2 + t^2 = 2 - A
+    if (__builtin_expect(r + t >= 1.0, 0)) {       // zero absorption                         :1057-1059
+        const double nm1 = s[S_NM1];
+        const double Tsub = t / (t + (1.0 - t) * nm1);
+        const double Rsub = 1.0 - Tsub;
+        const double den = 1.0 - Rsub * r;
+        tran = Ta * Tsub / den;
+        refl = Ra + Ta * Rsub * t / den;
+        return;
+    }
+    const double b = be * rcp(t);
+    // b^(N-1) = 2^((N-1) log2 b)                                                             :1049
+    const double y = fmin(log2_pos(b, mt.logt) * s[S_NM1], 500.0);
+    const double bNm1 = exp2_any(y, mt.exp2t);
+    const double bN2 = bNm1 * bNm1;
+    // With a = al/r:  kt = Ta bNm1 (al^2 - r^2)/X,  ks = Ra + Ta t al r (bN2 - 1)/X,
+    //                 X = al^2 bN2 - r^2 - al r^2 (bN2 - 1)      (algebraically :1052-1065, one division)
+    const double bm1 = bN2 - 1.0;
+    const double al2 = al * al, r2 = r * r;
+    const double X = fma(-(al * r2), bm1, fma(al2, bN2, -r2));
+    const double TaI = Ta * rcp(X);
+    tran = TaI * (bNm1 * (al2 - r2));
+    refl = fma(TaI * bm1, (t * al) * r, Ra);
+}
+
+// geometry-independent part of 4SAIL for one band (models.py:590-601, 637-642, 654-655, 714-719)
+struct Diffuse {
+    double m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd;
+};
+
+__device__ __forceinline__ void sail_diffuse(double rho, double tau, double rs, const double* __restrict__ s, const MathTables& mt,
+                                             Diffuse& d) {
+    double sigb = fma(s[S_DDB], rho, s[S_DDF] * tau);                 // :590
+    double sigf = fma(s[S_DDF], rho, s[S_DDB] * tau);                 // :591
+    sigb = sigb == 0.0 ? 1e-36 : sigb;                                // :594-595
+    sigf = sigf == 0.0 ? 1e-36 : sigf;
+    const double att = 1.0 - sigf;                                    // :600
+    d.m = sqrt_pos(fma(att, att, -(sigb * sigb)));                    // :601
+    d.e1 = exp_neg(d.m * s[S_NEGLAI], mt.exp2t);                      // :637
+    const double e2 = d.e1 * d.e1;
+    d.rinf = (att - d.m) * rcp(sigb);                                 // :639
+    const double rinf2 = d.rinf * d.rinf;
+    d.re = d.rinf * d.e1;
+    d.invden = rcp(fma(-rinf2, e2, 1.0));                             // :642
+    const double omr2 = 1.0 - rinf2;
+    d.inv_omr2 = rcp(omr2);
+    d.tdd = omr2 * d.e1 * d.invden;                                   // :654
+    d.rdd = d.rinf * (1.0 - e2) * d.invden;                           // :655
+    d.rsrdd = rs * d.rdd;
+    const double dn = fmax(1.0 - d.rsrdd, 1e-36);                     // :714-719
+    d.rs_invdn = rs * rcp(dn);
+}
+
+// geometry-dependent part of 4SAIL for one band (models.py:603-607, 644-678, 706-726, 765-789)
+struct Canopy {
+    double rsot, rddt, rsdt, rdot;        // BRF, BHR, DHR, HDR with soil
+    double rso, rsd, tsd, rdo, tdo;       // canopy-only terms
+};
+
+// |x| > thr decided on the high words only (integer pipe).  The threshold of J1's series branch is
+// soft: both branches agree to ~1e-13 around it, so a 2^-20-relative fuzz of the switch point is harmless.
+__device__ __forceinline__ bool abs_gt_hi(double x, int thr_hi) { return (__double2hiint(x) & 0x7fffffff) > thr_hi; }
+
+__device__ __forceinline__ void sail_directional(double rho, double tau, double rs, const Diffuse& d, const double* __restrict__ s,
+                                                 const double* __restrict__ g, int thr_hi, unsigned need, Canopy& o) {
+    const double k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO], lai = s[S_LAI];
+    const double sb = fma(g[G_SDB], rho, g[G_SDF] * tau);             // :603-607
+    const double sf = fma(g[G_SDF], rho, g[G_SDB] * tau);
+    const double vb = fma(g[G_DOB], rho, g[G_DOF] * tau);
+    const double vf = fma(g[G_DOF], rho, g[G_DOB] * tau);
+    const double w = fma(g[G_FS], rho, g[G_FT] * tau);
+    // J1(k,m), J2(k,m), J1(K,m), J2(K,m): 1/(k-m) and 1/(k+m) from ONE reciprocal of (k-m)(k+m)   :644-647, 765-789
+    double J1ks, J1ko, inv_kp, inv_Kp;
+    {
+        const double km = k - d.m, kp = k + d.m;
+        if (__builtin_expect(abs_gt_hi(km, thr_hi), 1)) {
+            const double i = rcp(km * kp);
+            inv_kp = i * km;
+            J1ks = (d.e1 - tss) * (i * kp);
+        } else {
+            const double del = km * lai;
+            inv_kp = rcp(kp);
+            J1ks = 0.5 * lai * (tss + d.e1) * (1.0 - del * del / 12.0);
+        }
+        const double Km = K - d.m, Kp = K + d.m;
+        if (__builtin_expect(abs_gt_hi(Km, thr_hi), 1)) {
+            const double i = rcp(Km * Kp);
+            inv_Kp = i * Km;
+            J1ko = (d.e1 - too) * (i * Kp);
+        } else {
+            const double del = Km * lai;
+            inv_Kp = rcp(Kp);
+            J1ko = 0.5 * lai * (too + d.e1) * (1.0 - del * del / 12.0);
+        }
+    }
+    const double J2ks = fma(-d.e1, tss, 1.0) * inv_kp;
+    const double J2ko = fma(-d.e1, too, 1.0) * inv_Kp;
+    const double u1 = fma(sb, d.rinf, sf), u2 = fma(sf, d.rinf, sb);  // :649-652
+    const double v1 = fma(vb, d.rinf, vf), v2 = fma(vf, d.rinf, vb);
+    const double Pss = u1 * J1ks, Qss = u2 * J2ks, Pv = v1 * J1ko, Qv = v2 * J2ko;
+    o.tsd = fma(-d.re, Qss, Pss) * d.invden;                          // :656-659
+    o.rsd = fma(-d.re, Pss, Qss) * d.invden;
+    o.tdo = fma(-d.re, Qv, Pv) * d.invden;
+    o.rdo = fma(-d.re, Pv, Qv) * d.invden;
+    const double g1 = fma(-J1ks, too, g[G_Z]) * inv_Kp;               // :668-669
+    const double g2 = fma(-J1ko, tss, g[G_Z]) * inv_kp;
+    const double T1 = (v2 * g1) * u1, T2 = (v1 * g2) * u2;            // :671-675
+    const double T3 = fma(o.rdo, Qss, o.tdo * Pss) * d.rinf;
+    const double rsod = (T1 + T2 - T3) * d.inv_omr2;                  // :678
+    o.rso = fma(w, g[G_LAISUM], rsod);                                // :706, :710
+    // soil coupling                                                                        :721-726
+    const double rsodt = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too) * d.rs_invdn;
+    o.rsot = fma(g[G_TSSTOO], rs, o.rso) + rsodt;
+    if (need & (1u << O_RDDT)) o.rddt = fma(d.tdd * d.tdd, d.rs_invdn, d.rdd);
+    if (need & (1u << O_RSDT)) o.rsdt = fma((o.tsd + tss) * d.tdd, d.rs_invdn, o.rsd);
+    if (need & (1u << O_RDOT)) o.rdot = fma(d.tdd * (o.tdo + too), d.rs_invdn, o.rdo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// band-mean partial sums: segmented warp reduction over the windows that touch this tile
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void mean_partials(const WindowMap* __restrict__ win, double v, int tile, int lane,
+                                              double* __restrict__ dst /* [ntotal] */, bool f32) {
+    if (f32) v = (double)(float)v;
+    const int ns = win->nslots[tile];
+    for (int j = 0; j < ns; ++j) {
+        const double x = ((win->mask[tile][j] >> lane) & 1u) ? v : 0.0;
+        const double sum = warp_sum(x);
+        if (lane == 0) dst[win->slot[tile][j]] = sum;
+    }
+}
+
+enum { MODE_PROSAIL = 0, MODE_SAIL = 1, MODE_PROSPECT = 2, MODE_SOIL = 3 };
+
+// ---------------------------------------------------------------------------------------------
+// main kernel.  grid = (band CTAs, item-chunk CTAs); block = 6 warps = 6 consecutive band tiles.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(CTA_THREADS, 3) k_bands(const SailArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SailSmem& sm = *reinterpret_cast<SailSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tslot = blockIdx.x * WARPS_PER_CTA + warp;
+    const int tile = a.only_active_tiles ? (tslot < a.win->ntiles_active ? a.win->active_tile[tslot] : -1) : tslot;
+    const int band = tile * 32 + lane;
+    const bool live = tile >= 0;
+    const bool valid = live && band < NB;
+
+    {   // math tables -> shared memory
+        const double2* src = reinterpret_cast<const double2*>(a.tables);
+        double2* dst = reinterpret_cast<double2*>(&sm.mt);
+        for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 16); i += CTA_THREADS) dst[i] = src[i];
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
+    long long chunk = blockIdx.y;
+    if (threadIdx.x == 0 && chunk < nchunks) stage_issue(a, &sm.stage[0], &sm.bar[0], chunk);
+
+    BandConst c;
+    {
+        const int bb = live ? band : 0;
+        const double* bc = a.bandc + bb;
+        c.kab = bc[C_KAB * NBP]; c.kxc = bc[C_KXC * NBP]; c.kan = bc[C_KAN * NBP]; c.kbr = bc[C_KBR * NBP];
+        c.kw = bc[C_KW * NBP]; c.km = bc[C_KM * NBP];
+        c.talf = bc[C_TALF * NBP]; c.t12 = bc[C_T12 * NBP]; c.t21 = bc[C_T21 * NBP];
+        c.ralf = 1.0 - c.talf; c.r12 = 1.0 - c.t12; c.r21 = 1.0 - c.t21;        // models.py:1012-1016
+        c.rs1 = bc[C_RS1 * NBP]; c.rs2 = bc[C_RS2 * NBP];
+    }
+    unsigned need = a.mean_mask;
+#pragma unroll
+    for (int i = 0; i < NOUT; ++i) need |= a.out[i] ? (1u << i) : 0u;
+    const int nt = a.win->ntotal;
+
+    for (unsigned it = 0; chunk < nchunks; chunk += gridDim.y, ++it) {
+        const int buf = it & 1;
+        const long long next = chunk + gridDim.y;
+        if (threadIdx.x == 0 && next < nchunks) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            stage_issue(a, &sm.stage[buf ^ 1], &sm.bar[buf ^ 1], next);
+        }
+        mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
+
+        if (live) {
+            const long long i0 = chunk * CHUNK;
+            const int n = (int)min((long long)CHUNK, a.nitems - i0);
+            const long long s0 = i0 / a.G;
+            long long s = s0;
+            int g = (int)(i0 - s0 * a.G);
+            bool fresh = true;
+            double rho = 0.0, tau = 0.0, rs = 0.0;
+            Diffuse d;
+            int thr_hi = 0;
+            for (int j = 0; j < n; ++j) {
+                const long long item = i0 + j;
+                const double* sr = sm.stage[buf].s + (int)(s - s0) * REC;
+                const double* gr = sm.stage[buf].g + j * REC;
+                double* pdst = a.partial + (item * a.nmean) * nt;
+                const long long orow = item * a.out_pitch + band;
+#define PB_EMIT(PLANE, VAL, MI)                                                              \
+    do {                                                                                     \
+        if (a.out[PLANE] && valid) __stcs(a.out[PLANE] + orow, (VAL));                       \
+        if (a.mean_mask & (1u << (PLANE))) { mean_partials(a.win, (VAL), tile, lane, pdst + (MI) * nt, a.f32_means); ++(MI); } \
+    } while (0)
+                if (MODE == MODE_SOIL) {
+                    rs = fma(sr[S_SOIL1], c.rs1, sr[S_SOIL2] * c.rs2);          // models.py:1917
+                    int mi = 0;
+                    PB_EMIT(O_RHO, rs, mi);
+                } else if (MODE == MODE_PROSPECT) {
+                    leaf_optics(c, sr, sm.mt, rho, tau);
+                    // ka, ke, om: models.py:1066-1068 (only needed for their band means)
+                    int mi = 0;
+                    PB_EMIT(O_LEAF_R, rho, mi);
+                    PB_EMIT(O_LEAF_T, tau, mi);
+                    if (a.mean_mask & (1u << O_RSOT)) {     // bits 0..2 double as ka / ke / om in this mode
+                        const double ka = 1.0 - rho - tau, ke = rho + ka, om = rho / ke;
+                        mean_partials(a.win, ka, tile, lane, pdst + (mi++) * nt, a.f32_means);
+                        mean_partials(a.win, ke, tile, lane, pdst + (mi++) * nt, a.f32_means);
+                        mean_partials(a.win, om, tile, lane, pdst + (mi++) * nt, a.f32_means);
+                    }
+                } else {
+                    if (fresh) {
+                        if (MODE == MODE_PROSAIL) {
+                            leaf_optics(c, sr, sm.mt, rho, tau);
+                            rs = fma(sr[S_SOIL1], c.rs1, sr[S_SOIL2] * c.rs2);  // models.py:1917
+                        } else {
+                            const int bb = valid ? band : 0;
+                            rho = a.in_r[s * a.in_pitch_r + bb];
+                            tau = a.in_t[s * a.in_pitch_t + bb];
+                            rs = a.in_rho[s * a.in_pitch_rho + bb];
+                        }
+                        sail_diffuse(rho, tau, rs, sr, sm.mt, d);
+                        // |k - m| lai <= 1e-3  <=>  |k - m| <= 1e-3 / lai   (threshold on the high word)
+                        thr_hi = __double2hiint(sr[S_THR]);
+                        fresh = false;
+                    }
+                    int mi = 0;
+                    if (sr[S_NOCANOPY] != 0.0) {                                 // lai <= 0: models.py:609-634
+                        PB_EMIT(O_RSOT, rs, mi); PB_EMIT(O_RDDT, rs, mi); PB_EMIT(O_RSDT, rs, mi); PB_EMIT(O_RDOT, rs, mi);
+                        PB_EMIT(O_RSO, 0.0, mi); PB_EMIT(O_RDD, 0.0, mi); PB_EMIT(O_TDD, 1.0, mi); PB_EMIT(O_RSD, 0.0, mi);
+                        PB_EMIT(O_TSD, 0.0, mi); PB_EMIT(O_RDO, 0.0, mi); PB_EMIT(O_TDO, 0.0, mi);
+                    } else {
+                        Canopy o;
+                        o.rddt = o.rsdt = o.rdot = 0.0;
+                        sail_directional(rho, tau, rs, d, sr, gr, thr_hi, need, o);
+                        PB_EMIT(O_RSOT, o.rsot, mi); PB_EMIT(O_RDDT, o.rddt, mi); PB_EMIT(O_RSDT, o.rsdt, mi); PB_EMIT(O_RDOT, o.rdot, mi);
+                        PB_EMIT(O_RSO, o.rso, mi); PB_EMIT(O_RDD, d.rdd, mi); PB_EMIT(O_TDD, d.tdd, mi); PB_EMIT(O_RSD, o.rsd, mi);
+                        PB_EMIT(O_TSD, o.tsd, mi); PB_EMIT(O_RDO, o.rdo, mi); PB_EMIT(O_TDO, o.tdo, mi);
+                    }
+                    PB_EMIT(O_KE, d.m, mi);
+                    PB_EMIT(O_LEAF_R, rho, mi);
+                    PB_EMIT(O_LEAF_T, tau, mi);
+                    PB_EMIT(O_RHO, rs, mi);
+                }
+#undef PB_EMIT
+                if (++g == a.G) { g = 0; ++s; fresh = true; }
+            }
+        }
+        __syncthreads();   // everyone is done with stage[buf] before it is refilled two iterations later
+    }
+}
+
+// band means = ordered sum of a window's slot partials / band count
+__global__ void k_finalize_means(const WindowMap* __restrict__ win, const double* __restrict__ partial, long long nrows /* nitems*nmean */,
+                                 double* __restrict__ means, float* __restrict__ means_f32) {
+    const int nw = win->nwindows, nt = win->ntotal;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * nw) return;
+    const long long row = idx / nw;
+    const int w = (int)(idx - row * nw);
+    double acc = 0.0;
+    for (int sl = win->wstart[w]; sl < win->wstart[w + 1]; ++sl) acc += partial[row * nt + sl];
+    const double mean = acc / (double)win->wcount[w];
+    if (means) means[idx] = mean;
+    if (means_f32) means_f32[idx] = (float)mean;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prologue: one warp per (parameter set, geometry).  Lanes 0..17 are the 18 leaf-inclination bins
+// (LIDF + volume-scattering sums, warp-shuffle reductions); lanes 0..19 are the 20 hotspot steps.
+// ---------------------------------------------------------------------------------------------
+struct PrologueArgs {
+    long long nsamples;
+    int G;                 // geometries per parameter set
+    int geom_per_sample;   // 1: iza/vza/raa have nsamples entries (G must be 1); 0: G entries shared by all sets
+    int lidf_type;         // 0 campbell (models.py:283-332), 1 verhoef (models.py:335-392)
+    int has_leaf, has_soil, has_canopy;
+    const double *N, *Cab, *Cxc, *Cbr, *Cw, *Cm, *Can;
+    const double *soil_refl, *soil_moist;
+    const double *lai, *hot, *lidf_a, *lidf_b;
+    const double *iza, *vza, *raa;   // radians, already normalised like core/_core.py:136-146
+    double* srec;
+    double* grec;
+    double* geom_out;      // optional [nitems][8]: VolScatt ks, ko, bf, Fs, Ft and tss, too, tsstoo
+    double* lidf_out;      // optional [nsamples][18]
+};
+
+#define PB_PI 3.14159265358979323846
+
+// volume scattering functions for one leaf zenith angle (degrees) -- models.py:177-258
+__device__ __forceinline__ void volscatt_volume(double tts, double tto, double psi, double ttl_deg, double& chi_s, double& chi_o,
+                                                double& frho, double& ftau) {
+    const double cts = cos(tts), cto = cos(tto), sts = sin(tts), sto = sin(tto), cospsi = cos(psi);
+    const double tl = ttl_deg * (PB_PI / 180.0);
+    const double clza = cos(tl), slza = sin(tl);
+    const double cs = clza * cts, co = clza * cto, ss = slza * sts, so = slza * sto;
+    double cosbts = 5.0, cosbto = 5.0;
+    if (fabs(ss) > 1e-6) cosbts = -cs / ss;
+    if (fabs(so) > 1e-6) cosbto = -co / so;
+    double bts, ds, bto, do_;
+    if (fabs(cosbts) < 1.0) { bts = acos(cosbts); ds = ss; } else { bts = PB_PI; ds = cs; }
+    chi_s = 2.0 / PB_PI * ((bts - PB_PI * 0.5) * cs + sin(bts) * ss);
+    if (fabs(cosbto) < 1.0) { bto = acos(cosbto); do_ = so; }
+    else if (tto < 90.0 * PB_PI / 180.0) { bto = PB_PI; do_ = co; }
+    else { bto = 0.0; do_ = -co; }
+    chi_o = 2.0 / PB_PI * ((bto - PB_PI * 0.5) * co + sin(bto) * so);
+    const double btran1 = fabs(bts - bto);
+    const double btran2 = PB_PI - fabs(bts + bto - PB_PI);
+    double bt1, bt2, bt3;
+    if (psi <= btran1) { bt1 = psi; bt2 = btran1; bt3 = btran2; }
+    else {
+        bt1 = btran1;
+        if (psi <= btran2) { bt2 = psi; bt3 = btran2; } else { bt2 = btran2; bt3 = psi; }
+    }
+    const double t1 = 2.0 * cs * co + ss * so * cospsi;
+    double t2 = 0.0;
+    if (bt2 > 0.0) t2 = sin(bt2) * (2.0 * ds * do_ + ss * so * cos(bt1) * cos(bt3));
+    const double denom = 2.0 * PB_PI * PB_PI;
+    frho = fmax(((PB_PI - bt2) * t1 + t2) / denom, 0.0);
+    ftau = fmax((-bt2 * t1 + t2) / denom, 0.0);
+}
+
+__global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nitems = a.nsamples * a.G;
+    if (item >= nitems) return;
+    const long long s = item / a.G;
+    const int g = (int)(item - s * a.G);
+
+    // ---- sample record (written by the g == 0 warp) ----
+    if (g == 0 && lane == 0) {
+        double* r = a.srec + s * REC;
+        for (int i = 0; i < REC; ++i) r[i] = 0.0;
+        if (a.has_leaf) {
+            const double N = a.N[s];
+            r[S_CAB] = a.Cab[s] / N; r[S_CXC] = a.Cxc[s] / N; r[S_CAN] = a.Can ? a.Can[s] / N : 0.0;
+            r[S_CBR] = a.Cbr[s] / N; r[S_CW] = a.Cw[s] / N; r[S_CM] = a.Cm[s] / N;
+            r[S_NM1] = N - 1.0;
+        }
+        if (a.has_soil) {
+            const double sr = a.soil_refl[s], mo = a.soil_moist[s];
+            r[S_SOIL1] = sr * mo;                 // rho = sRef (moisture rsoil1 + (1-moisture) rsoil2), models.py:1917
+            r[S_SOIL2] = sr * (1.0 - mo);
+        }
+    }
+    if (!a.has_canopy) return;
+
+    const double lai = a.lai[s], hot = a.hot[s];
+    const double la = a.lidf_a[s], lb = a.lidf_b ? a.lidf_b[s] : 0.0;
+    const long long gi = a.geom_per_sample ? s : g;
+    const double tts = a.iza[gi], tto = a.vza[gi], psi = a.raa[gi];
+
+    // ---- LIDF over 18 bins of 5 degrees ----
+    double lidf = 0.0;
+    if (a.lidf_type == 0) {                       // Campbell, models.py:301-330
+        const double excent = exp(-1.6184e-5 * la * la * la + 2.1145e-3 * la * la - 1.2390e-1 * la + 3.2491);
+        double freq = 0.0;
+        if (lane < 18) {
+            const double tl1 = (lane * 5.0) * PB_PI / 180.0, tl2 = ((lane + 1.0) * 5.0) * PB_PI / 180.0;
+            const double tn1 = tan(tl1), tn2 = tan(tl2);
+            const double x1 = excent / sqrt(1.0 + excent * excent * tn1 * tn1);
+            const double x2 = excent / sqrt(1.0 + excent * excent * tn2 * tn2);
+            if (excent == 1.0) {
+                freq = fabs(cos(tl1) - cos(tl2));
+            } else {
+                const double alph = excent / sqrt(fabs(1.0 - excent * excent));
+                const double alph2 = alph * alph, x12 = x1 * x1, x22 = x2 * x2;
+                if (excent > 1.0) {
+                    const double p1 = sqrt(alph2 + x12), p2 = sqrt(alph2 + x22);
+                    freq = fabs(x1 * p1 + alph2 * log(x1 + p1) - (x2 * p2 + alph2 * log(x2 + p2)));
+                } else {
+                    const double q1 = sqrt(alph2 - x12), q2 = sqrt(alph2 - x22);
+                    freq = fabs(x1 * q1 + alph2 * asin(x1 / alph) - (x2 * q2 + alph2 * asin(x2 / alph)));
+                }
+            }
+        }
+        const double sum0 = warp_sum(freq);
+        lidf = freq / sum0;
+    } else {                                      // Verhoef, models.py:366-390
+        // F(theta) at theta = lane*5 deg; lidf_i = F((i+1)*5) - F(i*5), F(90) = 1.
+        double f = 1.0;
+        if (lane < 18) {
+            const double tl1 = (lane * 5.0) * (PB_PI / 180.0);
+            if (la > 1.0) {
+                f = 1.0 - cos(tl1);
+            } else {
+                double x = 2.0 * tl1, y = 0.0, dx;
+                const double p = x;
+                int itn = 0;
+                do {
+                    y = la * sin(x) + 0.5 * lb * sin(2.0 * x);
+                    dx = 0.5 * (y - x + p);
+                    x += dx;
+                } while (fabs(dx) >= 1e-8 && ++itn < 4096);
+                f = (2.0 * y + p) / PB_PI;
+            }
+        }
+        const double fnext = __shfl_down_sync(0xffffffffu, f, 1);    // lane 17 receives lane 18's f = 1.0
+        lidf = lane < 18 ? fnext - f : 0.0;
+    }
+    if (a.lidf_out && g == 0 && lane < 18) a.lidf_out[s * 18 + lane] = lidf;
+
+    // ---- LIDF-weighted volume-scattering sums, models.py:144-175 ----
+    double ksli = 0.0, koli = 0.0, bfli = 0.0, sobli = 0.0, sofli = 0.0;
+    const double cts = cos(tts), cto = cos(tto);
+    if (lane < 18) {
+        const double ttl = lane * 5.0 + 2.5;
+        double chi_s, chi_o, frho, ftau;
+        volscatt_volume(tts, tto, psi, ttl, chi_s, chi_o, frho, ftau);
+        const double cttl = cos(ttl * (PB_PI / 180.0));
+        ksli = chi_s / cts * lidf;
+        koli = chi_o / cto * lidf;
+        bfli = cttl * cttl * lidf;
+        sobli = frho * PB_PI / (cts * cto) * lidf;
+        sofli = ftau * PB_PI / (cts * cto) * lidf;
+    }
+    const double k = warp_sum(ksli), K = warp_sum(koli), bf = warp_sum(bfli), Fs = warp_sum(sobli), Ft = warp_sum(sofli);
+
+    // ---- direct transmittances and the hotspot integral, models.py:664-666, 687-702, 731-763 ----
+    const bool nocanopy = !(lai > 0.0);
+    double tss = 1.0, too = 1.0, tsstoo = 1.0, sumint = 0.0, z = 0.0, alf = 1e36;
+    if (!nocanopy) {
+        tss = exp(-k * lai);
+        too = exp(-K * lai);
+        z = (1.0 - exp(-(k + K) * lai)) / (k + K);                   // Jfunc2(ks, ko, lai)
+        const double tants = tan(tts), tanto = tan(tto);
+        const double dso = sqrt(tants * tants + tanto * tanto - 2.0 * tants * tanto * cos(psi));
+        if (hot > 0.0) alf = (dso / hot) * 2.0 / (k + K);
+        if (alf == 0.0) {                                             // the pure hotspot
+            tsstoo = tss;
+            sumint = (1.0 - tss) / (k * lai);
+        } else {
+            const double fhot = lai * sqrt(K * k);
+            const double fint = (1.0 - exp(-alf)) * 0.05;
+            // lane i holds step istep = i + 1; (x1, y1, f1) come from lane i-1
+            double x2 = 1.0, y2 = 0.0, f2 = 1.0;
+            if (lane < 20) {
+                if (lane < 19) x2 = -log(1.0 - (lane + 1) * fint) / alf;
+                y2 = -(K + k) * lai * x2 + fhot * (1.0 - exp(-alf * x2)) / alf;
+                f2 = exp(y2);
+            }
+            double x1 = __shfl_up_sync(0xffffffffu, x2, 1), y1 = __shfl_up_sync(0xffffffffu, y2, 1),
+                   f1 = __shfl_up_sync(0xffffffffu, f2, 1);
+            if (lane == 0) { x1 = 0.0; y1 = 0.0; f1 = 1.0; }
+            const double term = lane < 20 ? (f2 - f1) * (x2 - x1) / (y2 - y1) : 0.0;
+            sumint = warp_sum(term);
+            tsstoo = __shfl_sync(0xffffffffu, f2, 19);
+            if (isnan(sumint)) sumint = 0.0;
+        }
+    }
+
+    if (lane == 0) {
+        double* r = a.grec + item * REC;
+        r[G_K] = k; r[G_KO] = K;
+        r[G_SDB] = 0.5 * (k + bf); r[G_SDF] = 0.5 * (k - bf);        // models.py:583-588
+        r[G_DOB] = 0.5 * (K + bf); r[G_DOF] = 0.5 * (K - bf);
+        r[G_FS] = Fs; r[G_FT] = Ft;
+        r[G_TSS] = tss; r[G_TOO] = too; r[G_TSSTOO] = tsstoo;
+        r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_BF] = bf; r[G_SUMINT] = sumint; r[G_ALF] = alf;
+        if (g == 0) {
+            double* sr = a.srec + s * REC;
+            sr[S_DDB] = 0.5 * (1.0 + bf); sr[S_DDF] = 0.5 * (1.0 - bf);
+            sr[S_NEGLAI] = -lai; sr[S_LAI] = lai; sr[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;
+            sr[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
+        }
+        if (a.geom_out) {
+            double* o = a.geom_out + item * 8;
+            o[0] = k; o[1] = K; o[2] = bf; o[3] = Fs; o[4] = Ft; o[5] = tss; o[6] = too; o[7] = tsstoo;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// test / calibration kernels
+// ---------------------------------------------------------------------------------------------
+// op: 0 rcp, 1 sqrt_pos, 2 exp_neg, 3 log2_pos, 4 exp2_any, 5 tau_plate
+__global__ void k_test_math(int op, long long n, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ tables) {
+    __shared__ MathTables mt;
+    for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 8); i += blockDim.x) reinterpret_cast<double*>(&mt)[i] = tables[i];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = in[i];
+    double y = 0.0;
+    switch (op) {
+        case 0: y = rcp(x); break;
+        case 1: y = sqrt_pos(x); break;
+        case 2: y = exp_neg(x, mt.exp2t); break;
+        case 3: y = log2_pos(x, mt.logt); break;
+        case 4: y = exp2_any(x, mt.exp2t); break;
+        default: y = tau_plate(x, mt.tau); break;
+    }
+    out[i] = y;
+}
+
+// DFMA throughput microbenchmark: 8 independent chains per thread, `iters` x 8 x 4 FMAs each.
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;
+}
+
+}  // namespace pb

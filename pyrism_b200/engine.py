@@ -1,0 +1,378 @@
+# -*- coding: utf-8 -*-
+"""Host-side engine: owns one ``prosail_handle_t`` per device and turns numpy (or raw device) arrays into
+calls of the C ABI.  It contains no arithmetic of the hot path -- only argument marshalling, broadcasting of
+scalar parameters, and buffer management.
+"""
+import ctypes as C
+import threading
+import weakref
+
+import numpy as np
+
+from . import _capi as capi
+from . import constants as K
+
+_f64 = np.float64
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _vec(x, n, name):
+    """Broadcast a scalar / length-1 / length-n parameter to a contiguous float64[n]."""
+    a = np.asarray(x, dtype=_f64).reshape(-1)
+    if a.size == 1 and n != 1:
+        a = np.full(n, a[0], dtype=_f64)
+    if a.size != n:
+        raise ValueError("parameter %s has %d values, expected 1 or %d" % (name, a.size, n))
+    return np.ascontiguousarray(a)
+
+
+def batch_size(*params):
+    """Common length of array-valued parameters (1 if all are scalars)."""
+    n = 1
+    for p in params:
+        if p is None:
+            continue
+        s = np.size(p)
+        if s != 1:
+            if n != 1 and s != n:
+                raise ValueError("array-valued parameters must share one length (%d vs %d)" % (n, s))
+            n = s
+    return n
+
+
+class PinnedPool(object):
+    """Page-locked host arrays (cudaHostAlloc) exposed as numpy arrays; freed when the last view dies."""
+
+    SMALL = 1 << 20      # below this a pageable numpy array is cheaper than cudaHostAlloc
+
+    @staticmethod
+    def empty(shape, dtype=_f64, force=False):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        if nbytes < PinnedPool.SMALL and not force:
+            return np.empty(shape, dtype=dtype)
+        lib = capi.load()
+        p = C.c_void_p()
+        capi.check(lib.prosail_host_alloc(nbytes, C.byref(p)))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        weakref.finalize(buf, lib.prosail_host_free, C.c_void_p(p.value))
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+class DeviceArray(object):
+    """A float64 device buffer owned by an Engine (used by the device-resident API and the bench)."""
+
+    def __init__(self, engine, shape, dtype=_f64):
+        self.engine = engine
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        capi.check(engine.lib.prosail_dev_alloc(engine.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+        self._fin = weakref.finalize(self, DeviceArray._free, engine.lib, engine.h, self.ptr)
+
+    @staticmethod
+    def _free(lib, h, ptr):
+        try:
+            lib.prosail_dev_free(h, C.c_void_p(ptr))
+        except Exception:
+            pass
+
+    def upload(self, host, stream=None):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert host.nbytes == self.nbytes, (host.nbytes, self.nbytes)
+        capi.check(self.engine.lib.prosail_memcpy_h2d(self.engine.h, C.c_void_p(self.ptr), _ptr(host), self.nbytes, stream))
+        self.engine.sync(stream)
+        return self
+
+    def download(self, out=None, stream=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=self.dtype)
+        capi.check(self.engine.lib.prosail_memcpy_d2h(self.engine.h, _ptr(out), C.c_void_p(self.ptr), self.nbytes, stream))
+        self.engine.sync(stream)
+        return out
+
+    def free(self):
+        self._fin()
+
+
+class Engine(object):
+    """One CUDA handle + uploaded constants on one device."""
+
+    def __init__(self, device=0, alpha=40, windows=K.DEFAULT_WINDOWS):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        capi.check(self.lib.prosail_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = int(device)
+        self._fin = weakref.finalize(self, self.lib.prosail_destroy, h)
+        self._alpha = {}
+        self._lock = threading.RLock()
+        capi.check(self.lib.prosail_set_soil_tables(self.h, _ptr(K.lib.soil.rsoil1), _ptr(K.lib.soil.rsoil2)))
+        self.set_alpha('5', alpha)
+        self.set_alpha('D', alpha)
+        self.windows = None
+        self.set_windows(windows)
+
+    # ---- constants -------------------------------------------------------------------------------------
+    def set_alpha(self, version, alpha):
+        """(Re)upload the coefficient set of ``version`` with the interface constants for ``alpha``."""
+        with self._lock:
+            if self._alpha.get(version) == float(alpha):
+                return
+            t = K.lib.p5 if version == '5' else K.lib.pd
+            talf, t12, t21 = K.interface_constants(version, alpha)
+            kan = t.Kan if version == 'D' else None
+            capi.check(self.lib.prosail_set_leaf_tables(self.h, 0 if version == '5' else 1, _ptr(t.Kab), _ptr(t.Kxc), _ptr(t.Kbr),
+                                                        _ptr(t.Kw), _ptr(t.Km), _ptr(kan), _ptr(talf), _ptr(t12), _ptr(t21)))
+            self._alpha[version] = float(alpha)
+
+    def set_windows(self, windows):
+        """Inclusive (lo_nm, hi_nm) windows for the band means (default: 6 Landsat-8 + 9 ASTER windows)."""
+        with self._lock:
+            windows = tuple((int(lo), int(hi)) for lo, hi in windows)
+            if windows == self.windows:
+                return
+            lo = np.ascontiguousarray([w[0] for w in windows], dtype=np.int32)
+            hi = np.ascontiguousarray([w[1] for w in windows], dtype=np.int32)
+            capi.check(self.lib.prosail_set_windows(self.h, len(windows), _ptr(lo), _ptr(hi)))
+            self.windows = windows
+
+    # ---- helpers ---------------------------------------------------------------------------------------
+    def sync(self, stream=None):
+        capi.check(self.lib.prosail_sync(self.h, stream))
+
+    def launch_count(self):
+        return int(self.lib.prosail_launch_count(self.h))
+
+    def device_info(self):
+        name = C.create_string_buffer(128)
+        sm = C.c_int()
+        mem = C.c_longlong()
+        capi.check(self.lib.prosail_device_info(self.h, name, 128, C.byref(sm), C.byref(mem)))
+        return dict(name=name.value.decode(), sm_count=sm.value, mem_bytes=mem.value)
+
+    def measure_fp64_peak(self, millis=200):
+        t = C.c_double()
+        capi.check(self.lib.prosail_measure_fp64_peak(self.h, int(millis), C.byref(t)))
+        return t.value
+
+    def test_math(self, op, x):
+        x = np.ascontiguousarray(x, dtype=_f64)
+        y = np.empty_like(x)
+        capi.check(self.lib.prosail_test_math(self.h, int(op), x.size, _ptr(x), _ptr(y), 1))
+        return y
+
+    def empty(self, shape, dtype=_f64):
+        return DeviceArray(self, shape, dtype)
+
+    def to_device(self, host):
+        host = np.ascontiguousarray(host, dtype=_f64)
+        return DeviceArray(self, host.shape).upload(host)
+
+    def timer_begin(self, stream=None):
+        capi.check(self.lib.prosail_timer_begin(self.h, stream))
+
+    def timer_end(self, stream=None):
+        ms = C.c_float()
+        capi.check(self.lib.prosail_timer_end(self.h, stream, C.byref(ms)))
+        return ms.value
+
+    # ---- struct builders (work for host numpy arrays and for DeviceArray) --------------------------------
+    @staticmethod
+    def _addr(a):
+        if a is None:
+            return None
+        if isinstance(a, DeviceArray):
+            return a.ptr
+        if isinstance(a, int):
+            return a
+        return a.ctypes.data
+
+    def _leaf(self, N, Cab, Cxc, Cbr, Cw, Cm, Can):
+        return capi.Leaf(*(self._addr(v) for v in (N, Cab, Cxc, Cbr, Cw, Cm, Can)))
+
+    def _soil(self, refl, moist):
+        return capi.Soil(self._addr(refl), self._addr(moist))
+
+    def _canopy(self, lidf_type, lidf_a, lidf_b, lai, hotspot, n_geom, geom_per_sample, iza, vza, raa):
+        return capi.Canopy(int(lidf_type), self._addr(lidf_a), self._addr(lidf_b), self._addr(lai), self._addr(hotspot),
+                           int(n_geom), int(geom_per_sample), self._addr(iza), self._addr(vza), self._addr(raa))
+
+    def _out(self, planes, pitch, mean_mask, means, geom, windows_only):
+        o = capi.Out()
+        for i in range(capi.NOUT):
+            o.plane[i] = self._addr(planes.get(i)) if planes else None
+        o.pitch = int(pitch)
+        o.mean_mask = int(mean_mask)
+        o.means = self._addr(means)
+        o.geom = self._addr(geom)
+        o.windows_only = int(windows_only)
+        return o
+
+    # ---- host-array API ----------------------------------------------------------------------------------
+    def prospect(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=None, version='5', alpha=40, means=False, out=None):
+        """Batched PROSPECT.  Returns dict(ks, kt[, means]) with ks/kt float64[n, 2101]; means float32[n, 5, nw]."""
+        with self._lock:
+            self.set_alpha(version, alpha)
+            n = batch_size(N, Cab, Cxc, Cbr, Cw, Cm, Can)
+            v = [_vec(p, n, nm) for p, nm in ((N, 'N'), (Cab, 'Cab'), (Cxc, 'Cxc'), (Cbr, 'Cbr'), (Cw, 'Cw'), (Cm, 'Cm'))]
+            can = _vec(Can, n, 'Can') if (version == 'D') else None
+            leaf = self._leaf(v[0], v[1], v[2], v[3], v[4], v[5], can)
+            out = out or {}
+            ks = out.get('ks')
+            kt = out.get('kt')
+            if ks is None:
+                ks = PinnedPool.empty((n, K.NBANDS))
+            if kt is None:
+                kt = PinnedPool.empty((n, K.NBANDS))
+            m = PinnedPool.empty((n, 5, len(self.windows)), np.float32) if means else None
+            capi.check(self.lib.prosail_prospect_f64(self.h, 0 if version == '5' else 1, n, C.byref(leaf), _ptr(ks), _ptr(kt),
+                                                     K.NBANDS, _ptr(m), 1, None))
+            res = dict(ks=ks, kt=kt)
+            if means:
+                res['means'] = m
+            return res
+
+    def soil(self, reflectance, moisture, means=False):
+        """Batched LSM.  Returns dict(rho float64[n, 2101][, means float32[n, 1, nw]])."""
+        with self._lock:
+            n = batch_size(reflectance, moisture)
+            r, mo = _vec(reflectance, n, 'reflectance'), _vec(moisture, n, 'moisture')
+            soil = self._soil(r, mo)
+            rho = PinnedPool.empty((n, K.NBANDS))
+            m = PinnedPool.empty((n, 1, len(self.windows)), np.float32) if means else None
+            capi.check(self.lib.prosail_soil_f64(self.h, n, C.byref(soil), _ptr(rho), K.NBANDS, _ptr(m), 1, None))
+            res = dict(rho=rho)
+            if means:
+                res['means'] = m
+            return res
+
+    def _canopy_host(self, n, iza, vza, raa, lai, hotspot, lidf_type, a, b, geom_per_sample):
+        iza = np.ascontiguousarray(np.asarray(iza, dtype=_f64).reshape(-1))
+        vza = np.ascontiguousarray(np.asarray(vza, dtype=_f64).reshape(-1))
+        raa = np.ascontiguousarray(np.asarray(raa, dtype=_f64).reshape(-1))
+        if not (iza.size == vza.size == raa.size):
+            raise ValueError("iza, vza, raa must have the same length")
+        if geom_per_sample:
+            if iza.size != n:
+                raise ValueError("per-sample geometry needs %d angles" % n)
+            G = 1
+        else:
+            G = iza.size
+        lt = {'campbell': capi.LIDF_CAMPBELL, 'verhoef': capi.LIDF_VERHOEF}[lidf_type]
+        keep = [iza, vza, raa, _vec(a, n, 'a'), _vec(0.0 if b is None else b, n, 'b'), _vec(lai, n, 'lai'),
+                _vec(hotspot, n, 'hotspot')]
+        can = self._canopy(lt, keep[3], keep[4], keep[5], keep[6], G, 1 if geom_per_sample else 0, iza, vza, raa)
+        return can, G, keep
+
+    def volscatt(self, iza, vza, raa, lidf_type='campbell', a=57, b=0, lai=0.0, hotspot=0.0, geom_per_sample=False):
+        """Batched VolScatt.coef: returns (geom float64[n, G, 8], lidf float64[n, 18]); angles in normalised radians."""
+        with self._lock:
+            n = batch_size(a, b, lai, hotspot) if not geom_per_sample else max(batch_size(a, b, lai, hotspot), np.size(iza))
+            can, G, keep = self._canopy_host(n, iza, vza, raa, lai, hotspot, lidf_type, a, b, geom_per_sample)
+            geom = np.empty((n, G, 8), dtype=_f64)
+            lidf = np.empty((n, capi.NLIDF), dtype=_f64)
+            capi.check(self.lib.prosail_volscatt_f64(self.h, n, C.byref(can), _ptr(geom), _ptr(lidf), 1, None))
+            return geom, lidf
+
+    def _alloc_out(self, n_items, planes, mean_planes, want_geom, out):
+        out = out or {}
+        bufs = {}
+        for p in planes:
+            a = out.get(capi.PLANE_NAMES[p])
+            bufs[p] = a if a is not None else PinnedPool.empty((n_items, K.NBANDS))
+        mask = 0
+        for p in mean_planes:
+            mask |= 1 << p
+        nmean = bin(mask).count("1")
+        means = (out.get('means') if out.get('means') is not None else
+                 PinnedPool.empty((n_items, nmean, len(self.windows)))) if nmean else None
+        geom = np.empty((n_items, 8), dtype=_f64) if want_geom else None
+        return bufs, mask, means, geom
+
+    def sail(self, ks, kt, rho, iza, vza, raa, lai, hotspot, lidf_type='campbell', a=57, b=0, planes=(capi.O_RSOT,),
+             mean_planes=(), geom_per_sample=False, want_geom=True, out=None):
+        """Batched SAIL with leaf/soil spectra given as arrays ([2101] broadcast or [n, 2101]).
+
+        Returns dict: plane name -> float64[n, G, 2101]; 'means' float64[n, G, nmean, nw]; 'geom' float64[n, G, 8].
+        """
+        with self._lock:
+            specs = []
+            n_spec = 1
+            for name, s_ in (('ks', ks), ('kt', kt), ('rho_surface', rho)):
+                s_ = np.ascontiguousarray(s_, dtype=_f64)
+                if s_.ndim == 1:
+                    s_ = s_.reshape(1, -1)
+                if s_.shape[-1] != K.NBANDS:
+                    raise AssertionError("%s must have 2101 values per spectrum" % name)
+                if s_.shape[0] != 1:
+                    n_spec = s_.shape[0]
+                specs.append(s_)
+            n = batch_size(lai, hotspot, a, b)
+            if geom_per_sample:
+                n = max(n, np.size(iza))
+            n = max(n, n_spec)
+            for s_ in specs:
+                if s_.shape[0] not in (1, n):
+                    raise ValueError("spectra must be [2101] or [%d, 2101]" % n)
+            can, G, keep = self._canopy_host(n, iza, vza, raa, lai, hotspot, lidf_type, a, b, geom_per_sample)
+            bufs, mask, means, geom = self._alloc_out(n * G, planes, mean_planes, want_geom, out)
+            o = self._out(bufs, K.NBANDS, mask, means, geom, 0)
+            pit = [0 if s_.shape[0] == 1 else K.NBANDS for s_ in specs]
+            capi.check(self.lib.prosail_sail_f64(self.h, n, _ptr(specs[0]), pit[0], _ptr(specs[1]), pit[1], _ptr(specs[2]), pit[2],
+                                                 C.byref(can), C.byref(o), 1, None))
+            return self._pack(bufs, means, geom, n, G)
+
+    def prosail(self, N, Cab, Cxc, Cbr, Cw, Cm, lai, hotspot, iza, vza, raa, soil_reflectance, soil_moisture, Can=None,
+                version='5', alpha=40, lidf_type='campbell', a=57, b=0, planes=(capi.O_RSOT,), mean_planes=(),
+                geom_per_sample=False, want_geom=False, windows_only=False, out=None):
+        """Fused PROSPECT -> LSM -> SAIL for n parameter sets x G geometries (host arrays in, host arrays out)."""
+        with self._lock:
+            self.set_alpha(version, alpha)
+            n = batch_size(N, Cab, Cxc, Cbr, Cw, Cm, Can, lai, hotspot, a, b, soil_reflectance, soil_moisture)
+            if geom_per_sample:
+                n = max(n, np.size(iza))
+            v = [_vec(p, n, nm) for p, nm in ((N, 'N'), (Cab, 'Cab'), (Cxc, 'Cxc'), (Cbr, 'Cbr'), (Cw, 'Cw'), (Cm, 'Cm'))]
+            can_ = _vec(Can, n, 'Can') if version == 'D' else None
+            leaf = self._leaf(v[0], v[1], v[2], v[3], v[4], v[5], can_)
+            sr, smo = _vec(soil_reflectance, n, 'soil_reflectance'), _vec(soil_moisture, n, 'soil_moisture')
+            soil = self._soil(sr, smo)
+            can, G, keep = self._canopy_host(n, iza, vza, raa, lai, hotspot, lidf_type, a, b, geom_per_sample)
+            if windows_only:
+                planes = ()
+            bufs, mask, means, geom = self._alloc_out(n * G, planes, mean_planes, want_geom, out)
+            o = self._out(bufs, K.NBANDS, mask, means, geom, 1 if windows_only else 0)
+            capi.check(self.lib.prosail_prosail_f64(self.h, 0 if version == '5' else 1, n, C.byref(leaf), C.byref(soil), C.byref(can),
+                                                    C.byref(o), 1, None))
+            return self._pack(bufs, means, geom, n, G)
+
+    @staticmethod
+    def _pack(bufs, means, geom, n, G):
+        res = {}
+        for p, a in bufs.items():
+            res[capi.PLANE_NAMES[p]] = a.reshape(n, G, K.NBANDS)
+        if means is not None:
+            res['means'] = means.reshape(n, G, means.shape[-2], means.shape[-1])
+        if geom is not None:
+            res['geom'] = geom.reshape(n, G, 8)
+        return res
+
+
+_engines = {}
+_engines_lock = threading.Lock()
+
+
+def get_engine(device=None):
+    """Process-wide engine for ``device`` (default: env PYRISM_B200_DEVICE or 0)."""
+    import os
+    if device is None:
+        device = int(os.environ.get("PYRISM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _engines_lock:
+        if device not in _engines:
+            _engines[device] = Engine(device)
+        return _engines[device]

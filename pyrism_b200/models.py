@@ -1,0 +1,338 @@
+# -*- coding: utf-8 -*-
+"""Drop-in, batched replacements for pyrism's optical model constructors.
+
+Same names, arguments, attributes and exception types as ``pyrism/models/models.py`` for
+``PROSPECT`` (:854-1239), ``LSM`` (:1871-2038), ``SAIL`` (:474-851), ``VolScatt`` (:29-258) and
+``LIDF.campbell / LIDF.verhoef`` (:283-392).  What is new:
+
+* every physical parameter may be an array: ``PROSPECT(N=array, ...)`` evaluates a batch; spectra then carry a
+  leading batch axis (``ks.shape == (B, 2101)``).  Scalars give exactly the reference shapes.
+* ``SAIL`` accepts several geometries at once (arrays for ``iza, vza, raa``): results are ``[B, G, 2101]``
+  (axes of length one are squeezed so that the scalar call returns ``(2101,)`` like the reference).
+* ``PROSAIL`` fuses PROSPECT -> LSM -> SAIL in one kernel launch (the LUT generator).
+
+All numbers come from the sm_100a kernels behind ``libprosail_b200.so``; there is no CPU implementation.
+"""
+from collections import namedtuple
+
+import numpy as np
+
+from . import _capi as capi
+from . import constants as K
+from .constants import lib
+from .core import Kernel, SailResult, dB, rad
+from .engine import get_engine, batch_size
+
+_L8 = namedtuple('L8', 'B2 B3 B4 B5 B6 B7')
+_ASTER = namedtuple('ASTER', 'B1 B2 B3 B4 B5 B6 B7 B8 B9')
+_NL8 = len(K.L8_BANDS)
+
+
+def _is_scalar_call(*params):
+    return all(np.ndim(p) == 0 for p in params if p is not None)
+
+
+def _band_tuples(means, fields=None):
+    """means[..., 15] (or [..., F, 15] with named fields) -> (L8 namedtuple, ASTER namedtuple)."""
+    names = fields.split() if fields else None
+
+    def pick(w):
+        if names is None:
+            return means[..., w][()]
+        T = namedtuple('B', names)
+        return T(*(means[..., f, w][()] for f in range(len(names))))
+    l8 = _L8(*(pick(w) for w in range(_NL8)))
+    aster = _ASTER(*(pick(_NL8 + w) for w in range(len(K.ASTER_BANDS))))
+    return l8, aster
+
+
+class _SpectralModel(object):
+    """select / cleanup shared by PROSPECT and LSM (models.py:1197-1239, 2013-2038)."""
+    _engine = None
+
+    def cleanup(self, name):
+        try:
+            delattr(self, name)
+        except TypeError:
+            for item in name:
+                delattr(self, item)
+
+    def _with_windows(self, windows, fn):
+        eng = self._engine
+        old = eng.windows
+        try:
+            eng.set_windows(windows)
+            return fn()
+        finally:
+            eng.set_windows(old)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class PROSPECT(_SpectralModel):
+    """PROSPECT-5 / PROSPECT-D leaf optical properties (models.py:854-1239), batched on the GPU.
+
+    Parameters as the reference: ``N, Cab, Cxc, Cbr, Cw, Cm, Can=0, alpha=40, version='5'``; each of the first
+    seven may be a scalar or a 1-D array (one entry per parameter set).
+
+    Attributes: ``l, n_l, ks, kt, ka, ke, om`` (float64 ``[2101]`` or ``[B, 2101]``), ``int`` (float32 table
+    ``[..., 2101, 6]`` of l, ks, kt, ka, ke, om), ``L8.Bx`` / ``ASTER.Bx`` namedtuples of float32 means of
+    (ks, kt, ka, ke, omega), the coefficient tables ``KN, Kab, Kxc, Kbr, Kw, Km, Kan`` and ``n_elems_list``.
+    """
+
+    def __init__(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=0, alpha=40, version='5', device=None):
+        self.N, self.Cab, self.Cxc, self.Cbr, self.Cw, self.Cm, self.Can = N, Cab, Cxc, Cbr, Cw, Cm, Can
+        self.alpha = alpha
+        self.ver = version
+        self.l = np.arange(400, 2501)
+        self.n_l = len(self.l)
+        if self.ver != '5' and self.ver != 'D':
+            raise ValueError("version must be '5' for PROSPECT 5 or 'D' for PROSPECT D. "
+                             "The actual version is: {}".format(str(self.ver)))
+        if self.ver == 'D' and np.any(np.asarray(self.Can) == 0):
+            raise AssertionError("For PROSPECT version D is the Anthocyanins value mandatory (!=0)")
+        t = lib.p5 if self.ver == '5' else lib.pd
+        self.KN, self.Kab, self.Kxc, self.Kbr, self.Kw, self.Km = t.KN, t.Kab, t.Kxc, t.Kbr, t.Kw, t.Km
+        self.Kan = np.zeros_like(self.Km) if self.ver == '5' else t.Kan
+        self.n_elems_list = [len(s) for s in [self.KN, self.Kab, self.Kxc, self.Kbr, self.Kw, self.Km, self.Kan]]
+
+        self._engine = get_engine(device)
+        self._scalar = _is_scalar_call(N, Cab, Cxc, Cbr, Cw, Cm, Can)
+        res = self._engine.prospect(N, Cab, Cxc, Cbr, Cw, Cm, Can=Can if self.ver == 'D' else None, version=self.ver,
+                                    alpha=alpha, means=True)
+        sq = (lambda a: a[0]) if self._scalar else (lambda a: a)
+        self.ks, self.kt = sq(res['ks']), sq(res['kt'])
+        self.L8, self.ASTER = _band_tuples(sq(res['means']), 'ks kt ka ke omega')
+
+    # ka, ke, om and the float32 table are views derived from ks/kt on first use (models.py:1066-1072)
+    @property
+    def ka(self):
+        return 1 - self.ks - self.kt
+
+    @property
+    def ke(self):
+        return self.ks + self.ka
+
+    @property
+    def om(self):
+        return self.ks / self.ke
+
+    @property
+    def int(self):
+        l = np.broadcast_to(self.l, self.ks.shape)
+        return np.stack([l, self.ks, self.kt, self.ka, self.ke, self.om], axis=-1).astype(np.float32)
+
+    def select(self, mins=None, maxs=None, function='mean'):
+        """float32 means of (ks, kt, ka, ke, om) over the inclusive window [mins, maxs] nm (models.py:1197-1225)."""
+        if function == 'mean':
+            def go():
+                r = self._engine.prospect(self.N, self.Cab, self.Cxc, self.Cbr, self.Cw, self.Cm,
+                                          Can=self.Can if self.ver == 'D' else None, version=self.ver, alpha=self.alpha,
+                                          means=True)
+                m = r['means'][..., 0]
+                return np.asarray(m[0] if self._scalar else m, dtype=np.float32)
+            return self._with_windows(((mins, maxs),), go)
+
+    def indices(self):
+        nir, red = self.select(851, 879), self.select(636, 673)
+        self.ndvi = (nir[..., 0] - red[..., 0]) / (nir[..., 0] + red[..., 0])
+        return self.ndvi
+
+
+# ---------------------------------------------------------------------------------------------------------
+class LSM(_SpectralModel):
+    """Lambertian soil reflectance (models.py:1871-2038): ``ref = reflectance (moisture rsoil1 + (1 - moisture) rsoil2)``."""
+
+    def __init__(self, reflectance, moisture, device=None):
+        self.l = np.arange(400, 2501)
+        self.sRef = reflectance
+        self.moisture = moisture
+        self._engine = get_engine(device)
+        self._scalar = _is_scalar_call(reflectance, moisture)
+        res = self._engine.soil(reflectance, moisture, means=True)
+        sq = (lambda a: a[0]) if self._scalar else (lambda a: a)
+        self.ref = sq(res['rho'])
+        self.L8, self.ASTER = _band_tuples(sq(res['means'])[..., 0, :])
+
+    @property
+    def int(self):
+        l = np.broadcast_to(self.l, self.ref.shape)
+        return np.stack([l, self.ref], axis=-1).astype(np.float32)
+
+    def select(self, mins, maxs, function='mean'):
+        if function == 'mean':
+            def go():
+                m = self._engine.soil(self.sRef, self.moisture, means=True)['means'][..., 0, 0]
+                return np.float32(m[0]) if self._scalar else np.asarray(m, dtype=np.float32)
+            return self._with_windows(((mins, maxs),), go)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class LIDF(object):
+    """Leaf inclination distribution functions, 18 bins of 5 degrees (models.py:262-392)."""
+
+    def __init__(self):
+        pass
+
+    @staticmethod
+    def _run(lidf_type, a, b, n_elements):
+        if n_elements != capi.NLIDF:
+            raise NotImplementedError("the GPU kernels use the reference's 18 leaf-inclination bins")
+        scalar = _is_scalar_call(a, b)
+        _, lidf = get_engine().volscatt(0.0, 0.0, 0.0, lidf_type=lidf_type, a=a, b=b)
+        return lidf[0] if scalar else lidf
+
+    @staticmethod
+    def campbell(a, n_elements=18):
+        return LIDF._run('campbell', a, 0.0, n_elements)
+
+    @staticmethod
+    def verhoef(a, b, n_elements=18):
+        return LIDF._run('verhoef', a, b, n_elements)
+
+
+class VolScatt(Kernel):
+    """Volume scattering / interception coefficients (models.py:29-175).
+
+    ``coef`` leaves ``ks, ko, bf, Fs, Ft, Fst`` as attributes: arrays over the geometries for scalar LIDF
+    parameters (as the reference), ``[B, G]`` when ``a``/``b`` are arrays.
+    """
+
+    def __init__(self, iza, vza, raa, angle_unit='DEG'):
+        super(VolScatt, self).__init__(iza, vza, raa, normalize=False, nbar=0.0, angle_unit=angle_unit, align=True)
+
+    def coef(self, lidf_type='verhoef', n_elements=18, **kwargs):
+        a = kwargs.pop('a', None)
+        b = kwargs.pop('b', None)
+        if kwargs:
+            raise TypeError('Unexpected **kwargs: %r' % kwargs)
+        if lidf_type == 'verhoef':
+            if a is None or b is None:
+                raise ValueError("for the verhoef function the parameter a and b must defined.")
+        elif lidf_type == 'campbell':
+            if a is None:
+                raise ValueError("for the campbell function the parameter alpha must defined.")
+            b = 0.0
+        else:
+            raise AttributeError("lad_method must be verhoef, nilson or campbell")
+        if n_elements != capi.NLIDF:
+            raise NotImplementedError("the GPU kernels use the reference's 18 leaf-inclination bins")
+        geom, lidf = get_engine().volscatt(self.iza, self.vza, self.raa, lidf_type=lidf_type, a=a, b=b)
+        self._set(geom, _is_scalar_call(a, b))
+        self.lidf = lidf[0] if _is_scalar_call(a, b) else lidf
+
+    def _set(self, geom, scalar):
+        g = geom[0] if scalar else geom                       # [G, 8] or [B, G, 8]
+        self.ks, self.ko, self.Fs, self.Ft = g[..., 0], g[..., 1], g[..., 3], g[..., 4]
+        bf = g[..., 2]
+        self.bf = bf[..., 0][()] if scalar else bf[..., 0]    # bf does not depend on the geometry
+        self.Fst = self.Fs + self.Ft
+
+
+# ---------------------------------------------------------------------------------------------------------
+_PLANES_SAIL = (capi.O_RSOT, capi.O_RDDT, capi.O_RSDT, capi.O_RDOT, capi.O_RSO, capi.O_RDD, capi.O_TDD, capi.O_RSD,
+                capi.O_TSD, capi.O_RDO, capi.O_TDO, capi.O_KE)
+_MEANS_SAIL = (capi.O_RSOT, capi.O_RDDT, capi.O_RSDT, capi.O_RDOT)
+
+
+class SAIL(Kernel):
+    """4SAIL canopy reflectance (models.py:474-851), batched over parameter sets and geometries.
+
+    Arguments as the reference.  ``ks, kt, rho_surface`` are ``[2101]`` (shared) or ``[B, 2101]``;
+    ``lai, hotspot, a, b`` scalars or ``[B]``; ``iza, vza, raa`` scalars or ``[G]``.
+    Attributes as the reference: ``BRF, BRDF, BHR, DHR, HDR`` (each ``SailResult(ref, refdB, L8, ASTER)``),
+    ``canopy`` (``BHR, BHT, DHR, DHT, HDR, HDT, BRF``), ``kt`` (= tsstoo), ``kt_iza`` (= tss), ``kt_vza`` (= too),
+    ``ke`` (= m), ``ks`` (leaf input), ``VollScat``, ``l``, plus the Kernel angle attributes.
+    """
+
+    def __init__(self, iza, vza, raa, ks, kt, lai, hotspot, rho_surface, lidf_type='campbell', a=57, b=0, normalize=False,
+                 nbar=0.0, angle_unit='DEG', device=None):
+        super(SAIL, self).__init__(iza=iza, vza=vza, raa=raa, normalize=normalize, nbar=nbar, angle_unit=angle_unit,
+                                   align=True)
+        for name, v in (("ks", ks), ("kt", kt), ("rho_surface", rho_surface)):
+            if np.shape(v)[-1:] != (2101,):
+                what = {"ks": "leaf reflectance", "kt": "leaf transmitance", "rho_surface": "surface reflectance"}[name]
+                raise AssertionError("{0} must contain continuous {1} values from from 400 until 2500 nm with a length of "
+                                     "2101. The actual length of {0} is {2}".format(name, what, str(np.shape(v)[-1:])))
+        if lidf_type != 'verhoef' and lidf_type != 'campbell':
+            raise AssertionError("The lidf_type must be 'verhoef' or 'campbell'")
+        self.ks = ks
+        self.lai = lai
+        self.hotspot = hotspot
+        self.rho_surface = rho_surface
+        self.l = np.arange(400, 2501)
+
+        eng = get_engine(device)
+        res = eng.sail(ks, kt, rho_surface, self.iza, self.vza, self.raa, lai, hotspot, lidf_type=lidf_type, a=a, b=b,
+                       planes=_PLANES_SAIL, mean_planes=_MEANS_SAIL, want_geom=True)
+        B, G = res['rsot'].shape[:2]
+        one_set = _is_scalar_call(lai, hotspot, a, b) and all(np.ndim(s) == 1 for s in (ks, kt, rho_surface))
+        self._finish(res, one_set, G)
+        self.VollScat = VolScatt(iza, vza, raa, angle_unit)
+        self.VollScat._set(res['geom'], one_set)
+
+    def _finish(self, res, one_set, G):
+        def sq(x):                                  # [B, G, ...] -> reference-like shapes
+            if one_set:
+                x = x[0]
+                if G == 1:
+                    x = x[0]
+            return x
+        geom = res['geom'][0] if one_set else res['geom']
+        self.kt = geom[..., 7]                      # tsstoo (models.py:569)
+        self.kt_iza = geom[..., 5]                  # tss
+        self.kt_vza = geom[..., 6]                  # too
+        self.ke = sq(res['ke'])
+        self.canopy = SailResult(BHR=sq(res['rdd']), BHT=sq(res['tdd']), DHR=sq(res['rsd']), DHT=sq(res['tsd']),
+                                 HDR=sq(res['rdo']), HDT=sq(res['tdo']), BRF=sq(res['rso']))
+        means = sq(res['means'])                    # [..., 4, 15]
+        eager = one_set and G == 1
+
+        def product(ref, m):
+            l8, aster = _band_tuples(m)
+            r = SailResult(ref=ref, L8=l8, ASTER=aster)
+            if eager:
+                r['refdB'] = dB(ref)
+            return r
+        rsot = sq(res['rsot'])
+        self.BRF = product(rsot, means[..., 0, :])
+        self.BRDF = product(rsot / np.pi, means[..., 0, :] / np.pi)
+        self.BHR = product(sq(res['rddt']), means[..., 1, :])
+        self.DHR = product(sq(res['rsdt']), means[..., 2, :])
+        self.HDR = product(sq(res['rdot']), means[..., 3, :])
+
+
+class PROSAIL(SAIL):
+    """Fused PROSPECT -> LSM -> SAIL (examples/prospect_sail.py:9-28) for batches: one launch, leaf and soil
+    spectra never leave the SM.  Leaf / soil / canopy parameters are scalars or ``[B]`` arrays, geometry scalars or
+    ``[G]`` arrays (or ``[B]`` with ``geom_per_sample=True``).  Attributes as :class:`SAIL`, plus ``leaf_ks``,
+    ``leaf_kt`` and ``rho_surface`` when ``keep_leaf=True``.
+    """
+
+    def __init__(self, N, Cab, Cxc, Cbr, Cw, Cm, lai, hotspot, iza, vza, raa, soil_reflectance=1.0, soil_moisture=0.5,
+                 Can=0, alpha=40, version='5', lidf_type='campbell', a=57, b=0, angle_unit='DEG', geom_per_sample=False,
+                 keep_leaf=False, device=None):
+        Kernel.__init__(self, iza=iza, vza=vza, raa=raa, normalize=False, nbar=0.0, angle_unit=angle_unit, align=True)
+        if version != '5' and version != 'D':
+            raise ValueError("version must be '5' for PROSPECT 5 or 'D' for PROSPECT D. "
+                             "The actual version is: {}".format(str(version)))
+        if version == 'D' and np.any(np.asarray(Can) == 0):
+            raise AssertionError("For PROSPECT version D is the Anthocyanins value mandatory (!=0)")
+        if lidf_type != 'verhoef' and lidf_type != 'campbell':
+            raise AssertionError("The lidf_type must be 'verhoef' or 'campbell'")
+        self.lai, self.hotspot = lai, hotspot
+        self.l = np.arange(400, 2501)
+        planes = _PLANES_SAIL + ((capi.O_LEAF_R, capi.O_LEAF_T, capi.O_RHO) if keep_leaf else ())
+        res = get_engine(device).prosail(N, Cab, Cxc, Cbr, Cw, Cm, lai, hotspot, self.iza, self.vza, self.raa, soil_reflectance,
+                                         soil_moisture, Can=Can, version=version, alpha=alpha, lidf_type=lidf_type, a=a, b=b,
+                                         planes=planes, mean_planes=_MEANS_SAIL, geom_per_sample=geom_per_sample,
+                                         want_geom=True)
+        G = res['rsot'].shape[1]
+        one_set = _is_scalar_call(N, Cab, Cxc, Cbr, Cw, Cm, Can, lai, hotspot, a, b, soil_reflectance, soil_moisture) \
+            and not geom_per_sample
+        self._finish(res, one_set, G)
+        if keep_leaf:
+            sq = (lambda x: x[0, 0]) if one_set else (lambda x: x[:, 0])
+            self.leaf_ks, self.leaf_kt, self.rho_surface = sq(res['leaf_r']), sq(res['leaf_t']), sq(res['rho'])
+            self.ks = self.leaf_ks
+        self.VollScat = VolScatt(iza, vza, raa, angle_unit)
+        self.VollScat._set(res['geom'], one_set)
