@@ -156,6 +156,11 @@ int prosail_timer_begin(prosail_handle_t* h, void* stream);
 int prosail_timer_end(prosail_handle_t* h, void* stream, float* ms);
 /* number of kernel launches issued through this handle so far */
 long long prosail_launch_count(prosail_handle_t* h);
+/* Per-kernel device timing: while enabled, every launch is bracketed by CUDA events on its stream.
+ * prosail_profile_read synchronises, returns summed milliseconds and launch counts for
+ * [0] the band kernel (PROSPECT/4SAIL arithmetic), [1] the prologue, [2] the band-mean finalisation, and resets. */
+int prosail_profile_enable(prosail_handle_t* h, int on);
+int prosail_profile_read(prosail_handle_t* h, double ms[3], long long count[3]);
 /* name, SM count, HBM bytes of the handle's device */
 int prosail_device_info(prosail_handle_t* h, char* name, int name_len, int* sm_count, long long* mem_bytes);
 

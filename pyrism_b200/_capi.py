@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libprosail_b200.so")
+LIB_PATH = os.environ.get("PYRISM_B200_LIB") or os.path.join(_HERE, "lib", "libprosail_b200.so")
 
 NBANDS = 2101
 NLIDF = 18
@@ -88,6 +88,8 @@ _SIGNATURES = {
     "prosail_timer_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "prosail_timer_end": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "prosail_launch_count": (C.c_longlong, [C.c_void_p]),
+    "prosail_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "prosail_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "prosail_device_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "prosail_measure_fp64_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "prosail_test_math": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]),

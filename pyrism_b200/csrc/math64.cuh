@@ -17,6 +17,30 @@
 
 namespace pb {
 
+// Polynomial / range-reduction constants live in constant memory so that DFMA takes them straight from the
+// constant bank (operand c[3][..]); as literals they would each cost two UMOV issue slots per use.
+// (Values whose low 32 bits are zero -- 0.5, 1.0, 64.0, the rounding magic -- are encodable as immediates.)
+enum { M_L2E64 = 0, M_LN2H, M_LN2L, M_E5, M_E4, M_E3, M_L5, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P5, M_P4, M_P3, M_P2, M_P1, M_COUNT };
+__constant__ double c_m[M_COUNT] = {
+    92.332482616893656877,       // 64 log2(e)
+    -0x1.62e42fefa0000p-7,       // -(ln2/64) high part (low 17 bits zero)
+    -0x1.cf79abc9e3b3ap-46,      // -(ln2/64) low part
+    0x1.1111111111111p-7,        // 1/120
+    0x1.5555555555555p-5,        // 1/24
+    0x1.5555555555555p-3,        // 1/6
+    0x1.2776c50ef9bfep-2,        // 1/(5 ln2)
+    -0x1.71547652b82fep-2,       // -1/(4 ln2)
+    0x1.ec709dc3a03fdp-2,        // 1/(3 ln2)
+    -0x1.71547652b82fep-1,       // -1/(2 ln2)
+    0x1.71547652b82fep+0,        // 1/ln2
+    4503601774854144.0,          // 2^52 + 2^31
+    0x1.5d87fe78a6731p-10,       // ln2^5/120
+    0x1.3b2ab6fba4e77p-7,        // ln2^4/24
+    0x1.c6b08d704a0c0p-5,        // ln2^3/6
+    0x1.ebfbdff82c58fp-3,        // ln2^2/2
+    0x1.62e42fefa39efp-1,        // ln2
+};
+
 // ---- shared-memory image of the lookup tables (copied once per CTA) ----
 struct alignas(16) MathTables {
     double tau[TAU_NROWS * TAU_ROW];   // piecewise polynomials of tau(k), see tools/gen_math_tables.py
@@ -54,13 +78,13 @@ __device__ __forceinline__ double sqrt_pos(double x) {
 // exp(x) for x <= 0 (clamped at -700): n = rint(64 x log2 e); exp = 2^(n>>6) * T[n&63] * P5(r).  10 FP64 ops.
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ exp2t) {
     x = fmax(x, -700.0);
-    const double t = fma(x, 92.332482616893656877, PB_MAGIC);      // 64*log2(e)
+    const double t = fma(x, c_m[M_L2E64], PB_MAGIC);
     const int n = __double2loint(t);
     const double nd = t - PB_MAGIC;
-    double r = fma(nd, -0x1.62e42fefa0000p-7, x);                   // ln2/64 high part (low 17 bits zero)
-    r = fma(nd, -0x1.cf79abc9e3b3ap-46, r);                         // ln2/64 low part
-    double p = fma(r, 0x1.1111111111111p-7, 0x1.5555555555555p-5);  // 1/120, 1/24
-    p = fma(r, p, 0x1.5555555555555p-3);                            // 1/6
+    double r = fma(nd, c_m[M_LN2H], x);
+    r = fma(nd, c_m[M_LN2L], r);
+    double p = fma(r, c_m[M_E5], c_m[M_E4]);
+    p = fma(r, p, c_m[M_E3]);
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
     p = fma(r, p, 1.0);
@@ -78,11 +102,11 @@ __device__ __forceinline__ double log2_pos(double b, const double* __restrict__ 
     const double r = fma(m, tc.x, -1.0);
     // E as a double without I2F: 2^52 + 2^31 + (E biased by 2^31), minus the constant.
     const int E = (hi >> 20) - 1023;
-    const double Ed = __hiloint2double(0x43300000, E ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
-    double q = fma(r, 0x1.2776c50ef9bfep-2, -0x1.71547652b82fep-2);  //  1/(5 ln2), -1/(4 ln2)
-    q = fma(r, q, 0x1.ec709dc3a03fdp-2);                             //  1/(3 ln2)
-    q = fma(r, q, -0x1.71547652b82fep-1);                            // -1/(2 ln2)
-    q = fma(r, q, 0x1.71547652b82fep+0);                             //  1/ln2
+    const double Ed = __hiloint2double(0x43300000, E ^ 0x80000000) - c_m[M_EBIAS];
+    double q = fma(r, c_m[M_L5], c_m[M_L4]);
+    q = fma(r, q, c_m[M_L3]);
+    q = fma(r, q, c_m[M_L2]);
+    q = fma(r, q, c_m[M_L1]);
     return fma(r, q, Ed + tc.y);
 }
 
@@ -92,10 +116,10 @@ __device__ __forceinline__ double exp2_any(double y, const double* __restrict__ 
     const int n = __double2loint(t);
     const double nd = t - PB_MAGIC;
     const double r = fma(nd, -0.015625, y);
-    double p = fma(r, 0x1.5d87fe78a6731p-10, 0x1.3b2ab6fba4e77p-7);  // ln2^5/120, ln2^4/24
-    p = fma(r, p, 0x1.c6b08d704a0c0p-5);                             // ln2^3/6
-    p = fma(r, p, 0x1.ebfbdff82c58fp-3);                             // ln2^2/2
-    p = fma(r, p, 0x1.62e42fefa39efp-1);                             // ln2
+    double p = fma(r, c_m[M_P5], c_m[M_P4]);
+    p = fma(r, p, c_m[M_P3]);
+    p = fma(r, p, c_m[M_P2]);
+    p = fma(r, p, c_m[M_P1]);
     p = fma(r, p, 1.0);
     const double v = exp2t[n & 63] * p;
     return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));

@@ -86,6 +86,27 @@ struct prosail_handle {
     Work work;           // device mode (caller's stream)
     Work slot[2];        // host mode pipeline
     long long launches = 0;
+    // optional per-kernel timing (CUDA events on the launching stream), see prosail_profile_*
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];   // 0 bands kernel, 1 prologue, 2 finalize
+};
+
+struct ProfScope {        // records an event pair around one launch when profiling is on
+    prosail_handle* h;
+    int kind;
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(prosail_handle* h_, int kind_, cudaStream_t st_) : h(h_), kind(kind_), st(st_) {
+        if (!h->profiling) return;
+        cudaEvent_t e0;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        h->prof[kind].push_back({e0, e1});
+    }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, st);
+    }
 };
 
 struct DeviceGuard {
@@ -167,19 +188,49 @@ static int validate(const prosail_handle* h, const Job& j) {
 // ------------------------------------------------------------------------------------------------
 // device-side execution of a job whose pointers are all device pointers
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, unsigned PLANES, unsigned MEANS>
 static int launch_bands(prosail_handle* h, const SailArgs& a, int band_ctas, cudaStream_t st) {
     const size_t smem = sizeof(SailSmem);
-    CK(cudaFuncSetAttribute(k_bands<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = k_bands<MODE, PLANES, MEANS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, smem));
+    occ = std::max(occ, 1);
     const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
-    // persistent-style grid: about 3 resident CTAs per SM (launch bound), split over the band CTAs
-    long long ychunks = std::max<long long>(1, (3LL * h->sm_count + band_ctas - 1) / band_ctas);
+    // persistent grid: exactly one wave -- never more CTAs than can be resident, so no tail wave
+    long long ychunks = std::max<long long>(1, ((long long)occ * h->sm_count) / band_ctas);
     ychunks = std::min(ychunks, nchunks);
     dim3 grid((unsigned)band_ctas, (unsigned)ychunks);
-    k_bands<MODE><<<grid, CTA_THREADS, smem, st>>>(a);
+    {
+        ProfScope ps(h, 0, st);
+        kern<<<grid, CTA_THREADS, smem, st>>>(a);
+    }
     h->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+
+// pick the kernel instance: compile-time plane sets for the LUT shapes, run-time selection otherwise
+static int dispatch_bands(prosail_handle* h, const Job& j, const SailArgs& a, int band_ctas, cudaStream_t st) {
+    unsigned planes = 0;
+    for (int i = 0; i < NOUT; ++i) planes |= j.plane[i] ? (1u << i) : 0u;
+    const unsigned BRF = 1u << O_RSOT, FOUR = 0xFu, LEAF = (1u << O_LEAF_R) | (1u << O_LEAF_T);
+    switch (j.mode) {
+        case MODE_PROSAIL:
+            if (planes == BRF && !j.mean_mask) return launch_bands<MODE_PROSAIL, BRF, 0>(h, a, band_ctas, st);
+            if (planes == FOUR && !j.mean_mask) return launch_bands<MODE_PROSAIL, FOUR, 0>(h, a, band_ctas, st);
+            if (planes == 0 && j.mean_mask == BRF && !j.f32_means) return launch_bands<MODE_PROSAIL, 0, BRF>(h, a, band_ctas, st);
+            return launch_bands<MODE_PROSAIL, RUNTIME, 0>(h, a, band_ctas, st);
+        case MODE_SAIL:
+            if (planes == BRF && !j.mean_mask) return launch_bands<MODE_SAIL, BRF, 0>(h, a, band_ctas, st);
+            if (planes == FOUR && !j.mean_mask) return launch_bands<MODE_SAIL, FOUR, 0>(h, a, band_ctas, st);
+            return launch_bands<MODE_SAIL, RUNTIME, 0>(h, a, band_ctas, st);
+        case MODE_PROSPECT:
+            if (planes == LEAF && !j.mean_mask) return launch_bands<MODE_PROSPECT, LEAF, 0>(h, a, band_ctas, st);
+            return launch_bands<MODE_PROSPECT, RUNTIME, 0>(h, a, band_ctas, st);
+        default:
+            return launch_bands<MODE_SOIL, RUNTIME, 0>(h, a, band_ctas, st);
+    }
 }
 
 static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st) {
@@ -225,7 +276,10 @@ static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st)
         {
             const long long threads = ni * 32;
             const unsigned blocks = (unsigned)((threads + 127) / 128);
-            k_prologue<<<blocks, 128, 0, st>>>(p);
+            {
+                ProfScope ps(h, 1, st);
+                k_prologue<<<blocks, 128, 0, st>>>(p);
+            }
             h->launches++;
             CK(cudaGetLastError());
         }
@@ -252,20 +306,17 @@ static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st)
         a.f32_means = j.f32_means;
         const int band_ctas = j.windows_only ? (h->h_win.ntiles_active + WARPS_PER_CTA - 1) / WARPS_PER_CTA : BAND_CTAS;
         if (band_ctas > 0) {
-            switch (j.mode) {
-                case MODE_PROSAIL: rc = launch_bands<MODE_PROSAIL>(h, a, band_ctas, st); break;
-                case MODE_SAIL: rc = launch_bands<MODE_SAIL>(h, a, band_ctas, st); break;
-                case MODE_PROSPECT: rc = launch_bands<MODE_PROSPECT>(h, a, band_ctas, st); break;
-                default: rc = launch_bands<MODE_SOIL>(h, a, band_ctas, st); break;
-            }
-            if (rc) return rc;
+            if ((rc = dispatch_bands(h, j, a, band_ctas, st))) return rc;
         }
         if (j.nmean > 0) {
             const long long rows = ni * j.nmean, total = rows * nw;
             const unsigned blocks = (unsigned)((total + 255) / 256);
-            k_finalize_means<<<blocks, 256, 0, st>>>(h->d_win, (const double*)w.partial.p, rows,
-                                                     j.means ? j.means + i0 * j.nmean * nw : nullptr,
-                                                     j.means_f32 ? j.means_f32 + i0 * j.nmean * nw : nullptr);
+            {
+                ProfScope ps(h, 2, st);
+                k_finalize_means<<<blocks, 256, 0, st>>>(h->d_win, (const double*)w.partial.p, rows,
+                                                         j.means ? j.means + i0 * j.nmean * nw : nullptr,
+                                                         j.means_f32 ? j.means_f32 + i0 * j.nmean * nw : nullptr);
+            }
             h->launches++;
             CK(cudaGetLastError());
         }
@@ -680,6 +731,31 @@ int prosail_timer_end(prosail_handle_t* h, void* stream, float* ms) {
     return 0;
 }
 long long prosail_launch_count(prosail_handle_t* h) { return h ? h->launches : 0; }
+
+int prosail_profile_enable(prosail_handle_t* h, int on) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    h->profiling = on != 0;
+    return 0;
+}
+
+int prosail_profile_read(prosail_handle_t* h, double* ms, long long* count) {
+    if (!h || !ms || !count) return fail(PROSAIL_E_ARG, "bad argument");
+    DeviceGuard guard(h->device);
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < 3; ++k) {
+        ms[k] = 0.0;
+        count[k] = (long long)h->prof[k].size();
+        for (auto& pr : h->prof[k]) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, pr.first, pr.second));
+            ms[k] += t;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        h->prof[k].clear();
+    }
+    return 0;
+}
 
 int prosail_device_info(prosail_handle_t* h, char* name, int name_len, int* sm_count, long long* mem_bytes) {
     if (!h) return fail(PROSAIL_E_ARG, "null handle");

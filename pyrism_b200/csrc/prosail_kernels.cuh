@@ -14,6 +14,10 @@
 
 namespace pb {
 
+#ifndef PB_MIN_CTAS
+#define PB_MIN_CTAS 3   /* resident CTAs per SM the band kernel is compiled for (register cap) */
+#endif
+
 constexpr int NB = 2101;          // wavelengths 400..2500 nm
 constexpr int NTILES = 66;        // 32-band warp tiles
 constexpr int NBP = NTILES * 32;  // padded band count (2112)
@@ -276,8 +280,8 @@ __device__ __forceinline__ void sail_directional(double rho, double tau, double 
 // ---------------------------------------------------------------------------------------------
 // band-mean partial sums: segmented warp reduction over the windows that touch this tile
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void mean_partials(const WindowMap* __restrict__ win, double v, int tile, int lane,
-                                              double* __restrict__ dst /* [ntotal] */, bool f32) {
+__device__ __forceinline__ void mean_partials_inl(const WindowMap* __restrict__ win, double v, int tile, int lane,
+                                                  double* __restrict__ dst /* [ntotal] */, bool f32) {
     if (f32) v = (double)(float)v;
     const int ns = win->nslots[tile];
     for (int j = 0; j < ns; ++j) {
@@ -286,14 +290,51 @@ __device__ __noinline__ void mean_partials(const WindowMap* __restrict__ win, do
         if (lane == 0) dst[win->slot[tile][j]] = sum;
     }
 }
+__device__ __noinline__ void mean_partials(const WindowMap* __restrict__ win, double v, int tile, int lane, double* __restrict__ dst,
+                                           bool f32) {
+    mean_partials_inl(win, v, tile, lane, dst, f32);
+}
 
 enum { MODE_PROSAIL = 0, MODE_SAIL = 1, MODE_PROSPECT = 2, MODE_SOIL = 3 };
+
+// Template value of PLANES meaning "planes and means are selected at run time from SailArgs" (the general
+// drop-in path).  Any other value is a compile-time plane mask (and MEANS a compile-time mean mask): the LUT
+// kernels, where per-item pointer tests, predicated stores and call overhead would cost issue slots.
+constexpr unsigned RUNTIME = 0x80000000u;
+
+struct EmitCtx {
+    const SailArgs& a;
+    bool valid;
+    int tile, lane, nt;
+    long long orow;      // item * pitch + band
+    double* pdst;        // partial sums of this item
+    int mi;              // running index of the mean plane
+};
+
+template <unsigned PLANES, unsigned MEANS, int PLANE>
+__device__ __forceinline__ void emit(EmitCtx& e, double v) {
+    if (PLANES == RUNTIME) {
+        if (e.a.out[PLANE] && e.valid) __stcs(e.a.out[PLANE] + e.orow, v);
+        if (e.a.mean_mask & (1u << PLANE)) {
+            mean_partials(e.a.win, v, e.tile, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+            ++e.mi;
+        }
+    } else {
+        if ((PLANES >> PLANE) & 1u) {
+            if (e.valid) __stcs(e.a.out[PLANE] + e.orow, v);
+        }
+        if ((MEANS >> PLANE) & 1u) {
+            mean_partials_inl(e.a.win, v, e.tile, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+            ++e.mi;
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // main kernel.  grid = (band CTAs, item-chunk CTAs); block = 6 warps = 6 consecutive band tiles.
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(CTA_THREADS, 3) k_bands(const SailArgs a) {
+template <int MODE, unsigned PLANES, unsigned MEANS>
+__global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SailSmem& sm = *reinterpret_cast<SailSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,10 +370,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_bands(const SailArgs a) {
         c.ralf = 1.0 - c.talf; c.r12 = 1.0 - c.t12; c.r21 = 1.0 - c.t21;        // models.py:1012-1016
         c.rs1 = bc[C_RS1 * NBP]; c.rs2 = bc[C_RS2 * NBP];
     }
-    unsigned need = a.mean_mask;
+    unsigned need;
+    if (PLANES == RUNTIME) {
+        need = a.mean_mask;
 #pragma unroll
-    for (int i = 0; i < NOUT; ++i) need |= a.out[i] ? (1u << i) : 0u;
-    const int nt = a.win->ntotal;
+        for (int i = 0; i < NOUT; ++i) need |= a.out[i] ? (1u << i) : 0u;
+    } else {
+        need = PLANES | MEANS;
+    }
+    constexpr bool ANY_MEANS = PLANES == RUNTIME || MEANS != 0;
+    const int nt = ANY_MEANS ? a.win->ntotal : 0;
+    const int nmean = ANY_MEANS ? a.nmean : 0;
 
     for (unsigned it = 0; chunk < nchunks; chunk += gridDim.y, ++it) {
         const int buf = it & 1;
@@ -353,32 +401,23 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_bands(const SailArgs a) {
             double rho = 0.0, tau = 0.0, rs = 0.0;
             Diffuse d;
             int thr_hi = 0;
+            const double* sr = sm.stage[buf].s;
+            const double* gr = sm.stage[buf].g;
+            EmitCtx e{a, valid, tile, lane, nt, i0 * a.out_pitch + band, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
             for (int j = 0; j < n; ++j) {
-                const long long item = i0 + j;
-                const double* sr = sm.stage[buf].s + (int)(s - s0) * REC;
-                const double* gr = sm.stage[buf].g + j * REC;
-                double* pdst = a.partial + (item * a.nmean) * nt;
-                const long long orow = item * a.out_pitch + band;
-#define PB_EMIT(PLANE, VAL, MI)                                                              \
-    do {                                                                                     \
-        if (a.out[PLANE] && valid) __stcs(a.out[PLANE] + orow, (VAL));                       \
-        if (a.mean_mask & (1u << (PLANE))) { mean_partials(a.win, (VAL), tile, lane, pdst + (MI) * nt, a.f32_means); ++(MI); } \
-    } while (0)
+                e.mi = 0;
                 if (MODE == MODE_SOIL) {
                     rs = fma(sr[S_SOIL1], c.rs1, sr[S_SOIL2] * c.rs2);          // models.py:1917
-                    int mi = 0;
-                    PB_EMIT(O_RHO, rs, mi);
+                    emit<PLANES, MEANS, O_RHO>(e, rs);
                 } else if (MODE == MODE_PROSPECT) {
                     leaf_optics(c, sr, sm.mt, rho, tau);
-                    // ka, ke, om: models.py:1066-1068 (only needed for their band means)
-                    int mi = 0;
-                    PB_EMIT(O_LEAF_R, rho, mi);
-                    PB_EMIT(O_LEAF_T, tau, mi);
-                    if (a.mean_mask & (1u << O_RSOT)) {     // bits 0..2 double as ka / ke / om in this mode
-                        const double ka = 1.0 - rho - tau, ke = rho + ka, om = rho / ke;
-                        mean_partials(a.win, ka, tile, lane, pdst + (mi++) * nt, a.f32_means);
-                        mean_partials(a.win, ke, tile, lane, pdst + (mi++) * nt, a.f32_means);
-                        mean_partials(a.win, om, tile, lane, pdst + (mi++) * nt, a.f32_means);
+                    emit<PLANES, MEANS, O_LEAF_R>(e, rho);
+                    emit<PLANES, MEANS, O_LEAF_T>(e, tau);
+                    if (PLANES == RUNTIME && (a.mean_mask & (1u << O_RSOT))) {   // bits 0..2 double as ka / ke / om here
+                        const double ka = 1.0 - rho - tau, ke = rho + ka, om = rho / ke;      // models.py:1066-1068
+                        mean_partials(a.win, ka, tile, lane, e.pdst + (e.mi++) * nt, a.f32_means);
+                        mean_partials(a.win, ke, tile, lane, e.pdst + (e.mi++) * nt, a.f32_means);
+                        mean_partials(a.win, om, tile, lane, e.pdst + (e.mi++) * nt, a.f32_means);
                     }
                 } else {
                     if (fresh) {
@@ -396,26 +435,33 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_bands(const SailArgs a) {
                         thr_hi = __double2hiint(sr[S_THR]);
                         fresh = false;
                     }
-                    int mi = 0;
-                    if (sr[S_NOCANOPY] != 0.0) {                                 // lai <= 0: models.py:609-634
-                        PB_EMIT(O_RSOT, rs, mi); PB_EMIT(O_RDDT, rs, mi); PB_EMIT(O_RSDT, rs, mi); PB_EMIT(O_RDOT, rs, mi);
-                        PB_EMIT(O_RSO, 0.0, mi); PB_EMIT(O_RDD, 0.0, mi); PB_EMIT(O_TDD, 1.0, mi); PB_EMIT(O_RSD, 0.0, mi);
-                        PB_EMIT(O_TSD, 0.0, mi); PB_EMIT(O_RDO, 0.0, mi); PB_EMIT(O_TDO, 0.0, mi);
+                    if (__builtin_expect(sr[S_NOCANOPY] != 0.0, 0)) {            // lai <= 0: models.py:609-634
+                        emit<PLANES, MEANS, O_RSOT>(e, rs); emit<PLANES, MEANS, O_RDDT>(e, rs);
+                        emit<PLANES, MEANS, O_RSDT>(e, rs); emit<PLANES, MEANS, O_RDOT>(e, rs);
+                        emit<PLANES, MEANS, O_RSO>(e, 0.0); emit<PLANES, MEANS, O_RDD>(e, 0.0);
+                        emit<PLANES, MEANS, O_TDD>(e, 1.0); emit<PLANES, MEANS, O_RSD>(e, 0.0);
+                        emit<PLANES, MEANS, O_TSD>(e, 0.0); emit<PLANES, MEANS, O_RDO>(e, 0.0);
+                        emit<PLANES, MEANS, O_TDO>(e, 0.0);
                     } else {
                         Canopy o;
                         o.rddt = o.rsdt = o.rdot = 0.0;
                         sail_directional(rho, tau, rs, d, sr, gr, thr_hi, need, o);
-                        PB_EMIT(O_RSOT, o.rsot, mi); PB_EMIT(O_RDDT, o.rddt, mi); PB_EMIT(O_RSDT, o.rsdt, mi); PB_EMIT(O_RDOT, o.rdot, mi);
-                        PB_EMIT(O_RSO, o.rso, mi); PB_EMIT(O_RDD, d.rdd, mi); PB_EMIT(O_TDD, d.tdd, mi); PB_EMIT(O_RSD, o.rsd, mi);
-                        PB_EMIT(O_TSD, o.tsd, mi); PB_EMIT(O_RDO, o.rdo, mi); PB_EMIT(O_TDO, o.tdo, mi);
+                        emit<PLANES, MEANS, O_RSOT>(e, o.rsot); emit<PLANES, MEANS, O_RDDT>(e, o.rddt);
+                        emit<PLANES, MEANS, O_RSDT>(e, o.rsdt); emit<PLANES, MEANS, O_RDOT>(e, o.rdot);
+                        emit<PLANES, MEANS, O_RSO>(e, o.rso); emit<PLANES, MEANS, O_RDD>(e, d.rdd);
+                        emit<PLANES, MEANS, O_TDD>(e, d.tdd); emit<PLANES, MEANS, O_RSD>(e, o.rsd);
+                        emit<PLANES, MEANS, O_TSD>(e, o.tsd); emit<PLANES, MEANS, O_RDO>(e, o.rdo);
+                        emit<PLANES, MEANS, O_TDO>(e, o.tdo);
                     }
-                    PB_EMIT(O_KE, d.m, mi);
-                    PB_EMIT(O_LEAF_R, rho, mi);
-                    PB_EMIT(O_LEAF_T, tau, mi);
-                    PB_EMIT(O_RHO, rs, mi);
+                    emit<PLANES, MEANS, O_KE>(e, d.m);
+                    emit<PLANES, MEANS, O_LEAF_R>(e, rho);
+                    emit<PLANES, MEANS, O_LEAF_T>(e, tau);
+                    emit<PLANES, MEANS, O_RHO>(e, rs);
                 }
-#undef PB_EMIT
-                if (++g == a.G) { g = 0; ++s; fresh = true; }
+                gr += REC;
+                e.orow += a.out_pitch;
+                if (ANY_MEANS) e.pdst += nmean * nt;
+                if (++g == a.G) { g = 0; ++s; sr += REC; fresh = true; }
             }
         }
         __syncthreads();   // everyone is done with stage[buf] before it is refilled two iterations later

@@ -149,6 +149,16 @@ class Engine(object):
     def launch_count(self):
         return int(self.lib.prosail_launch_count(self.h))
 
+    def profile(self, on=True):
+        capi.check(self.lib.prosail_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """-> {'bands': (ms, launches), 'prologue': (...), 'finalize': (...)} since the last read."""
+        ms = (C.c_double * 3)()
+        cnt = (C.c_longlong * 3)()
+        capi.check(self.lib.prosail_profile_read(self.h, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(('bands', 'prologue', 'finalize'))}
+
     def device_info(self):
         name = C.create_string_buffer(128)
         sm = C.c_int()
@@ -350,6 +360,32 @@ class Engine(object):
             capi.check(self.lib.prosail_prosail_f64(self.h, 0 if version == '5' else 1, n, C.byref(leaf), C.byref(soil), C.byref(can),
                                                     C.byref(o), 1, None))
             return self._pack(bufs, means, geom, n, G)
+
+    # ---- device-resident API (inputs and outputs stay in HBM; asynchronous on `stream`) ---------------------
+    def prosail_device(self, n, leaf, soil, canopy, planes, pitch=K.NBANDS, mean_planes=(), means=None, version='5',
+                       lidf_type='campbell', n_geom=1, geom_per_sample=False, windows_only=False, stream=None):
+        """Fused PROSAIL on DeviceArrays.
+
+        leaf: dict N, Cab, Cxc, Cbr, Cw, Cm[, Can]; soil: dict reflectance, moisture; canopy: dict lidf_a[, lidf_b], lai,
+        hotspot, iza, vza, raa (normalised radians); planes: {plane index: DeviceArray [n*n_geom, pitch]}.
+        """
+        lf = self._leaf(leaf['N'], leaf['Cab'], leaf['Cxc'], leaf['Cbr'], leaf['Cw'], leaf['Cm'], leaf.get('Can'))
+        so = self._soil(soil['reflectance'], soil['moisture'])
+        lt = {'campbell': capi.LIDF_CAMPBELL, 'verhoef': capi.LIDF_VERHOEF}[lidf_type]
+        ca = self._canopy(lt, canopy['lidf_a'], canopy.get('lidf_b'), canopy['lai'], canopy['hotspot'], n_geom,
+                          1 if geom_per_sample else 0, canopy['iza'], canopy['vza'], canopy['raa'])
+        mask = 0
+        for p in mean_planes:
+            mask |= 1 << p
+        o = self._out(planes, pitch, mask, means, None, 1 if windows_only else 0)
+        capi.check(self.lib.prosail_prosail_f64(self.h, 0 if version == '5' else 1, int(n), C.byref(lf), C.byref(so), C.byref(ca),
+                                                C.byref(o), 0, stream))
+
+    def prospect_device(self, n, leaf, ks, kt, pitch=K.NBANDS, version='5', stream=None):
+        """Leaf-only batch on DeviceArrays (ks, kt: [n, pitch])."""
+        lf = self._leaf(leaf['N'], leaf['Cab'], leaf['Cxc'], leaf['Cbr'], leaf['Cw'], leaf['Cm'], leaf.get('Can'))
+        capi.check(self.lib.prosail_prospect_f64(self.h, 0 if version == '5' else 1, int(n), C.byref(lf), C.c_void_p(self._addr(ks)),
+                                                 C.c_void_p(self._addr(kt)), int(pitch), None, 0, stream))
 
     @staticmethod
     def _pack(bufs, means, geom, n, G):

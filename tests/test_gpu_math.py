@@ -1,0 +1,64 @@
+"""fp64 primitives of the kernels, evaluated on the GPU through prosail_test_math(), against numpy / mpmath."""
+import mpmath as mp
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+rng = np.random.default_rng(2026)
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+def test_rcp_and_sqrt(engine):
+    x = np.concatenate([rng.uniform(1e-3, 1e3, 50000), 10.0 ** rng.uniform(-200, 200, 50000)])
+    assert rel(engine.test_math(0, x), 1.0 / x) < 4e-16
+    assert rel(engine.test_math(0, -x), -1.0 / x) < 4e-16
+    assert rel(engine.test_math(1, x), np.sqrt(x)) < 4e-16
+    assert np.array_equal(engine.test_math(1, np.array([0.0, -1.0])), [0.0, 0.0])
+
+
+def test_exp_of_nonpositive(engine):
+    x = -np.concatenate([rng.uniform(0, 60, 50000), 10.0 ** rng.uniform(-14, 2.8, 50000), [0.0, 700.0, 5000.0]])
+    got = engine.test_math(2, x)
+    want = np.exp(np.maximum(x, -700.0))
+    assert rel(got, want) < 6e-16
+
+
+def test_log2_exp2(engine):
+    x = np.concatenate([rng.uniform(1.0, 4.0, 50000), 10.0 ** rng.uniform(0, 300, 20000), 1.0 + 10.0 ** rng.uniform(-12, 0, 20000)])
+    got = engine.test_math(3, x)
+    want = np.array([float(mp.log(mp.mpf(float(v)), 2)) for v in x[::37]])
+    # design accuracy: degree-5 series on |r| <= 2^-8 -> absolute error <= 2^-48 / (6 ln 2) = 8.5e-16 (plus rounding)
+    assert np.max(np.abs(got[::37] - want) / np.maximum(np.abs(want), 1.0)) < 1.2e-15
+    assert np.max(np.abs(got - np.log2(x)) / np.maximum(np.log2(x), 1.0)) < 1.5e-15
+    y = np.concatenate([rng.uniform(-300, 500, 50000), rng.uniform(-1, 1, 20000)])
+    assert rel(engine.test_math(4, y), np.exp2(y)) < 6e-16
+
+
+def test_tau_against_mpmath(engine):
+    """tau(k) = (1-k)e^-k + k^2 E1(k) (models.py:953-957) over the whole argument range, incl. the interval edges."""
+    edges = np.concatenate([2.0 ** np.arange(-31, 7), np.arange(2, 65, 0.5), [np.nextafter(2.0, 0), np.nextafter(64.0, 0), np.nextafter(1.0, 0)]])
+    k = np.concatenate([10.0 ** rng.uniform(-12, 1.8, 3000), rng.uniform(0, 64, 3000), edges, edges * (1 + 1e-15)])
+    k = k[k > 0]
+    mp.mp.dps = 40
+    want = np.array([float((1 - mp.mpf(float(v))) * mp.exp(-mp.mpf(float(v))) + mp.mpf(float(v)) ** 2 * mp.e1(mp.mpf(float(v)))) for v in k])
+    got = engine.test_math(5, k)
+    assert np.max(np.abs(got - want)) < 1e-15
+    inside = k < 64
+    assert rel(got[inside], want[inside]) < 1e-12
+    # outside the tabulated range
+    assert np.array_equal(engine.test_math(5, np.array([0.0, -3.0])), [1.0, 1.0])          # k <= 0 -> tau = 1
+    big = np.array([64.0, 80.0, 200.0, 700.0])
+    wb = np.array([float((1 - mp.mpf(v)) * mp.exp(-mp.mpf(v)) + mp.mpf(v) ** 2 * mp.e1(mp.mpf(v))) for v in big])
+    gb = engine.test_math(5, big)
+    assert np.all(np.isfinite(gb)) and np.max(np.abs(gb - wb)) < 1e-30 and rel(gb[:3], wb[:3]) < 1e-6
+
+
+def test_tau_against_scipy_expi(engine):
+    """...and against the reference's own formulation with scipy.special.expi."""
+    from scipy.special import expi
+    k = 10.0 ** rng.uniform(-6, 1.7, 20000)
+    want = (1 - k) * np.exp(-k) + k ** 2 * (-expi(-k))
+    assert np.max(np.abs(engine.test_math(5, k) - want)) < 2e-15

@@ -1,0 +1,358 @@
+"""Parity of the CUDA path (through the C ABI / the drop-in classes) with the CPU oracle, the stored outputs of the live
+reference and the reference's own golden files.  Tolerances: 1e-9 absolute for fp64 spectra and means (north star), float32
+eps for the PROSPECT/LSM band means that the reference itself computes in float32."""
+import numpy as np
+import pytest
+
+import pyrism_b200 as pb
+from pyrism_b200 import _capi as capi
+from oracle import prosail_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+TOL_F32 = 2e-6
+L8N = [w[0] for w in orc.L8_WINDOWS]
+ASN = [w[0] for w in orc.ASTER_WINDOWS]
+rng = np.random.default_rng(20261019)
+
+
+def lhs(n):
+    return dict(N=rng.uniform(1, 3, n), Cab=rng.uniform(5, 90, n), Cxc=rng.uniform(1, 25, n), Cbr=rng.uniform(0, 1, n),
+                Cw=rng.uniform(0.001, 0.05, n), Cm=rng.uniform(0.001, 0.02, n))
+
+
+# ------------------------------------------------------------------------------------------------------------ PROSPECT
+@pytest.mark.parametrize("version", ['5', 'D'])
+def test_prospect_batch_vs_oracle(version):
+    n = 200
+    P = lhs(n)
+    Can = rng.uniform(0.1, 8, n)
+    p = pb.PROSPECT(version=version, Can=Can if version == 'D' else 0, **P)
+    assert p.ks.shape == (n, 2101) and p.ks.dtype == np.float64
+    for i in range(n):
+        o = orc.prospect(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], Can=Can[i] if version == 'D' else 0,
+                         version=version)
+        for q in ('ks', 'kt', 'ka', 'ke', 'om'):
+            assert np.max(np.abs(getattr(p, q)[i] - o[q])) <= TOL, (q, i)
+        got = np.array([[getattr(getattr(p.L8, b), f)[i] for f in ('ks', 'kt', 'ka', 'ke', 'omega')] for b in L8N])
+        assert np.max(np.abs(got - np.array([o['L8'][b] for b in L8N]))) <= TOL_F32
+        got = np.array([[getattr(getattr(p.ASTER, b), f)[i] for f in ('ks', 'kt', 'ka', 'ke', 'omega')] for b in ASN])
+        assert np.max(np.abs(got - np.array([o['ASTER'][b] for b in ASN]))) <= TOL_F32
+    assert p.L8.B2.ks.dtype == np.float32
+
+
+def test_prospect_vs_live_reference_outputs(cases):
+    B = cases["band_index"]
+    for x, ver, out, l8 in zip(cases["leaf_in"], cases["leaf_version"], cases["leaf_out"], cases["leaf_L8"]):
+        p = pb.PROSPECT(*x[:6], Can=x[6], version=str(ver))
+        assert p.ks.shape == (2101,)
+        got = np.stack([p.ks, p.kt, p.ka, p.ke, p.om])[:, B]
+        assert np.max(np.abs(got - out)) <= TOL
+        got = np.array([[getattr(getattr(p.L8, b), f) for f in ('ks', 'kt', 'ka', 'ke', 'omega')] for b in L8N])
+        assert np.max(np.abs(got - l8)) <= TOL_F32
+
+
+def test_prospect_reference_golden_files(fixtures):
+    """The reference's own tests (tests/test_prospect_prosail.py:34-70) run against the CUDA path."""
+    w, refl, trans = fixtures["prospect5_spectrum"].T
+    p = pb.PROSPECT(N=2.1, Cab=40, Cxc=10., Cbr=0.1, Cw=0.015, Cm=0.009, version='5')
+    assert np.allclose(refl, p.ks, atol=1e-4) and np.allclose(trans, p.kt, atol=1e-4)
+    lrt = fixtures["prospect_d_LRT"]
+    p = pb.PROSPECT(N=1.2, Cab=30, Cxc=10., Cbr=0.0, Cw=0.015, Cm=0.009, Can=1, version="D")
+    assert np.allclose(lrt[:, 1], p.ks, atol=1e-4) and np.allclose(lrt[:, 2], p.kt, atol=1e-4)
+
+
+def test_prospect_attribute_surface():
+    p = pb.PROSPECT(N=1.5, Cab=35, Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055)
+    assert p.l.shape == (2101,) and p.l[0] == 400 and p.n_l == 2101 and p.ver == '5' and p.alpha == 40
+    assert p.int.shape == (2101, 6) and p.int.dtype == np.float32 and p.n_elems_list == [2101] * 7
+    assert np.array_equal(p.Kan, np.zeros(2101, dtype=np.float32)) and p.KN.dtype == np.float32
+    o = orc.prospect(1.5, 35, 5, 0.15, 0.003, 0.0055)
+    assert np.allclose(p.int, o['int'], atol=TOL_F32)
+    # select / indices (models.py:1197-1231)
+    sel = p.select(851, 879)
+    want = o['int'][(orc.WAVELENGTHS >= 851) & (orc.WAVELENGTHS <= 879)][:, 1:].mean(axis=0)
+    assert sel.dtype == np.float32 and np.allclose(sel, want, atol=TOL_F32)
+    red = o['int'][(orc.WAVELENGTHS >= 636) & (orc.WAVELENGTHS <= 673)][:, 1].mean()
+    assert abs(p.indices() - (want[0] - red) / (want[0] + red)) < 1e-5
+    p.cleanup('ndvi')
+    assert not hasattr(p, 'ndvi')
+    # a different leaf-surface cone alpha re-derives the interface constants
+    p57 = pb.PROSPECT(N=1.5, Cab=35, Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055, alpha=57)
+    o57 = orc.prospect(1.5, 35, 5, 0.15, 0.003, 0.0055, alpha=57)
+    assert np.max(np.abs(p57.ks - o57['ks'])) <= TOL and np.max(np.abs(p57.ks - p.ks)) > 1e-5
+    p40 = pb.PROSPECT(N=1.5, Cab=35, Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055)
+    assert np.array_equal(p40.ks, p.ks)
+
+
+def test_prospect_extreme_absorption():
+    """Arguments of tau() from ~0 (zero-absorption Stokes branch, models.py:1057-1059) up to k > 64."""
+    o = orc.prospect(1.5, 0.0, 0.0, 0.0, 0.0, 0.0)
+    p = pb.PROSPECT(1.5, 0.0, 0.0, 0.0, 0.0, 0.0)
+    assert np.max(np.abs(p.ks - o['ks'])) <= 1e-7 and np.max(np.abs(p.kt - o['kt'])) <= 1e-7     # 0/0 limit: noise in the reference itself
+    for kw in (dict(N=1.0, Cab=1e-3, Cxc=0, Cbr=0, Cw=1e-6, Cm=1e-6), dict(N=3.0, Cab=200, Cxc=60, Cbr=3, Cw=0.3, Cm=0.1),
+               dict(N=1.0, Cab=0, Cxc=0, Cbr=0, Cw=1.0, Cm=0.0)):
+        o = orc.prospect(**kw)
+        p = pb.PROSPECT(**kw)
+        ok = np.isfinite(o['ks'])
+        assert ok.sum() > 1500 and np.all(np.isfinite(p.ks))
+        assert np.max(np.abs(p.ks[ok] - o['ks'][ok])) <= TOL and np.max(np.abs(p.kt[ok] - o['kt'][ok])) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------------------ LSM
+def test_lsm():
+    r, m = rng.uniform(0.3, 1.2, 9), rng.uniform(0, 1, 9)
+    s = pb.LSM(reflectance=r, moisture=m)
+    assert s.ref.shape == (9, 2101)
+    for i in range(9):
+        o = orc.lsm(r[i], m[i])
+        assert np.max(np.abs(s.ref[i] - o['ref'])) <= TOL
+        assert abs(s.L8.B5[i] - o['L8']['B5']) <= TOL_F32 and abs(s.ASTER.B9[i] - o['ASTER']['B9']) <= TOL_F32
+    s1 = pb.LSM(reflectance=3.14 / 4, moisture=0.15)
+    o = orc.lsm(3.14 / 4, 0.15)
+    assert s1.ref.shape == (2101,) and s1.int.shape == (2101, 2) and np.max(np.abs(s1.ref - o['ref'])) <= TOL
+    assert isinstance(s1.L8.B2, np.float32)
+    f32 = o['ref'].astype(np.float32)
+    assert abs(s1.select(500, 600) - f32[100:201].mean()) <= TOL_F32
+
+
+# ------------------------------------------------------------------------------------------------------------ LIDF / VolScatt
+def test_lidf_and_volscatt_known_answers(cases):
+    """tests/test_volscat.py of the reference + the stored LIDF outputs of the live reference."""
+    for a, ref in zip(cases["lidf_campbell_a"], cases["lidf_campbell"]):
+        assert np.max(np.abs(pb.LIDF.campbell(a) - ref)) <= 1e-13
+    for (a, b), ref in zip(cases["lidf_verhoef_ab"], cases["lidf_verhoef"]):
+        assert np.max(np.abs(pb.LIDF.verhoef(a, b) - ref)) <= 1e-13
+    assert np.allclose(pb.LIDF.verhoef(0, 0, n_elements=18), np.zeros(18) + 0.05555556, atol=1e-4)
+    v = pb.VolScatt(50, 30, 50)
+    v.coef(a=0, b=0, lidf_type='verhoef')
+    got = (v.ks[0], v.ko[0], v.bf, v.Fs[0], v.Ft[0])
+    assert np.allclose(got, (0.823188863879162, 0.6867716425258737, 0.5, 0.6217351737543753, 0.011166182392885724), atol=1e-13)
+    v.coef(a=0, lidf_type='campbell')
+    got = (v.ks[0], v.ko[0], v.bf, v.Fs[0], v.Ft[0])
+    assert np.allclose(got, (0.9948675435577432, 0.9940524814594064, 0.9891027449943284, 0.9915874551449064, 7.491316140639147e-05), atol=1e-13)
+    assert np.allclose(v.Fst, v.Fs + v.Ft)
+    # batched LIDF parameters
+    a = rng.uniform(20, 80, 7)
+    v.coef(a=a, lidf_type='campbell')
+    assert v.ks.shape == (7, 1)
+    iza, vza, raa, *_ = orc.kernel_angles(50, 30, 50)
+    for i in range(7):
+        want = orc.volscatt_coef(iza, vza, raa, orc.lidf_campbell(a[i]))
+        assert np.allclose((v.ks[i, 0], v.ko[i, 0], v.bf[i], v.Fs[i, 0], v.Ft[i, 0]), want, atol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------------------ SAIL / PROSAIL
+CAN_PAIRS = (('BRF', 'rsot'), ('BHR', 'rddt'), ('DHR', 'rsdt'), ('HDR', 'rdot'))
+CANOPY_PAIRS = (('BRF', 'rso'), ('BHR', 'rdd'), ('BHT', 'tdd'), ('DHR', 'rsd'), ('DHT', 'tsd'), ('HDR', 'rdo'), ('HDT', 'tdo'))
+
+
+def check_sail_object(c, o, idx=()):
+    for attr, key in CAN_PAIRS:
+        assert np.max(np.abs(getattr(c, attr).ref[idx] - o[key])) <= TOL, attr
+        for b in L8N:
+            assert abs(getattr(getattr(c, attr).L8, b)[idx] - o['L8'][attr][b]) <= TOL
+        for b in ASN:
+            assert abs(getattr(getattr(c, attr).ASTER, b)[idx] - o['ASTER'][attr][b]) <= TOL
+    assert np.max(np.abs(c.BRDF.ref[idx] - o['rsot'] / np.pi)) <= TOL and abs(c.BRDF.L8.B4[idx] - o['L8']['BRDF']['B4']) <= TOL
+    for attr, key in CANOPY_PAIRS:
+        assert np.max(np.abs(c.canopy[attr][idx] - o[key])) <= TOL, attr
+    assert np.max(np.abs(c.ke[idx] - o['ke'])) <= TOL
+    for got, key in ((c.kt, 'tsstoo'), (c.kt_iza, 'tss'), (c.kt_vza, 'too'), (c.VollScat.ks, 'vol_ks'), (c.VollScat.ko, 'vol_ko'),
+                     (c.VollScat.Fs, 'Fs'), (c.VollScat.Ft, 'Ft')):
+        assert abs(np.asarray(got)[idx if idx else 0] - o[key]) <= TOL, key
+
+
+def test_readme_example_drop_in():
+    """examples/prospect_sail.py (BASELINE config 1), as P5 (the literal README call) and as D with Can = 1."""
+    for ver, can in (('5', 0), ('D', 1.0)):
+        leaf = pb.PROSPECT(N=1.5, Cab=35, Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055, Can=can, version=ver)
+        soil = pb.LSM(reflectance=3.14 / 4, moisture=0.15)
+        can_ = pb.SAIL(iza=35, vza=30, raa=50, ks=leaf.ks, kt=leaf.kt, rho_surface=soil.ref, lidf_type='campbell', lai=3, hotspot=0.25)
+        lf, so, o = orc.prosail(1.5, 35, 5, 0.15, 0.003, 0.0055, 3, 0.25, 35, 30, 50, 3.14 / 4, 0.15, Can=can, version=ver)
+        assert can_.BRF.ref.shape == (2101,) and can_.kt.shape == (1,) and can_.VollScat.ks.shape == (1,) and np.ndim(can_.VollScat.bf) == 0
+        check_sail_object(can_, o)
+        assert np.allclose(can_.BRF.refdB, 10 * np.log10(o['rsot']), atol=1e-8)
+        assert np.allclose(can_.izaDeg, 35) and can_.l[-1] == 2500 and can_.ks is leaf.ks
+
+
+def test_sail_reference_golden_file(fixtures):
+    """tests/test_prospect_prosail.py:77-120 against the CUDA path."""
+    w, resv, hdr, sdr, bhr, dhr = fixtures["REFL_CAN"].T
+    lsm = pb.LSM(reflectance=1, moisture=1)
+    leaf = pb.PROSPECT(N=1.5, Cab=40, Cxc=8., Cbr=0.0, Cw=0.01, Cm=0.009, version="5")
+    sail = pb.SAIL(iza=30, vza=10, raa=0, ks=leaf.ks, kt=leaf.kt, lai=3, hotspot=0.01, rho_surface=lsm.ref, a=-0.35, b=-0.15, lidf_type='verhoef')
+    assert np.allclose(sdr, sail.BRF.ref, atol=0.01) and np.allclose(hdr, sail.HDR.ref, atol=0.01)
+    assert np.allclose(bhr, sail.BHR.ref, atol=0.01) and np.allclose(dhr, sail.DHR.ref, atol=0.01)
+
+
+def test_canopy_cases_of_live_reference(cases):
+    """Every stored reference case (LHS + README + the reference's test case + edge cases: lai = 0, hotspot = 0, exact
+    hotspot geometry, negative view zenith, verhoef a > 1, nadir, large zenith, tiny lai) through SAIL and through PROSAIL."""
+    B = cases["band_index"]
+    rows = list(cases["can_spectra_rows"])
+    for x, ver, lt, spec, scal, l8 in zip(cases["can_in"], cases["can_version"], cases["can_lidf"], cases["can_spectra"], cases["can_scalars"],
+                                          cases["can_L8"]):
+        N, Cab, Cxc, Cbr, Cw, Cm, Can, lai, hot, la, lb, sr, sm, iza, vza, raa = x
+        fused = pb.PROSAIL(N, Cab, Cxc, Cbr, Cw, Cm, lai, hot, iza, vza, raa, soil_reflectance=sr, soil_moisture=sm, Can=Can, version=str(ver),
+                           lidf_type=str(lt), a=la, b=lb, keep_leaf=True)
+        leaf = pb.PROSPECT(N, Cab, Cxc, Cbr, Cw, Cm, Can=Can, version=str(ver))
+        soil = pb.LSM(sr, sm)
+        split = pb.SAIL(iza, vza, raa, leaf.ks, leaf.kt, lai, hot, soil.ref, lidf_type=str(lt), a=la, b=lb)
+        for c in (fused, split):
+            for attr, key in CAN_PAIRS:
+                assert np.max(np.abs(getattr(c, attr).ref[B] - spec[rows.index(key)])) <= TOL, (attr, x)
+            for attr, key in CANOPY_PAIRS:
+                assert np.max(np.abs(c.canopy[attr][B] - spec[rows.index(key)])) <= TOL, (attr, x)
+            assert np.max(np.abs(c.ke[B] - spec[rows.index('ke')])) <= TOL
+            got = np.array([c.kt[0], c.kt_iza[0], c.kt_vza[0], c.VollScat.ks[0], c.VollScat.ko[0], c.VollScat.bf, c.VollScat.Fs[0], c.VollScat.Ft[0]])
+            assert np.max(np.abs(got - scal)) <= TOL
+            got = np.array([[getattr(getattr(c, p).L8, b) for b in L8N] for p in ('BRF', 'BRDF', 'BHR', 'DHR', 'HDR')])
+            assert np.max(np.abs(got - l8)) <= TOL
+        assert np.max(np.abs(fused.leaf_ks[B] - spec[rows.index('ks')])) <= TOL and np.max(np.abs(fused.rho_surface[B] - spec[rows.index('rho')])) <= TOL
+
+
+@pytest.mark.parametrize("lidf_type", ['campbell', 'verhoef'])
+def test_prosail_batch_multi_geometry_vs_oracle(lidf_type):
+    n = 48
+    P = lhs(n)
+    lai, hot = rng.uniform(0.1, 8, n), rng.uniform(0.01, 0.5, n)
+    sr, sm = rng.uniform(0.3, 1.2, n), rng.uniform(0, 1, n)
+    a = rng.uniform(20, 80, n) if lidf_type == 'campbell' else rng.uniform(-0.6, 0.6, n)
+    b = np.zeros(n) if lidf_type == 'campbell' else rng.uniform(-0.35, 0.35, n)
+    iza, vza, raa = np.array([35.0, 10.0, 60.0, 0.0]), np.array([30.0, 45.0, 0.0, 0.0]), np.array([50.0, 120.0, 180.0, 0.0])
+    m = pb.PROSAIL(lai=lai, hotspot=hot, iza=iza, vza=vza, raa=raa, soil_reflectance=sr, soil_moisture=sm, lidf_type=lidf_type, a=a, b=b, **P)
+    assert m.BRF.ref.shape == (n, 4, 2101) and m.kt.shape == (n, 4)
+    for i in range(n):
+        for g in range(4):
+            _, _, o = orc.prosail(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], lai[i], hot[i], iza[g], vza[g], raa[g],
+                                  sr[i], sm[i], lidf_type=lidf_type, a=a[i], b=b[i])
+            check_sail_object(m, o, idx=(i, g))
+
+
+def test_sail_batched_spectra_and_shared_spectra():
+    n = 6
+    P = lhs(n)
+    leaf = pb.PROSPECT(**P)
+    soil = pb.LSM(0.9, 0.3)
+    lai = rng.uniform(0.5, 6, n)
+    c = pb.SAIL(iza=[20, 50], vza=[10, 40], raa=[0, 90], ks=leaf.ks, kt=leaf.kt, lai=lai, hotspot=0.1, rho_surface=soil.ref, a=45)
+    assert c.BRF.ref.shape == (n, 2, 2101)
+    for i in range(n):
+        o = orc.sail(50, 40, 90, leaf.ks[i], leaf.kt[i], lai[i], 0.1, soil.ref, a=45)
+        assert np.max(np.abs(c.BRF.ref[i, 1] - o['rsot'])) <= TOL and np.max(np.abs(c.HDR.ref[i, 1] - o['rdot'])) <= TOL
+    one = pb.SAIL(iza=[20, 50], vza=[10, 40], raa=[0, 90], ks=leaf.ks[0], kt=leaf.kt[0], lai=2.0, hotspot=0.1, rho_surface=soil.ref, a=45)
+    assert one.BRF.ref.shape == (2, 2101)
+    o = orc.sail(20, 10, 0, leaf.ks[0], leaf.kt[0], 2.0, 0.1, soil.ref, a=45)
+    assert np.max(np.abs(one.BRF.ref[0] - o['rsot'])) <= TOL
+    rad = pb.SAIL(iza=np.radians(50), vza=np.radians(40), raa=np.radians(90), ks=leaf.ks[0], kt=leaf.kt[0], lai=2.0, hotspot=0.1,
+                  rho_surface=soil.ref, a=45, angle_unit='RAD')
+    assert np.max(np.abs(rad.BRF.ref - one.BRF.ref[1])) <= 1e-12
+
+
+def test_j1_series_branch_is_exercised():
+    """|k - m| lai <= 1e-3 (models.py:777-779): pick a lai that puts bands of the spectrum on both sides of the switch."""
+    leaf = pb.PROSPECT(N=1.5, Cab=40, Cxc=8., Cbr=0.0, Cw=0.01, Cm=0.009)
+    soil = pb.LSM(1.0, 0.5)
+    hits = 0
+    for iza, lai in ((30, 0.02), (48, 0.05), (55, 0.01), (20, 0.03)):
+        o = orc.sail(iza, 10, 30, leaf.ks, leaf.kt, lai, 0.05, soil.ref)
+        hits += int(np.sum(np.abs((o['vol_ks'] - o['ke']) * lai) <= 1e-3))
+        c = pb.SAIL(iza, 10, 30, leaf.ks, leaf.kt, lai, 0.05, soil.ref)
+        assert np.max(np.abs(c.BRF.ref - o['rsot'])) <= TOL and np.max(np.abs(c.canopy.DHT - o['tsd'])) <= TOL
+    assert hits > 0
+
+
+# ------------------------------------------------------------------------------------------------------------ engine-level properties
+def test_specialised_kernels_agree_bitwise_with_the_general_one(engine):
+    """The LUT instances (compile-time plane sets) and the run-time-selected instance are the same arithmetic."""
+    n = 3000
+    P = lhs(n)
+    args = (P['N'], P['Cab'], P['Cxc'], P['Cbr'], P['Cw'], P['Cm'], rng.uniform(0.1, 8, n), rng.uniform(0.01, 0.5, n), np.radians([35.0]),
+            np.radians([30.0]), np.radians([50.0]), rng.uniform(0.3, 1.2, n), rng.uniform(0, 1, n))
+    kw = dict(lidf_type='campbell', a=rng.uniform(20, 80, n))
+    brf = engine.prosail(*args, planes=(capi.O_RSOT,), **kw)
+    four = engine.prosail(*args, planes=(capi.O_RSOT, capi.O_RDDT, capi.O_RSDT, capi.O_RDOT), **kw)
+    gen = engine.prosail(*args, planes=(capi.O_RSOT, capi.O_RDDT, capi.O_RSDT, capi.O_RDOT, capi.O_KE), mean_planes=(capi.O_RSOT,), **kw)
+    wo = engine.prosail(*args, mean_planes=(capi.O_RSOT,), windows_only=True, **kw)
+    assert np.array_equal(brf['rsot'], four['rsot']) and np.array_equal(brf['rsot'], gen['rsot'])
+    for k in ('rddt', 'rsdt', 'rdot'):
+        assert np.array_equal(four[k], gen[k])
+    assert np.array_equal(wo['means'], gen['means'])
+    # band means = plain inclusive means of the spectrum (models.py:811-851)
+    for w, (lo, hi) in enumerate(engine.windows):
+        assert np.max(np.abs(gen['means'][:, 0, 0, w] - brf['rsot'][:, 0, lo - 400:hi - 400 + 1].mean(axis=1))) <= 1e-14
+    assert np.all(np.isfinite(brf['rsot'])) and brf['rsot'].min() >= 0 and brf['rsot'].max() <= 1.5
+
+
+def test_result_of_a_parameter_set_does_not_depend_on_the_batch_around_it(engine):
+    """Size-independent property used at full LUT sizes: row i of a 100k batch == the same set evaluated alone (bitwise)."""
+    n = 100000
+    P = lhs(n)
+    lai, hot, a = rng.uniform(0.1, 8, n), rng.uniform(0.01, 0.5, n), rng.uniform(20, 80, n)
+    sr, sm = rng.uniform(0.3, 1.2, n), rng.uniform(0, 1, n)
+    g = (np.radians([35.0]), np.radians([30.0]), np.radians([50.0]))
+    big = engine.prosail(P['N'], P['Cab'], P['Cxc'], P['Cbr'], P['Cw'], P['Cm'], lai, hot, *g, sr, sm, lidf_type='campbell', a=a)['rsot']
+    assert big.shape == (n, 1, 2101) and np.all(np.isfinite(big))
+    for i in (0, 1, 31, 32, 4097, 65535, n - 1):
+        one = engine.prosail(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], lai[i], hot[i], *g, sr[i], sm[i],
+                             lidf_type='campbell', a=a[i])['rsot']
+        assert np.array_equal(one[0, 0], big[i, 0])
+        _, _, o = orc.prosail(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], lai[i], hot[i], 35, 30, 50, sr[i], sm[i], a=a[i])
+        assert np.max(np.abs(big[i, 0] - o['rsot'])) <= TOL
+
+
+def test_device_resident_api_matches_host_api(engine):
+    n = 5000
+    P = lhs(n)
+    extra = dict(lai=rng.uniform(0.1, 8, n), hotspot=rng.uniform(0.01, 0.5, n), lidf_a=rng.uniform(20, 80, n), sr=rng.uniform(0.3, 1.2, n),
+                 sm=rng.uniform(0, 1, n))
+    g = np.radians([35.0, 30.0, 50.0])
+    host = engine.prosail(P['N'], P['Cab'], P['Cxc'], P['Cbr'], P['Cw'], P['Cm'], extra['lai'], extra['hotspot'], g[0:1], g[1:2], g[2:3], extra['sr'],
+                          extra['sm'], lidf_type='campbell', a=extra['lidf_a'])['rsot'][:, 0]
+    dev = {k: engine.to_device(v) for k, v in {**P, **extra}.items()}
+    out = engine.empty((n, 2112))
+    engine.prosail_device(n, {k: dev[k] for k in P}, {"reflectance": dev['sr'], "moisture": dev['sm']},
+                          {"lidf_a": dev['lidf_a'], "lai": dev['lai'], "hotspot": dev['hotspot'], "iza": engine.to_device(g[0:1]),
+                           "vza": engine.to_device(g[1:2]), "raa": engine.to_device(g[2:3])}, {capi.O_RSOT: out}, pitch=2112)
+    engine.sync()
+    assert np.array_equal(out.download()[:, :2101], host)
+    ks, kt = engine.empty((n, 2101)), engine.empty((n, 2101))
+    engine.prospect_device(n, {k: dev[k] for k in P}, ks, kt)
+    engine.sync()
+    hp = engine.prospect(**P)
+    assert np.array_equal(ks.download(), hp['ks']) and np.array_equal(kt.download(), hp['kt'])
+
+
+def test_per_sample_geometry(engine):
+    n = 40
+    P = lhs(n)
+    iza, vza, raa = rng.uniform(0, 70, n), rng.uniform(0, 60, n), rng.uniform(0, 180, n)
+    m = pb.PROSAIL(lai=3.0, hotspot=0.2, iza=iza, vza=vza, raa=raa, soil_reflectance=1.0, soil_moisture=0.5, a=57, geom_per_sample=True, **P)
+    assert m.BRF.ref.shape == (n, 1, 2101)
+    for i in range(0, n, 7):
+        _, _, o = orc.prosail(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], 3.0, 0.2, iza[i], vza[i], raa[i], 1.0, 0.5)
+        assert np.max(np.abs(m.BRF.ref[i, 0] - o['rsot'])) <= TOL
+
+
+def test_custom_windows_and_c_abi_errors(engine):
+    old = engine.windows
+    try:
+        engine.set_windows([(400, 2500), (700, 700), (2495, 2600)])
+        r = engine.soil(1.0, 0.3, means=True)
+        rho = r['rho'][0]
+        assert np.allclose(r['means'][0, 0], [rho.astype(np.float32).mean(), np.float32(rho[300]), rho[2095:].astype(np.float32).mean()], atol=TOL_F32)
+        with pytest.raises(capi.ProsailError):
+            engine.set_windows([(3000, 3100)])
+        with pytest.raises(capi.ProsailError):
+            engine.set_windows([(400, 2500)] * 9)          # more than 8 windows over one 32-band tile
+    finally:
+        engine.set_windows(old)
+    import ctypes as C
+    rc = engine.lib.prosail_prospect_f64(engine.h, 7, 1, C.byref(capi.Leaf()), None, None, 2101, None, 1, None)
+    assert rc == -1 and b"version must be" in engine.lib.prosail_last_error()
+    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, C.byref(capi.Leaf()), None, None, 2101, None, 1, None)
+    assert rc == -1 and b"null leaf" in engine.lib.prosail_last_error()
+    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, None, None, None, 2101, None, 1, None)
+    assert rc == -1
+    assert engine.launch_count() > 0

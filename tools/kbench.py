@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Kernel-level timing of the fused PROSAIL kernel (device-resident inputs/outputs) for tuning experiments.
+usage: [PYRISM_B200_LIB=path.so] python tools/kbench.py [samples] [reps] [planes: brf|four|leaf]"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import bench
+import pyrism_b200 as pb
+from pyrism_b200 import _capi as capi
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+what = sys.argv[3] if len(sys.argv) > 3 else "brf"
+eng = pb.Engine(0)
+P = bench.lhs(S, 123)
+geom = np.deg2rad(np.array(bench.GEOM_DEG))
+dev = {k: eng.to_device(v) for k, v in P.items()}
+leaf = {k: dev[k] for k in ("N", "Cab", "Cxc", "Cbr", "Cw", "Cm")}
+soil = {"reflectance": dev["soil_refl"], "moisture": dev["soil_moist"]}
+canopy = {"lidf_a": dev["lidf_a"], "lai": dev["lai"], "hotspot": dev["hotspot"], "iza": eng.to_device(geom[0:1]),
+          "vza": eng.to_device(geom[1:2]), "raa": eng.to_device(geom[2:3])}
+if what == "leaf":
+    ks, kt = eng.empty((S, 2101)), eng.empty((S, 2101))
+    step = lambda: eng.prospect_device(S, leaf, ks, kt)
+else:
+    planes = {capi.O_RSOT: eng.empty((S, 2101))}
+    if what == "four":
+        for p in (capi.O_RDDT, capi.O_RSDT, capi.O_RDOT):
+            planes[p] = eng.empty((S, 2101))
+    step = lambda: eng.prosail_device(S, leaf, soil, canopy, planes)
+for _ in range(3):
+    step()
+eng.sync()
+eng.profile(True); eng.profile_read()
+for _ in range(reps):
+    step()
+pr = eng.profile_read()
+ms = pr['bands'][0] / pr['bands'][1]
+print("%s lib=%s S=%d kernel %.3f ms  -> %.3e spectra/s   prologue %.3f ms" % (what, os.path.basename(capi.LIB_PATH), S, ms, S / ms * 1e3, pr['prologue'][0] / max(pr['prologue'][1], 1)))
