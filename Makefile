@@ -1,6 +1,6 @@
 # Builds libprosail_b200.so (sm_100a only) in-tree.  `make` here or __graft_entry__.build().
 NVCC ?= nvcc
-NVFLAGS ?= -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC
+NVFLAGS ?= -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC
 SRC := pyrism_b200/csrc/prosail_api.cu
 HDR := pyrism_b200/csrc/prosail_kernels.cuh pyrism_b200/csrc/math64.cuh pyrism_b200/csrc/math_tables.inc include/prosail_b200.h
 LIB := pyrism_b200/lib/libprosail_b200.so

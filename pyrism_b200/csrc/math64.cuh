@@ -125,47 +125,56 @@ __device__ __forceinline__ double exp2_any(double y, const double* __restrict__ 
     return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
 }
 
-// tau(k) = (1-k) e^-k + k^2 E1(k)   (reference models.py:953-957; tau = 1 for k <= 0).
-// Interval index, scale S (a power of two) and the row address come from integer ops on the bits of k;
-// the FP64 pipe sees 1 FMA (local variable) + TAU_DEG FMAs (Horner).
-__device__ __forceinline__ double tau_plate(double k, const double* __restrict__ tab) {
+// ---- tau(k) = (1-k) e^-k + k^2 E1(k)   (reference models.py:953-957; tau = 1 for k <= 0) ----
+//
+// Fast path: branch-free table evaluation for k in [2^TAU_EMIN, 2^(TAU_EMAX+1)) = [6.1e-5, 32).  The interval index,
+// the scale S (a power of two) and the row address come from integer operations on the bits of k; the FP64 pipe
+// sees 1 FMA (local variable) + TAU_DEG FMAs (Horner).  Arguments outside the range are clamped to a valid row
+// (the value is then meaningless) and flagged in `rare`; the caller repairs flagged lanes with tau_rare() after
+// both evaluations of a thread have been issued.
+__device__ __forceinline__ double tau_fast(double k, const double* __restrict__ tab, bool& rare) {
     const int hi = __double2hiint(k);
-    const int E = (hi >> 20) - 1023;
-    if (__builtin_expect(E >= 6 || E < TAU_EMIN, 0)) {
-        if (!(k > 0.0)) return 1.0;                              // k <= 0 (or NaN): reference leaves tau = 1
-        if (E < TAU_EMIN) return fma(-2.0, k, 1.0);              // k < 2^-30: |k^2 ln k| < 2e-17
-        // k >= 64: tau < 1e-29; asymptotic series of k e^k E1(k) (relative accuracy ~1e-8, absolute < 1e-37)
-        const double ik = 1.0 / k;
-        double s = fma(ik, -5040.0, 720.0);
-        s = fma(ik, s, -120.0);
-        s = fma(ik, s, 24.0);
-        s = fma(ik, s, -6.0);
-        s = fma(ik, s, 2.0);
-        return exp(-k) * s * ik;
-    }
-    const bool lowk = E <= 0;
-    const int sb = lowk ? 2 : E + 1;
-    const int j = (hi & 0x000FFFFF) >> (20 - sb);
-    const int idx = lowk ? ((E - TAU_EMIN) << 2) + j : TAU_NA - 4 + (2 << E) + j;
-    const int sexp = lowk ? 3 - E : 2;
-    const double S = __hiloint2double((1023 + sexp) << 20, 0);
+    const int E0 = (hi >> 20) - 1023;
+    const int E = min(max(E0, TAU_EMIN), TAU_EMAX);
+    rare = E != E0;
+    const int e1 = max(E, 1);                                      // sub-interval bits: 2 below k = 2, E + 1 above
+    const int j = (hi & 0x000FFFFF) >> (19 - e1);
+    const int idx = (TAU_NA - 4) + j + (E <= 0 ? (E << 2) : (2 << E));
+    const double S = __hiloint2double((1026 - min(E, 1)) << 20, 0);   // 2^(3 - min(E, 1))
     const double2* row = reinterpret_cast<const double2*>(tab + idx * TAU_ROW);
-    double2 c01 = row[0];                                          // O, c0
+    const double2 c01 = row[0];                                    // O, c0
     const double u = fma(k, S, -c01.x);
-    double acc;
-    {
-        static_assert(TAU_DEG % 2 == 0, "row layout assumes an even degree (TAU_ROW even)");
-        double2 c = row[TAU_ROW / 2 - 1];                          // c[D-1], c[D]
-        acc = fma(u, c.y, c.x);
+    static_assert(TAU_DEG % 2 == 0, "row layout assumes an even degree (TAU_ROW even)");
+    double2 c = row[TAU_ROW / 2 - 1];                              // c[D-1], c[D]
+    double acc = fma(u, c.y, c.x);
 #pragma unroll
-        for (int q = TAU_ROW / 2 - 2; q >= 1; --q) {
-            c = row[q];
-            acc = fma(u, acc, c.y);
-            acc = fma(u, acc, c.x);
-        }
-        acc = fma(u, acc, c01.y);
+    for (int q = TAU_ROW / 2 - 2; q >= 1; --q) {
+        c = row[q];
+        acc = fma(u, acc, c.y);
+        acc = fma(u, acc, c.x);
     }
-    return acc;
+    return fma(u, acc, c01.y);
+}
+
+// Rare path (never taken for realistic leaves, k in [6e-4, 16]): k <= 0, k < 2^-14, k >= 32.  Plain IEEE arithmetic.
+__device__ __noinline__ double tau_rare(double k) {
+    if (!(k > 0.0)) return 1.0;                                    // k <= 0 (or NaN): the reference leaves tau = 1
+    if (k < 1.0) {
+        // E1(k) = -gamma - ln k + k - k^2/4 + k^3/18 - ...   (k < 6.1e-5: the first omitted term is below 1e-27)
+        const double e1 = -0.57721566490153286061 - log(k) + k * (1.0 - k * (0.25 - k * (1.0 / 18.0)));
+        return (1.0 - k) * exp(-k) + k * k * e1;
+    }
+    // k >= 32: E1(k) = e^-k / (k + 1 - 1/(k + 3 - 4/(k + 5 - 9/(k + 7 - ...))))   (12 levels: < 1e-16 relative)
+    double d = k + 25.0;
+    for (int i = 12; i >= 1; --i) d = k + (2 * i - 1) - (double)(i * i) / d;
+    return exp(-k) * ((1.0 - k) + k * k / d);
+}
+
+// full-range tau (test kernel, and the reference point for the fast path)
+__device__ __forceinline__ double tau_plate(double k, const double* __restrict__ tab) {
+    bool rare;
+    const double t = tau_fast(k, tab, rare);
+    return rare ? tau_rare(k) : t;
 }
 
 // warp-level sum of a double (5 butterfly steps).

@@ -189,18 +189,21 @@ static int validate(const prosail_handle* h, const Job& j) {
 // device-side execution of a job whose pointers are all device pointers
 // ------------------------------------------------------------------------------------------------
 template <int MODE, unsigned PLANES, unsigned MEANS>
-static int launch_bands(prosail_handle* h, const SailArgs& a, int band_ctas, cudaStream_t st) {
+static int launch_bands(prosail_handle* h, SailArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(SailSmem);
-    auto kern = k_bands<MODE, PLANES, MEANS>;
+    auto kern = a.G == 1 ? k_bands<MODE, PLANES, MEANS, true> : k_bands<MODE, PLANES, MEANS, false>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, smem));
     occ = std::max(occ, 1);
     const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
-    // persistent grid: exactly one wave -- never more CTAs than can be resident, so no tail wave
-    long long ychunks = std::max<long long>(1, ((long long)occ * h->sm_count) / band_ctas);
-    ychunks = std::min(ychunks, nchunks);
-    dim3 grid((unsigned)band_ctas, (unsigned)ychunks);
+    // persistent grid, exactly one wave: as many warps as can be resident, split into ranges of ntile2 warps
+    const long long resident_warps = (long long)occ * h->sm_count * WARPS_PER_CTA;
+    long long nranges = std::max<long long>(1, resident_warps / a.ntile2);
+    nranges = std::min(nranges, nchunks);
+    a.nranges = (int)nranges;
+    const long long warps = nranges * a.ntile2;
+    const unsigned grid = (unsigned)((warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
     {
         ProfScope ps(h, 0, st);
         kern<<<grid, CTA_THREADS, smem, st>>>(a);
@@ -211,25 +214,25 @@ static int launch_bands(prosail_handle* h, const SailArgs& a, int band_ctas, cud
 }
 
 // pick the kernel instance: compile-time plane sets for the LUT shapes, run-time selection otherwise
-static int dispatch_bands(prosail_handle* h, const Job& j, const SailArgs& a, int band_ctas, cudaStream_t st) {
+static int dispatch_bands(prosail_handle* h, const Job& j, SailArgs& a, cudaStream_t st) {
     unsigned planes = 0;
     for (int i = 0; i < NOUT; ++i) planes |= j.plane[i] ? (1u << i) : 0u;
     const unsigned BRF = 1u << O_RSOT, FOUR = 0xFu, LEAF = (1u << O_LEAF_R) | (1u << O_LEAF_T);
     switch (j.mode) {
         case MODE_PROSAIL:
-            if (planes == BRF && !j.mean_mask) return launch_bands<MODE_PROSAIL, BRF, 0>(h, a, band_ctas, st);
-            if (planes == FOUR && !j.mean_mask) return launch_bands<MODE_PROSAIL, FOUR, 0>(h, a, band_ctas, st);
-            if (planes == 0 && j.mean_mask == BRF && !j.f32_means) return launch_bands<MODE_PROSAIL, 0, BRF>(h, a, band_ctas, st);
-            return launch_bands<MODE_PROSAIL, RUNTIME, 0>(h, a, band_ctas, st);
+            if (planes == BRF && !j.mean_mask) return launch_bands<MODE_PROSAIL, BRF, 0>(h, a, st);
+            if (planes == FOUR && !j.mean_mask) return launch_bands<MODE_PROSAIL, FOUR, 0>(h, a, st);
+            if (planes == 0 && j.mean_mask == BRF && !j.f32_means) return launch_bands<MODE_PROSAIL, 0, BRF>(h, a, st);
+            return launch_bands<MODE_PROSAIL, RUNTIME, 0>(h, a, st);
         case MODE_SAIL:
-            if (planes == BRF && !j.mean_mask) return launch_bands<MODE_SAIL, BRF, 0>(h, a, band_ctas, st);
-            if (planes == FOUR && !j.mean_mask) return launch_bands<MODE_SAIL, FOUR, 0>(h, a, band_ctas, st);
-            return launch_bands<MODE_SAIL, RUNTIME, 0>(h, a, band_ctas, st);
+            if (planes == BRF && !j.mean_mask) return launch_bands<MODE_SAIL, BRF, 0>(h, a, st);
+            if (planes == FOUR && !j.mean_mask) return launch_bands<MODE_SAIL, FOUR, 0>(h, a, st);
+            return launch_bands<MODE_SAIL, RUNTIME, 0>(h, a, st);
         case MODE_PROSPECT:
-            if (planes == LEAF && !j.mean_mask) return launch_bands<MODE_PROSPECT, LEAF, 0>(h, a, band_ctas, st);
-            return launch_bands<MODE_PROSPECT, RUNTIME, 0>(h, a, band_ctas, st);
+            if (planes == LEAF && !j.mean_mask) return launch_bands<MODE_PROSPECT, LEAF, 0>(h, a, st);
+            return launch_bands<MODE_PROSPECT, RUNTIME, 0>(h, a, st);
         default:
-            return launch_bands<MODE_SOIL, RUNTIME, 0>(h, a, band_ctas, st);
+            return launch_bands<MODE_SOIL, RUNTIME, 0>(h, a, st);
     }
 }
 
@@ -304,9 +307,9 @@ static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st)
         a.nmean = j.nmean;
         a.only_active_tiles = j.windows_only;
         a.f32_means = j.f32_means;
-        const int band_ctas = j.windows_only ? (h->h_win.ntiles_active + WARPS_PER_CTA - 1) / WARPS_PER_CTA : BAND_CTAS;
-        if (band_ctas > 0) {
-            if ((rc = dispatch_bands(h, j, a, band_ctas, st))) return rc;
+        a.ntile2 = j.windows_only ? h->h_win.ntiles2_active : NT2;
+        if (a.ntile2 > 0) {
+            if ((rc = dispatch_bands(h, j, a, st))) return rc;
         }
         if (j.nmean > 0) {
             const long long rows = ni * j.nmean, total = rows * nw;
@@ -573,6 +576,8 @@ int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, co
     m.ntotal = slot;
     for (int t = 0; t < NTILES; ++t)
         if (touched[t]) m.active_tile[m.ntiles_active++] = t;
+    for (int t = 0; t < NT2; ++t)
+        if (touched[2 * t] || touched[2 * t + 1]) m.active_tile2[m.ntiles2_active++] = t;
     DeviceGuard guard(h->device);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h->d_win, &m, sizeof m, cudaMemcpyHostToDevice));

@@ -1,12 +1,17 @@
 // sm_100a kernels for the batched PROSPECT-5/D -> 4SAIL -> band-mean path.
 //
-// Mapping (all kernels): one THREAD owns one wavelength and keeps that band's constants
+// Mapping (band kernel): one THREAD owns TWO wavelengths (b and b + 32) and keeps their constants
 // (6-7 specific absorption coefficients, 3 interface transmissivities, 2 soil spectra) in registers;
-// a WARP owns 32 consecutive bands (66 warp tiles cover 2101 bands, 99.5% lane efficiency) and walks
-// over the work items (parameter set x geometry).  Per-item scalars come from 128-byte records that
-// the prologue kernel packs and that each CTA stages into shared memory with bulk async copies
-// (cp.async.bulk + mbarrier, double buffered), so the inner loop touches HBM only for the coalesced
-// 256-byte-per-warp stores of the output spectra.
+// a WARP owns 64 consecutive bands (33 double tiles cover 2101 bands, 99.5% lane efficiency) and walks
+// over the work items (parameter set x geometry).  The two bands of a thread are two independent
+// dependency chains in one instruction stream: the path is bound by the FP64 pipe (DFMA latency 8.6
+// cycles at one warp instruction per 2 cycles per SM sub-partition, measured), and with ~4 resident warps
+// per sub-partition it is this 2-way ILP that keeps the pipe fed.  Rare cases (arguments outside the tau
+// table, zero absorption, the J1 series branch) are flagged in the branch-free fast path and repaired
+// afterwards, so that the hot loop is a handful of large basic blocks the scheduler can interleave.
+// Per-item scalars come from 128-byte records that the prologue kernel packs and that each CTA stages
+// into shared memory with bulk async copies (cp.async.bulk + mbarrier, double buffered), so the inner
+// loop touches HBM only for the coalesced 256-byte-per-warp stores of the output spectra.
 //
 // Reference (ibaris/pyrism 0.0.5, pyrism/models/models.py) lines are cited at each step.
 #pragma once
@@ -15,16 +20,23 @@
 namespace pb {
 
 #ifndef PB_MIN_CTAS
-#define PB_MIN_CTAS 3   /* resident CTAs per SM the band kernel is compiled for (register cap) */
+#define PB_MIN_CTAS 4   /* resident CTAs per SM the band kernel is compiled for (register cap: 128 at 4 x 4 warps) */
+#endif
+
+#ifndef PB_CHUNK
+#define PB_CHUNK 8
+#endif
+#ifndef PB_WARPS
+#define PB_WARPS 4      /* warps per CTA; warps are independent (own staging buffers), the CTA only shares the math tables */
 #endif
 
 constexpr int NB = 2101;          // wavelengths 400..2500 nm
-constexpr int NTILES = 66;        // 32-band warp tiles
+constexpr int NTILES = 66;        // 32-band tiles (unit of the band-mean window map)
 constexpr int NBP = NTILES * 32;  // padded band count (2112)
-constexpr int WARPS_PER_CTA = 6;  // 66 = 11 x 6
+constexpr int NT2 = NTILES / 2;   // 64-band double tiles, one per warp
+constexpr int WARPS_PER_CTA = PB_WARPS;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
-constexpr int BAND_CTAS = NTILES / WARPS_PER_CTA;   // 11
-constexpr int CHUNK = 32;         // work items per shared-memory stage
+constexpr int CHUNK = PB_CHUNK;   // work items per shared-memory stage (per warp)
 constexpr int REC = 16;           // doubles per record (128 B)
 constexpr int MAX_TILE_SLOTS = 8; // windows that may overlap one 32-band tile
 constexpr int MAX_WINDOWS = 64;
@@ -48,8 +60,10 @@ struct WindowMap {                       // which band-mean windows touch which 
     int wstart[MAX_WINDOWS + 1];             // slots of window w: [wstart[w], wstart[w+1])
     int wcount[MAX_WINDOWS];                 // number of bands in window w
     int nwindows, ntotal;
-    int ntiles_active;                       // tiles touched by at least one window
+    int ntiles_active;                       // 32-band tiles touched by at least one window
     int active_tile[NTILES];
+    int ntiles2_active;                      // 64-band double tiles touched by at least one window
+    int active_tile2[NT2];
 };
 
 struct SailArgs {
@@ -60,6 +74,8 @@ struct SailArgs {
     const double* grec;        // [nitems][REC]
     long long nitems;
     int G;                     // geometries per sample (item = s*G + g)
+    int ntile2;                // double tiles visited (33, or the active ones in windows-only mode)
+    int nranges;               // item-chunk ranges: warp gw works on double tile gw % ntile2, chunks gw / ntile2 + i * nranges
     // SAIL-only mode: leaf / soil spectra from memory, row pitch in elements (0 = one spectrum for all samples)
     const double* in_r; const double* in_t; const double* in_rho;
     long long in_pitch_r, in_pitch_t, in_pitch_rho;
@@ -104,10 +120,14 @@ struct alignas(128) Stage {
     double g[CHUNK * REC];   // geometry records of the chunk
 };
 
+constexpr int KPLANES = 8;                 // kab kxc kan kbr kw km rs1 rs2: used once per item -> shared memory, not registers
+constexpr int KSTRIDE = 2 * CTA_THREADS;   // doubles per plane: [u][thread]
+
 struct alignas(128) SailSmem {
-    MathTables mt;
-    Stage stage[2];
-    uint64_t bar[2];
+    MathTables mt;                         // shared by the CTA, read-only after the prologue
+    Stage stage[WARPS_PER_CTA][2];         // per-warp double-buffered record staging: no CTA-wide barrier in the loop
+    double kc[KPLANES * KSTRIDE];          // conflict-free: consecutive lanes read consecutive doubles
+    uint64_t bar[WARPS_PER_CTA][2];
 };
 
 // issue the two bulk copies of one chunk (called by one thread)
@@ -126,23 +146,30 @@ __device__ __forceinline__ void stage_issue(const SailArgs& a, Stage* st, uint64
 // per-band device functions
 // ---------------------------------------------------------------------------------------------
 struct BandConst {
-    double kab, kxc, kan, kbr, kw, km;      // specific absorption coefficients
-    double talf, ralf, t12, r12, t21, r21;  // interface terms (models.py:1011-1016)
-    double rs1, rs2;                        // soil spectra
+    double talf, ralf, t12, r12, t21, r21;  // interface terms (models.py:1011-1016), register resident
 };
+enum { KC_KAB = 0, KC_KXC, KC_KAN, KC_KBR, KC_KW, KC_KM, KC_RS1, KC_RS2 };   // planes of SailSmem::kc
 
 // PROSPECT for one band and one parameter set: leaf reflectance (ks) and transmittance (kt).
 // models.py:949-959 (kall, tau), 1019-1025 (one layer), 1043-1068 (Stokes, N layers).
-__device__ __forceinline__ void leaf_optics(const BandConst& c, const double* __restrict__ s, const MathTables& mt,
-                                            double& refl, double& tran) {
+__device__ __forceinline__ double leaf_kall(const double* __restrict__ kc, const double* __restrict__ s) {
     // kall = sum_i C_i K_i / N ; the division by N is folded into the record (C_i / N)      :950-951
-    double kall = s[S_CAB] * c.kab;
-    kall = fma(s[S_CXC], c.kxc, kall);
-    kall = fma(s[S_CAN], c.kan, kall);
-    kall = fma(s[S_CBR], c.kbr, kall);
-    kall = fma(s[S_CW], c.kw, kall);
-    kall = fma(s[S_CM], c.km, kall);
-    const double tau = tau_plate(kall, mt.tau);                                               // :953-957
+    double kall = s[S_CAB] * kc[KC_KAB * KSTRIDE];
+    kall = fma(s[S_CXC], kc[KC_KXC * KSTRIDE], kall);
+    kall = fma(s[S_CAN], kc[KC_KAN * KSTRIDE], kall);
+    kall = fma(s[S_CBR], kc[KC_KBR * KSTRIDE], kall);
+    kall = fma(s[S_CW], kc[KC_KW * KSTRIDE], kall);
+    return fma(s[S_CM], kc[KC_KM * KSTRIDE], kall);
+}
+// soil reflectance of the LSM mix, models.py:1917
+__device__ __forceinline__ double soil_rho(const double* __restrict__ kc, const double* __restrict__ s) {
+    return fma(s[S_SOIL1], kc[KC_RS1 * KSTRIDE], s[S_SOIL2] * kc[KC_RS2 * KSTRIDE]);
+}
+
+// Branch-free plate + Stokes stage.  Returns true when r + t >= 1 (zero absorption, models.py:1057-1059); the
+// values written are then meaningless and leaf_zero_absorption() must be called for that band.
+__device__ __forceinline__ bool leaf_layers_fast(const BandConst& c, double tau, double nm1, const MathTables& mt, double& refl,
+                                                 double& tran) {
     // one layer                                                                              :1019-1025
     const double x = c.r21 * tau;
     const double inv = rcp(fma(-x, x, 1.0));
@@ -160,18 +187,9 @@ __device__ __forceinline__ void leaf_optics(const BandConst& c, const double* __
     const double hD = 0.5 * D;
     const double al = fma(0.5, A, hD);             // a * r   (a of :1046)
     const double be = fma(-0.5, A, 1.0 + hD);      // b * t   (b of :1047), using 1 - r^2 + t^2 = 2 - A
-    if (__builtin_expect(r + t >= 1.0, 0)) {       // zero absorption                         :1057-1059
-        const double nm1 = s[S_NM1];
-        const double Tsub = t / (t + (1.0 - t) * nm1);
-        const double Rsub = 1.0 - Tsub;
-        const double den = 1.0 - Rsub * r;
-        tran = Ta * Tsub / den;
-        refl = Ra + Ta * Rsub * t / den;
-        return;
-    }
     const double b = be * rcp(t);
     // b^(N-1) = 2^((N-1) log2 b)                                                             :1049
-    const double y = fmin(log2_pos(b, mt.logt) * s[S_NM1], 500.0);
+    const double y = fmin(log2_pos(b, mt.logt) * nm1, 500.0);
     const double bNm1 = exp2_any(y, mt.exp2t);
     const double bN2 = bNm1 * bNm1;
     // With a = al/r:  kt = Ta bNm1 (al^2 - r^2)/X,  ks = Ra + Ta t al r (bN2 - 1)/X,
@@ -182,6 +200,46 @@ __device__ __forceinline__ void leaf_optics(const BandConst& c, const double* __
     const double TaI = Ta * rcp(X);
     tran = TaI * (bNm1 * (al2 - r2));
     refl = fma(TaI * bm1, (t * al) * r, Ra);
+    return r + t >= 1.0;
+}
+
+// zero-absorption case (r + t >= 1), exactly as models.py:1057-1065 with IEEE divisions (rare path)
+__device__ __forceinline__ void leaf_zero_absorption(const BandConst& c, double tau, double nm1, double& refl, double& tran) {
+    const double x = c.r21 * tau;
+    const double den1 = 1.0 - x * x;
+    const double Ta = c.talf * tau * c.t21 / den1;
+    const double Ra = c.ralf + x * Ta;
+    const double t = c.t12 * tau * c.t21 / den1;
+    const double r = c.r12 + x * t;
+    const double Tsub = t / (t + (1.0 - t) * nm1);
+    const double Rsub = 1.0 - Tsub;
+    const double den = 1.0 - Rsub * r;
+    tran = Ta * Tsub / den;
+    refl = Ra + Ta * Rsub * t / den;
+}
+
+// both bands of a thread: the two chains are independent and written back to back so that they interleave
+__device__ __forceinline__ void leaf_optics2(const BandConst (&c)[2], const double* __restrict__ kc, const double* __restrict__ s,
+                                             const MathTables& mt, double (&refl)[2], double (&tran)[2]) {
+    double kall[2], tau[2];
+    bool rare[2], zero[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) kall[u] = leaf_kall(kc + u * CTA_THREADS, s);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) tau[u] = tau_fast(kall[u], mt.tau, rare[u]);                   // :953-957
+    if (__builtin_expect(rare[0] | rare[1], 0)) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (rare[u]) tau[u] = tau_rare(kall[u]);
+    }
+    const double nm1 = s[S_NM1];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) zero[u] = leaf_layers_fast(c[u], tau[u], nm1, mt, refl[u], tran[u]);
+    if (__builtin_expect(zero[0] | zero[1], 0)) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (zero[u]) leaf_zero_absorption(c[u], tau[u], nm1, refl[u], tran[u]);
+    }
 }
 
 // geometry-independent part of 4SAIL for one band (models.py:590-601, 637-642, 654-655, 714-719)
@@ -212,7 +270,6 @@ __device__ __forceinline__ void sail_diffuse(double rho, double tau, double rs, 
     d.rs_invdn = rs * rcp(dn);
 }
 
-// geometry-dependent part of 4SAIL for one band (models.py:603-607, 644-678, 706-726, 765-789)
 struct Canopy {
     double rsot, rddt, rsdt, rdot;        // BRF, BHR, DHR, HDR with soil
     double rso, rsd, tsd, rdo, tdo;       // canopy-only terms
@@ -222,6 +279,49 @@ struct Canopy {
 // soft: both branches agree to ~1e-13 around it, so a 2^-20-relative fuzz of the switch point is harmless.
 __device__ __forceinline__ bool abs_gt_hi(double x, int thr_hi) { return (__double2hiint(x) & 0x7fffffff) > thr_hi; }
 
+// Branch-free geometry-dependent part of 4SAIL (models.py:603-607, 644-678, 706-726, 765-789).  Returns true when
+// one of the J1 terms needs its series form (|k - m| lai <= 1e-3, models.py:777-779); the caller then re-evaluates
+// that band with sail_directional().
+__device__ __forceinline__ bool sail_directional_fast(double rho, double tau, double rs, const Diffuse& d, const double* __restrict__ g,
+                                                      int thr_hi, unsigned need, Canopy& o) {
+    const double k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO];
+    const double sb = fma(g[G_SDB], rho, g[G_SDF] * tau);             // :603-607
+    const double sf = fma(g[G_SDF], rho, g[G_SDB] * tau);
+    const double vb = fma(g[G_DOB], rho, g[G_DOF] * tau);
+    const double vf = fma(g[G_DOF], rho, g[G_DOB] * tau);
+    const double w = fma(g[G_FS], rho, g[G_FT] * tau);
+    // 1/(k-m) and 1/(k+m) from ONE reciprocal of (k-m)(k+m)                                 :644-647, 765-789
+    const double km = k - d.m, kp = k + d.m, Km = K - d.m, Kp = K + d.m;
+    const bool rare = !(abs_gt_hi(km, thr_hi) && abs_gt_hi(Km, thr_hi));
+    const double ik = rcp(km * kp), iK = rcp(Km * Kp);
+    const double inv_kp = ik * km, inv_Kp = iK * Km;
+    const double J1ks = (d.e1 - tss) * (ik * kp);
+    const double J1ko = (d.e1 - too) * (iK * Kp);
+    const double J2ks = fma(-d.e1, tss, 1.0) * inv_kp;
+    const double J2ko = fma(-d.e1, too, 1.0) * inv_Kp;
+    const double u1 = fma(sb, d.rinf, sf), u2 = fma(sf, d.rinf, sb);  // :649-652
+    const double v1 = fma(vb, d.rinf, vf), v2 = fma(vf, d.rinf, vb);
+    const double Pss = u1 * J1ks, Qss = u2 * J2ks, Pv = v1 * J1ko, Qv = v2 * J2ko;
+    o.tsd = fma(-d.re, Qss, Pss) * d.invden;                          // :656-659
+    o.rsd = fma(-d.re, Pss, Qss) * d.invden;
+    o.tdo = fma(-d.re, Qv, Pv) * d.invden;
+    o.rdo = fma(-d.re, Pv, Qv) * d.invden;
+    const double g1 = fma(-J1ks, too, g[G_Z]) * inv_Kp;               // :668-669
+    const double g2 = fma(-J1ko, tss, g[G_Z]) * inv_kp;
+    const double T1 = (v2 * g1) * u1, T2 = (v1 * g2) * u2;            // :671-675
+    const double T3 = fma(o.rdo, Qss, o.tdo * Pss) * d.rinf;
+    const double rsod = (T1 + T2 - T3) * d.inv_omr2;                  // :678
+    o.rso = fma(w, g[G_LAISUM], rsod);                                // :706, :710
+    // soil coupling                                                                        :721-726
+    const double rsodt = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too) * d.rs_invdn;
+    o.rsot = fma(g[G_TSSTOO], rs, o.rso) + rsodt;
+    if (need & (1u << O_RDDT)) o.rddt = fma(d.tdd * d.tdd, d.rs_invdn, d.rdd);
+    if (need & (1u << O_RSDT)) o.rsdt = fma((o.tsd + tss) * d.tdd, d.rs_invdn, o.rsd);
+    if (need & (1u << O_RDOT)) o.rdot = fma(d.tdd * (o.tdo + too), d.rs_invdn, o.rdo);
+    return rare;
+}
+
+// geometry-dependent part of 4SAIL for one band with J1's series branch (models.py:765-785): the repair path
 __device__ __forceinline__ void sail_directional(double rho, double tau, double rs, const Diffuse& d, const double* __restrict__ s,
                                                  const double* __restrict__ g, int thr_hi, unsigned need, Canopy& o) {
     const double k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO], lai = s[S_LAI];
@@ -304,71 +404,86 @@ constexpr unsigned RUNTIME = 0x80000000u;
 
 struct EmitCtx {
     const SailArgs& a;
-    bool valid;
-    int tile, lane, nt;
-    long long orow;      // item * pitch + band
+    bool valid[2];       // band u of this thread exists (< 2101)
+    int tile[2];         // 32-band tile of band u (index into the window map)
+    int lane, nt;
+    long long orow;      // item * pitch + band[0]   (band[1] = band[0] + 32)
     double* pdst;        // partial sums of this item
     int mi;              // running index of the mean plane
 };
 
 template <unsigned PLANES, unsigned MEANS, int PLANE>
-__device__ __forceinline__ void emit(EmitCtx& e, double v) {
+__device__ __forceinline__ void emit(EmitCtx& e, double v0, double v1) {
     if (PLANES == RUNTIME) {
-        if (e.a.out[PLANE] && e.valid) __stcs(e.a.out[PLANE] + e.orow, v);
+        if (e.a.out[PLANE]) {
+            if (e.valid[0]) __stcs(e.a.out[PLANE] + e.orow, v0);
+            if (e.valid[1]) __stcs(e.a.out[PLANE] + e.orow + 32, v1);
+        }
         if (e.a.mean_mask & (1u << PLANE)) {
-            mean_partials(e.a.win, v, e.tile, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+            mean_partials(e.a.win, v0, e.tile[0], e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+            mean_partials(e.a.win, v1, e.tile[1], e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
             ++e.mi;
         }
     } else {
         if ((PLANES >> PLANE) & 1u) {
-            if (e.valid) __stcs(e.a.out[PLANE] + e.orow, v);
+            if (e.valid[0]) __stcs(e.a.out[PLANE] + e.orow, v0);
+            if (e.valid[1]) __stcs(e.a.out[PLANE] + e.orow + 32, v1);
         }
         if ((MEANS >> PLANE) & 1u) {
-            mean_partials_inl(e.a.win, v, e.tile, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+            mean_partials_inl(e.a.win, v0, e.tile[0], e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+            mean_partials_inl(e.a.win, v1, e.tile[1], e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
             ++e.mi;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// main kernel.  grid = (band CTAs, item-chunk CTAs); block = 6 warps = 6 consecutive band tiles.
+// main kernel.  1-D grid of independent warps: warp gw owns the 64-band double tile gw % ntile2 and walks the item
+// chunks gw / ntile2, + nranges, + 2 nranges, ...  The CTA only shares the read-only math tables.
 // ---------------------------------------------------------------------------------------------
-template <int MODE, unsigned PLANES, unsigned MEANS>
+// G1 = true: one geometry per parameter set (the LUT shape) -- every item starts a new parameter set, so nothing
+// is carried between loop iterations and the register allocator sees purely loop-local state.
+template <int MODE, unsigned PLANES, unsigned MEANS, bool G1>
 __global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SailSmem& sm = *reinterpret_cast<SailSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tslot = blockIdx.x * WARPS_PER_CTA + warp;
-    const int tile = a.only_active_tiles ? (tslot < a.win->ntiles_active ? a.win->active_tile[tslot] : -1) : tslot;
-    const int band = tile * 32 + lane;
-    const bool live = tile >= 0;
-    const bool valid = live && band < NB;
+    const int gw = blockIdx.x * WARPS_PER_CTA + warp;                 // global warp id
+    const int range = gw / a.ntile2;
+    const int tslot = gw - range * a.ntile2;
+    const bool live = range < a.nranges;
+    const int t2 = !live ? 0 : (a.only_active_tiles ? a.win->active_tile2[tslot] : tslot);
+    const int band0 = t2 * 64 + lane;      // this thread's bands: band0 and band0 + 32
+    Stage* const stage = sm.stage[warp];
+    uint64_t* const bar = sm.bar[warp];
 
     {   // math tables -> shared memory
         const double2* src = reinterpret_cast<const double2*>(a.tables);
         double2* dst = reinterpret_cast<double2*>(&sm.mt);
         for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 16); i += CTA_THREADS) dst[i] = src[i];
     }
-    if (threadIdx.x == 0) {
-        mbar_init(&sm.bar[0], 1);
-        mbar_init(&sm.bar[1], 1);
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();       // the only CTA-wide barrier: tables and barriers are ready
 
     const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
-    long long chunk = blockIdx.y;
-    if (threadIdx.x == 0 && chunk < nchunks) stage_issue(a, &sm.stage[0], &sm.bar[0], chunk);
+    long long chunk = live ? range : nchunks;
+    if (lane == 0 && chunk < nchunks) stage_issue(a, &stage[0], &bar[0], chunk);
 
-    BandConst c;
-    {
-        const int bb = live ? band : 0;
-        const double* bc = a.bandc + bb;
-        c.kab = bc[C_KAB * NBP]; c.kxc = bc[C_KXC * NBP]; c.kan = bc[C_KAN * NBP]; c.kbr = bc[C_KBR * NBP];
-        c.kw = bc[C_KW * NBP]; c.km = bc[C_KM * NBP];
-        c.talf = bc[C_TALF * NBP]; c.t12 = bc[C_T12 * NBP]; c.t21 = bc[C_T21 * NBP];
-        c.ralf = 1.0 - c.talf; c.r12 = 1.0 - c.t12; c.r21 = 1.0 - c.t21;        // models.py:1012-1016
-        c.rs1 = bc[C_RS1 * NBP]; c.rs2 = bc[C_RS2 * NBP];
+    BandConst c[2];
+    const double* kc = sm.kc + threadIdx.x;        // this thread's column of the once-per-item constants
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const double* bc = a.bandc + (live ? band0 + 32 * u : 0);     // NBP = 33 * 64: always in range
+        double* k = sm.kc + u * CTA_THREADS + threadIdx.x;            // only this thread reads these back: no barrier needed
+        k[KC_KAB * KSTRIDE] = bc[C_KAB * NBP]; k[KC_KXC * KSTRIDE] = bc[C_KXC * NBP]; k[KC_KAN * KSTRIDE] = bc[C_KAN * NBP];
+        k[KC_KBR * KSTRIDE] = bc[C_KBR * NBP]; k[KC_KW * KSTRIDE] = bc[C_KW * NBP]; k[KC_KM * KSTRIDE] = bc[C_KM * NBP];
+        k[KC_RS1 * KSTRIDE] = bc[C_RS1 * NBP]; k[KC_RS2 * KSTRIDE] = bc[C_RS2 * NBP];
+        c[u].talf = bc[C_TALF * NBP]; c[u].t12 = bc[C_T12 * NBP]; c[u].t21 = bc[C_T21 * NBP];
+        c[u].ralf = 1.0 - c[u].talf; c[u].r12 = 1.0 - c[u].t12; c[u].r21 = 1.0 - c[u].t21;     // models.py:1012-1016
     }
     unsigned need;
     if (PLANES == RUNTIME) {
@@ -382,89 +497,116 @@ __global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailAr
     const int nt = ANY_MEANS ? a.win->ntotal : 0;
     const int nmean = ANY_MEANS ? a.nmean : 0;
 
-    for (unsigned it = 0; chunk < nchunks; chunk += gridDim.y, ++it) {
+    for (unsigned it = 0; chunk < nchunks; chunk += a.nranges, ++it) {
         const int buf = it & 1;
-        const long long next = chunk + gridDim.y;
-        if (threadIdx.x == 0 && next < nchunks) {
+        const long long next = chunk + a.nranges;
+        if (lane == 0 && next < nchunks) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            stage_issue(a, &sm.stage[buf ^ 1], &sm.bar[buf ^ 1], next);
+            stage_issue(a, &stage[buf ^ 1], &bar[buf ^ 1], next);
         }
-        mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
+        mbar_wait(&bar[buf], (it >> 1) & 1u);
 
-        if (live) {
+        {
             const long long i0 = chunk * CHUNK;
             const int n = (int)min((long long)CHUNK, a.nitems - i0);
-            const long long s0 = i0 / a.G;
+            const long long s0 = G1 ? i0 : i0 / a.G;
             long long s = s0;
-            int g = (int)(i0 - s0 * a.G);
+            int g = G1 ? 0 : (int)(i0 - s0 * a.G);
             bool fresh = true;
-            double rho = 0.0, tau = 0.0, rs = 0.0;
-            Diffuse d;
+            double rho[2] = {0.0, 0.0}, tau[2] = {0.0, 0.0}, rs[2] = {0.0, 0.0};
+            Diffuse d[2];
             int thr_hi = 0;
-            const double* sr = sm.stage[buf].s;
-            const double* gr = sm.stage[buf].g;
-            EmitCtx e{a, valid, tile, lane, nt, i0 * a.out_pitch + band, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
+            const double* sr = stage[buf].s;
+            const double* gr = stage[buf].g;
+            EmitCtx e{a, {band0 < NB, band0 + 32 < NB}, {2 * t2, 2 * t2 + 1}, lane, nt, i0 * a.out_pitch + band0,
+                      ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
             for (int j = 0; j < n; ++j) {
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {
-                    rs = fma(sr[S_SOIL1], c.rs1, sr[S_SOIL2] * c.rs2);          // models.py:1917
-                    emit<PLANES, MEANS, O_RHO>(e, rs);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) rs[u] = soil_rho(kc + u * CTA_THREADS, sr);
+                    emit<PLANES, MEANS, O_RHO>(e, rs[0], rs[1]);
                 } else if (MODE == MODE_PROSPECT) {
-                    leaf_optics(c, sr, sm.mt, rho, tau);
-                    emit<PLANES, MEANS, O_LEAF_R>(e, rho);
-                    emit<PLANES, MEANS, O_LEAF_T>(e, tau);
+                    leaf_optics2(c, kc, sr, sm.mt, rho, tau);
+                    emit<PLANES, MEANS, O_LEAF_R>(e, rho[0], rho[1]);
+                    emit<PLANES, MEANS, O_LEAF_T>(e, tau[0], tau[1]);
                     if (PLANES == RUNTIME && (a.mean_mask & (1u << O_RSOT))) {   // bits 0..2 double as ka / ke / om here
-                        const double ka = 1.0 - rho - tau, ke = rho + ka, om = rho / ke;      // models.py:1066-1068
-                        mean_partials(a.win, ka, tile, lane, e.pdst + (e.mi++) * nt, a.f32_means);
-                        mean_partials(a.win, ke, tile, lane, e.pdst + (e.mi++) * nt, a.f32_means);
-                        mean_partials(a.win, om, tile, lane, e.pdst + (e.mi++) * nt, a.f32_means);
+                        double ka[2], ke[2], om[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {                            // models.py:1066-1068
+                            ka[u] = 1.0 - rho[u] - tau[u];
+                            ke[u] = rho[u] + ka[u];
+                            om[u] = rho[u] / ke[u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            mean_partials(a.win, ka[u], e.tile[u], lane, e.pdst + e.mi * nt, a.f32_means);
+                            mean_partials(a.win, ke[u], e.tile[u], lane, e.pdst + (e.mi + 1) * nt, a.f32_means);
+                            mean_partials(a.win, om[u], e.tile[u], lane, e.pdst + (e.mi + 2) * nt, a.f32_means);
+                        }
+                        e.mi += 3;
                     }
                 } else {
-                    if (fresh) {
+                    if (G1 || fresh) {
                         if (MODE == MODE_PROSAIL) {
-                            leaf_optics(c, sr, sm.mt, rho, tau);
-                            rs = fma(sr[S_SOIL1], c.rs1, sr[S_SOIL2] * c.rs2);  // models.py:1917
+                            leaf_optics2(c, kc, sr, sm.mt, rho, tau);
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) rs[u] = soil_rho(kc + u * CTA_THREADS, sr);
                         } else {
-                            const int bb = valid ? band : 0;
-                            rho = a.in_r[s * a.in_pitch_r + bb];
-                            tau = a.in_t[s * a.in_pitch_t + bb];
-                            rs = a.in_rho[s * a.in_pitch_rho + bb];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int bb = e.valid[u] ? band0 + 32 * u : 0;
+                                rho[u] = a.in_r[s * a.in_pitch_r + bb];
+                                tau[u] = a.in_t[s * a.in_pitch_t + bb];
+                                rs[u] = a.in_rho[s * a.in_pitch_rho + bb];
+                            }
                         }
-                        sail_diffuse(rho, tau, rs, sr, sm.mt, d);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) sail_diffuse(rho[u], tau[u], rs[u], sr, sm.mt, d[u]);
                         // |k - m| lai <= 1e-3  <=>  |k - m| <= 1e-3 / lai   (threshold on the high word)
                         thr_hi = __double2hiint(sr[S_THR]);
                         fresh = false;
                     }
                     if (__builtin_expect(sr[S_NOCANOPY] != 0.0, 0)) {            // lai <= 0: models.py:609-634
-                        emit<PLANES, MEANS, O_RSOT>(e, rs); emit<PLANES, MEANS, O_RDDT>(e, rs);
-                        emit<PLANES, MEANS, O_RSDT>(e, rs); emit<PLANES, MEANS, O_RDOT>(e, rs);
-                        emit<PLANES, MEANS, O_RSO>(e, 0.0); emit<PLANES, MEANS, O_RDD>(e, 0.0);
-                        emit<PLANES, MEANS, O_TDD>(e, 1.0); emit<PLANES, MEANS, O_RSD>(e, 0.0);
-                        emit<PLANES, MEANS, O_TSD>(e, 0.0); emit<PLANES, MEANS, O_RDO>(e, 0.0);
-                        emit<PLANES, MEANS, O_TDO>(e, 0.0);
+                        emit<PLANES, MEANS, O_RSOT>(e, rs[0], rs[1]); emit<PLANES, MEANS, O_RDDT>(e, rs[0], rs[1]);
+                        emit<PLANES, MEANS, O_RSDT>(e, rs[0], rs[1]); emit<PLANES, MEANS, O_RDOT>(e, rs[0], rs[1]);
+                        emit<PLANES, MEANS, O_RSO>(e, 0.0, 0.0); emit<PLANES, MEANS, O_RDD>(e, 0.0, 0.0);
+                        emit<PLANES, MEANS, O_TDD>(e, 1.0, 1.0); emit<PLANES, MEANS, O_RSD>(e, 0.0, 0.0);
+                        emit<PLANES, MEANS, O_TSD>(e, 0.0, 0.0); emit<PLANES, MEANS, O_RDO>(e, 0.0, 0.0);
+                        emit<PLANES, MEANS, O_TDO>(e, 0.0, 0.0);
                     } else {
-                        Canopy o;
-                        o.rddt = o.rsdt = o.rdot = 0.0;
-                        sail_directional(rho, tau, rs, d, sr, gr, thr_hi, need, o);
-                        emit<PLANES, MEANS, O_RSOT>(e, o.rsot); emit<PLANES, MEANS, O_RDDT>(e, o.rddt);
-                        emit<PLANES, MEANS, O_RSDT>(e, o.rsdt); emit<PLANES, MEANS, O_RDOT>(e, o.rdot);
-                        emit<PLANES, MEANS, O_RSO>(e, o.rso); emit<PLANES, MEANS, O_RDD>(e, d.rdd);
-                        emit<PLANES, MEANS, O_TDD>(e, d.tdd); emit<PLANES, MEANS, O_RSD>(e, o.rsd);
-                        emit<PLANES, MEANS, O_TSD>(e, o.tsd); emit<PLANES, MEANS, O_RDO>(e, o.rdo);
-                        emit<PLANES, MEANS, O_TDO>(e, o.tdo);
+                        Canopy o[2];
+                        bool rare[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            o[u].rddt = o[u].rsdt = o[u].rdot = 0.0;
+                            rare[u] = sail_directional_fast(rho[u], tau[u], rs[u], d[u], gr, thr_hi, need, o[u]);
+                        }
+                        if (__builtin_expect(rare[0] | rare[1], 0)) {
+#pragma unroll
+                            for (int u = 0; u < 2; ++u)
+                                if (rare[u]) sail_directional(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
+                        }
+                        emit<PLANES, MEANS, O_RSOT>(e, o[0].rsot, o[1].rsot); emit<PLANES, MEANS, O_RDDT>(e, o[0].rddt, o[1].rddt);
+                        emit<PLANES, MEANS, O_RSDT>(e, o[0].rsdt, o[1].rsdt); emit<PLANES, MEANS, O_RDOT>(e, o[0].rdot, o[1].rdot);
+                        emit<PLANES, MEANS, O_RSO>(e, o[0].rso, o[1].rso); emit<PLANES, MEANS, O_RDD>(e, d[0].rdd, d[1].rdd);
+                        emit<PLANES, MEANS, O_TDD>(e, d[0].tdd, d[1].tdd); emit<PLANES, MEANS, O_RSD>(e, o[0].rsd, o[1].rsd);
+                        emit<PLANES, MEANS, O_TSD>(e, o[0].tsd, o[1].tsd); emit<PLANES, MEANS, O_RDO>(e, o[0].rdo, o[1].rdo);
+                        emit<PLANES, MEANS, O_TDO>(e, o[0].tdo, o[1].tdo);
                     }
-                    emit<PLANES, MEANS, O_KE>(e, d.m);
-                    emit<PLANES, MEANS, O_LEAF_R>(e, rho);
-                    emit<PLANES, MEANS, O_LEAF_T>(e, tau);
-                    emit<PLANES, MEANS, O_RHO>(e, rs);
+                    emit<PLANES, MEANS, O_KE>(e, d[0].m, d[1].m);
+                    emit<PLANES, MEANS, O_LEAF_R>(e, rho[0], rho[1]);
+                    emit<PLANES, MEANS, O_LEAF_T>(e, tau[0], tau[1]);
+                    emit<PLANES, MEANS, O_RHO>(e, rs[0], rs[1]);
                 }
                 gr += REC;
                 e.orow += a.out_pitch;
                 if (ANY_MEANS) e.pdst += nmean * nt;
-                if (++g == a.G) { g = 0; ++s; sr += REC; fresh = true; }
+                if (G1) { ++s; sr += REC; }
+                else if (++g == a.G) { g = 0; ++s; sr += REC; fresh = true; }
             }
         }
-        __syncthreads();   // everyone is done with stage[buf] before it is refilled two iterations later
+        __syncwarp();      // all lanes are done with stage[buf] before lane 0 refills it in the next iteration
     }
 }
 
