@@ -19,22 +19,19 @@ namespace pb {
 
 // Polynomial / range-reduction constants live in constant memory so that DFMA takes them straight from the
 // constant bank (operand c[3][..]); as literals they would each cost two UMOV issue slots per use.
-// (Values whose low 32 bits are zero -- 0.5, 1.0, 64.0, the rounding magic -- are encodable as immediates.)
-enum { M_L2E64 = 0, M_LN2H, M_LN2L, M_E5, M_E4, M_E3, M_L5, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P5, M_P4, M_P3, M_P2, M_P1, M_COUNT };
+// (Values whose low 32 bits are zero -- 0.5, 1.0, 256.0, the rounding magic -- are encodable as immediates.)
+enum { M_L2E256 = 0, M_LN2H, M_LN2L, M_E4, M_E3, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P4, M_P3, M_P2, M_P1, M_COUNT };
 __constant__ double c_m[M_COUNT] = {
-    92.332482616893656877,       // 64 log2(e)
-    -0x1.62e42fefa0000p-7,       // -(ln2/64) high part (low 17 bits zero)
-    -0x1.cf79abc9e3b3ap-46,      // -(ln2/64) low part
-    0x1.1111111111111p-7,        // 1/120
+    369.32993046757462751,       // 256 log2(e)
+    -0x1.62e42fe000000p-9,       // -(ln2/256) high part (29 significant bits: n * hi is exact for |n| < 2^24)
+    -0x1.f473de6af278fp-38,      // -(ln2/256) low part
     0x1.5555555555555p-5,        // 1/24
     0x1.5555555555555p-3,        // 1/6
-    0x1.2776c50ef9bfep-2,        // 1/(5 ln2)
     -0x1.71547652b82fep-2,       // -1/(4 ln2)
     0x1.ec709dc3a03fdp-2,        // 1/(3 ln2)
     -0x1.71547652b82fep-1,       // -1/(2 ln2)
     0x1.71547652b82fep+0,        // 1/ln2
     4503601774854144.0,          // 2^52 + 2^31
-    0x1.5d87fe78a6731p-10,       // ln2^5/120
     0x1.3b2ab6fba4e77p-7,        // ln2^4/24
     0x1.c6b08d704a0c0p-5,        // ln2^3/6
     0x1.ebfbdff82c58fp-3,        // ln2^2/2
@@ -44,9 +41,13 @@ __constant__ double c_m[M_COUNT] = {
 // ---- shared-memory image of the lookup tables (copied once per CTA) ----
 struct alignas(16) MathTables {
     double tau[TAU_NROWS * TAU_ROW];   // piecewise polynomials of tau(k), see tools/gen_math_tables.py
-    double exp2t[64];                  // 2^(j/64)
-    double logt[256];                  // pairs (1/c_i, log2 c_i), c_i = 1 + (i+.5)/128
+    double exp2t[256];                 // 2^(j/256)
+    double logt[512];                  // pairs (1/c_i, log2 c_i), c_i = 1 + (i+.5)/256
 };
+
+// Sign/threshold tests on the high word run on the integer pipe instead of costing an FP64-pipe DSETP.
+__device__ __forceinline__ bool is_pos(double x) { return __double2hiint(x) > 0; }          // x > 0 (normal)
+__device__ __forceinline__ bool is_zero(double x) { return ((__double2hiint(x) << 1) | __double2loint(x)) == 0; }
 
 // 1/x: MUFU.RCP64H seed (upper-32-bit approximation, ~2^-20) + one cubic step (3 DFMA) -> ~1 ulp.
 __device__ __forceinline__ double rcp(double x) {
@@ -54,75 +55,70 @@ __device__ __forceinline__ double rcp(double x) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
     double p = fma(e, e, e);
-    y = fma(y, p, y);
-#ifdef PB_RCP_EXTRA_STEP
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-#endif
-    return y;
+    return fma(y, p, y);
 }
 
-// sqrt(x), x > 0: MUFU.RSQ64H seed + two coupled Goldschmidt steps (7 FP64 ops).  x <= 0 -> 0.
+// sqrt(x), x > 0: MUFU.RSQ64H seed y (~2^-20) + one cubic step: with t = x y, e = 1 - t y:
+// sqrt(x) = t (1 + e/2 + 3 e^2/8 + O(e^3)).  5 FP64 ops.  x <= 0 -> 0 (integer-pipe select).
 __device__ __forceinline__ double sqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double g = x * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    return x > 0.0 ? g : 0.0;
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(e, 0.375, 0.5) * e;
+    const double g = fma(t, p, t);
+    return is_pos(x) ? g : 0.0;
 }
 
-// exp(x) for x <= 0 (clamped at -700): n = rint(64 x log2 e); exp = 2^(n>>6) * T[n&63] * P5(r).  10 FP64 ops.
+// exp(x) for x <= 0 (clamped at -700): n = rint(256 x log2 e); exp = 2^(n>>8) * T[n&255] * P4(r), |r| <= ln2/512.
+// 9 FP64 ops + one table load.
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ exp2t) {
-    x = fmax(x, -700.0);
-    const double t = fma(x, c_m[M_L2E64], PB_MAGIC);
+    x = (__double2hiint(x) & 0x7fffffff) > 0x4085E000 ? -700.0 : x;       // |x| > 700 (integer pipe)
+    const double t = fma(x, c_m[M_L2E256], PB_MAGIC);
     const int n = __double2loint(t);
     const double nd = t - PB_MAGIC;
     double r = fma(nd, c_m[M_LN2H], x);
     r = fma(nd, c_m[M_LN2L], r);
-    double p = fma(r, c_m[M_E5], c_m[M_E4]);
-    p = fma(r, p, c_m[M_E3]);
+    double p = fma(r, c_m[M_E4], c_m[M_E3]);
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
     p = fma(r, p, 1.0);
-    const double v = exp2t[n & 63] * p;
-    return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+    const double v = exp2t[n & 255] * p;
+    return __hiloint2double(__double2hiint(v) + ((n >> 8) << 20), __double2loint(v));
 }
 
-// log2(b) for normal b > 0: b = 2^E m, m in [1,2); i = top 7 mantissa bits; r = m/c_i - 1, |r| <= 2^-8;
-// log2 b = E + log2 c_i + log2(1+r) with a degree-5 series.  8 FP64 ops + one 16-byte table load.
+// log2(b) for normal b > 0: b = 2^E m, m in [1,2); i = top 8 mantissa bits; r = m/c_i - 1, |r| <= 2^-9;
+// log2 b = E + log2 c_i + log2(1+r) with a degree-4 series (absolute error <= 2^-45/(5 ln 2) = 8e-15).
+// 7 FP64 ops + one 16-byte table load.
 __device__ __forceinline__ double log2_pos(double b, const double* __restrict__ logt) {
     const int hi = __double2hiint(b);
-    const int i = (hi >> 13) & 127;
+    const int i = (hi >> 12) & 255;
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(b));
     const double2 tc = *reinterpret_cast<const double2*>(logt + 2 * i);
     const double r = fma(m, tc.x, -1.0);
     // E as a double without I2F: 2^52 + 2^31 + (E biased by 2^31), minus the constant.
     const int E = (hi >> 20) - 1023;
     const double Ed = __hiloint2double(0x43300000, E ^ 0x80000000) - c_m[M_EBIAS];
-    double q = fma(r, c_m[M_L5], c_m[M_L4]);
-    q = fma(r, q, c_m[M_L3]);
+    double q = fma(r, c_m[M_L4], c_m[M_L3]);
     q = fma(r, q, c_m[M_L2]);
     q = fma(r, q, c_m[M_L1]);
     return fma(r, q, Ed + tc.y);
 }
 
-// 2^y for |y| < 1000: n = rint(64 y); r = y - n/64 (exact); 2^y = 2^(n>>6) T[n&63] P5(r ln2).  9 FP64 ops.
+// 2^y for y < 1000 (clamped at 500): n = rint(256 y); r = y - n/256 (exact); 2^y = 2^(n>>8) T[n&255] P4(r ln2).
+// 8 FP64 ops + one table load.
 __device__ __forceinline__ double exp2_any(double y, const double* __restrict__ exp2t) {
-    const double t = fma(y, 64.0, PB_MAGIC);
+    y = __double2hiint(y) > 0x407F4000 ? 500.0 : y;                       // y > 500 (integer pipe; negative y passes)
+    const double t = fma(y, 256.0, PB_MAGIC);
     const int n = __double2loint(t);
     const double nd = t - PB_MAGIC;
-    const double r = fma(nd, -0.015625, y);
-    double p = fma(r, c_m[M_P5], c_m[M_P4]);
-    p = fma(r, p, c_m[M_P3]);
+    const double r = fma(nd, -0.00390625, y);
+    double p = fma(r, c_m[M_P4], c_m[M_P3]);
     p = fma(r, p, c_m[M_P2]);
     p = fma(r, p, c_m[M_P1]);
     p = fma(r, p, 1.0);
-    const double v = exp2t[n & 63] * p;
-    return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+    const double v = exp2t[n & 255] * p;
+    return __hiloint2double(__double2hiint(v) + ((n >> 8) << 20), __double2loint(v));
 }
 
 // ---- tau(k) = (1-k) e^-k + k^2 E1(k)   (reference models.py:953-957; tau = 1 for k <= 0) ----

@@ -20,14 +20,14 @@
 namespace pb {
 
 #ifndef PB_MIN_CTAS
-#define PB_MIN_CTAS 4   /* resident CTAs per SM the band kernel is compiled for (register cap: 128 at 4 x 4 warps) */
+#define PB_MIN_CTAS 1   /* resident CTAs per SM the band kernel is compiled for (16 warps x 128 registers fill the register file) */
 #endif
 
 #ifndef PB_CHUNK
 #define PB_CHUNK 8
 #endif
 #ifndef PB_WARPS
-#define PB_WARPS 4      /* warps per CTA; warps are independent (own staging buffers), the CTA only shares the math tables */
+#define PB_WARPS 16     /* warps per CTA (one CTA per SM); warps are independent (own staging buffers), the CTA only shares the math tables */
 #endif
 
 constexpr int NB = 2101;          // wavelengths 400..2500 nm
@@ -181,7 +181,8 @@ __device__ __forceinline__ bool leaf_layers_fast(const BandConst& c, double tau,
     // Stokes: D^2 = (1+r+t)(1+r-t)(1-r+t)(1-r-t)                                             :1043
     const double p = 1.0 + r, q = 1.0 - r;
     const double P12 = (p + t) * (p - t);
-    const double P34 = (q + t) * (q - t);
+    const double qmt = q - t;                      // 1 - r - t: <= 0 flags zero absorption
+    const double P34 = (q + t) * qmt;
     const double D = sqrt_pos(P12 * P34);
     const double A = fma(-2.0, r, P12);            // 1 + r^2 - t^2
     const double hD = 0.5 * D;
@@ -189,7 +190,7 @@ __device__ __forceinline__ bool leaf_layers_fast(const BandConst& c, double tau,
     const double be = fma(-0.5, A, 1.0 + hD);      // b * t   (b of :1047), using 1 - r^2 + t^2 = 2 - A
     const double b = be * rcp(t);
     // b^(N-1) = 2^((N-1) log2 b)                                                             :1049
-    const double y = fmin(log2_pos(b, mt.logt) * nm1, 500.0);
+    const double y = log2_pos(b, mt.logt) * nm1;
     const double bNm1 = exp2_any(y, mt.exp2t);
     const double bN2 = bNm1 * bNm1;
     // With a = al/r:  kt = Ta bNm1 (al^2 - r^2)/X,  ks = Ra + Ta t al r (bN2 - 1)/X,
@@ -200,7 +201,7 @@ __device__ __forceinline__ bool leaf_layers_fast(const BandConst& c, double tau,
     const double TaI = Ta * rcp(X);
     tran = TaI * (bNm1 * (al2 - r2));
     refl = fma(TaI * bm1, (t * al) * r, Ra);
-    return r + t >= 1.0;
+    return !is_pos(qmt);                           // r + t >= 1, tested on the sign of 1 - r - t (integer pipe)
 }
 
 // zero-absorption case (r + t >= 1), exactly as models.py:1057-1065 with IEEE divisions (rare path)
@@ -251,8 +252,8 @@ __device__ __forceinline__ void sail_diffuse(double rho, double tau, double rs, 
                                              Diffuse& d) {
     double sigb = fma(s[S_DDB], rho, s[S_DDF] * tau);                 // :590
     double sigf = fma(s[S_DDF], rho, s[S_DDB] * tau);                 // :591
-    sigb = sigb == 0.0 ? 1e-36 : sigb;                                // :594-595
-    sigf = sigf == 0.0 ? 1e-36 : sigf;
+    sigb = is_zero(sigb) ? 1e-36 : sigb;                              // :594-595 (tests on the integer pipe)
+    sigf = is_zero(sigf) ? 1e-36 : sigf;
     const double att = 1.0 - sigf;                                    // :600
     d.m = sqrt_pos(fma(att, att, -(sigb * sigb)));                    // :601
     d.e1 = exp_neg(d.m * s[S_NEGLAI], mt.exp2t);                      // :637
@@ -266,7 +267,8 @@ __device__ __forceinline__ void sail_diffuse(double rho, double tau, double rs, 
     d.tdd = omr2 * d.e1 * d.invden;                                   // :654
     d.rdd = d.rinf * (1.0 - e2) * d.invden;                           // :655
     d.rsrdd = rs * d.rdd;
-    const double dn = fmax(1.0 - d.rsrdd, 1e-36);                     // :714-719
+    double dn = 1.0 - d.rsrdd;                                        // :714-719
+    dn = __double2hiint(dn) < 0x38754484 ? 1e-36 : dn;                // dn < 1e-36 (high word of 1e-36; negatives too)
     d.rs_invdn = rs * rcp(dn);
 }
 

@@ -30,9 +30,9 @@ def test_log2_exp2(engine):
     x = np.concatenate([rng.uniform(1.0, 4.0, 50000), 10.0 ** rng.uniform(0, 300, 20000), 1.0 + 10.0 ** rng.uniform(-12, 0, 20000)])
     got = engine.test_math(3, x)
     want = np.array([float(mp.log(mp.mpf(float(v)), 2)) for v in x[::37]])
-    # design accuracy: degree-5 series on |r| <= 2^-8 -> absolute error <= 2^-48 / (6 ln 2) = 8.5e-16 (plus rounding)
-    assert np.max(np.abs(got[::37] - want) / np.maximum(np.abs(want), 1.0)) < 1.2e-15
-    assert np.max(np.abs(got - np.log2(x)) / np.maximum(np.log2(x), 1.0)) < 1.5e-15
+    # design accuracy: degree-4 series on |r| <= 2^-9 -> absolute error <= 2^-45 / (5 ln 2) = 8.2e-15 (plus rounding)
+    assert np.max(np.abs(got[::37] - want) / np.maximum(np.abs(want), 1.0)) < 1.2e-14
+    assert np.max(np.abs(got - np.log2(x)) / np.maximum(np.log2(x), 1.0)) < 1.2e-14
     y = np.concatenate([rng.uniform(-300, 500, 50000), rng.uniform(-1, 1, 20000)])
     assert rel(engine.test_math(4, y), np.exp2(y)) < 6e-16
 
