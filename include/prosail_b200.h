@@ -156,6 +156,10 @@ int prosail_timer_begin(prosail_handle_t* h, void* stream);
 int prosail_timer_end(prosail_handle_t* h, void* stream, float* ms);
 /* number of kernel launches issued through this handle so far */
 long long prosail_launch_count(prosail_handle_t* h);
+/* The LIDF / volume-scattering / hotspot prologue exists in two mappings: one warp per (set, geometry) with the 18 leaf
+ * bins across lanes and shuffle reductions (lowest latency, small batches) and one thread per (set, geometry)
+ * (highest throughput).  Batches of at least `min_items` items use the latter (default 2048; 0 = always). */
+int prosail_set_prologue_threshold(prosail_handle_t* h, long long min_items);
 /* Per-kernel device timing: while enabled, every launch is bracketed by CUDA events on its stream.
  * prosail_profile_read synchronises, returns summed milliseconds and launch counts for
  * [0] the band kernel (PROSPECT/4SAIL arithmetic), [1] the prologue, [2] the band-mean finalisation, and resets. */

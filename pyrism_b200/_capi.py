@@ -88,6 +88,7 @@ _SIGNATURES = {
     "prosail_timer_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "prosail_timer_end": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "prosail_launch_count": (C.c_longlong, [C.c_void_p]),
+    "prosail_set_prologue_threshold": (C.c_int, [C.c_void_p, C.c_longlong]),
     "prosail_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "prosail_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "prosail_device_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),

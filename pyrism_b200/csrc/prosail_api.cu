@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -80,6 +81,8 @@ struct prosail_handle {
     bool have_leaf[2] = {false, false};
     bool have_soil = false;
     double* d_tables = nullptr;
+    AngleTables* d_angles = nullptr;
+    long long prologue_thread_min = 2048;   // items from which the thread-per-item prologue is used
     WindowMap* d_win = nullptr;
     WindowMap h_win;
     bool have_win = false;
@@ -277,11 +280,12 @@ static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st)
         p.geom_out = j.geom ? j.geom + i0 * 8 : nullptr;
         p.lidf_out = j.lidf ? j.lidf + s0 * PROSAIL_NLIDF : nullptr;
         {
-            const long long threads = ni * 32;
-            const unsigned blocks = (unsigned)((threads + 127) / 128);
-            {
-                ProfScope ps(h, 1, st);
-                k_prologue<<<blocks, 128, 0, st>>>(p);
+            ProfScope ps(h, 1, st);
+            if (ni >= h->prologue_thread_min) {     // throughput variant: one thread per item
+                k_prologue_t<<<(unsigned)((ni + 127) / 128), 128, 0, st>>>(p, h->d_angles);
+            } else {                                // latency variant: one warp per item, leaf bins across lanes
+                const long long threads = ni * 32;
+                k_prologue<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p);
             }
             h->launches++;
             CK(cudaGetLastError());
@@ -477,6 +481,23 @@ int prosail_create(int device, prosail_handle_t** out) {
         CK(cudaMalloc(&h->d_tables, sizeof(MathTables)));
         CK(cudaMemcpy(h->d_tables, img.data(), sizeof(MathTables), cudaMemcpyHostToDevice));
     }
+    {   // leaf-angle tables, with the reference's own ways of converting degrees (np.radians vs angle*pi/180)
+        AngleTables t;
+        const double pi = 3.14159265358979323846;
+        for (int i = 0; i < 18; ++i) {
+            const double ttl = i * 5.0 + 2.5;
+            t.cl[i] = std::cos(ttl * (pi / 180.0));
+            t.sl[i] = std::sin(ttl * (pi / 180.0));
+        }
+        for (int i = 0; i <= 18; ++i) {
+            const double tl = (i * 5.0) * pi / 180.0;
+            t.tan_e[i] = std::tan(tl);
+            t.cos_e[i] = std::cos(tl);
+            t.edge[i] = (i * 5.0) * (pi / 180.0);
+        }
+        CK(cudaMalloc(&h->d_angles, sizeof(AngleTables)));
+        CK(cudaMemcpy(h->d_angles, &t, sizeof(AngleTables), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&h->d_win, sizeof(WindowMap)));
     CK(cudaMemset(h->d_win, 0, sizeof(WindowMap)));
     memset(&h->h_win, 0, sizeof(WindowMap));
@@ -497,6 +518,7 @@ void prosail_destroy(prosail_handle_t* h) {
     }
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_win) cudaFree(h->d_win);
+    if (h->d_angles) cudaFree(h->d_angles);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -736,6 +758,12 @@ int prosail_timer_end(prosail_handle_t* h, void* stream, float* ms) {
     return 0;
 }
 long long prosail_launch_count(prosail_handle_t* h) { return h ? h->launches : 0; }
+
+int prosail_set_prologue_threshold(prosail_handle_t* h, long long min_items) {
+    if (!h || min_items < 0) return fail(PROSAIL_E_ARG, "bad argument");
+    h->prologue_thread_min = min_items;
+    return 0;
+}
 
 int prosail_profile_enable(prosail_handle_t* h, int on) {
     if (!h) return fail(PROSAIL_E_ARG, "null handle");

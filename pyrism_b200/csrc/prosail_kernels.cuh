@@ -834,6 +834,218 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// prologue, throughput variant: one THREAD per (parameter set, geometry), used for large batches.
+// Everything that is uniform for an item (cos/sin of the sun/view angles, exp terms) is computed once per
+// item instead of once per lane, the 18 leaf bins and 20 hotspot steps are loops in the same order as the
+// reference (so the sums round like models.py:154-175 and 749-759), and the trigonometry of
+// VolScatt.volume is reduced to two acos per bin: with cb = cos(beta), sb = sqrt(1 - cb^2),
+//   cos(btran1) = cos(bts - bto),  sin(btran1) = |sin(bts - bto)|,
+//   cos(btran2) = cos(bts + bto),  sin(btran2) = |sin(bts + bto)|      (btran2 = pi - |bts + bto - pi|).
+// ---------------------------------------------------------------------------------------------
+struct AngleTables {            // filled on the host by prosail_create with the reference's own expressions
+    double cl[18], sl[18];      // cos / sin of the bin centres 2.5, 7.5, ... deg   (np.radians(ttl), models.py:202-203)
+    double tan_e[19], cos_e[19];   // tan / cos of the bin edges i * 5 deg, i = 0..18  (rad(i * step), models.py:306-311)
+    double edge[19];            // the edges in radians as LIDF.verhoef computes them (np.radians(angle), models.py:372)
+};
+
+__global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const AngleTables* __restrict__ at) {
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nitems = a.nsamples * a.G;
+    if (item >= nitems) return;
+    const long long s = item / a.G;
+    const int g = (int)(item - s * a.G);
+
+    double srec[REC];
+#pragma unroll
+    for (int i = 0; i < REC; ++i) srec[i] = 0.0;
+    if (g == 0) {
+        if (a.has_leaf) {
+            const double N = a.N[s];
+            srec[S_CAB] = a.Cab[s] / N; srec[S_CXC] = a.Cxc[s] / N; srec[S_CAN] = a.Can ? a.Can[s] / N : 0.0;
+            srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
+            srec[S_NM1] = N - 1.0;
+        }
+        if (a.has_soil) {
+            const double sr = a.soil_refl[s], mo = a.soil_moist[s];
+            srec[S_SOIL1] = sr * mo;              // rho = sRef (moisture rsoil1 + (1-moisture) rsoil2), models.py:1917
+            srec[S_SOIL2] = sr * (1.0 - mo);
+        }
+    }
+    if (!a.has_canopy) {
+        if (g == 0) {
+            double2* dst = reinterpret_cast<double2*>(a.srec + s * REC);
+#pragma unroll
+            for (int i = 0; i < REC / 2; ++i) dst[i] = make_double2(srec[2 * i], srec[2 * i + 1]);
+        }
+        return;
+    }
+
+    const double lai = a.lai[s], hot = a.hot[s];
+    const double la = a.lidf_a[s], lb = a.lidf_b ? a.lidf_b[s] : 0.0;
+    const long long gi = a.geom_per_sample ? s : g;
+    const double tts = a.iza[gi], tto = a.vza[gi], psi = a.raa[gi];
+    double sts, cts, sto, cto, spsi, cpsi;
+    sincos(tts, &sts, &cts);
+    sincos(tto, &sto, &cto);
+    sincos(psi, &spsi, &cpsi);
+
+    // ---- LIDF over 18 bins of 5 degrees ----
+    double lidf[18];
+    if (a.lidf_type == 0) {                       // Campbell, models.py:301-330
+        const double excent = exp(-1.6184e-5 * la * la * la + 2.1145e-3 * la * la - 1.2390e-1 * la + 3.2491);
+        const double e2 = excent * excent;
+        double sum0 = 0.0;
+        if (excent == 1.0) {
+#pragma unroll 1
+            for (int i = 0; i < 18; ++i) { lidf[i] = fabs(at->cos_e[i] - at->cos_e[i + 1]); sum0 += lidf[i]; }
+        } else {
+            const double alph = excent / sqrt(fabs(1.0 - e2));
+            const double alph2 = alph * alph;
+            const bool prolate = excent > 1.0;
+            double Fprev = 0.0;
+#pragma unroll 1
+            for (int i = 0; i <= 18; ++i) {       // F at the 19 bin edges; freq_i = |F_i - F_{i+1}|
+                const double tn = at->tan_e[i];
+                const double x = excent / sqrt(1.0 + e2 * tn * tn);
+                const double x2 = x * x;
+                double F;
+                if (prolate) { const double p = sqrt(alph2 + x2); F = x * p + alph2 * log(x + p); }
+                else { const double q = sqrt(alph2 - x2); F = x * q + alph2 * asin(x / alph); }
+                if (i > 0) { lidf[i - 1] = fabs(Fprev - F); sum0 += lidf[i - 1]; }
+                Fprev = F;
+            }
+        }
+#pragma unroll 1
+        for (int i = 0; i < 18; ++i) lidf[i] = lidf[i] / sum0;
+    } else {                                      // Verhoef, models.py:366-390: F(theta) from 85 deg down to 0
+        double Fhi = 1.0;
+#pragma unroll 1
+        for (int i = 17; i >= 0; --i) {
+            const double tl1 = at->edge[i];
+            double f;
+            if (la > 1.0) {
+                f = 1.0 - at->cos_e[i];
+            } else {
+                double x = 2.0 * tl1, y = 0.0, dx;
+                const double p = x;
+                int itn = 0;
+                do {
+                    double sx, cx;
+                    sincos(x, &sx, &cx);
+                    y = la * sx + 0.5 * lb * (2.0 * sx * cx);          // sin 2x = 2 sin x cos x
+                    dx = 0.5 * (y - x + p);
+                    x += dx;
+                } while (fabs(dx) >= 1e-8 && ++itn < 4096);
+                f = (2.0 * y + p) / PB_PI;
+            }
+            lidf[i] = Fhi - f;
+            Fhi = f;
+        }
+    }
+    if (a.lidf_out && g == 0) {
+#pragma unroll 1
+        for (int i = 0; i < 18; ++i) a.lidf_out[s * 18 + i] = lidf[i];
+    }
+
+    // ---- LIDF-weighted volume-scattering sums, models.py:144-258 ----
+    double k = 0.0, K = 0.0, bf = 0.0, Fs = 0.0, Ft = 0.0;
+    const double ctscto = cts * cto;
+    const bool view_up = tto < 90.0 * PB_PI / 180.0;
+#pragma unroll 1
+    for (int i = 0; i < 18; ++i) {
+        const double clza = at->cl[i], slza = at->sl[i];
+        const double cs = clza * cts, co = clza * cto, ss = slza * sts, so = slza * sto;
+        double cbs = 5.0, cbo = 5.0;
+        if (fabs(ss) > 1e-6) cbs = -cs / ss;
+        if (fabs(so) > 1e-6) cbo = -co / so;
+        double bts, ds, sbs, bto, do_, sbo;
+        if (fabs(cbs) < 1.0) { bts = acos(cbs); ds = ss; sbs = sqrt(1.0 - cbs * cbs); }
+        else { bts = PB_PI; ds = cs; cbs = -1.0; sbs = 0.0; }
+        const double chi_s = 2.0 / PB_PI * ((bts - PB_PI * 0.5) * cs + sbs * ss);
+        if (fabs(cbo) < 1.0) { bto = acos(cbo); do_ = so; sbo = sqrt(1.0 - cbo * cbo); }
+        else if (view_up) { bto = PB_PI; do_ = co; cbo = -1.0; sbo = 0.0; }
+        else { bto = 0.0; do_ = -co; cbo = 1.0; sbo = 0.0; }
+        const double chi_o = 2.0 / PB_PI * ((bto - PB_PI * 0.5) * co + sbo * so);
+        const double btran1 = fabs(bts - bto);
+        const double btran2 = PB_PI - fabs(bts + bto - PB_PI);
+        const double cc = cbs * cbo, sscp = sbs * sbo, sc = sbs * cbo, cs_ = cbs * sbo;
+        const double cos1 = cc + sscp, sin1 = fabs(sc - cs_);        // btran1
+        const double cos2 = cc - sscp, sin2 = fabs(sc + cs_);        // btran2
+        double bt2, sin_bt2, cos_bt1, cos_bt3;
+        if (psi <= btran1) { bt2 = btran1; sin_bt2 = sin1; cos_bt1 = cpsi; cos_bt3 = cos2; }
+        else if (psi <= btran2) { bt2 = psi; sin_bt2 = spsi; cos_bt1 = cos1; cos_bt3 = cos2; }
+        else { bt2 = btran2; sin_bt2 = sin2; cos_bt1 = cos1; cos_bt3 = cpsi; }
+        const double t1 = 2.0 * cs * co + ss * so * cpsi;
+        double t2 = 0.0;
+        if (bt2 > 0.0) t2 = sin_bt2 * (2.0 * ds * do_ + ss * so * cos_bt1 * cos_bt3);
+        const double denom = 2.0 * PB_PI * PB_PI;
+        const double frho = fmax(((PB_PI - bt2) * t1 + t2) / denom, 0.0);
+        const double ftau = fmax((-bt2 * t1 + t2) / denom, 0.0);
+        const double w = lidf[i];
+        k += chi_s / cts * w;
+        K += chi_o / cto * w;
+        bf += clza * clza * w;
+        Fs += frho * PB_PI / ctscto * w;
+        Ft += ftau * PB_PI / ctscto * w;
+    }
+
+    // ---- direct transmittances and the hotspot integral, models.py:664-666, 687-702, 731-763 ----
+    const bool nocanopy = !(lai > 0.0);
+    double tss = 1.0, too = 1.0, tsstoo = 1.0, sumint = 0.0, z = 0.0, alf = 1e36;
+    if (!nocanopy) {
+        tss = exp(-k * lai);
+        too = exp(-K * lai);
+        z = (1.0 - tss * too) / (k + K);                              // Jfunc2(ks, ko, lai): exp(-(k+K) lai) = tss too
+        const double tants = sts / cts, tanto = sto / cto;
+        const double dso = sqrt(fmax(tants * tants + tanto * tanto - 2.0 * tants * tanto * cpsi, 0.0));
+        if (hot > 0.0) alf = (dso / hot) * 2.0 / (k + K);
+        if (alf == 0.0) {                                             // the pure hotspot
+            tsstoo = tss;
+            sumint = (1.0 - tss) / (k * lai);
+        } else {
+            const double fhot = lai * sqrt(K * k);
+            const double fint = (1.0 - exp(-alf)) * 0.05;
+            double x1 = 0.0, y1 = 0.0, f1 = 1.0;
+#pragma unroll 1
+            for (int istep = 1; istep <= 20; ++istep) {
+                const double x2 = istep < 20 ? -log(1.0 - istep * fint) / alf : 1.0;
+                const double y2 = -(K + k) * lai * x2 + fhot * (1.0 - exp(-alf * x2)) / alf;
+                const double f2 = exp(y2);
+                sumint += (f2 - f1) * (x2 - x1) / (y2 - y1);
+                x1 = x2; y1 = y2; f1 = f2;
+            }
+            tsstoo = f1;
+            if (isnan(sumint)) sumint = 0.0;
+        }
+    }
+
+    double grec[REC];
+    grec[G_K] = k; grec[G_KO] = K;
+    grec[G_SDB] = 0.5 * (k + bf); grec[G_SDF] = 0.5 * (k - bf);      // models.py:583-588
+    grec[G_DOB] = 0.5 * (K + bf); grec[G_DOF] = 0.5 * (K - bf);
+    grec[G_FS] = Fs; grec[G_FT] = Ft;
+    grec[G_TSS] = tss; grec[G_TOO] = too; grec[G_TSSTOO] = tsstoo;
+    grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_BF] = bf; grec[G_SUMINT] = sumint; grec[G_ALF] = alf;
+    {
+        double2* dst = reinterpret_cast<double2*>(a.grec + item * REC);
+#pragma unroll
+        for (int i = 0; i < REC / 2; ++i) dst[i] = make_double2(grec[2 * i], grec[2 * i + 1]);
+    }
+    if (g == 0) {
+        srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
+        srec[S_NEGLAI] = -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;
+        srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
+        double2* dst = reinterpret_cast<double2*>(a.srec + s * REC);
+#pragma unroll
+        for (int i = 0; i < REC / 2; ++i) dst[i] = make_double2(srec[2 * i], srec[2 * i + 1]);
+    }
+    if (a.geom_out) {
+        double* o = a.geom_out + item * 8;
+        o[0] = k; o[1] = K; o[2] = bf; o[3] = Fs; o[4] = Ft; o[5] = tss; o[6] = too; o[7] = tsstoo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // test / calibration kernels
 // ---------------------------------------------------------------------------------------------
 // op: 0 rcp, 1 sqrt_pos, 2 exp_neg, 3 log2_pos, 4 exp2_any, 5 tau_plate

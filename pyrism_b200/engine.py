@@ -149,6 +149,10 @@ class Engine(object):
     def launch_count(self):
         return int(self.lib.prosail_launch_count(self.h))
 
+    def set_prologue_threshold(self, min_items=2048):
+        """Batches with at least ``min_items`` (set x geometry) items use the thread-per-item prologue kernel."""
+        capi.check(self.lib.prosail_set_prologue_threshold(self.h, int(min_items)))
+
     def profile(self, on=True):
         capi.check(self.lib.prosail_profile_enable(self.h, 1 if on else 0))
 

@@ -294,12 +294,51 @@ def test_result_of_a_parameter_set_does_not_depend_on_the_batch_around_it(engine
     g = (np.radians([35.0]), np.radians([30.0]), np.radians([50.0]))
     big = engine.prosail(P['N'], P['Cab'], P['Cxc'], P['Cbr'], P['Cw'], P['Cm'], lai, hot, *g, sr, sm, lidf_type='campbell', a=a)['rsot']
     assert big.shape == (n, 1, 2101) and np.all(np.isfinite(big))
-    for i in (0, 1, 31, 32, 4097, 65535, n - 1):
-        one = engine.prosail(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], lai[i], hot[i], *g, sr[i], sm[i],
-                             lidf_type='campbell', a=a[i])['rsot']
-        assert np.array_equal(one[0, 0], big[i, 0])
-        _, _, o = orc.prosail(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], lai[i], hot[i], 35, 30, 50, sr[i], sm[i], a=a[i])
-        assert np.max(np.abs(big[i, 0] - o['rsot'])) <= TOL
+    try:
+        for i in (0, 1, 31, 32, 4097, 65535, n - 1):
+            args = (P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], lai[i], hot[i], *g, sr[i], sm[i])
+            engine.set_prologue_threshold(0)                 # same prologue mapping as the big batch: bitwise equal
+            one = engine.prosail(*args, lidf_type='campbell', a=a[i])['rsot']
+            assert np.array_equal(one[0, 0], big[i, 0])
+            engine.set_prologue_threshold(1 << 40)           # warp-per-item mapping: equal up to summation order
+            one = engine.prosail(*args, lidf_type='campbell', a=a[i])['rsot']
+            assert np.max(np.abs(one[0, 0] - big[i, 0])) <= 1e-13
+            _, _, o = orc.prosail(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], lai[i], hot[i], 35, 30, 50, sr[i], sm[i], a=a[i])
+            assert np.max(np.abs(big[i, 0] - o['rsot'])) <= TOL
+    finally:
+        engine.set_prologue_threshold(2048)
+
+
+@pytest.mark.parametrize("lidf_type", ['campbell', 'verhoef'])
+def test_both_prologue_mappings_vs_oracle(engine, lidf_type):
+    """warp-per-item (shuffle reductions) and thread-per-item prologue kernels against the oracle's VolScatt / hotspot terms."""
+    n = 96
+    lai, hot = rng.uniform(0.0, 8, n), rng.uniform(0.0, 0.5, n)
+    lai[:3] = 0.0
+    hot[3:6] = 0.0
+    a = rng.uniform(20, 80, n) if lidf_type == 'campbell' else rng.uniform(-0.6, 0.6, n)
+    b = np.zeros(n) if lidf_type == 'campbell' else rng.uniform(-0.35, 0.35, n)
+    if lidf_type == 'verhoef':
+        a[6], b[6] = 1.5, 0.0
+        a[7], b[7] = 0.0, 0.0
+    izad, vzad, raad = np.array([35.0, 0.0, 60.0, 30.0, 70.0]), np.array([30.0, 0.0, 60.0, 30.0, 10.0]), np.array([50.0, 0.0, 0.0, 0.0, 180.0])
+    out = {}
+    try:
+        for name, thr in (('thread', 0), ('warp', 1 << 40)):
+            engine.set_prologue_threshold(thr)
+            out[name] = engine.volscatt(np.radians(izad), np.radians(vzad), np.radians(raad), lidf_type=lidf_type, a=a, b=b, lai=lai, hotspot=hot)
+    finally:
+        engine.set_prologue_threshold(2048)
+    assert np.max(np.abs(out['thread'][0] - out['warp'][0])) <= 1e-13 and np.max(np.abs(out['thread'][1] - out['warp'][1])) <= 1e-14
+    ks = np.full(2101, 0.3)
+    for i in range(0, n, 5):
+        lidf = orc.lidf_campbell(a[i]) if lidf_type == 'campbell' else orc.lidf_verhoef(a[i], b[i])
+        assert np.max(np.abs(out['thread'][1][i] - lidf)) <= 1e-13
+        for g in range(5):
+            o = orc.sail(izad[g], vzad[g], raad[g], ks, ks, lai[i], hot[i], ks, lidf_type=lidf_type, a=a[i], b=b[i])
+            want = np.array([o['vol_ks'], o['vol_ko'], o['bf'], o['Fs'], o['Ft'], o['tss'], o['too'], o['tsstoo']], dtype=np.float64)
+            for name in ('thread', 'warp'):
+                assert np.max(np.abs(out[name][0][i, g] - want)) <= 1e-12, (name, i, g)
 
 
 def test_device_resident_api_matches_host_api(engine):
