@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 NB = 2101
 FLOPS_PER_BAND = 234            # PROSPECT 83 + 4SAIL 151, div/sqrt/exp/E1/pow counted as ONE flop each
 BYTES_PER_SPECTRUM = NB * 8     # one fp64 output plane
+NCU_DRAM_BYTES_PER_SPECTRUM = (4.378456e9 + 91.992576e6) / 262144   # measured, see profiles/r1_k_bands_prosail_brf.txt
 SEED = 20261019 + 2             # config index 2
 GEOM_DEG = (35.0, 30.0, 50.0)
 
@@ -57,11 +58,12 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []          # (host time, csv line)
+        self.t_begin = None
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -69,11 +71,16 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def begin(self):
+        """Mark the start of the timed region: only samples taken from here on are reported."""
+        self.t_begin = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.time() + 0.02
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -81,7 +88,9 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t_begin is not None and not (self.t_begin <= ts <= t_end):
+                continue
             f = [c.strip() for c in r.split(",")]
             if len(f) < 7:
                 continue
@@ -174,7 +183,7 @@ def workload_config(samples, gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples", type=int, default=1000000, help="parameter sets per GPU per step")
@@ -226,13 +235,15 @@ def main():
 
     fp64_peak = eng.measure_fp64_peak(200)       # live roofline denominator (MEASURED_PEAKS.json has no fp64 entry)
 
+    sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi takes a while to emit its first line
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     eng.profile(True)
     eng.profile_read()
     l0 = eng.launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.begin()
     eng.timer_begin()
     for _ in range(args.steps):
         step()
@@ -299,7 +310,9 @@ def main():
                 "peak_source": "DFMA microbenchmark measured in this run (prosail_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
                 "flops_per_band": FLOPS_PER_BAND, "kernel_ms_avg": k_avg, "kernel_launches": int(k_n),
                 "kernel_share_of_step": k_ms / ms if world == 1 else None,
-                "traffic": None,
+                # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+                # (profiles/r1_k_bands_prosail_brf.txt: 4.470 GB for 262144 spectra = 17053 B per spectrum), scaled to this launch
+                "traffic": spectra_per_launch * NCU_DRAM_BYTES_PER_SPECTRUM,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                         "algorithmic_bytes_per_spectrum": BYTES_PER_SPECTRUM}}
