@@ -1,0 +1,89 @@
+// fp32 primitives for the fp32 mode of the PROSAIL kernels (sm_100a).  Same names as the fp64 set in
+// math64.cuh, selected by overload: the band kernel is one template over the real type.
+//
+// In fp32 the transcendental seeds of the SFU (MUFU.RCP / RSQ / EX2 / LG2, ~1-2 ulp) are already at working
+// precision, so no refinement steps are needed; what needs care instead is cancellation (handled in the kernel:
+// rinf = sigb/(att+m), J1 through expm1, see prosail_kernels.cuh).  Target of the mode: <= 1e-5 absolute in
+// reflectance / transmittance against the float64 reference (north star).
+#pragma once
+#include "math64.cuh"
+
+namespace pb {
+
+struct alignas(16) MathTablesF {
+    float tau[TAU_NROWS * TAU_ROW_F];   // degree-5 piecewise polynomials of tau(k), rows [O, c0..c5, pad]
+};
+
+template <typename T> struct Tables;
+template <> struct Tables<double> { typedef MathTables type; };
+template <> struct Tables<float> { typedef MathTablesF type; };
+
+__device__ __forceinline__ bool is_pos(float x) { return __float_as_int(x) > 0; }
+__device__ __forceinline__ bool is_zero(float x) { return (__float_as_int(x) << 1) == 0; }
+
+__device__ __forceinline__ float rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_pos(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return is_pos(x) ? y : 0.0f;
+}
+__device__ __forceinline__ float exp2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float log2_fast(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// exp(x), x <= 0
+__device__ __forceinline__ float exp_neg(float x, const MathTablesF&) { return exp2_fast(x * 1.4426950408889634f); }
+// b^e, b > 0
+__device__ __forceinline__ float pow_pos(float b, float e, const MathTablesF&) { return exp2_fast(fminf(log2_fast(b) * e, 120.0f)); }
+// expm1(x)/x for moderate |x| (J1 of 4SAIL in fp32): series below 0.25, direct above
+__device__ __forceinline__ float expm1_over_x(float x) {
+    if (fabsf(x) < 0.25f) {
+        float p = fmaf(x, 1.0f / 5040.0f, 1.0f / 720.0f);
+        p = fmaf(x, p, 1.0f / 120.0f);
+        p = fmaf(x, p, 1.0f / 24.0f);
+        p = fmaf(x, p, 1.0f / 6.0f);
+        p = fmaf(x, p, 0.5f);
+        return fmaf(x, p, 1.0f);
+    }
+    return (exp2_fast(x * 1.4426950408889634f) - 1.0f) * rcp(x);
+}
+
+// tau(k) table path in float: same interval scheme as the fp64 table (k in [2^-14, 32)), index from the float bits.
+__device__ __forceinline__ float tau_fast(float k, const float* __restrict__ tab, bool& rare) {
+    const int bits = __float_as_int(k);
+    const int E0 = (bits >> 23) - 127;
+    const int E = min(max(E0, TAU_EMIN), TAU_EMAX);
+    rare = E != E0;
+    const int e1 = max(E, 1);
+    const int j = (bits & 0x007FFFFF) >> (22 - e1);
+    const int idx = (TAU_NA - 4) + j + (E <= 0 ? (E << 2) : (2 << E));
+    const float S = __int_as_float((130 - min(E, 1)) << 23);        // 2^(3 - min(E, 1))
+    const float4* row = reinterpret_cast<const float4*>(tab + idx * TAU_ROW_F);
+    const float4 a = row[0], b = row[1];                            // O c0 c1 c2 | c3 c4 c5 pad
+    const float u = fmaf(k, S, -a.x);
+    float acc = fmaf(u, b.z, b.y);
+    acc = fmaf(u, acc, b.x);
+    acc = fmaf(u, acc, a.w);
+    acc = fmaf(u, acc, a.z);
+    return fmaf(u, acc, a.y);
+}
+__device__ __forceinline__ float tau_rare(float k) { return (float)tau_rare((double)k); }
+
+__device__ __forceinline__ const float* tau_table(const MathTablesF& mt) { return mt.tau; }
+__device__ __forceinline__ const double* tau_table(const MathTables& mt) { return mt.tau; }
+
+// fp64 twins of the two helpers that only exist to keep the kernel template type-agnostic
+__device__ __forceinline__ double pow_pos(double b, double e, const MathTables& mt) { return exp2_any(log2_pos(b, mt.logt) * e, mt.exp2t); }
+__device__ __forceinline__ double exp_neg(double x, const MathTables& mt) { return exp_neg(x, mt.exp2t); }
+
+}  // namespace pb
