@@ -95,6 +95,18 @@ typedef struct prosail_out {
     int windows_only;            /* 1: evaluate only the wavelengths inside some window (planes must be NULL) */
 } prosail_out_t;
 
+/* fp32 mode (BASELINE north star: <= 1e-5 absolute against the float64 reference): spectra, planes and means are
+ * float arrays; the per-set parameters stay float64 (the per-set prologue -- LIDF, volume scattering, hotspot -- is
+ * always evaluated in float64, it is < 3% of the work and has real cancellations). */
+typedef struct prosail_out_f32 {
+    float* plane[PROSAIL_NOUT];
+    long long pitch;
+    unsigned mean_mask;
+    float* means;
+    double* geom;
+    int windows_only;
+} prosail_out_f32_t;
+
 /* ---- lifetime --------------------------------------------------------------------------------------- */
 /* Replaces the import-time global `lib = get_data_*()` (models.py:16-19): create a handle on `device`. */
 int prosail_create(int device, prosail_handle_t** out);
@@ -142,6 +154,17 @@ int prosail_sail_f64(prosail_handle_t* h, long long n, const double* ks, long lo
  * and soil spectra in HBM: the LUT-production kernel. */
 int prosail_prosail_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_soil_t* soil,
                         const prosail_canopy_t* canopy, const prosail_out_t* out, int on_host, void* stream);
+
+/* fp32 mode of the four entry points above: same semantics, float spectra in and out (tolerance 1e-5 absolute). */
+int prosail_prospect_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, float* ks, float* kt,
+                         long long pitch, float* means_f32, int on_host, void* stream);
+int prosail_soil_f32(prosail_handle_t* h, long long n, const prosail_soil_t* soil, float* rho, long long pitch,
+                     float* means_f32, int on_host, void* stream);
+int prosail_sail_f32(prosail_handle_t* h, long long n, const float* ks, long long pitch_ks, const float* kt,
+                     long long pitch_kt, const float* rho, long long pitch_rho, const prosail_canopy_t* canopy,
+                     const prosail_out_f32_t* out, int on_host, void* stream);
+int prosail_prosail_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_soil_t* soil,
+                        const prosail_canopy_t* canopy, const prosail_out_f32_t* out, int on_host, void* stream);
 
 /* ---- memory / stream helpers (so that a host without torch/cupy can drive the device API) -------------- */
 int prosail_dev_alloc(prosail_handle_t* h, long long bytes, void** out);

@@ -95,6 +95,9 @@ _SIGNATURES = {
     "prosail_measure_fp64_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "prosail_test_math": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]),
 }
+# fp32 mode: same argument lists (prosail_out_f32_t has the layout of prosail_out_t with float planes / means)
+for _n in ("prosail_prospect", "prosail_soil", "prosail_sail", "prosail_prosail"):
+    _SIGNATURES[_n + "_f32"] = _SIGNATURES[_n + "_f64"]
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 
 

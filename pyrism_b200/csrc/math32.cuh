@@ -11,7 +11,7 @@
 namespace pb {
 
 struct alignas(16) MathTablesF {
-    float tau[TAU_NROWS * TAU_ROW_F];   // degree-5 piecewise polynomials of tau(k), rows [O, c0..c5, pad]
+    float tau[TAU_NROWS * TAU_ROW_F];   // degree-5 piecewise polynomials of g(k) = (1 - tau(k))/k, rows [O, c0..c5, pad]
 };
 
 template <typename T> struct Tables;
@@ -20,6 +20,13 @@ template <> struct Tables<float> { typedef MathTablesF type; };
 
 __device__ __forceinline__ bool is_pos(float x) { return __float_as_int(x) > 0; }
 __device__ __forceinline__ bool is_zero(float x) { return (__float_as_int(x) << 1) == 0; }
+__device__ __forceinline__ int hi_word(float x) { return __float_as_int(x); }
+__device__ __forceinline__ bool below_tiny(float x) { return __float_as_int(x) < 0x03AA2425; }   // x < 1e-36f, negatives too
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
 __device__ __forceinline__ float rcp(float x) {
     float y;
@@ -58,7 +65,8 @@ __device__ __forceinline__ float expm1_over_x(float x) {
     return (exp2_fast(x * 1.4426950408889634f) - 1.0f) * rcp(x);
 }
 
-// tau(k) table path in float: same interval scheme as the fp64 table (k in [2^-14, 32)), index from the float bits.
+// g(k) = (1 - tau(k))/k table path in float: same interval scheme as the fp64 tau table (k in [2^-14, 32)), index from
+// the float bits.  The kernel forms 1 - tau = k g(k) (relative error ~1e-7) and tau = 1 - k g(k).
 __device__ __forceinline__ float tau_fast(float k, const float* __restrict__ tab, bool& rare) {
     const int bits = __float_as_int(k);
     const int E0 = (bits >> 23) - 127;
@@ -77,13 +85,5 @@ __device__ __forceinline__ float tau_fast(float k, const float* __restrict__ tab
     acc = fmaf(u, acc, a.z);
     return fmaf(u, acc, a.y);
 }
-__device__ __forceinline__ float tau_rare(float k) { return (float)tau_rare((double)k); }
-
-__device__ __forceinline__ const float* tau_table(const MathTablesF& mt) { return mt.tau; }
-__device__ __forceinline__ const double* tau_table(const MathTables& mt) { return mt.tau; }
-
-// fp64 twins of the two helpers that only exist to keep the kernel template type-agnostic
-__device__ __forceinline__ double pow_pos(double b, double e, const MathTables& mt) { return exp2_any(log2_pos(b, mt.logt) * e, mt.exp2t); }
-__device__ __forceinline__ double exp_neg(double x, const MathTables& mt) { return exp_neg(x, mt.exp2t); }
 
 }  // namespace pb

@@ -48,6 +48,11 @@ struct alignas(16) MathTables {
 // Sign/threshold tests on the high word run on the integer pipe instead of costing an FP64-pipe DSETP.
 __device__ __forceinline__ bool is_pos(double x) { return __double2hiint(x) > 0; }          // x > 0 (normal)
 __device__ __forceinline__ bool is_zero(double x) { return ((__double2hiint(x) << 1) | __double2loint(x)) == 0; }
+__device__ __forceinline__ int hi_word(double x) { return __double2hiint(x); }
+__device__ __forceinline__ bool below_tiny(double x) { return __double2hiint(x) < 0x38754484; }   // x < 1e-36 (high word of 1e-36), negatives too
+// |x| > thr decided on the high words only (integer pipe).  The threshold of 4SAIL's J1 series branch is
+// soft: both branches agree to ~1e-13 around it, so a 2^-20-relative fuzz of the switch point is harmless.
+__device__ __forceinline__ bool abs_gt_hi(double x, int thr_hi) { return (__double2hiint(x) & 0x7fffffff) > thr_hi; }
 
 // 1/x: MUFU.RCP64H seed (upper-32-bit approximation, ~2^-20) + one cubic step (3 DFMA) -> ~1 ulp.
 __device__ __forceinline__ double rcp(double x) {
@@ -120,6 +125,10 @@ __device__ __forceinline__ double exp2_any(double y, const double* __restrict__ 
     const double v = exp2t[n & 255] * p;
     return __hiloint2double(__double2hiint(v) + ((n >> 8) << 20), __double2loint(v));
 }
+
+// type-generic spellings used by the kernel template (the float twins are in math32.cuh)
+__device__ __forceinline__ double pow_pos(double b, double e, const MathTables& mt) { return exp2_any(log2_pos(b, mt.logt) * e, mt.exp2t); }
+__device__ __forceinline__ double exp_neg(double x, const MathTables& mt) { return exp_neg(x, mt.exp2t); }
 
 // ---- tau(k) = (1-k) e^-k + k^2 E1(k)   (reference models.py:953-957; tau = 1 for k <= 0) ----
 //

@@ -78,9 +78,11 @@ struct prosail_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     double* d_bandc[2] = {nullptr, nullptr};
+    float* d_bandc_f[2] = {nullptr, nullptr};   // float image of the same planes (fp32 mode)
     bool have_leaf[2] = {false, false};
     bool have_soil = false;
     double* d_tables = nullptr;
+    float* d_tables_f = nullptr;               // MathTablesF image (fp32 mode)
     AngleTables* d_angles = nullptr;
     long long prologue_thread_min = 2048;   // items from which the thread-per-item prologue is used
     WindowMap* d_win = nullptr;
@@ -137,19 +139,21 @@ struct Job {
     prosail_leaf_t leaf{};
     prosail_soil_t soil{};
     prosail_canopy_t can{};
-    const double *in_r = nullptr, *in_t = nullptr, *in_rho = nullptr;
+    bool f32 = false;          // fp32 mode: spectra, planes and means are float arrays
+    const void *in_r = nullptr, *in_t = nullptr, *in_rho = nullptr;   // element type = f32 ? float : double
     long long pr = 0, pt = 0, prho = 0;
-    double* plane[NOUT] = {};
+    void* plane[NOUT] = {};
     long long pitch = NB;
     unsigned mean_mask = 0;
     int nmean = 0;
-    double* means = nullptr;
+    void* means = nullptr;
     float* means_f32 = nullptr;
     double* geom = nullptr;
     double* lidf = nullptr;
     int windows_only = 0;
     int f32_means = 0;
     int G() const { return has_canopy ? can.n_geom : 1; }
+    size_t esz() const { return f32 ? 4 : 8; }
 };
 
 static int validate(const prosail_handle* h, const Job& j) {
@@ -191,10 +195,15 @@ static int validate(const prosail_handle* h, const Job& j) {
 // ------------------------------------------------------------------------------------------------
 // device-side execution of a job whose pointers are all device pointers
 // ------------------------------------------------------------------------------------------------
-template <int MODE, unsigned PLANES, unsigned MEANS>
-static int launch_bands(prosail_handle* h, SailArgs& a, cudaStream_t st) {
-    const size_t smem = sizeof(SailSmem);
-    auto kern = a.G == 1 ? k_bands<MODE, PLANES, MEANS, true> : k_bands<MODE, PLANES, MEANS, false>;
+template <typename T> static inline const T* off(const void* p, long long n) { return static_cast<const T*>(p) + n; }
+template <typename T> static inline T* off(void* p, long long n) { return static_cast<T*>(p) + n; }
+static inline void* offb(void* p, long long n, size_t esz) { return static_cast<char*>(p) + n * (long long)esz; }
+static inline const void* offb(const void* p, long long n, size_t esz) { return static_cast<const char*>(p) + n * (long long)esz; }
+
+template <typename T, int MODE, unsigned PLANES, unsigned MEANS>
+static int launch_bands(prosail_handle* h, SailArgs<T>& a, cudaStream_t st) {
+    const size_t smem = sizeof(SailSmem<T>);
+    auto kern = a.G == 1 ? k_bands<T, MODE, PLANES, MEANS, true> : k_bands<T, MODE, PLANES, MEANS, false>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, smem));
@@ -217,29 +226,39 @@ static int launch_bands(prosail_handle* h, SailArgs& a, cudaStream_t st) {
 }
 
 // pick the kernel instance: compile-time plane sets for the LUT shapes, run-time selection otherwise
-static int dispatch_bands(prosail_handle* h, const Job& j, SailArgs& a, cudaStream_t st) {
+template <typename T>
+static int dispatch_bands(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
     unsigned planes = 0;
     for (int i = 0; i < NOUT; ++i) planes |= j.plane[i] ? (1u << i) : 0u;
-    const unsigned BRF = 1u << O_RSOT, FOUR = 0xFu, LEAF = (1u << O_LEAF_R) | (1u << O_LEAF_T);
+    constexpr unsigned BRF = 1u << O_RSOT, FOUR = 0xFu, LEAF = (1u << O_LEAF_R) | (1u << O_LEAF_T);
     switch (j.mode) {
         case MODE_PROSAIL:
-            if (planes == BRF && !j.mean_mask) return launch_bands<MODE_PROSAIL, BRF, 0>(h, a, st);
-            if (planes == FOUR && !j.mean_mask) return launch_bands<MODE_PROSAIL, FOUR, 0>(h, a, st);
-            if (planes == 0 && j.mean_mask == BRF && !j.f32_means) return launch_bands<MODE_PROSAIL, 0, BRF>(h, a, st);
-            return launch_bands<MODE_PROSAIL, RUNTIME, 0>(h, a, st);
+            if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, BRF, 0>(h, a, st);
+            if (planes == FOUR && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, FOUR, 0>(h, a, st);
+            if (planes == 0 && j.mean_mask == BRF && !j.f32_means) return launch_bands<T, MODE_PROSAIL, 0, BRF>(h, a, st);
+            return launch_bands<T, MODE_PROSAIL, RUNTIME, 0>(h, a, st);
         case MODE_SAIL:
-            if (planes == BRF && !j.mean_mask) return launch_bands<MODE_SAIL, BRF, 0>(h, a, st);
-            if (planes == FOUR && !j.mean_mask) return launch_bands<MODE_SAIL, FOUR, 0>(h, a, st);
-            return launch_bands<MODE_SAIL, RUNTIME, 0>(h, a, st);
+            if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_SAIL, BRF, 0>(h, a, st);
+            if (planes == FOUR && !j.mean_mask) return launch_bands<T, MODE_SAIL, FOUR, 0>(h, a, st);
+            return launch_bands<T, MODE_SAIL, RUNTIME, 0>(h, a, st);
         case MODE_PROSPECT:
-            if (planes == LEAF && !j.mean_mask) return launch_bands<MODE_PROSPECT, LEAF, 0>(h, a, st);
-            return launch_bands<MODE_PROSPECT, RUNTIME, 0>(h, a, st);
+            if (planes == LEAF && !j.mean_mask) return launch_bands<T, MODE_PROSPECT, LEAF, 0>(h, a, st);
+            return launch_bands<T, MODE_PROSPECT, RUNTIME, 0>(h, a, st);
         default:
-            return launch_bands<MODE_SOIL, RUNTIME, 0>(h, a, st);
+            return launch_bands<T, MODE_SOIL, RUNTIME, 0>(h, a, st);
     }
 }
 
-static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st) {
+template <typename T> static const T* bandc_of(const prosail_handle* h, int v);
+template <> const double* bandc_of<double>(const prosail_handle* h, int v) { return h->d_bandc[v]; }
+template <> const float* bandc_of<float>(const prosail_handle* h, int v) { return h->d_bandc_f[v]; }
+template <typename T> static const void* tables_of(const prosail_handle* h);
+template <> const void* tables_of<double>(const prosail_handle* h) { return h->d_tables; }
+template <> const void* tables_of<float>(const prosail_handle* h) { return h->d_tables_f; }
+
+template <typename T>
+static int run_device_t(prosail_handle* h, const Job& j, Work& w, cudaStream_t st) {
+    constexpr size_t ES = sizeof(T);
     const int G = j.G();
     const long long nitems_total = j.n * G;
     if (nitems_total == 0) return 0;
@@ -247,16 +266,16 @@ static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st)
     const int nt = h->have_win ? h->h_win.ntotal : 0;
     // slab = bounded workspace
     long long cap_items = 1LL << 20;
-    if (j.nmean > 0) cap_items = std::min<long long>(cap_items, std::max<long long>(4096, (1LL << 30) / ((long long)j.nmean * std::max(nt, 1) * 8)));
+    if (j.nmean > 0) cap_items = std::min<long long>(cap_items, std::max<long long>(4096, (1LL << 30) / ((long long)j.nmean * std::max(nt, 1) * (long long)ES)));
     const long long slab_samples = std::max<long long>(1, cap_items / G);
 
     for (long long s0 = 0; s0 < j.n; s0 += slab_samples) {
         const long long ns = std::min(slab_samples, j.n - s0);
         const long long ni = ns * G, i0 = s0 * G;
         int rc;
-        if ((rc = w.srec.reserve((size_t)ns * REC * 8))) return rc;
-        if ((rc = w.grec.reserve((size_t)std::max<long long>(ni, 1) * REC * 8))) return rc;
-        if (j.nmean > 0 && (rc = w.partial.reserve((size_t)ni * j.nmean * nt * 8))) return rc;
+        if ((rc = w.srec.reserve((size_t)ns * REC * ES))) return rc;
+        if ((rc = w.grec.reserve((size_t)std::max<long long>(ni, 1) * REC * ES))) return rc;
+        if (j.nmean > 0 && (rc = w.partial.reserve((size_t)ni * j.nmean * nt * ES))) return rc;
 
         PrologueArgs p{};
         p.nsamples = ns;
@@ -275,39 +294,39 @@ static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st)
             const long long go = j.can.geom_per_sample ? s0 : 0;
             p.iza = j.can.iza + go; p.vza = j.can.vza + go; p.raa = j.can.raa + go;
         }
-        p.srec = (double*)w.srec.p;
-        p.grec = (double*)w.grec.p;
+        p.srec = w.srec.p;
+        p.grec = w.grec.p;
         p.geom_out = j.geom ? j.geom + i0 * 8 : nullptr;
         p.lidf_out = j.lidf ? j.lidf + s0 * PROSAIL_NLIDF : nullptr;
         {
             ProfScope ps(h, 1, st);
             if (ni >= h->prologue_thread_min) {     // throughput variant: one thread per item
-                k_prologue_t<<<(unsigned)((ni + 127) / 128), 128, 0, st>>>(p, h->d_angles);
+                k_prologue_t<T><<<(unsigned)((ni + 127) / 128), 128, 0, st>>>(p, h->d_angles);
             } else {                                // latency variant: one warp per item, leaf bins across lanes
                 const long long threads = ni * 32;
-                k_prologue<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p);
+                k_prologue<T><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p);
             }
             h->launches++;
             CK(cudaGetLastError());
         }
         if (j.mode < 0) continue;   // volscatt-only job
 
-        SailArgs a{};
-        a.bandc = h->d_bandc[j.has_leaf ? j.version : 0];
-        a.tables = h->d_tables;
+        SailArgs<T> a{};
+        a.bandc = bandc_of<T>(h, j.has_leaf ? j.version : 0);
+        a.tables = tables_of<T>(h);
         a.win = h->d_win;
-        a.srec = (const double*)w.srec.p;
-        a.grec = (const double*)w.grec.p;
+        a.srec = (const T*)w.srec.p;
+        a.grec = (const T*)w.grec.p;
         a.nitems = ni;
         a.G = G;
         if (j.mode == MODE_SAIL) {
-            a.in_r = j.in_r + s0 * j.pr; a.in_t = j.in_t + s0 * j.pt; a.in_rho = j.in_rho + s0 * j.prho;
+            a.in_r = off<T>(j.in_r, s0 * j.pr); a.in_t = off<T>(j.in_t, s0 * j.pt); a.in_rho = off<T>(j.in_rho, s0 * j.prho);
             a.in_pitch_r = j.pr; a.in_pitch_t = j.pt; a.in_pitch_rho = j.prho;
         }
-        for (int i = 0; i < NOUT; ++i) a.out[i] = j.plane[i] ? j.plane[i] + i0 * j.pitch : nullptr;
+        for (int i = 0; i < NOUT; ++i) a.out[i] = j.plane[i] ? off<T>(j.plane[i], i0 * j.pitch) : nullptr;
         a.out_pitch = j.pitch;
         a.mean_mask = j.mean_mask;
-        a.partial = (double*)w.partial.p;
+        a.partial = (T*)w.partial.p;
         a.nmean = j.nmean;
         a.only_active_tiles = j.windows_only;
         a.f32_means = j.f32_means;
@@ -320,8 +339,8 @@ static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st)
             const unsigned blocks = (unsigned)((total + 255) / 256);
             {
                 ProfScope ps(h, 2, st);
-                k_finalize_means<<<blocks, 256, 0, st>>>(h->d_win, (const double*)w.partial.p, rows,
-                                                         j.means ? j.means + i0 * j.nmean * nw : nullptr,
+                k_finalize_means<T><<<blocks, 256, 0, st>>>(h->d_win, (const T*)w.partial.p, rows,
+                                                         j.means ? off<T>(j.means, i0 * j.nmean * nw) : nullptr,
                                                          j.means_f32 ? j.means_f32 + i0 * j.nmean * nw : nullptr);
             }
             h->launches++;
@@ -329,6 +348,10 @@ static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st)
         }
     }
     return 0;
+}
+
+static int run_device(prosail_handle* h, const Job& j, Work& w, cudaStream_t st) {
+    return j.f32 ? run_device_t<float>(h, j, w, st) : run_device_t<double>(h, j, w, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -351,8 +374,9 @@ static int run_host(prosail_handle* h, const Job& j) {
     const int nw = h->have_win ? h->h_win.nwindows : 0;
     int nplanes = 0;
     for (int i = 0; i < NOUT; ++i) nplanes += j.plane[i] ? 1 : 0;
-    const size_t out_per_item = (size_t)nplanes * j.pitch * 8 + (size_t)j.nmean * nw * 8 + 64 + 256;
-    size_t in_per_sample = 16 * 8 + (j.mode == MODE_SAIL ? (size_t)(j.pr + j.pt + j.prho) * 8 : 0) + PROSAIL_NLIDF * 8;
+    const size_t ES = j.esz();
+    const size_t out_per_item = (size_t)nplanes * j.pitch * ES + (size_t)j.nmean * nw * 8 + 64 + 256;
+    size_t in_per_sample = 16 * 8 + (j.mode == MODE_SAIL ? (size_t)(j.pr + j.pt + j.prho) * ES : 0) + PROSAIL_NLIDF * 8;
     const size_t per_sample = out_per_item * G + in_per_sample;
     long long slab = std::max<long long>(1, (long long)((256ull << 20) / per_sample));
     slab = std::min<long long>(slab, std::max<long long>(1, (j.n + 1) / 2));      // at least two slabs to overlap copies
@@ -368,7 +392,7 @@ static int run_host(prosail_handle* h, const Job& j) {
         // ---- inputs ----
         size_t in_bytes = 20 * (((size_t)ns * 8 + 255) & ~(size_t)255) + 3 * ((((size_t)G) * 8 + 255) & ~(size_t)255) + 4096;
         if (j.mode == MODE_SAIL)
-            for (long long p : {j.pr, j.pt, j.prho}) in_bytes += (((size_t)(p ? ns * p : NB) * 8 + 255) & ~(size_t)255);
+            for (long long p : {j.pr, j.pt, j.prho}) in_bytes += (((size_t)(p ? ns * p : NB) * ES + 255) & ~(size_t)255);
         if ((rc = w.in.reserve(in_bytes))) return rc;
         Carver ci(w.in.p);
         Job d = j;
@@ -399,16 +423,20 @@ static int run_host(prosail_handle* h, const Job& j) {
             if ((rc = up(j.can.iza + go, gc, &d.can.iza)) || (rc = up(j.can.vza + go, gc, &d.can.vza)) || (rc = up(j.can.raa + go, gc, &d.can.raa))) return rc;
         }
         if (j.mode == MODE_SAIL) {
-            auto upspec = [&](const double* src, long long pitch, const double** dst) -> int {
-                return pitch == 0 ? up(src, (size_t)NB, dst) : up(src + s0 * pitch, (size_t)ns * pitch, dst);
+            auto upspec = [&](const void* src, long long pitch, const void** dst) -> int {
+                const size_t count = pitch == 0 ? (size_t)NB : (size_t)ns * pitch;
+                char* p = ci.take<char>(count * ES);
+                CK(cudaMemcpyAsync(p, offb(src, s0 * pitch, ES), count * ES, cudaMemcpyHostToDevice, st));
+                *dst = p;
+                return 0;
             };
             if ((rc = upspec(j.in_r, j.pr, &d.in_r)) || (rc = upspec(j.in_t, j.pt, &d.in_t)) || (rc = upspec(j.in_rho, j.prho, &d.in_rho))) return rc;
         }
         // ---- outputs ----
         if ((rc = w.out.reserve(out_per_item * (size_t)ni + (size_t)ns * PROSAIL_NLIDF * 8 + 8192))) return rc;
         Carver co(w.out.p);
-        for (int i = 0; i < NOUT; ++i) d.plane[i] = j.plane[i] ? co.take<double>((size_t)ni * j.pitch) : nullptr;
-        d.means = j.means ? co.take<double>((size_t)ni * j.nmean * nw) : nullptr;
+        for (int i = 0; i < NOUT; ++i) d.plane[i] = j.plane[i] ? co.take<char>((size_t)ni * j.pitch * ES) : nullptr;
+        d.means = j.means ? co.take<char>((size_t)ni * j.nmean * nw * ES) : nullptr;
         d.means_f32 = j.means_f32 ? co.take<float>((size_t)ni * j.nmean * nw) : nullptr;
         d.geom = j.geom ? co.take<double>((size_t)ni * 8) : nullptr;
         d.lidf = j.lidf ? co.take<double>((size_t)ns * PROSAIL_NLIDF) : nullptr;
@@ -416,8 +444,8 @@ static int run_host(prosail_handle* h, const Job& j) {
         if ((rc = run_device(h, d, w, st))) return rc;
 
         for (int i = 0; i < NOUT; ++i)
-            if (j.plane[i]) CK(cudaMemcpyAsync(j.plane[i] + i0 * j.pitch, d.plane[i], (size_t)ni * j.pitch * 8, cudaMemcpyDeviceToHost, st));
-        if (j.means) CK(cudaMemcpyAsync(j.means + i0 * j.nmean * nw, d.means, (size_t)ni * j.nmean * nw * 8, cudaMemcpyDeviceToHost, st));
+            if (j.plane[i]) CK(cudaMemcpyAsync(offb(j.plane[i], i0 * j.pitch, ES), d.plane[i], (size_t)ni * j.pitch * ES, cudaMemcpyDeviceToHost, st));
+        if (j.means) CK(cudaMemcpyAsync(offb(j.means, i0 * j.nmean * nw, ES), d.means, (size_t)ni * j.nmean * nw * ES, cudaMemcpyDeviceToHost, st));
         if (j.means_f32) CK(cudaMemcpyAsync(j.means_f32 + i0 * j.nmean * nw, d.means_f32, (size_t)ni * j.nmean * nw * 4, cudaMemcpyDeviceToHost, st));
         if (j.geom) CK(cudaMemcpyAsync(j.geom + i0 * 8, d.geom, (size_t)ni * 8 * 8, cudaMemcpyDeviceToHost, st));
         if (j.lidf) CK(cudaMemcpyAsync(j.lidf + s0 * PROSAIL_NLIDF, d.lidf, (size_t)ns * PROSAIL_NLIDF * 8, cudaMemcpyDeviceToHost, st));
@@ -470,6 +498,8 @@ int prosail_create(int device, prosail_handle_t** out) {
         CK(cudaEventRecord(h->slot[i].done, h->slot[i].stream));
         CK(cudaMalloc(&h->d_bandc[i], sizeof(double) * NCONST * NBP));
         CK(cudaMemset(h->d_bandc[i], 0, sizeof(double) * NCONST * NBP));
+        CK(cudaMalloc(&h->d_bandc_f[i], sizeof(float) * NCONST * NBP));
+        CK(cudaMemset(h->d_bandc_f[i], 0, sizeof(float) * NCONST * NBP));
     }
     // math tables image
     {
@@ -480,6 +510,9 @@ int prosail_create(int device, prosail_handle_t** out) {
         memcpy(mt->logt, h_log_table, sizeof(mt->logt));
         CK(cudaMalloc(&h->d_tables, sizeof(MathTables)));
         CK(cudaMemcpy(h->d_tables, img.data(), sizeof(MathTables), cudaMemcpyHostToDevice));
+        static_assert(sizeof(MathTablesF) == sizeof(h_tau_table_f), "float table image out of sync");
+        CK(cudaMalloc(&h->d_tables_f, sizeof(MathTablesF)));
+        CK(cudaMemcpy(h->d_tables_f, h_tau_table_f, sizeof(MathTablesF), cudaMemcpyHostToDevice));
     }
     {   // leaf-angle tables, with the reference's own ways of converting degrees (np.radians vs angle*pi/180)
         AngleTables t;
@@ -515,8 +548,10 @@ void prosail_destroy(prosail_handle_t* h) {
         if (h->slot[i].stream) cudaStreamDestroy(h->slot[i].stream);
         if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
         if (h->d_bandc[i]) cudaFree(h->d_bandc[i]);
+        if (h->d_bandc_f[i]) cudaFree(h->d_bandc_f[i]);
     }
     if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_tables_f) cudaFree(h->d_tables_f);
     if (h->d_win) cudaFree(h->d_win);
     if (h->d_angles) cudaFree(h->d_angles);
     if (h->t0) cudaEventDestroy(h->t0);
@@ -544,8 +579,19 @@ int prosail_set_leaf_tables(prosail_handle_t* h, int version, const float* Kab, 
     for (int i = NB; i < NBP; ++i) {   // padding lanes: benign constants (band 2100 replicated) so that they never trap
         for (int p = 0; p < 9; ++p) img[(size_t)p * NBP + i] = img[(size_t)p * NBP + NB - 1];
     }
+    // float image for the fp32 mode: the same nine planes rounded once, plus the complements 1 - talf, 1 - t12, 1 - t21
+    // rounded from their float64 values (in float, 1 - t12 would carry the rounding error of t12 ~ 0.95 into r12 ~ 0.05)
+    std::vector<float> imgf((size_t)NCONST * NBP, 0.0f);
+    for (size_t i = 0; i < (size_t)9 * NBP; ++i) imgf[i] = (float)img[i];
+    for (int i = 0; i < NBP; ++i) {
+        imgf[(size_t)C_RALF * NBP + i] = (float)(1.0 - img[(size_t)C_TALF * NBP + i]);
+        imgf[(size_t)C_R12 * NBP + i] = (float)(1.0 - img[(size_t)C_T12 * NBP + i]);
+        imgf[(size_t)C_R21 * NBP + i] = (float)(1.0 - img[(size_t)C_T21 * NBP + i]);
+    }
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h->d_bandc[version], img.data(), img.size() * 8, cudaMemcpyHostToDevice));
+    for (int pl : {C_KAB, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RALF, C_R12, C_R21})   // not the soil planes
+        CK(cudaMemcpy(h->d_bandc_f[version] + (size_t)pl * NBP, imgf.data() + (size_t)pl * NBP, (size_t)NBP * 4, cudaMemcpyHostToDevice));
     h->have_leaf[version] = true;
     return 0;
 }
@@ -561,7 +607,11 @@ int prosail_set_soil_tables(prosail_handle_t* h, const float* rsoil1, const floa
         img[(size_t)NBP + i] = (double)rsoil2[k];
     }
     CK(cudaDeviceSynchronize());
-    for (int v = 0; v < 2; ++v) CK(cudaMemcpy(h->d_bandc[v] + (size_t)C_RS1 * NBP, img.data(), img.size() * 8, cudaMemcpyHostToDevice));
+    std::vector<float> imgf(img.begin(), img.end());
+    for (int v = 0; v < 2; ++v) {
+        CK(cudaMemcpy(h->d_bandc[v] + (size_t)C_RS1 * NBP, img.data(), img.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_bandc_f[v] + (size_t)C_RS1 * NBP, imgf.data(), imgf.size() * 4, cudaMemcpyHostToDevice));
+    }
     h->have_soil = true;
     return 0;
 }
@@ -608,10 +658,11 @@ int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, co
     return 0;
 }
 
-int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, double* ks, double* kt,
+static int prospect_impl(prosail_handle_t* h, bool f32, int version, long long n, const prosail_leaf_t* leaf, void* ks, void* kt,
                          long long pitch, float* means_f32, int on_host, void* stream) {
     if (!leaf) return fail(PROSAIL_E_ARG, "null leaf struct");
     Job j;
+    j.f32 = f32;
     j.mode = MODE_PROSPECT;
     j.version = version;
     j.n = n;
@@ -627,11 +678,20 @@ int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const pr
     }
     return run(h, j, on_host, stream);
 }
+int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, double* ks, double* kt,
+                         long long pitch, float* means_f32, int on_host, void* stream) {
+    return prospect_impl(h, false, version, n, leaf, ks, kt, pitch, means_f32, on_host, stream);
+}
+int prosail_prospect_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, float* ks, float* kt,
+                         long long pitch, float* means_f32, int on_host, void* stream) {
+    return prospect_impl(h, true, version, n, leaf, ks, kt, pitch, means_f32, on_host, stream);
+}
 
-int prosail_soil_f64(prosail_handle_t* h, long long n, const prosail_soil_t* soil, double* rho, long long pitch, float* means_f32,
+static int soil_impl(prosail_handle_t* h, bool f32, long long n, const prosail_soil_t* soil, void* rho, long long pitch, float* means_f32,
                      int on_host, void* stream) {
     if (!soil) return fail(PROSAIL_E_ARG, "null soil struct");
     Job j;
+    j.f32 = f32;
     j.mode = MODE_SOIL;
     j.n = n;
     j.has_soil = true;
@@ -644,6 +704,14 @@ int prosail_soil_f64(prosail_handle_t* h, long long n, const prosail_soil_t* soi
         j.f32_means = 1;
     }
     return run(h, j, on_host, stream);
+}
+int prosail_soil_f64(prosail_handle_t* h, long long n, const prosail_soil_t* soil, double* rho, long long pitch, float* means_f32,
+                     int on_host, void* stream) {
+    return soil_impl(h, false, n, soil, rho, pitch, means_f32, on_host, stream);
+}
+int prosail_soil_f32(prosail_handle_t* h, long long n, const prosail_soil_t* soil, float* rho, long long pitch, float* means_f32,
+                     int on_host, void* stream) {
+    return soil_impl(h, true, n, soil, rho, pitch, means_f32, on_host, stream);
 }
 
 int prosail_volscatt_f64(prosail_handle_t* h, long long n, const prosail_canopy_t* canopy, double* geom, double* lidf, int on_host,
@@ -660,7 +728,9 @@ int prosail_volscatt_f64(prosail_handle_t* h, long long n, const prosail_canopy_
     return run(h, j, on_host, stream);
 }
 
-static void copy_out(Job& j, const prosail_out_t* out) {
+extern "C++" {
+template <class OUT>
+static void copy_out(Job& j, const OUT* out) {
     for (int i = 0; i < NOUT; ++i) j.plane[i] = out->plane[i];
     j.pitch = out->pitch;
     j.mean_mask = out->mean_mask;
@@ -668,14 +738,17 @@ static void copy_out(Job& j, const prosail_out_t* out) {
     j.geom = out->geom;
     j.windows_only = out->windows_only;
 }
+}
 
-int prosail_sail_f64(prosail_handle_t* h, long long n, const double* ks, long long pitch_ks, const double* kt, long long pitch_kt,
-                     const double* rho, long long pitch_rho, const prosail_canopy_t* canopy, const prosail_out_t* out, int on_host,
-                     void* stream) {
+extern "C++" {
+template <class OUT>
+static int sail_impl(prosail_handle_t* h, bool f32, long long n, const void* ks, long long pitch_ks, const void* kt, long long pitch_kt,
+                     const void* rho, long long pitch_rho, const prosail_canopy_t* canopy, const OUT* out, int on_host, void* stream) {
     if (!canopy || !out) return fail(PROSAIL_E_ARG, "null canopy / out struct");
     for (long long p : {pitch_ks, pitch_kt, pitch_rho})
         if (p != 0 && p < NB) return fail(PROSAIL_E_ARG, "input pitch must be 0 (broadcast) or >= %d", NB);
     Job j;
+    j.f32 = f32;
     j.mode = MODE_SAIL;
     j.n = n;
     j.has_canopy = true;
@@ -684,14 +757,28 @@ int prosail_sail_f64(prosail_handle_t* h, long long n, const double* ks, long lo
     j.in_t = kt; j.pt = pitch_kt;
     j.in_rho = rho; j.prho = pitch_rho;
     copy_out(j, out);
-    if (j.mean_mask & ((1u << O_LEAF_R) | (1u << O_LEAF_T) | (1u << O_RHO))) return fail(PROSAIL_E_ARG, "means of input spectra are not provided by prosail_sail_f64");
+    if (j.mean_mask & ((1u << O_LEAF_R) | (1u << O_LEAF_T) | (1u << O_RHO))) return fail(PROSAIL_E_ARG, "means of input spectra are not provided by prosail_sail_*");
     return run(h, j, on_host, stream);
 }
+}
+int prosail_sail_f64(prosail_handle_t* h, long long n, const double* ks, long long pitch_ks, const double* kt, long long pitch_kt,
+                     const double* rho, long long pitch_rho, const prosail_canopy_t* canopy, const prosail_out_t* out, int on_host,
+                     void* stream) {
+    return sail_impl(h, false, n, ks, pitch_ks, kt, pitch_kt, rho, pitch_rho, canopy, out, on_host, stream);
+}
+int prosail_sail_f32(prosail_handle_t* h, long long n, const float* ks, long long pitch_ks, const float* kt, long long pitch_kt,
+                     const float* rho, long long pitch_rho, const prosail_canopy_t* canopy, const prosail_out_f32_t* out, int on_host,
+                     void* stream) {
+    return sail_impl(h, true, n, ks, pitch_ks, kt, pitch_kt, rho, pitch_rho, canopy, out, on_host, stream);
+}
 
-int prosail_prosail_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_soil_t* soil,
-                        const prosail_canopy_t* canopy, const prosail_out_t* out, int on_host, void* stream) {
+extern "C++" {
+template <class OUT>
+static int prosail_impl(prosail_handle_t* h, bool f32, int version, long long n, const prosail_leaf_t* leaf, const prosail_soil_t* soil,
+                        const prosail_canopy_t* canopy, const OUT* out, int on_host, void* stream) {
     if (!leaf || !soil || !canopy || !out) return fail(PROSAIL_E_ARG, "null leaf / soil / canopy / out struct");
     Job j;
+    j.f32 = f32;
     j.mode = MODE_PROSAIL;
     j.version = version;
     j.n = n;
@@ -701,6 +788,15 @@ int prosail_prosail_f64(prosail_handle_t* h, int version, long long n, const pro
     j.can = *canopy;
     copy_out(j, out);
     return run(h, j, on_host, stream);
+}
+}
+int prosail_prosail_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_soil_t* soil,
+                        const prosail_canopy_t* canopy, const prosail_out_t* out, int on_host, void* stream) {
+    return prosail_impl(h, false, version, n, leaf, soil, canopy, out, on_host, stream);
+}
+int prosail_prosail_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_soil_t* soil,
+                        const prosail_canopy_t* canopy, const prosail_out_f32_t* out, int on_host, void* stream) {
+    return prosail_impl(h, true, version, n, leaf, soil, canopy, out, on_host, stream);
 }
 
 // ---- helpers ----

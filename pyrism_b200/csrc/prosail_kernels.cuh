@@ -15,7 +15,9 @@
 //
 // Reference (ibaris/pyrism 0.0.5, pyrism/models/models.py) lines are cited at each step.
 #pragma once
-#include "math64.cuh"
+#include <type_traits>
+
+#include "math32.cuh"
 
 namespace pb {
 
@@ -43,7 +45,8 @@ constexpr int MAX_WINDOWS = 64;
 constexpr int MAX_SLOTS = 256;
 
 // planes of the per-band constant array  double[NCONST][NBP]
-enum { C_KAB = 0, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RS1, C_RS2, NCONST };
+enum { C_KAB = 0, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RS1, C_RS2, C_RALF, C_R12, C_R21, NCONST };
+// (C_RALF.. = 1 - talf, 1 - t12, 1 - t21: only the float image carries them, rounded once from the float64 values)
 
 // sample record (per parameter set)
 enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DDB, S_DDF, S_NEGLAI, S_LAI, S_NOCANOPY, S_THR };
@@ -66,23 +69,24 @@ struct WindowMap {                       // which band-mean windows touch which 
     int active_tile2[NT2];
 };
 
+template <typename T>
 struct SailArgs {
-    const double* bandc;       // [NCONST][NBP]
-    const double* tables;      // MathTables image in global memory
+    const T* bandc;            // [NCONST][NBP]
+    const void* tables;        // Tables<T>::type image in global memory
     const WindowMap* win;      // band-mean window map (global memory, read uniformly)
-    const double* srec;        // [nsamples][REC]
-    const double* grec;        // [nitems][REC]
+    const T* srec;             // [nsamples][REC]
+    const T* grec;             // [nitems][REC]
     long long nitems;
     int G;                     // geometries per sample (item = s*G + g)
     int ntile2;                // double tiles visited (33, or the active ones in windows-only mode)
     int nranges;               // item-chunk ranges: warp gw works on double tile gw % ntile2, chunks gw / ntile2 + i * nranges
     // SAIL-only mode: leaf / soil spectra from memory, row pitch in elements (0 = one spectrum for all samples)
-    const double* in_r; const double* in_t; const double* in_rho;
+    const T* in_r; const T* in_t; const T* in_rho;
     long long in_pitch_r, in_pitch_t, in_pitch_rho;
-    double* out[NOUT];         // output planes [nitems][pitch] (NULL = not requested)
+    T* out[NOUT];              // output planes [nitems][pitch] (NULL = not requested)
     long long out_pitch;
     unsigned mean_mask;        // planes whose band means are accumulated
-    double* partial;           // [nitems][nmean][ntotal slots]
+    T* partial;                // [nitems][nmean][ntotal slots]
     int nmean;
     int only_active_tiles;     // 1: visit only tiles touched by a window (band-mean-only LUTs)
     int f32_means;             // 1: round values to float before averaging (PROSPECT/LSM convention, models.py:1071)
@@ -115,46 +119,53 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+template <typename T>
 struct alignas(128) Stage {
-    double s[CHUNK * REC];   // sample records spanned by the chunk
-    double g[CHUNK * REC];   // geometry records of the chunk
+    T s[CHUNK * REC];        // sample records spanned by the chunk
+    T g[CHUNK * REC];        // geometry records of the chunk
 };
 
 constexpr int KPLANES = 8;                 // kab kxc kan kbr kw km rs1 rs2: used once per item -> shared memory, not registers
-constexpr int KSTRIDE = 2 * CTA_THREADS;   // doubles per plane: [u][thread]
+constexpr int KSTRIDE = 2 * CTA_THREADS;   // elements per plane: [u][thread]
 
+template <typename T>
 struct alignas(128) SailSmem {
-    MathTables mt;                         // shared by the CTA, read-only after the prologue
-    Stage stage[WARPS_PER_CTA][2];         // per-warp double-buffered record staging: no CTA-wide barrier in the loop
-    double kc[KPLANES * KSTRIDE];          // conflict-free: consecutive lanes read consecutive doubles
+    typename Tables<T>::type mt;           // shared by the CTA, read-only after the prologue
+    Stage<T> stage[WARPS_PER_CTA][2];      // per-warp double-buffered record staging: no CTA-wide barrier in the loop
+    T kc[KPLANES * KSTRIDE];               // conflict-free: consecutive lanes read consecutive elements
     uint64_t bar[WARPS_PER_CTA][2];
 };
 
 // issue the two bulk copies of one chunk (called by one thread)
-__device__ __forceinline__ void stage_issue(const SailArgs& a, Stage* st, uint64_t* bar, long long chunk) {
+template <typename T>
+__device__ __forceinline__ void stage_issue(const SailArgs<T>& a, Stage<T>* st, uint64_t* bar, long long chunk) {
     const long long i0 = chunk * CHUNK;
     const long long i1 = min(i0 + (long long)CHUNK, a.nitems);
     const long long s0 = i0 / a.G, s1 = (i1 - 1) / a.G;
-    const uint32_t gbytes = (uint32_t)(i1 - i0) * REC * 8u;
-    const uint32_t sbytes = (uint32_t)(s1 - s0 + 1) * REC * 8u;
+    const uint32_t gbytes = (uint32_t)(i1 - i0) * REC * (uint32_t)sizeof(T);
+    const uint32_t sbytes = (uint32_t)(s1 - s0 + 1) * REC * (uint32_t)sizeof(T);
     mbar_expect_tx(bar, gbytes + sbytes);
     bulk_g2s(st->g, a.grec + i0 * REC, gbytes, bar);
     bulk_g2s(st->s, a.srec + s0 * REC, sbytes, bar);
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-band device functions
+// per-band device functions (T = double: the parity path; T = float: the fp32 mode, <= 1e-5 absolute)
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 struct BandConst {
-    double talf, ralf, t12, r12, t21, r21;  // interface terms (models.py:1011-1016), register resident
+    T talf, ralf, t12, r12, t21, r21;  // interface terms (models.py:1011-1016), register resident
 };
 enum { KC_KAB = 0, KC_KXC, KC_KAN, KC_KBR, KC_KW, KC_KM, KC_RS1, KC_RS2 };   // planes of SailSmem::kc
 
+template <typename T> __device__ __forceinline__ constexpr bool is_f32() { return std::is_same<T, float>::value; }
+
 // PROSPECT for one band and one parameter set: leaf reflectance (ks) and transmittance (kt).
 // models.py:949-959 (kall, tau), 1019-1025 (one layer), 1043-1068 (Stokes, N layers).
-__device__ __forceinline__ double leaf_kall(const double* __restrict__ kc, const double* __restrict__ s) {
+template <typename T>
+__device__ __forceinline__ T leaf_kall(const T* __restrict__ kc, const T* __restrict__ s) {
     // kall = sum_i C_i K_i / N ; the division by N is folded into the record (C_i / N)      :950-951
-    double kall = s[S_CAB] * kc[KC_KAB * KSTRIDE];
+    T kall = s[S_CAB] * kc[KC_KAB * KSTRIDE];
     kall = fma(s[S_CXC], kc[KC_KXC * KSTRIDE], kall);
     kall = fma(s[S_CAN], kc[KC_KAN * KSTRIDE], kall);
     kall = fma(s[S_CBR], kc[KC_KBR * KSTRIDE], kall);
@@ -162,238 +173,340 @@ __device__ __forceinline__ double leaf_kall(const double* __restrict__ kc, const
     return fma(s[S_CM], kc[KC_KM * KSTRIDE], kall);
 }
 // soil reflectance of the LSM mix, models.py:1917
-__device__ __forceinline__ double soil_rho(const double* __restrict__ kc, const double* __restrict__ s) {
+template <typename T>
+__device__ __forceinline__ T soil_rho(const T* __restrict__ kc, const T* __restrict__ s) {
     return fma(s[S_SOIL1], kc[KC_RS1 * KSTRIDE], s[S_SOIL2] * kc[KC_RS2 * KSTRIDE]);
 }
 
 // Branch-free plate + Stokes stage.  Returns true when r + t >= 1 (zero absorption, models.py:1057-1059); the
 // values written are then meaningless and leaf_zero_absorption() must be called for that band.
-__device__ __forceinline__ bool leaf_layers_fast(const BandConst& c, double tau, double nm1, const MathTables& mt, double& refl,
-                                                 double& tran) {
+template <typename T, typename MT>
+__device__ __forceinline__ bool leaf_layers_fast(const BandConst<T>& c, T tau, T nm1, const MT& mt, T& refl, T& tran) {
+    const T one = T(1), half = T(0.5);
     // one layer                                                                              :1019-1025
-    const double x = c.r21 * tau;
-    const double inv = rcp(fma(-x, x, 1.0));
-    const double tt = tau * c.t21 * inv;
-    const double Ta = c.talf * tt;
-    const double t = c.t12 * tt;
-    const double Ra = fma(x, Ta, c.ralf);
-    const double r = fma(x, t, c.r12);
+    const T x = c.r21 * tau;
+    const T inv = rcp(fma(-x, x, one));
+    const T tt = tau * c.t21 * inv;
+    const T Ta = c.talf * tt;
+    const T t = c.t12 * tt;
+    const T Ra = fma(x, Ta, c.ralf);
+    const T r = fma(x, t, c.r12);
     // Stokes: D^2 = (1+r+t)(1+r-t)(1-r+t)(1-r-t)                                             :1043
-    const double p = 1.0 + r, q = 1.0 - r;
-    const double P12 = (p + t) * (p - t);
-    const double qmt = q - t;                      // 1 - r - t: <= 0 flags zero absorption
-    const double P34 = (q + t) * qmt;
-    const double D = sqrt_pos(P12 * P34);
-    const double A = fma(-2.0, r, P12);            // 1 + r^2 - t^2
-    const double hD = 0.5 * D;
-    const double al = fma(0.5, A, hD);             // a * r   (a of :1046)
-    const double be = fma(-0.5, A, 1.0 + hD);      // b * t   (b of :1047), using 1 - r^2 + t^2 = 2 - A
-    const double b = be * rcp(t);
+    const T p = one + r, q = one - r;
+    const T P12 = (p + t) * (p - t);
+    const T qmt = q - t;                           // 1 - r - t: <= 0 flags zero absorption
+    const T P34 = (q + t) * qmt;
+    const T D = sqrt_pos(P12 * P34);
+    const T A = fma(T(-2), r, P12);                // 1 + r^2 - t^2
+    const T hD = half * D;
+    const T al = fma(half, A, hD);                 // a * r   (a of :1046)
+    const T be = fma(-half, A, one + hD);          // b * t   (b of :1047), using 1 - r^2 + t^2 = 2 - A
+    const T b = be * rcp(t);
     // b^(N-1) = 2^((N-1) log2 b)                                                             :1049
-    const double y = log2_pos(b, mt.logt) * nm1;
-    const double bNm1 = exp2_any(y, mt.exp2t);
-    const double bN2 = bNm1 * bNm1;
+    const T bNm1 = pow_pos(b, nm1, mt);
+    const T bN2 = bNm1 * bNm1;
     // With a = al/r:  kt = Ta bNm1 (al^2 - r^2)/X,  ks = Ra + Ta t al r (bN2 - 1)/X,
     //                 X = al^2 bN2 - r^2 - al r^2 (bN2 - 1)      (algebraically :1052-1065, one division)
-    const double bm1 = bN2 - 1.0;
-    const double al2 = al * al, r2 = r * r;
-    const double X = fma(-(al * r2), bm1, fma(al2, bN2, -r2));
-    const double TaI = Ta * rcp(X);
+    const T bm1 = bN2 - one;
+    const T al2 = al * al, r2 = r * r;
+    const T X = fma(-(al * r2), bm1, fma(al2, bN2, -r2));
+    const T TaI = Ta * rcp(X);
     tran = TaI * (bNm1 * (al2 - r2));
     refl = fma(TaI * bm1, (t * al) * r, Ra);
     return !is_pos(qmt);                           // r + t >= 1, tested on the sign of 1 - r - t (integer pipe)
 }
 
 // zero-absorption case (r + t >= 1), exactly as models.py:1057-1065 with IEEE divisions (rare path)
-__device__ __forceinline__ void leaf_zero_absorption(const BandConst& c, double tau, double nm1, double& refl, double& tran) {
-    const double x = c.r21 * tau;
-    const double den1 = 1.0 - x * x;
-    const double Ta = c.talf * tau * c.t21 / den1;
-    const double Ra = c.ralf + x * Ta;
-    const double t = c.t12 * tau * c.t21 / den1;
-    const double r = c.r12 + x * t;
-    const double Tsub = t / (t + (1.0 - t) * nm1);
-    const double Rsub = 1.0 - Tsub;
-    const double den = 1.0 - Rsub * r;
+template <typename T>
+__device__ __forceinline__ void leaf_zero_absorption(const BandConst<T>& c, T tau, T nm1, T& refl, T& tran) {
+    const T one = T(1);
+    const T x = c.r21 * tau;
+    const T den1 = one - x * x;
+    const T Ta = c.talf * tau * c.t21 / den1;
+    const T Ra = c.ralf + x * Ta;
+    const T t = c.t12 * tau * c.t21 / den1;
+    const T r = c.r12 + x * t;
+    const T Tsub = t / (t + (one - t) * nm1);
+    const T Rsub = one - Tsub;
+    const T den = one - Rsub * r;
     tran = Ta * Tsub / den;
     refl = Ra + Ta * Rsub * t / den;
 }
 
+// ---- float (fp32 mode) variants of the plate + Stokes stage ----
+// In float the reference's formulas lose everything near zero absorption: 1 - r - t is a difference of O(1) terms and
+// a - 1, b - 1, b^(2(N-1)) - 1 are differences again.  This version is cancellation-free:
+//   1 - r - t = t12 (1 - tau)/(1 - r21 tau)              (uses r21 + t21 = 1; 1 - tau = k g(k) from the table, relative 1e-7)
+//   a r - r   = ((1 - r - t)(1 - r + t) + D)/2 ,   b t - t = ((1 - r - t)(1 + r - t) + D)/2
+//   X = (a r)^2 b^(2(N-1)) - r^2 - a r r^2 (b^(2(N-1)) - 1) = da (al + r) + al (b^(2(N-1)) - 1)(al - r^2)   (all terms >= 0)
+// Measured against the float64 oracle: <= 1e-6 for k >= 1e-4; below the table range (k < 2^-14, incl. k <= 0) the lane
+// is flagged and re-evaluated in float64 by leaf_exact_f32().
+__device__ __forceinline__ void leaf_layers_f32(const BandConst<float>& c, float omt, float nm1, float& refl, float& tran) {
+    const float tau = 1.0f - omt;
+    const float x = c.r21 * tau;
+    const float inv = rcp(fmaf(-x, x, 1.0f));
+    const float tt = tau * c.t21 * inv;
+    const float Ta = c.talf * tt;
+    const float t = c.t12 * tt;
+    const float Ra = fmaf(x, Ta, c.ralf);
+    const float r = fmaf(x, t, c.r12);
+    const float p = 1.0f + r, q = 1.0f - r;
+    const float qmt = (c.t12 * omt) * (fmaf(x, inv, inv));        // t12 (1 - tau) (1 + x)/(1 - x^2)
+    const float P12 = (p + t) * (p - t);
+    const float P34 = (q + t) * qmt;
+    const float D = sqrt_pos(P12 * P34);
+    const float da = 0.5f * (P34 + D);
+    const float al = r + da;
+    const float db = 0.5f * fmaf(qmt, p - t, D);
+    const float b = fmaf(db, rcp(t), 1.0f);
+    const float bNm1 = exp2_fast(fminf(log2_fast(b) * nm1, 60.0f));  // opaque plates: b^(N-1) saturates (its square must stay finite)
+    const float bN2 = bNm1 * bNm1;
+    const float bm1 = bN2 - 1.0f;
+    const float dal = da * (al + r);                              // (a r)^2 - r^2
+    const float X = fmaf(al * bm1, fmaf(-r, r, al), dal);
+    const float TaI = Ta * rcp(X);
+    tran = TaI * (bNm1 * dal);
+    refl = fmaf(TaI * bm1, (t * al) * r, Ra);
+}
+
+// rare lanes of the float path (k outside [2^-14, 32)): the whole plate + Stokes stage in float64 with IEEE divisions and
+// libm, exactly as models.py:953-957, 1019-1025, 1043-1065 (zero-absorption branch included)
+__device__ __noinline__ void leaf_exact_f32(const BandConst<float>& c, float kall, float nm1f, float& refl, float& tran) {
+    const double tau = tau_rare((double)kall);
+    const double t21 = c.t21, r21 = c.r21, t12 = c.t12, r12 = c.r12, talf = c.talf, ralf = c.ralf, nm1 = nm1f;
+    const double x = r21 * tau;
+    const double den1 = 1.0 - x * x;
+    const double Ta = talf * tau * t21 / den1;
+    const double Ra = ralf + x * Ta;
+    const double t = t12 * tau * t21 / den1;
+    const double r = r12 + x * t;
+    if (!(t > 1e-280)) {                                          // opaque plate (k > ~640): nothing is transmitted
+        tran = 0.0f;
+        refl = (float)Ra;
+        return;
+    }
+    const double qmt = t12 * (1.0 - tau) / (1.0 - x);
+    double Rsub, Tsub;
+    if (!(qmt > 0.0)) {                                           // r + t >= 1                    :1057-1059
+        Tsub = t / (t + (1.0 - t) * nm1);
+        Rsub = 1.0 - Tsub;
+    } else {
+        const double D = sqrt((1.0 + r + t) * (1.0 + r - t) * (1.0 - r + t) * qmt);
+        const double da = 0.5 * ((1.0 - r + t) * qmt + D);       // a r - r
+        const double db = 0.5 * ((1.0 + r - t) * qmt + D);       // b t - t
+        const double a = 1.0 + da / r;
+        const double lb = log1p(db / t);
+        const double bNm1 = exp(nm1 * lb);
+        const double bm1 = expm1(2.0 * nm1 * lb);                 // b^(2(N-1)) - 1
+        const double am1 = da / r * (2.0 + da / r);               // a^2 - 1
+        const double den = am1 + a * a * bm1;                     // a^2 b^(2(N-1)) - 1
+        if (den > 0.0) {
+            Rsub = a * bm1 / den;                                 // :1052-1054
+            Tsub = bNm1 * am1 / den;
+        } else {
+            Tsub = t / (t + (1.0 - t) * nm1);
+            Rsub = 1.0 - Tsub;
+        }
+    }
+    const double den = 1.0 - Rsub * r;
+    tran = (float)(Ta * Tsub / den);                              // :1062-1065
+    refl = (float)(Ra + Ta * Rsub * t / den);
+}
+
 // both bands of a thread: the two chains are independent and written back to back so that they interleave
-__device__ __forceinline__ void leaf_optics2(const BandConst (&c)[2], const double* __restrict__ kc, const double* __restrict__ s,
-                                             const MathTables& mt, double (&refl)[2], double (&tran)[2]) {
-    double kall[2], tau[2];
-    bool rare[2], zero[2];
+template <typename T, typename MT>
+__device__ __forceinline__ void leaf_optics2(const BandConst<T> (&c)[2], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
+                                             T (&refl)[2], T (&tran)[2]) {
+    T kall[2];
+    bool rare[2];
+    const T nm1 = s[S_NM1];
 #pragma unroll
     for (int u = 0; u < 2; ++u) kall[u] = leaf_kall(kc + u * CTA_THREADS, s);
+    if constexpr (std::is_same<T, float>::value) {
+        float omt[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) tau[u] = tau_fast(kall[u], mt.tau, rare[u]);                   // :953-957
-    if (__builtin_expect(rare[0] | rare[1], 0)) {
+        for (int u = 0; u < 2; ++u) omt[u] = kall[u] * tau_fast(kall[u], mt.tau, rare[u]);     // 1 - tau = k g(k)
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-            if (rare[u]) tau[u] = tau_rare(kall[u]);
-    }
-    const double nm1 = s[S_NM1];
+        for (int u = 0; u < 2; ++u) leaf_layers_f32(c[u], omt[u], nm1, refl[u], tran[u]);
+        if (__builtin_expect(rare[0] | rare[1], 0)) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) zero[u] = leaf_layers_fast(c[u], tau[u], nm1, mt, refl[u], tran[u]);
-    if (__builtin_expect(zero[0] | zero[1], 0)) {
+            for (int u = 0; u < 2; ++u)
+                if (rare[u]) leaf_exact_f32(c[u], kall[u], nm1, refl[u], tran[u]);
+        }
+    } else {
+        T tau[2];
+        bool zero[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-            if (zero[u]) leaf_zero_absorption(c[u], tau[u], nm1, refl[u], tran[u]);
+        for (int u = 0; u < 2; ++u) tau[u] = tau_fast(kall[u], mt.tau, rare[u]);               // :953-957
+        if (__builtin_expect(rare[0] | rare[1], 0)) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (rare[u]) tau[u] = tau_rare(kall[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) zero[u] = leaf_layers_fast(c[u], tau[u], nm1, mt, refl[u], tran[u]);
+        if (__builtin_expect(zero[0] | zero[1], 0)) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (zero[u]) leaf_zero_absorption(c[u], tau[u], nm1, refl[u], tran[u]);
+        }
     }
 }
 
 // geometry-independent part of 4SAIL for one band (models.py:590-601, 637-642, 654-655, 714-719)
+template <typename T>
 struct Diffuse {
-    double m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd;
+    T m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd;
 };
 
-__device__ __forceinline__ void sail_diffuse(double rho, double tau, double rs, const double* __restrict__ s, const MathTables& mt,
-                                             Diffuse& d) {
-    double sigb = fma(s[S_DDB], rho, s[S_DDF] * tau);                 // :590
-    double sigf = fma(s[S_DDF], rho, s[S_DDB] * tau);                 // :591
-    sigb = is_zero(sigb) ? 1e-36 : sigb;                              // :594-595 (tests on the integer pipe)
-    sigf = is_zero(sigf) ? 1e-36 : sigf;
-    const double att = 1.0 - sigf;                                    // :600
-    d.m = sqrt_pos(fma(att, att, -(sigb * sigb)));                    // :601
-    d.e1 = exp_neg(d.m * s[S_NEGLAI], mt.exp2t);                      // :637
-    const double e2 = d.e1 * d.e1;
-    d.rinf = (att - d.m) * rcp(sigb);                                 // :639
-    const double rinf2 = d.rinf * d.rinf;
+template <typename T, typename MT>
+__device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __restrict__ s, const MT& mt, Diffuse<T>& d) {
+    const T one = T(1), tiny = T(1e-36);
+    T sigb = fma(s[S_DDB], rho, s[S_DDF] * tau);                      // :590
+    T sigf = fma(s[S_DDF], rho, s[S_DDB] * tau);                      // :591
+    sigb = is_zero(sigb) ? tiny : sigb;                               // :594-595 (tests on the integer pipe)
+    sigf = is_zero(sigf) ? tiny : sigf;
+    const T att = one - sigf;                                         // :600
+    if constexpr (std::is_same<T, float>::value) {
+        // float: m^2 = (att - sigb)(att + sigb) and rinf = sigb/(att + m) avoid the two cancellations of :601, :639
+        d.m = sqrt_pos((att - sigb) * (att + sigb));
+        d.rinf = sigb * rcp(att + d.m);
+    } else {
+        d.m = sqrt_pos(fma(att, att, -(sigb * sigb)));                // :601
+        d.rinf = (att - d.m) * rcp(sigb);                             // :639
+    }
+    d.e1 = exp_neg(d.m * s[S_NEGLAI], mt);                            // :637
+    const T e2 = d.e1 * d.e1;
+    const T rinf2 = d.rinf * d.rinf;
     d.re = d.rinf * d.e1;
-    d.invden = rcp(fma(-rinf2, e2, 1.0));                             // :642
-    const double omr2 = 1.0 - rinf2;
+    d.invden = rcp(fma(-rinf2, e2, one));                             // :642
+    const T omr2 = one - rinf2;
     d.inv_omr2 = rcp(omr2);
     d.tdd = omr2 * d.e1 * d.invden;                                   // :654
-    d.rdd = d.rinf * (1.0 - e2) * d.invden;                           // :655
+    d.rdd = d.rinf * (one - e2) * d.invden;                           // :655
     d.rsrdd = rs * d.rdd;
-    double dn = 1.0 - d.rsrdd;                                        // :714-719
-    dn = __double2hiint(dn) < 0x38754484 ? 1e-36 : dn;                // dn < 1e-36 (high word of 1e-36; negatives too)
+    T dn = one - d.rsrdd;                                             // :714-719
+    dn = below_tiny(dn) ? tiny : dn;                                  // dn < 1e-36 (integer-pipe test; negatives too)
     d.rs_invdn = rs * rcp(dn);
 }
 
+template <typename T>
 struct Canopy {
-    double rsot, rddt, rsdt, rdot;        // BRF, BHR, DHR, HDR with soil
-    double rso, rsd, tsd, rdo, tdo;       // canopy-only terms
+    T rsot, rddt, rsdt, rdot;        // BRF, BHR, DHR, HDR with soil
+    T rso, rsd, tsd, rdo, tdo;       // canopy-only terms
 };
 
-// |x| > thr decided on the high words only (integer pipe).  The threshold of J1's series branch is
-// soft: both branches agree to ~1e-13 around it, so a 2^-20-relative fuzz of the switch point is harmless.
-__device__ __forceinline__ bool abs_gt_hi(double x, int thr_hi) { return (__double2hiint(x) & 0x7fffffff) > thr_hi; }
-
-// Branch-free geometry-dependent part of 4SAIL (models.py:603-607, 644-678, 706-726, 765-789).  Returns true when
-// one of the J1 terms needs its series form (|k - m| lai <= 1e-3, models.py:777-779); the caller then re-evaluates
-// that band with sail_directional().
-__device__ __forceinline__ bool sail_directional_fast(double rho, double tau, double rs, const Diffuse& d, const double* __restrict__ g,
-                                                      int thr_hi, unsigned need, Canopy& o) {
-    const double k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO];
-    const double sb = fma(g[G_SDB], rho, g[G_SDF] * tau);             // :603-607
-    const double sf = fma(g[G_SDF], rho, g[G_SDB] * tau);
-    const double vb = fma(g[G_DOB], rho, g[G_DOF] * tau);
-    const double vf = fma(g[G_DOF], rho, g[G_DOB] * tau);
-    const double w = fma(g[G_FS], rho, g[G_FT] * tau);
-    // 1/(k-m) and 1/(k+m) from ONE reciprocal of (k-m)(k+m)                                 :644-647, 765-789
-    const double km = k - d.m, kp = k + d.m, Km = K - d.m, Kp = K + d.m;
-    const bool rare = !(abs_gt_hi(km, thr_hi) && abs_gt_hi(Km, thr_hi));
-    const double ik = rcp(km * kp), iK = rcp(Km * Kp);
-    const double inv_kp = ik * km, inv_Kp = iK * Km;
-    const double J1ks = (d.e1 - tss) * (ik * kp);
-    const double J1ko = (d.e1 - too) * (iK * Kp);
-    const double J2ks = fma(-d.e1, tss, 1.0) * inv_kp;
-    const double J2ko = fma(-d.e1, too, 1.0) * inv_Kp;
-    const double u1 = fma(sb, d.rinf, sf), u2 = fma(sf, d.rinf, sb);  // :649-652
-    const double v1 = fma(vb, d.rinf, vf), v2 = fma(vf, d.rinf, vb);
-    const double Pss = u1 * J1ks, Qss = u2 * J2ks, Pv = v1 * J1ko, Qv = v2 * J2ko;
+// common tail of the directional part once J1(k,m), J1(K,m), 1/(k+m), 1/(K+m) are known
+// (models.py:603-607, 649-678, 706-726)
+template <typename T>
+__device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>& d, const T* __restrict__ g, T J1ks, T J1ko, T inv_kp,
+                                            T inv_Kp, unsigned need, Canopy<T>& o) {
+    const T one = T(1);
+    const T tss = g[G_TSS], too = g[G_TOO];
+    const T sb = fma(g[G_SDB], rho, g[G_SDF] * tau);                  // :603-607
+    const T sf = fma(g[G_SDF], rho, g[G_SDB] * tau);
+    const T vb = fma(g[G_DOB], rho, g[G_DOF] * tau);
+    const T vf = fma(g[G_DOF], rho, g[G_DOB] * tau);
+    const T w = fma(g[G_FS], rho, g[G_FT] * tau);
+    const T J2ks = fma(-d.e1, tss, one) * inv_kp;
+    const T J2ko = fma(-d.e1, too, one) * inv_Kp;
+    const T u1 = fma(sb, d.rinf, sf), u2 = fma(sf, d.rinf, sb);       // :649-652
+    const T v1 = fma(vb, d.rinf, vf), v2 = fma(vf, d.rinf, vb);
+    const T Pss = u1 * J1ks, Qss = u2 * J2ks, Pv = v1 * J1ko, Qv = v2 * J2ko;
     o.tsd = fma(-d.re, Qss, Pss) * d.invden;                          // :656-659
     o.rsd = fma(-d.re, Pss, Qss) * d.invden;
     o.tdo = fma(-d.re, Qv, Pv) * d.invden;
     o.rdo = fma(-d.re, Pv, Qv) * d.invden;
-    const double g1 = fma(-J1ks, too, g[G_Z]) * inv_Kp;               // :668-669
-    const double g2 = fma(-J1ko, tss, g[G_Z]) * inv_kp;
-    const double T1 = (v2 * g1) * u1, T2 = (v1 * g2) * u2;            // :671-675
-    const double T3 = fma(o.rdo, Qss, o.tdo * Pss) * d.rinf;
-    const double rsod = (T1 + T2 - T3) * d.inv_omr2;                  // :678
+    const T g1 = fma(-J1ks, too, g[G_Z]) * inv_Kp;                    // :668-669
+    const T g2 = fma(-J1ko, tss, g[G_Z]) * inv_kp;
+    const T T1 = (v2 * g1) * u1, T2 = (v1 * g2) * u2;                 // :671-675
+    const T T3 = fma(o.rdo, Qss, o.tdo * Pss) * d.rinf;
+    const T rsod = (T1 + T2 - T3) * d.inv_omr2;                       // :678
     o.rso = fma(w, g[G_LAISUM], rsod);                                // :706, :710
     // soil coupling                                                                        :721-726
-    const double rsodt = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too) * d.rs_invdn;
+    const T rsodt = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too) * d.rs_invdn;
     o.rsot = fma(g[G_TSSTOO], rs, o.rso) + rsodt;
     if (need & (1u << O_RDDT)) o.rddt = fma(d.tdd * d.tdd, d.rs_invdn, d.rdd);
     if (need & (1u << O_RSDT)) o.rsdt = fma((o.tsd + tss) * d.tdd, d.rs_invdn, o.rsd);
     if (need & (1u << O_RDOT)) o.rdot = fma(d.tdd * (o.tdo + too), d.rs_invdn, o.rdo);
-    return rare;
 }
 
-// geometry-dependent part of 4SAIL for one band with J1's series branch (models.py:765-785): the repair path
-__device__ __forceinline__ void sail_directional(double rho, double tau, double rs, const Diffuse& d, const double* __restrict__ s,
-                                                 const double* __restrict__ g, int thr_hi, unsigned need, Canopy& o) {
-    const double k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO], lai = s[S_LAI];
-    const double sb = fma(g[G_SDB], rho, g[G_SDF] * tau);             // :603-607
-    const double sf = fma(g[G_SDF], rho, g[G_SDB] * tau);
-    const double vb = fma(g[G_DOB], rho, g[G_DOF] * tau);
-    const double vf = fma(g[G_DOF], rho, g[G_DOB] * tau);
-    const double w = fma(g[G_FS], rho, g[G_FT] * tau);
+// Branch-free geometry-dependent part of 4SAIL (models.py:603-607, 644-678, 706-726, 765-789).
+// double: returns true when one of the J1 terms needs its series form (|k - m| lai <= 1e-3, models.py:777-779); the
+// caller then re-evaluates that band with sail_directional().
+// float: J1(k,m) = (e^{-m t} - e^{-k t})/(k - m) = e^{-k t} t expm1(d)/d with d = (k - m) t has no cancellation for any d,
+// so there is no series branch and the function never returns true.
+template <typename T>
+__device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const Diffuse<T>& d, const T* __restrict__ s,
+                                                      const T* __restrict__ g, int thr_hi, unsigned need, Canopy<T>& o) {
+    const T k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO];
+    const T km = k - d.m, kp = k + d.m, Km = K - d.m, Kp = K + d.m;
+    if constexpr (std::is_same<T, float>::value) {
+        const T lai = s[S_LAI];
+        const T J1ks = (tss * lai) * expm1_over_x(km * lai);
+        const T J1ko = (too * lai) * expm1_over_x(Km * lai);
+        sail_couple(rho, tau, rs, d, g, J1ks, J1ko, rcp(kp), rcp(Kp), need, o);
+        return false;
+    } else {
+        // 1/(k-m) and 1/(k+m) from ONE reciprocal of (k-m)(k+m)                             :644-647, 765-789
+        const bool rare = !(abs_gt_hi(km, thr_hi) && abs_gt_hi(Km, thr_hi));
+        const T ik = rcp(km * kp), iK = rcp(Km * Kp);
+        const T J1ks = (d.e1 - tss) * (ik * kp);
+        const T J1ko = (d.e1 - too) * (iK * Kp);
+        sail_couple(rho, tau, rs, d, g, J1ks, J1ko, ik * km, iK * Km, need, o);
+        return rare;
+    }
+}
+
+// geometry-dependent part of 4SAIL for one band with J1's series branch (models.py:765-785): the repair path (double)
+template <typename T>
+__device__ __forceinline__ void sail_directional(T rho, T tau, T rs, const Diffuse<T>& d, const T* __restrict__ s,
+                                                 const T* __restrict__ g, int thr_hi, unsigned need, Canopy<T>& o) {
+    const T k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO], lai = s[S_LAI];
+    const T half = T(0.5), one = T(1);
     // J1(k,m), J2(k,m), J1(K,m), J2(K,m): 1/(k-m) and 1/(k+m) from ONE reciprocal of (k-m)(k+m)   :644-647, 765-789
-    double J1ks, J1ko, inv_kp, inv_Kp;
+    T J1ks, J1ko, inv_kp, inv_Kp;
     {
-        const double km = k - d.m, kp = k + d.m;
+        const T km = k - d.m, kp = k + d.m;
         if (__builtin_expect(abs_gt_hi(km, thr_hi), 1)) {
-            const double i = rcp(km * kp);
+            const T i = rcp(km * kp);
             inv_kp = i * km;
             J1ks = (d.e1 - tss) * (i * kp);
         } else {
-            const double del = km * lai;
+            const T del = km * lai;
             inv_kp = rcp(kp);
-            J1ks = 0.5 * lai * (tss + d.e1) * (1.0 - del * del / 12.0);
+            J1ks = half * lai * (tss + d.e1) * (one - del * del / T(12));
         }
-        const double Km = K - d.m, Kp = K + d.m;
+        const T Km = K - d.m, Kp = K + d.m;
         if (__builtin_expect(abs_gt_hi(Km, thr_hi), 1)) {
-            const double i = rcp(Km * Kp);
+            const T i = rcp(Km * Kp);
             inv_Kp = i * Km;
             J1ko = (d.e1 - too) * (i * Kp);
         } else {
-            const double del = Km * lai;
+            const T del = Km * lai;
             inv_Kp = rcp(Kp);
-            J1ko = 0.5 * lai * (too + d.e1) * (1.0 - del * del / 12.0);
+            J1ko = half * lai * (too + d.e1) * (one - del * del / T(12));
         }
     }
-    const double J2ks = fma(-d.e1, tss, 1.0) * inv_kp;
-    const double J2ko = fma(-d.e1, too, 1.0) * inv_Kp;
-    const double u1 = fma(sb, d.rinf, sf), u2 = fma(sf, d.rinf, sb);  // :649-652
-    const double v1 = fma(vb, d.rinf, vf), v2 = fma(vf, d.rinf, vb);
-    const double Pss = u1 * J1ks, Qss = u2 * J2ks, Pv = v1 * J1ko, Qv = v2 * J2ko;
-    o.tsd = fma(-d.re, Qss, Pss) * d.invden;                          // :656-659
-    o.rsd = fma(-d.re, Pss, Qss) * d.invden;
-    o.tdo = fma(-d.re, Qv, Pv) * d.invden;
-    o.rdo = fma(-d.re, Pv, Qv) * d.invden;
-    const double g1 = fma(-J1ks, too, g[G_Z]) * inv_Kp;               // :668-669
-    const double g2 = fma(-J1ko, tss, g[G_Z]) * inv_kp;
-    const double T1 = (v2 * g1) * u1, T2 = (v1 * g2) * u2;            // :671-675
-    const double T3 = fma(o.rdo, Qss, o.tdo * Pss) * d.rinf;
-    const double rsod = (T1 + T2 - T3) * d.inv_omr2;                  // :678
-    o.rso = fma(w, g[G_LAISUM], rsod);                                // :706, :710
-    // soil coupling                                                                        :721-726
-    const double rsodt = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too) * d.rs_invdn;
-    o.rsot = fma(g[G_TSSTOO], rs, o.rso) + rsodt;
-    if (need & (1u << O_RDDT)) o.rddt = fma(d.tdd * d.tdd, d.rs_invdn, d.rdd);
-    if (need & (1u << O_RSDT)) o.rsdt = fma((o.tsd + tss) * d.tdd, d.rs_invdn, o.rsd);
-    if (need & (1u << O_RDOT)) o.rdot = fma(d.tdd * (o.tdo + too), d.rs_invdn, o.rdo);
+    sail_couple(rho, tau, rs, d, g, J1ks, J1ko, inv_kp, inv_Kp, need, o);
 }
 
 // ---------------------------------------------------------------------------------------------
 // band-mean partial sums: segmented warp reduction over the windows that touch this tile
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mean_partials_inl(const WindowMap* __restrict__ win, double v, int tile, int lane,
-                                                  double* __restrict__ dst /* [ntotal] */, bool f32) {
-    if (f32) v = (double)(float)v;
+template <typename T>
+__device__ __forceinline__ void mean_partials_inl(const WindowMap* __restrict__ win, T v, int tile, int lane,
+                                                  T* __restrict__ dst /* [ntotal] */, bool f32) {
+    if (!is_f32<T>() && f32) v = (T)(float)v;
     const int ns = win->nslots[tile];
     for (int j = 0; j < ns; ++j) {
-        const double x = ((win->mask[tile][j] >> lane) & 1u) ? v : 0.0;
-        const double sum = warp_sum(x);
+        const T x = ((win->mask[tile][j] >> lane) & 1u) ? v : T(0);
+        const T sum = warp_sum(x);
         if (lane == 0) dst[win->slot[tile][j]] = sum;
     }
 }
-__device__ __noinline__ void mean_partials(const WindowMap* __restrict__ win, double v, int tile, int lane, double* __restrict__ dst,
-                                           bool f32) {
+template <typename T>
+__device__ __noinline__ void mean_partials(const WindowMap* __restrict__ win, T v, int tile, int lane, T* __restrict__ dst, bool f32) {
     mean_partials_inl(win, v, tile, lane, dst, f32);
 }
 
@@ -404,18 +517,19 @@ enum { MODE_PROSAIL = 0, MODE_SAIL = 1, MODE_PROSPECT = 2, MODE_SOIL = 3 };
 // kernels, where per-item pointer tests, predicated stores and call overhead would cost issue slots.
 constexpr unsigned RUNTIME = 0x80000000u;
 
+template <typename T>
 struct EmitCtx {
-    const SailArgs& a;
+    const SailArgs<T>& a;
     bool valid[2];       // band u of this thread exists (< 2101)
     int tile[2];         // 32-band tile of band u (index into the window map)
     int lane, nt;
     long long orow;      // item * pitch + band[0]   (band[1] = band[0] + 32)
-    double* pdst;        // partial sums of this item
+    T* pdst;             // partial sums of this item
     int mi;              // running index of the mean plane
 };
 
-template <unsigned PLANES, unsigned MEANS, int PLANE>
-__device__ __forceinline__ void emit(EmitCtx& e, double v0, double v1) {
+template <unsigned PLANES, unsigned MEANS, int PLANE, typename T>
+__device__ __forceinline__ void emit(EmitCtx<T>& e, T v0, T v1) {
     if (PLANES == RUNTIME) {
         if (e.a.out[PLANE]) {
             if (e.valid[0]) __stcs(e.a.out[PLANE] + e.orow, v0);
@@ -439,16 +553,22 @@ __device__ __forceinline__ void emit(EmitCtx& e, double v0, double v1) {
     }
 }
 
+// resident CTAs per SM the kernel is compiled for: double needs 128 registers (16 warps fill the register file);
+// float fits in 64, so two CTAs share an SM and cover the MUFU / LDS latencies with twice the warps
+template <typename T> __host__ __device__ constexpr int min_ctas() { return std::is_same<T, float>::value ? 2 : PB_MIN_CTAS; }
+
 // ---------------------------------------------------------------------------------------------
 // main kernel.  1-D grid of independent warps: warp gw owns the 64-band double tile gw % ntile2 and walks the item
 // chunks gw / ntile2, + nranges, + 2 nranges, ...  The CTA only shares the read-only math tables.
 // ---------------------------------------------------------------------------------------------
 // G1 = true: one geometry per parameter set (the LUT shape) -- every item starts a new parameter set, so nothing
 // is carried between loop iterations and the register allocator sees purely loop-local state.
-template <int MODE, unsigned PLANES, unsigned MEANS, bool G1>
-__global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailArgs a) {
+template <typename T, int MODE, unsigned PLANES, unsigned MEANS, bool G1>
+__global__ void __launch_bounds__(CTA_THREADS, min_ctas<T>()) k_bands(const SailArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    SailSmem& sm = *reinterpret_cast<SailSmem*>(smem_raw);
+    typedef typename Tables<T>::type MT;
+    SailSmem<T>& sm = *reinterpret_cast<SailSmem<T>*>(smem_raw);
+    const T zero_ = T(0), one = T(1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * WARPS_PER_CTA + warp;                 // global warp id
     const int range = gw / a.ntile2;
@@ -456,13 +576,13 @@ __global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailAr
     const bool live = range < a.nranges;
     const int t2 = !live ? 0 : (a.only_active_tiles ? a.win->active_tile2[tslot] : tslot);
     const int band0 = t2 * 64 + lane;      // this thread's bands: band0 and band0 + 32
-    Stage* const stage = sm.stage[warp];
+    Stage<T>* const stage = sm.stage[warp];
     uint64_t* const bar = sm.bar[warp];
 
     {   // math tables -> shared memory
-        const double2* src = reinterpret_cast<const double2*>(a.tables);
-        double2* dst = reinterpret_cast<double2*>(&sm.mt);
-        for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 16); i += CTA_THREADS) dst[i] = src[i];
+        const uint4* src = reinterpret_cast<const uint4*>(a.tables);
+        uint4* dst = reinterpret_cast<uint4*>(&sm.mt);
+        for (int i = threadIdx.x; i < (int)(sizeof(MT) / 16); i += CTA_THREADS) dst[i] = src[i];
     }
     if (lane == 0) {
         mbar_init(&bar[0], 1);
@@ -475,17 +595,21 @@ __global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailAr
     long long chunk = live ? range : nchunks;
     if (lane == 0 && chunk < nchunks) stage_issue(a, &stage[0], &bar[0], chunk);
 
-    BandConst c[2];
-    const double* kc = sm.kc + threadIdx.x;        // this thread's column of the once-per-item constants
+    BandConst<T> c[2];
+    const T* kc = sm.kc + threadIdx.x;             // this thread's column of the once-per-item constants
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-        const double* bc = a.bandc + (live ? band0 + 32 * u : 0);     // NBP = 33 * 64: always in range
-        double* k = sm.kc + u * CTA_THREADS + threadIdx.x;            // only this thread reads these back: no barrier needed
+        const T* bc = a.bandc + (live ? band0 + 32 * u : 0);          // NBP = 33 * 64: always in range
+        T* k = sm.kc + u * CTA_THREADS + threadIdx.x;                 // only this thread reads these back: no barrier needed
         k[KC_KAB * KSTRIDE] = bc[C_KAB * NBP]; k[KC_KXC * KSTRIDE] = bc[C_KXC * NBP]; k[KC_KAN * KSTRIDE] = bc[C_KAN * NBP];
         k[KC_KBR * KSTRIDE] = bc[C_KBR * NBP]; k[KC_KW * KSTRIDE] = bc[C_KW * NBP]; k[KC_KM * KSTRIDE] = bc[C_KM * NBP];
         k[KC_RS1 * KSTRIDE] = bc[C_RS1 * NBP]; k[KC_RS2 * KSTRIDE] = bc[C_RS2 * NBP];
         c[u].talf = bc[C_TALF * NBP]; c[u].t12 = bc[C_T12 * NBP]; c[u].t21 = bc[C_T21 * NBP];
-        c[u].ralf = 1.0 - c[u].talf; c[u].r12 = 1.0 - c[u].t12; c[u].r21 = 1.0 - c[u].t21;     // models.py:1012-1016
+        if constexpr (std::is_same<T, float>::value) {      // the complements are uploaded (rounded from float64) instead of being recomputed in float
+            c[u].ralf = bc[C_RALF * NBP]; c[u].r12 = bc[C_R12 * NBP]; c[u].r21 = bc[C_R21 * NBP];
+        } else {
+            c[u].ralf = one - c[u].talf; c[u].r12 = one - c[u].t12; c[u].r21 = one - c[u].t21;     // models.py:1012-1016
+        }
     }
     unsigned need;
     if (PLANES == RUNTIME) {
@@ -515,13 +639,13 @@ __global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailAr
             long long s = s0;
             int g = G1 ? 0 : (int)(i0 - s0 * a.G);
             bool fresh = true;
-            double rho[2] = {0.0, 0.0}, tau[2] = {0.0, 0.0}, rs[2] = {0.0, 0.0};
-            Diffuse d[2];
+            T rho[2] = {zero_, zero_}, tau[2] = {zero_, zero_}, rs[2] = {zero_, zero_};
+            Diffuse<T> d[2];
             int thr_hi = 0;
-            const double* sr = stage[buf].s;
-            const double* gr = stage[buf].g;
-            EmitCtx e{a, {band0 < NB, band0 + 32 < NB}, {2 * t2, 2 * t2 + 1}, lane, nt, i0 * a.out_pitch + band0,
-                      ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
+            const T* sr = stage[buf].s;
+            const T* gr = stage[buf].g;
+            EmitCtx<T> e{a, {band0 < NB, band0 + 32 < NB}, {2 * t2, 2 * t2 + 1}, lane, nt, i0 * a.out_pitch + band0,
+                         ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
             for (int j = 0; j < n; ++j) {
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {
@@ -533,10 +657,10 @@ __global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailAr
                     emit<PLANES, MEANS, O_LEAF_R>(e, rho[0], rho[1]);
                     emit<PLANES, MEANS, O_LEAF_T>(e, tau[0], tau[1]);
                     if (PLANES == RUNTIME && (a.mean_mask & (1u << O_RSOT))) {   // bits 0..2 double as ka / ke / om here
-                        double ka[2], ke[2], om[2];
+                        T ka[2], ke[2], om[2];
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {                            // models.py:1066-1068
-                            ka[u] = 1.0 - rho[u] - tau[u];
+                            ka[u] = one - rho[u] - tau[u];
                             ke[u] = rho[u] + ka[u];
                             om[u] = rho[u] / ke[u];
                         }
@@ -566,28 +690,30 @@ __global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailAr
 #pragma unroll
                         for (int u = 0; u < 2; ++u) sail_diffuse(rho[u], tau[u], rs[u], sr, sm.mt, d[u]);
                         // |k - m| lai <= 1e-3  <=>  |k - m| <= 1e-3 / lai   (threshold on the high word)
-                        thr_hi = __double2hiint(sr[S_THR]);
+                        thr_hi = hi_word(sr[S_THR]);
                         fresh = false;
                     }
-                    if (__builtin_expect(sr[S_NOCANOPY] != 0.0, 0)) {            // lai <= 0: models.py:609-634
+                    if (__builtin_expect(sr[S_NOCANOPY] != zero_, 0)) {          // lai <= 0: models.py:609-634
                         emit<PLANES, MEANS, O_RSOT>(e, rs[0], rs[1]); emit<PLANES, MEANS, O_RDDT>(e, rs[0], rs[1]);
                         emit<PLANES, MEANS, O_RSDT>(e, rs[0], rs[1]); emit<PLANES, MEANS, O_RDOT>(e, rs[0], rs[1]);
-                        emit<PLANES, MEANS, O_RSO>(e, 0.0, 0.0); emit<PLANES, MEANS, O_RDD>(e, 0.0, 0.0);
-                        emit<PLANES, MEANS, O_TDD>(e, 1.0, 1.0); emit<PLANES, MEANS, O_RSD>(e, 0.0, 0.0);
-                        emit<PLANES, MEANS, O_TSD>(e, 0.0, 0.0); emit<PLANES, MEANS, O_RDO>(e, 0.0, 0.0);
-                        emit<PLANES, MEANS, O_TDO>(e, 0.0, 0.0);
+                        emit<PLANES, MEANS, O_RSO>(e, zero_, zero_); emit<PLANES, MEANS, O_RDD>(e, zero_, zero_);
+                        emit<PLANES, MEANS, O_TDD>(e, one, one); emit<PLANES, MEANS, O_RSD>(e, zero_, zero_);
+                        emit<PLANES, MEANS, O_TSD>(e, zero_, zero_); emit<PLANES, MEANS, O_RDO>(e, zero_, zero_);
+                        emit<PLANES, MEANS, O_TDO>(e, zero_, zero_);
                     } else {
-                        Canopy o[2];
+                        Canopy<T> o[2];
                         bool rare[2];
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
-                            o[u].rddt = o[u].rsdt = o[u].rdot = 0.0;
-                            rare[u] = sail_directional_fast(rho[u], tau[u], rs[u], d[u], gr, thr_hi, need, o[u]);
+                            o[u].rddt = o[u].rsdt = o[u].rdot = zero_;
+                            rare[u] = sail_directional_fast(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
                         }
-                        if (__builtin_expect(rare[0] | rare[1], 0)) {
+                        if constexpr (!std::is_same<T, float>::value) {
+                            if (__builtin_expect(rare[0] | rare[1], 0)) {
 #pragma unroll
-                            for (int u = 0; u < 2; ++u)
-                                if (rare[u]) sail_directional(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
+                                for (int u = 0; u < 2; ++u)
+                                    if (rare[u]) sail_directional(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
+                            }
                         }
                         emit<PLANES, MEANS, O_RSOT>(e, o[0].rsot, o[1].rsot); emit<PLANES, MEANS, O_RDDT>(e, o[0].rddt, o[1].rddt);
                         emit<PLANES, MEANS, O_RSDT>(e, o[0].rsdt, o[1].rsdt); emit<PLANES, MEANS, O_RDOT>(e, o[0].rdot, o[1].rdot);
@@ -613,17 +739,18 @@ __global__ void __launch_bounds__(CTA_THREADS, PB_MIN_CTAS) k_bands(const SailAr
 }
 
 // band means = ordered sum of a window's slot partials / band count
-__global__ void k_finalize_means(const WindowMap* __restrict__ win, const double* __restrict__ partial, long long nrows /* nitems*nmean */,
-                                 double* __restrict__ means, float* __restrict__ means_f32) {
+template <typename T>
+__global__ void k_finalize_means(const WindowMap* __restrict__ win, const T* __restrict__ partial, long long nrows /* nitems*nmean */,
+                                 T* __restrict__ means, float* __restrict__ means_f32) {
     const int nw = win->nwindows, nt = win->ntotal;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nrows * nw) return;
     const long long row = idx / nw;
     const int w = (int)(idx - row * nw);
     double acc = 0.0;
-    for (int sl = win->wstart[w]; sl < win->wstart[w + 1]; ++sl) acc += partial[row * nt + sl];
+    for (int sl = win->wstart[w]; sl < win->wstart[w + 1]; ++sl) acc += (double)partial[row * nt + sl];
     const double mean = acc / (double)win->wcount[w];
-    if (means) means[idx] = mean;
+    if (means) means[idx] = (T)mean;
     if (means_f32) means_f32[idx] = (float)mean;
 }
 
@@ -641,8 +768,8 @@ struct PrologueArgs {
     const double *soil_refl, *soil_moist;
     const double *lai, *hot, *lidf_a, *lidf_b;
     const double *iza, *vza, *raa;   // radians, already normalised like core/_core.py:136-146
-    double* srec;
-    double* grec;
+    void* srec;            // [nsamples][REC] of T (the kernel's template type: double, or float for the fp32 mode)
+    void* grec;            // [nitems][REC] of T
     double* geom_out;      // optional [nitems][8]: VolScatt ks, ko, bf, Fs, Ft and tss, too, tsstoo
     double* lidf_out;      // optional [nsamples][18]
 };
@@ -682,6 +809,21 @@ __device__ __forceinline__ void volscatt_volume(double tts, double tto, double p
     ftau = fmax((-bt2 * t1 + t2) / denom, 0.0);
 }
 
+// write one 16-element record as T (double: 128 B, float: 64 B) with 16-byte stores
+template <typename T>
+__device__ __forceinline__ void store_rec(void* base, long long idx, const double (&rec)[REC]) {
+    if constexpr (std::is_same<T, float>::value) {
+        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(base) + idx * REC);
+#pragma unroll
+        for (int i = 0; i < REC / 4; ++i) dst[i] = make_float4((float)rec[4 * i], (float)rec[4 * i + 1], (float)rec[4 * i + 2], (float)rec[4 * i + 3]);
+    } else {
+        double2* dst = reinterpret_cast<double2*>(static_cast<double*>(base) + idx * REC);
+#pragma unroll
+        for (int i = 0; i < REC / 2; ++i) dst[i] = make_double2(rec[2 * i], rec[2 * i + 1]);
+    }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
     const int lane = threadIdx.x & 31;
     const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -690,23 +832,25 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
     const long long s = item / a.G;
     const int g = (int)(item - s * a.G);
 
-    // ---- sample record (written by the g == 0 warp) ----
-    if (g == 0 && lane == 0) {
-        double* r = a.srec + s * REC;
-        for (int i = 0; i < REC; ++i) r[i] = 0.0;
-        if (a.has_leaf) {
-            const double N = a.N[s];
-            r[S_CAB] = a.Cab[s] / N; r[S_CXC] = a.Cxc[s] / N; r[S_CAN] = a.Can ? a.Can[s] / N : 0.0;
-            r[S_CBR] = a.Cbr[s] / N; r[S_CW] = a.Cw[s] / N; r[S_CM] = a.Cm[s] / N;
-            r[S_NM1] = N - 1.0;
-        }
-        if (a.has_soil) {
-            const double sr = a.soil_refl[s], mo = a.soil_moist[s];
-            r[S_SOIL1] = sr * mo;                 // rho = sRef (moisture rsoil1 + (1-moisture) rsoil2), models.py:1917
-            r[S_SOIL2] = sr * (1.0 - mo);
-        }
+    // ---- sample record (written by lane 0 of the g == 0 warp) ----
+    double srec[REC];
+#pragma unroll
+    for (int i = 0; i < REC; ++i) srec[i] = 0.0;
+    if (a.has_leaf) {
+        const double N = a.N[s];
+        srec[S_CAB] = a.Cab[s] / N; srec[S_CXC] = a.Cxc[s] / N; srec[S_CAN] = a.Can ? a.Can[s] / N : 0.0;
+        srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
+        srec[S_NM1] = N - 1.0;
     }
-    if (!a.has_canopy) return;
+    if (a.has_soil) {
+        const double sr = a.soil_refl[s], mo = a.soil_moist[s];
+        srec[S_SOIL1] = sr * mo;                  // rho = sRef (moisture rsoil1 + (1-moisture) rsoil2), models.py:1917
+        srec[S_SOIL2] = sr * (1.0 - mo);
+    }
+    if (!a.has_canopy) {
+        if (g == 0 && lane == 0) store_rec<T>(a.srec, s, srec);
+        return;
+    }
 
     const double lai = a.lai[s], hot = a.hot[s];
     const double la = a.lidf_a[s], lb = a.lidf_b ? a.lidf_b[s] : 0.0;
@@ -813,18 +957,19 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
     }
 
     if (lane == 0) {
-        double* r = a.grec + item * REC;
+        double r[REC];
         r[G_K] = k; r[G_KO] = K;
         r[G_SDB] = 0.5 * (k + bf); r[G_SDF] = 0.5 * (k - bf);        // models.py:583-588
         r[G_DOB] = 0.5 * (K + bf); r[G_DOF] = 0.5 * (K - bf);
         r[G_FS] = Fs; r[G_FT] = Ft;
         r[G_TSS] = tss; r[G_TOO] = too; r[G_TSSTOO] = tsstoo;
         r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_BF] = bf; r[G_SUMINT] = sumint; r[G_ALF] = alf;
+        store_rec<T>(a.grec, item, r);
         if (g == 0) {
-            double* sr = a.srec + s * REC;
-            sr[S_DDB] = 0.5 * (1.0 + bf); sr[S_DDF] = 0.5 * (1.0 - bf);
-            sr[S_NEGLAI] = -lai; sr[S_LAI] = lai; sr[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;
-            sr[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
+            srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
+            srec[S_NEGLAI] = -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;
+            srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
+            store_rec<T>(a.srec, s, srec);
         }
         if (a.geom_out) {
             double* o = a.geom_out + item * 8;
@@ -848,6 +993,7 @@ struct AngleTables {            // filled on the host by prosail_create with the
     double edge[19];            // the edges in radians as LIDF.verhoef computes them (np.radians(angle), models.py:372)
 };
 
+template <typename T>
 __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const AngleTables* __restrict__ at) {
     const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nitems = a.nsamples * a.G;
@@ -872,11 +1018,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
         }
     }
     if (!a.has_canopy) {
-        if (g == 0) {
-            double2* dst = reinterpret_cast<double2*>(a.srec + s * REC);
-#pragma unroll
-            for (int i = 0; i < REC / 2; ++i) dst[i] = make_double2(srec[2 * i], srec[2 * i + 1]);
-        }
+        if (g == 0) store_rec<T>(a.srec, s, srec);
         return;
     }
 
@@ -1026,18 +1168,12 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
     grec[G_FS] = Fs; grec[G_FT] = Ft;
     grec[G_TSS] = tss; grec[G_TOO] = too; grec[G_TSSTOO] = tsstoo;
     grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_BF] = bf; grec[G_SUMINT] = sumint; grec[G_ALF] = alf;
-    {
-        double2* dst = reinterpret_cast<double2*>(a.grec + item * REC);
-#pragma unroll
-        for (int i = 0; i < REC / 2; ++i) dst[i] = make_double2(grec[2 * i], grec[2 * i + 1]);
-    }
+    store_rec<T>(a.grec, item, grec);
     if (g == 0) {
         srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
         srec[S_NEGLAI] = -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;
         srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
-        double2* dst = reinterpret_cast<double2*>(a.srec + s * REC);
-#pragma unroll
-        for (int i = 0; i < REC / 2; ++i) dst[i] = make_double2(srec[2 * i], srec[2 * i + 1]);
+        store_rec<T>(a.srec, s, srec);
     }
     if (a.geom_out) {
         double* o = a.geom_out + item * 8;

@@ -13,6 +13,15 @@ from . import _capi as capi
 from . import constants as K
 
 _f64 = np.float64
+_f32 = np.float32
+
+
+def _real(dtype):
+    """Result dtype of a call: float64 (the parity path) or float32 (the fp32 mode, <= 1e-5 absolute)."""
+    dt = np.dtype(dtype)
+    if dt not in (np.dtype(_f64), np.dtype(_f32)):
+        raise ValueError("dtype must be float64 or float32, not %s" % dt)
+    return dt
 
 
 def _ptr(a):
@@ -229,8 +238,12 @@ class Engine(object):
         return o
 
     # ---- host-array API ----------------------------------------------------------------------------------
-    def prospect(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=None, version='5', alpha=40, means=False, out=None):
-        """Batched PROSPECT.  Returns dict(ks, kt[, means]) with ks/kt float64[n, 2101]; means float32[n, 5, nw]."""
+    def _fn(self, name, dt):
+        return getattr(self.lib, "%s_%s" % (name, "f32" if dt == np.dtype(_f32) else "f64"))
+
+    def prospect(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=None, version='5', alpha=40, means=False, out=None, dtype=_f64):
+        """Batched PROSPECT.  Returns dict(ks, kt[, means]) with ks/kt dtype[n, 2101]; means float32[n, 5, nw]."""
+        dt = _real(dtype)
         with self._lock:
             self.set_alpha(version, alpha)
             n = batch_size(N, Cab, Cxc, Cbr, Cw, Cm, Can)
@@ -241,26 +254,28 @@ class Engine(object):
             ks = out.get('ks')
             kt = out.get('kt')
             if ks is None:
-                ks = PinnedPool.empty((n, K.NBANDS))
+                ks = PinnedPool.empty((n, K.NBANDS), dt)
             if kt is None:
-                kt = PinnedPool.empty((n, K.NBANDS))
+                kt = PinnedPool.empty((n, K.NBANDS), dt)
+            assert ks.dtype == dt and kt.dtype == dt
             m = PinnedPool.empty((n, 5, len(self.windows)), np.float32) if means else None
-            capi.check(self.lib.prosail_prospect_f64(self.h, 0 if version == '5' else 1, n, C.byref(leaf), _ptr(ks), _ptr(kt),
-                                                     K.NBANDS, _ptr(m), 1, None))
+            capi.check(self._fn("prosail_prospect", dt)(self.h, 0 if version == '5' else 1, n, C.byref(leaf), _ptr(ks), _ptr(kt),
+                                                        K.NBANDS, _ptr(m), 1, None))
             res = dict(ks=ks, kt=kt)
             if means:
                 res['means'] = m
             return res
 
-    def soil(self, reflectance, moisture, means=False):
-        """Batched LSM.  Returns dict(rho float64[n, 2101][, means float32[n, 1, nw]])."""
+    def soil(self, reflectance, moisture, means=False, dtype=_f64):
+        """Batched LSM.  Returns dict(rho dtype[n, 2101][, means float32[n, 1, nw]])."""
+        dt = _real(dtype)
         with self._lock:
             n = batch_size(reflectance, moisture)
             r, mo = _vec(reflectance, n, 'reflectance'), _vec(moisture, n, 'moisture')
             soil = self._soil(r, mo)
-            rho = PinnedPool.empty((n, K.NBANDS))
+            rho = PinnedPool.empty((n, K.NBANDS), dt)
             m = PinnedPool.empty((n, 1, len(self.windows)), np.float32) if means else None
-            capi.check(self.lib.prosail_soil_f64(self.h, n, C.byref(soil), _ptr(rho), K.NBANDS, _ptr(m), 1, None))
+            capi.check(self._fn("prosail_soil", dt)(self.h, n, C.byref(soil), _ptr(rho), K.NBANDS, _ptr(m), 1, None))
             res = dict(rho=rho)
             if means:
                 res['means'] = m
@@ -294,32 +309,34 @@ class Engine(object):
             capi.check(self.lib.prosail_volscatt_f64(self.h, n, C.byref(can), _ptr(geom), _ptr(lidf), 1, None))
             return geom, lidf
 
-    def _alloc_out(self, n_items, planes, mean_planes, want_geom, out):
+    def _alloc_out(self, n_items, planes, mean_planes, want_geom, out, dt=np.dtype(_f64)):
         out = out or {}
         bufs = {}
         for p in planes:
             a = out.get(capi.PLANE_NAMES[p])
-            bufs[p] = a if a is not None else PinnedPool.empty((n_items, K.NBANDS))
+            bufs[p] = a if a is not None else PinnedPool.empty((n_items, K.NBANDS), dt)
+            assert bufs[p].dtype == dt, "output buffer dtype does not match the requested precision"
         mask = 0
         for p in mean_planes:
             mask |= 1 << p
         nmean = bin(mask).count("1")
         means = (out.get('means') if out.get('means') is not None else
-                 PinnedPool.empty((n_items, nmean, len(self.windows)))) if nmean else None
+                 PinnedPool.empty((n_items, nmean, len(self.windows)), dt)) if nmean else None
         geom = np.empty((n_items, 8), dtype=_f64) if want_geom else None
         return bufs, mask, means, geom
 
     def sail(self, ks, kt, rho, iza, vza, raa, lai, hotspot, lidf_type='campbell', a=57, b=0, planes=(capi.O_RSOT,),
-             mean_planes=(), geom_per_sample=False, want_geom=True, out=None):
+             mean_planes=(), geom_per_sample=False, want_geom=True, out=None, dtype=_f64):
         """Batched SAIL with leaf/soil spectra given as arrays ([2101] broadcast or [n, 2101]).
 
-        Returns dict: plane name -> float64[n, G, 2101]; 'means' float64[n, G, nmean, nw]; 'geom' float64[n, G, 8].
+        Returns dict: plane name -> dtype[n, G, 2101]; 'means' dtype[n, G, nmean, nw]; 'geom' float64[n, G, 8].
         """
+        dt = _real(dtype)
         with self._lock:
             specs = []
             n_spec = 1
             for name, s_ in (('ks', ks), ('kt', kt), ('rho_surface', rho)):
-                s_ = np.ascontiguousarray(s_, dtype=_f64)
+                s_ = np.ascontiguousarray(s_, dtype=dt)
                 if s_.ndim == 1:
                     s_ = s_.reshape(1, -1)
                 if s_.shape[-1] != K.NBANDS:
@@ -335,17 +352,18 @@ class Engine(object):
                 if s_.shape[0] not in (1, n):
                     raise ValueError("spectra must be [2101] or [%d, 2101]" % n)
             can, G, keep = self._canopy_host(n, iza, vza, raa, lai, hotspot, lidf_type, a, b, geom_per_sample)
-            bufs, mask, means, geom = self._alloc_out(n * G, planes, mean_planes, want_geom, out)
+            bufs, mask, means, geom = self._alloc_out(n * G, planes, mean_planes, want_geom, out, dt)
             o = self._out(bufs, K.NBANDS, mask, means, geom, 0)
             pit = [0 if s_.shape[0] == 1 else K.NBANDS for s_ in specs]
-            capi.check(self.lib.prosail_sail_f64(self.h, n, _ptr(specs[0]), pit[0], _ptr(specs[1]), pit[1], _ptr(specs[2]), pit[2],
+            capi.check(self._fn("prosail_sail", dt)(self.h, n, _ptr(specs[0]), pit[0], _ptr(specs[1]), pit[1], _ptr(specs[2]), pit[2],
                                                  C.byref(can), C.byref(o), 1, None))
             return self._pack(bufs, means, geom, n, G)
 
     def prosail(self, N, Cab, Cxc, Cbr, Cw, Cm, lai, hotspot, iza, vza, raa, soil_reflectance, soil_moisture, Can=None,
                 version='5', alpha=40, lidf_type='campbell', a=57, b=0, planes=(capi.O_RSOT,), mean_planes=(),
-                geom_per_sample=False, want_geom=False, windows_only=False, out=None):
+                geom_per_sample=False, want_geom=False, windows_only=False, out=None, dtype=_f64):
         """Fused PROSPECT -> LSM -> SAIL for n parameter sets x G geometries (host arrays in, host arrays out)."""
+        dt = _real(dtype)
         with self._lock:
             self.set_alpha(version, alpha)
             n = batch_size(N, Cab, Cxc, Cbr, Cw, Cm, Can, lai, hotspot, a, b, soil_reflectance, soil_moisture)
@@ -359,15 +377,15 @@ class Engine(object):
             can, G, keep = self._canopy_host(n, iza, vza, raa, lai, hotspot, lidf_type, a, b, geom_per_sample)
             if windows_only:
                 planes = ()
-            bufs, mask, means, geom = self._alloc_out(n * G, planes, mean_planes, want_geom, out)
+            bufs, mask, means, geom = self._alloc_out(n * G, planes, mean_planes, want_geom, out, dt)
             o = self._out(bufs, K.NBANDS, mask, means, geom, 1 if windows_only else 0)
-            capi.check(self.lib.prosail_prosail_f64(self.h, 0 if version == '5' else 1, n, C.byref(leaf), C.byref(soil), C.byref(can),
+            capi.check(self._fn("prosail_prosail", dt)(self.h, 0 if version == '5' else 1, n, C.byref(leaf), C.byref(soil), C.byref(can),
                                                     C.byref(o), 1, None))
             return self._pack(bufs, means, geom, n, G)
 
     # ---- device-resident API (inputs and outputs stay in HBM; asynchronous on `stream`) ---------------------
     def prosail_device(self, n, leaf, soil, canopy, planes, pitch=K.NBANDS, mean_planes=(), means=None, version='5',
-                       lidf_type='campbell', n_geom=1, geom_per_sample=False, windows_only=False, stream=None):
+                       lidf_type='campbell', n_geom=1, geom_per_sample=False, windows_only=False, stream=None, dtype=_f64):
         """Fused PROSAIL on DeviceArrays.
 
         leaf: dict N, Cab, Cxc, Cbr, Cw, Cm[, Can]; soil: dict reflectance, moisture; canopy: dict lidf_a[, lidf_b], lai,
@@ -382,14 +400,14 @@ class Engine(object):
         for p in mean_planes:
             mask |= 1 << p
         o = self._out(planes, pitch, mask, means, None, 1 if windows_only else 0)
-        capi.check(self.lib.prosail_prosail_f64(self.h, 0 if version == '5' else 1, int(n), C.byref(lf), C.byref(so), C.byref(ca),
-                                                C.byref(o), 0, stream))
+        capi.check(self._fn("prosail_prosail", _real(dtype))(self.h, 0 if version == '5' else 1, int(n), C.byref(lf), C.byref(so),
+                                                             C.byref(ca), C.byref(o), 0, stream))
 
-    def prospect_device(self, n, leaf, ks, kt, pitch=K.NBANDS, version='5', stream=None):
+    def prospect_device(self, n, leaf, ks, kt, pitch=K.NBANDS, version='5', stream=None, dtype=_f64):
         """Leaf-only batch on DeviceArrays (ks, kt: [n, pitch])."""
         lf = self._leaf(leaf['N'], leaf['Cab'], leaf['Cxc'], leaf['Cbr'], leaf['Cw'], leaf['Cm'], leaf.get('Can'))
-        capi.check(self.lib.prosail_prospect_f64(self.h, 0 if version == '5' else 1, int(n), C.byref(lf), C.c_void_p(self._addr(ks)),
-                                                 C.c_void_p(self._addr(kt)), int(pitch), None, 0, stream))
+        capi.check(self._fn("prosail_prospect", _real(dtype))(self.h, 0 if version == '5' else 1, int(n), C.byref(lf),
+                                                              C.c_void_p(self._addr(ks)), C.c_void_p(self._addr(kt)), int(pitch), None, 0, stream))
 
     @staticmethod
     def _pack(bufs, means, geom, n, G):

@@ -10,6 +10,8 @@ Same names, arguments, attributes and exception types as ``pyrism/models/models.
 * ``SAIL`` accepts several geometries at once (arrays for ``iza, vza, raa``): results are ``[B, G, 2101]``
   (axes of length one are squeezed so that the scalar call returns ``(2101,)`` like the reference).
 * ``PROSAIL`` fuses PROSPECT -> LSM -> SAIL in one kernel launch (the LUT generator).
+* ``dtype=np.float32`` selects the fp32 mode of the kernels (float spectra, <= 1e-5 absolute against the float64
+  reference); the default ``np.float64`` is the parity path (<= 1e-9).
 
 All numbers come from the sm_100a kernels behind ``libprosail_b200.so``; there is no CPU implementation.
 """
@@ -79,7 +81,8 @@ class PROSPECT(_SpectralModel):
     (ks, kt, ka, ke, omega), the coefficient tables ``KN, Kab, Kxc, Kbr, Kw, Km, Kan`` and ``n_elems_list``.
     """
 
-    def __init__(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=0, alpha=40, version='5', device=None):
+    def __init__(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=0, alpha=40, version='5', device=None, dtype=np.float64):
+        self.dtype = np.dtype(dtype)      # float64 = the parity path; float32 = the fp32 mode (<= 1e-5 absolute)
         self.N, self.Cab, self.Cxc, self.Cbr, self.Cw, self.Cm, self.Can = N, Cab, Cxc, Cbr, Cw, Cm, Can
         self.alpha = alpha
         self.ver = version
@@ -98,7 +101,7 @@ class PROSPECT(_SpectralModel):
         self._engine = get_engine(device)
         self._scalar = _is_scalar_call(N, Cab, Cxc, Cbr, Cw, Cm, Can)
         res = self._engine.prospect(N, Cab, Cxc, Cbr, Cw, Cm, Can=Can if self.ver == 'D' else None, version=self.ver,
-                                    alpha=alpha, means=True)
+                                    alpha=alpha, means=True, dtype=self.dtype)
         sq = (lambda a: a[0]) if self._scalar else (lambda a: a)
         self.ks, self.kt = sq(res['ks']), sq(res['kt'])
         self.L8, self.ASTER = _band_tuples(sq(res['means']), 'ks kt ka ke omega')
@@ -127,7 +130,7 @@ class PROSPECT(_SpectralModel):
             def go():
                 r = self._engine.prospect(self.N, self.Cab, self.Cxc, self.Cbr, self.Cw, self.Cm,
                                           Can=self.Can if self.ver == 'D' else None, version=self.ver, alpha=self.alpha,
-                                          means=True)
+                                          means=True, dtype=self.dtype)
                 m = r['means'][..., 0]
                 return np.asarray(m[0] if self._scalar else m, dtype=np.float32)
             return self._with_windows(((mins, maxs),), go)
@@ -142,13 +145,14 @@ class PROSPECT(_SpectralModel):
 class LSM(_SpectralModel):
     """Lambertian soil reflectance (models.py:1871-2038): ``ref = reflectance (moisture rsoil1 + (1 - moisture) rsoil2)``."""
 
-    def __init__(self, reflectance, moisture, device=None):
+    def __init__(self, reflectance, moisture, device=None, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
         self.l = np.arange(400, 2501)
         self.sRef = reflectance
         self.moisture = moisture
         self._engine = get_engine(device)
         self._scalar = _is_scalar_call(reflectance, moisture)
-        res = self._engine.soil(reflectance, moisture, means=True)
+        res = self._engine.soil(reflectance, moisture, means=True, dtype=self.dtype)
         sq = (lambda a: a[0]) if self._scalar else (lambda a: a)
         self.ref = sq(res['rho'])
         self.L8, self.ASTER = _band_tuples(sq(res['means'])[..., 0, :])
@@ -161,7 +165,7 @@ class LSM(_SpectralModel):
     def select(self, mins, maxs, function='mean'):
         if function == 'mean':
             def go():
-                m = self._engine.soil(self.sRef, self.moisture, means=True)['means'][..., 0, 0]
+                m = self._engine.soil(self.sRef, self.moisture, means=True, dtype=self.dtype)['means'][..., 0, 0]
                 return np.float32(m[0]) if self._scalar else np.asarray(m, dtype=np.float32)
             return self._with_windows(((mins, maxs),), go)
 
@@ -245,7 +249,7 @@ class SAIL(Kernel):
     """
 
     def __init__(self, iza, vza, raa, ks, kt, lai, hotspot, rho_surface, lidf_type='campbell', a=57, b=0, normalize=False,
-                 nbar=0.0, angle_unit='DEG', device=None):
+                 nbar=0.0, angle_unit='DEG', device=None, dtype=np.float64):
         super(SAIL, self).__init__(iza=iza, vza=vza, raa=raa, normalize=normalize, nbar=nbar, angle_unit=angle_unit,
                                    align=True)
         for name, v in (("ks", ks), ("kt", kt), ("rho_surface", rho_surface)):
@@ -263,7 +267,7 @@ class SAIL(Kernel):
 
         eng = get_engine(device)
         res = eng.sail(ks, kt, rho_surface, self.iza, self.vza, self.raa, lai, hotspot, lidf_type=lidf_type, a=a, b=b,
-                       planes=_PLANES_SAIL, mean_planes=_MEANS_SAIL, want_geom=True)
+                       planes=_PLANES_SAIL, mean_planes=_MEANS_SAIL, want_geom=True, dtype=dtype)
         B, G = res['rsot'].shape[:2]
         one_set = _is_scalar_call(lai, hotspot, a, b) and all(np.ndim(s) == 1 for s in (ks, kt, rho_surface))
         self._finish(res, one_set, G)
@@ -310,7 +314,7 @@ class PROSAIL(SAIL):
 
     def __init__(self, N, Cab, Cxc, Cbr, Cw, Cm, lai, hotspot, iza, vza, raa, soil_reflectance=1.0, soil_moisture=0.5,
                  Can=0, alpha=40, version='5', lidf_type='campbell', a=57, b=0, angle_unit='DEG', geom_per_sample=False,
-                 keep_leaf=False, device=None):
+                 keep_leaf=False, device=None, dtype=np.float64):
         Kernel.__init__(self, iza=iza, vza=vza, raa=raa, normalize=False, nbar=0.0, angle_unit=angle_unit, align=True)
         if version != '5' and version != 'D':
             raise ValueError("version must be '5' for PROSPECT 5 or 'D' for PROSPECT D. "
@@ -325,7 +329,7 @@ class PROSAIL(SAIL):
         res = get_engine(device).prosail(N, Cab, Cxc, Cbr, Cw, Cm, lai, hotspot, self.iza, self.vza, self.raa, soil_reflectance,
                                          soil_moisture, Can=Can, version=version, alpha=alpha, lidf_type=lidf_type, a=a, b=b,
                                          planes=planes, mean_planes=_MEANS_SAIL, geom_per_sample=geom_per_sample,
-                                         want_geom=True)
+                                         want_geom=True, dtype=dtype)
         G = res['rsot'].shape[1]
         one_set = _is_scalar_call(N, Cab, Cxc, Cbr, Cw, Cm, Can, lai, hotspot, a, b, soil_reflectance, soil_moisture) \
             and not geom_per_sample

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel-level timing of the fused PROSAIL kernel (device-resident inputs/outputs) for tuning experiments.
-usage: [PYRISM_B200_LIB=path.so] python tools/kbench.py [samples] [reps] [planes: brf|four|leaf]"""
+usage: [PYRISM_B200_LIB=path.so] python tools/kbench.py [samples] [reps] [planes: brf|four|leaf|means] [f64|f32]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -10,6 +10,7 @@ from pyrism_b200 import _capi as capi
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 what = sys.argv[3] if len(sys.argv) > 3 else "brf"
+dt = np.float32 if (len(sys.argv) > 4 and sys.argv[4] == "f32") else np.float64
 eng = pb.Engine(0)
 P = bench.lhs(S, 123)
 geom = np.deg2rad(np.array(bench.GEOM_DEG))
@@ -19,14 +20,17 @@ soil = {"reflectance": dev["soil_refl"], "moisture": dev["soil_moist"]}
 canopy = {"lidf_a": dev["lidf_a"], "lai": dev["lai"], "hotspot": dev["hotspot"], "iza": eng.to_device(geom[0:1]),
           "vza": eng.to_device(geom[1:2]), "raa": eng.to_device(geom[2:3])}
 if what == "leaf":
-    ks, kt = eng.empty((S, 2101)), eng.empty((S, 2101))
-    step = lambda: eng.prospect_device(S, leaf, ks, kt)
+    ks, kt = eng.empty((S, 2101), dt), eng.empty((S, 2101), dt)
+    step = lambda: eng.prospect_device(S, leaf, ks, kt, dtype=dt)
+elif what == "means":
+    means = eng.empty((S, 1, len(eng.windows)), dt)
+    step = lambda: eng.prosail_device(S, leaf, soil, canopy, None, mean_planes=(capi.O_RSOT,), means=means, windows_only=True, dtype=dt)
 else:
-    planes = {capi.O_RSOT: eng.empty((S, 2101))}
+    planes = {capi.O_RSOT: eng.empty((S, 2101), dt)}
     if what == "four":
         for p in (capi.O_RDDT, capi.O_RSDT, capi.O_RDOT):
-            planes[p] = eng.empty((S, 2101))
-    step = lambda: eng.prosail_device(S, leaf, soil, canopy, planes)
+            planes[p] = eng.empty((S, 2101), dt)
+    step = lambda: eng.prosail_device(S, leaf, soil, canopy, planes, dtype=dt)
 for _ in range(3):
     step()
 eng.sync()
@@ -35,4 +39,4 @@ for _ in range(reps):
     step()
 pr = eng.profile_read()
 ms = pr['bands'][0] / pr['bands'][1]
-print("%s lib=%s S=%d kernel %.3f ms  -> %.3e spectra/s   prologue %.3f ms" % (what, os.path.basename(capi.LIB_PATH), S, ms, S / ms * 1e3, pr['prologue'][0] / max(pr['prologue'][1], 1)))
+print("%s %s lib=%s S=%d kernel %.3f ms  -> %.3e spectra/s   prologue %.3f ms" % (what, np.dtype(dt).name, os.path.basename(capi.LIB_PATH), S, ms, S / ms * 1e3, pr['prologue'][0] / max(pr['prologue'][1], 1)))
