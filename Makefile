@@ -1,19 +1,25 @@
 # Builds libprosail_b200.so (sm_100a only) in-tree.  `make` here or __graft_entry__.build().
 NVCC ?= nvcc
 NVFLAGS ?= -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC
+# tuning experiments: make variant NAME=nu3 EXTRA=-DPB_NU=3  ->  pyrism_b200/lib/variants/libprosail_nu3.so (PYRISM_B200_LIB selects it)
+EXTRA ?=
 SRC := pyrism_b200/csrc/prosail_api.cu
-HDR := pyrism_b200/csrc/prosail_kernels.cuh pyrism_b200/csrc/math64.cuh pyrism_b200/csrc/math_tables.inc include/prosail_b200.h
+HDR := pyrism_b200/csrc/prosail_kernels.cuh pyrism_b200/csrc/math64.cuh pyrism_b200/csrc/math32.cuh pyrism_b200/csrc/math_tables.inc include/prosail_b200.h
 LIB := pyrism_b200/lib/libprosail_b200.so
 
 all: $(LIB)
 
 $(LIB): $(SRC) $(HDR)
 	mkdir -p pyrism_b200/lib
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC)
+	$(NVCC) $(NVFLAGS) $(EXTRA) -shared -o $@ $(SRC)
+
+variant: $(SRC) $(HDR)
+	mkdir -p pyrism_b200/lib/variants
+	$(NVCC) $(NVFLAGS) $(EXTRA) -shared -o pyrism_b200/lib/variants/libprosail_$(NAME).so $(SRC)
 
 ptxas: $(SRC) $(HDR)
-	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o /tmp/libprosail_b200_v.so $(SRC)
+	$(NVCC) $(NVFLAGS) $(EXTRA) -Xptxas -v -shared -o /tmp/libprosail_b200_v.so $(SRC)
 
 clean:
 	rm -f $(LIB)
-.PHONY: all clean ptxas
+.PHONY: all clean ptxas variant

@@ -33,11 +33,12 @@ __device__ __forceinline__ float rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float sqrt_pos(float x) {
+__device__ __forceinline__ float sqrt_raw(float x) {
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return is_pos(x) ? y : 0.0f;
+    return y;
 }
+__device__ __forceinline__ float sqrt_pos(float x) { return is_pos(x) ? sqrt_raw(x) : 0.0f; }
 __device__ __forceinline__ float exp2_fast(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -65,20 +65,25 @@ __device__ __forceinline__ double rcp(double x) {
 
 // sqrt(x), x > 0: MUFU.RSQ64H seed y (~2^-20) + one cubic step: with t = x y, e = 1 - t y:
 // sqrt(x) = t (1 + e/2 + 3 e^2/8 + O(e^3)).  5 FP64 ops.  x <= 0 -> 0 (integer-pipe select).
-__device__ __forceinline__ double sqrt_pos(double x) {
+// sqrt_raw: no guard -- the caller knows x > 0 (or repairs / discards the lane afterwards).
+__device__ __forceinline__ double sqrt_raw(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double t = x * y;
     const double e = fma(-t, y, 1.0);
     const double p = fma(e, 0.375, 0.5) * e;
-    const double g = fma(t, p, t);
+    return fma(t, p, t);
+}
+__device__ __forceinline__ double sqrt_pos(double x) {
+    const double g = sqrt_raw(x);
     return is_pos(x) ? g : 0.0;
 }
 
-// exp(x) for x <= 0 (clamped at -700): n = rint(256 x log2 e); exp = 2^(n>>8) * T[n&255] * P4(r), |r| <= ln2/512.
+// exp(x) for x <= 0 (clamped at about -700; positive x is outside the contract): n = rint(256 x log2 e); exp = 2^(n>>8) * T[n&255] * P4(r), |r| <= ln2/512.
 // 9 FP64 ops + one table load.
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ exp2t) {
-    x = (__double2hiint(x) & 0x7fffffff) > 0x4085E000 ? -700.0 : x;       // |x| > 700 (integer pipe)
+    // clamp at about -700: for x <= 0 the high word grows (as an unsigned integer) with |x|, so ONE integer min does it
+    x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC085E000u), __double2loint(x));
     const double t = fma(x, c_m[M_L2E256], PB_MAGIC);
     const int n = __double2loint(t);
     const double nd = t - PB_MAGIC;
@@ -110,10 +115,11 @@ __device__ __forceinline__ double log2_pos(double b, const double* __restrict__ 
     return fma(r, q, Ed + tc.y);
 }
 
-// 2^y for y < 1000 (clamped at 500): n = rint(256 y); r = y - n/256 (exact); 2^y = 2^(n>>8) T[n&255] P4(r ln2).
+// 2^y (clamped at about 500): n = rint(256 y); r = y - n/256 (exact); 2^y = 2^(n>>8) T[n&255] P4(r ln2).
 // 8 FP64 ops + one table load.
 __device__ __forceinline__ double exp2_any(double y, const double* __restrict__ exp2t) {
-    y = __double2hiint(y) > 0x407F4000 ? 500.0 : y;                       // y > 500 (integer pipe; negative y passes)
+    // clamp at about 500: one signed integer min on the high word (negative y has a negative high word and passes)
+    y = __hiloint2double(min(__double2hiint(y), 0x407F4000), __double2loint(y));
     const double t = fma(y, 256.0, PB_MAGIC);
     const int n = __double2loint(t);
     const double nd = t - PB_MAGIC;
@@ -150,6 +156,20 @@ __device__ __forceinline__ double tau_fast(double k, const double* __restrict__ 
     const double2 c01 = row[0];                                    // O, c0
     const double u = fma(k, S, -c01.x);
     static_assert(TAU_DEG % 2 == 0, "row layout assumes an even degree (TAU_ROW even)");
+#ifdef PB_TAU_EVENODD
+    // even / odd split: two Horner chains in u^2 (depth 7 instead of 10, one extra multiply)
+    const double u2 = u * u;
+    double2 c = row[TAU_ROW / 2 - 1];                              // c[D-1], c[D]
+    double po = c.x, pe = c.y;
+#pragma unroll
+    for (int q = TAU_ROW / 2 - 2; q >= 1; --q) {
+        c = row[q];                                                // c[2q-1], c[2q]
+        po = fma(u2, po, c.x);
+        pe = fma(u2, pe, c.y);
+    }
+    pe = fma(u2, pe, c01.y);
+    return fma(u, po, pe);
+#else
     double2 c = row[TAU_ROW / 2 - 1];                              // c[D-1], c[D]
     double acc = fma(u, c.y, c.x);
 #pragma unroll
@@ -159,6 +179,7 @@ __device__ __forceinline__ double tau_fast(double k, const double* __restrict__ 
         acc = fma(u, acc, c.x);
     }
     return fma(u, acc, c01.y);
+#endif
 }
 
 // Rare path (never taken for realistic leaves, k in [6e-4, 16]): k <= 0, k < 2^-14, k >= 32.  Plain IEEE arithmetic.

@@ -200,25 +200,35 @@ template <typename T> static inline T* off(void* p, long long n) { return static
 static inline void* offb(void* p, long long n, size_t esz) { return static_cast<char*>(p) + n * (long long)esz; }
 static inline const void* offb(const void* p, long long n, size_t esz) { return static_cast<const char*>(p) + n * (long long)esz; }
 
+#ifndef PB_NU
+#define PB_NU 2          /* bands per thread of the fp64 band kernel (2 or 3) */
+#endif
+// kernel configuration per real type: see struct Cfg in prosail_kernels.cuh
+template <typename T> struct CfgOf { typedef Cfg<PB_NU, PB_NU == 3 ? 12 : PB_WARPS> type; };
+template <> struct CfgOf<float> { typedef Cfg<2, PB_WARPS> type; };
+
 template <typename T, int MODE, unsigned PLANES, unsigned MEANS>
-static int launch_bands(prosail_handle* h, SailArgs<T>& a, cudaStream_t st) {
-    const size_t smem = sizeof(SailSmem<T>);
-    auto kern = a.G == 1 ? k_bands<T, MODE, PLANES, MEANS, true> : k_bands<T, MODE, PLANES, MEANS, false>;
+static int launch_bands(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
+    typedef typename CfgOf<T>::type CF;
+    const size_t smem = sizeof(SailSmem<T, CF>);
+    auto kern = a.G == 1 ? k_bands<T, CF, MODE, PLANES, MEANS, true> : k_bands<T, CF, MODE, PLANES, MEANS, false>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CF::THREADS, smem));
     occ = std::max(occ, 1);
+    a.ngroups = j.windows_only ? h->h_win.ngroups_active[CF::NU - 2] : CF::NGROUPS;
+    if (a.ngroups == 0) return 0;
     const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
-    // persistent grid, exactly one wave: as many warps as can be resident, split into ranges of ntile2 warps
-    const long long resident_warps = (long long)occ * h->sm_count * WARPS_PER_CTA;
-    long long nranges = std::max<long long>(1, resident_warps / a.ntile2);
+    // persistent grid, exactly one wave: as many warps as can be resident, split into ranges of ngroups warps
+    const long long resident_warps = (long long)occ * h->sm_count * CF::WARPS;
+    long long nranges = std::max<long long>(1, resident_warps / a.ngroups);
     nranges = std::min(nranges, nchunks);
     a.nranges = (int)nranges;
-    const long long warps = nranges * a.ntile2;
-    const unsigned grid = (unsigned)((warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    const long long warps = nranges * a.ngroups;
+    const unsigned grid = (unsigned)((warps + CF::WARPS - 1) / CF::WARPS);
     {
         ProfScope ps(h, 0, st);
-        kern<<<grid, CTA_THREADS, smem, st>>>(a);
+        kern<<<grid, CF::THREADS, smem, st>>>(a);
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -233,19 +243,19 @@ static int dispatch_bands(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaS
     constexpr unsigned BRF = 1u << O_RSOT, FOUR = 0xFu, LEAF = (1u << O_LEAF_R) | (1u << O_LEAF_T);
     switch (j.mode) {
         case MODE_PROSAIL:
-            if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, BRF, 0>(h, a, st);
-            if (planes == FOUR && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, FOUR, 0>(h, a, st);
-            if (planes == 0 && j.mean_mask == BRF && !j.f32_means) return launch_bands<T, MODE_PROSAIL, 0, BRF>(h, a, st);
-            return launch_bands<T, MODE_PROSAIL, RUNTIME, 0>(h, a, st);
+            if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, BRF, 0>(h, j, a, st);
+            if (planes == FOUR && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, FOUR, 0>(h, j, a, st);
+            if (planes == 0 && j.mean_mask == BRF && !j.f32_means) return launch_bands<T, MODE_PROSAIL, 0, BRF>(h, j, a, st);
+            return launch_bands<T, MODE_PROSAIL, RUNTIME, 0>(h, j, a, st);
         case MODE_SAIL:
-            if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_SAIL, BRF, 0>(h, a, st);
-            if (planes == FOUR && !j.mean_mask) return launch_bands<T, MODE_SAIL, FOUR, 0>(h, a, st);
-            return launch_bands<T, MODE_SAIL, RUNTIME, 0>(h, a, st);
+            if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_SAIL, BRF, 0>(h, j, a, st);
+            if (planes == FOUR && !j.mean_mask) return launch_bands<T, MODE_SAIL, FOUR, 0>(h, j, a, st);
+            return launch_bands<T, MODE_SAIL, RUNTIME, 0>(h, j, a, st);
         case MODE_PROSPECT:
-            if (planes == LEAF && !j.mean_mask) return launch_bands<T, MODE_PROSPECT, LEAF, 0>(h, a, st);
-            return launch_bands<T, MODE_PROSPECT, RUNTIME, 0>(h, a, st);
+            if (planes == LEAF && !j.mean_mask) return launch_bands<T, MODE_PROSPECT, LEAF, 0>(h, j, a, st);
+            return launch_bands<T, MODE_PROSPECT, RUNTIME, 0>(h, j, a, st);
         default:
-            return launch_bands<T, MODE_SOIL, RUNTIME, 0>(h, a, st);
+            return launch_bands<T, MODE_SOIL, RUNTIME, 0>(h, j, a, st);
     }
 }
 
@@ -330,10 +340,7 @@ static int run_device_t(prosail_handle* h, const Job& j, Work& w, cudaStream_t s
         a.nmean = j.nmean;
         a.only_active_tiles = j.windows_only;
         a.f32_means = j.f32_means;
-        a.ntile2 = j.windows_only ? h->h_win.ntiles2_active : NT2;
-        if (a.ntile2 > 0) {
-            if ((rc = dispatch_bands(h, j, a, st))) return rc;
-        }
+        if ((rc = dispatch_bands(h, j, a, st))) return rc;
         if (j.nmean > 0) {
             const long long rows = ni * j.nmean, total = rows * nw;
             const unsigned blocks = (unsigned)((total + 255) / 256);
@@ -648,8 +655,12 @@ int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, co
     m.ntotal = slot;
     for (int t = 0; t < NTILES; ++t)
         if (touched[t]) m.active_tile[m.ntiles_active++] = t;
-    for (int t = 0; t < NT2; ++t)
-        if (touched[2 * t] || touched[2 * t + 1]) m.active_tile2[m.ntiles2_active++] = t;
+    for (int nu = 2; nu <= 3; ++nu)          // groups of nu tiles touched by a window (the windows-only kernels visit only those)
+        for (int g = 0; g < NTILES / nu; ++g) {
+            bool any = false;
+            for (int u = 0; u < nu; ++u) any = any || touched[nu * g + u];
+            if (any) m.active_group[nu - 2][m.ngroups_active[nu - 2]++] = g;
+        }
     DeviceGuard guard(h->device);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h->d_win, &m, sizeof m, cudaMemcpyHostToDevice));

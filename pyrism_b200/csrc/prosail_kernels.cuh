@@ -1,12 +1,12 @@
 // sm_100a kernels for the batched PROSPECT-5/D -> 4SAIL -> band-mean path.
 //
-// Mapping (band kernel): one THREAD owns TWO wavelengths (b and b + 32) and keeps their constants
-// (6-7 specific absorption coefficients, 3 interface transmissivities, 2 soil spectra) in registers;
-// a WARP owns 64 consecutive bands (33 double tiles cover 2101 bands, 99.5% lane efficiency) and walks
-// over the work items (parameter set x geometry).  The two bands of a thread are two independent
+// Mapping (band kernel): one THREAD owns NU wavelengths (b, b + 32, ...; NU = 2 or 3, struct Cfg) and keeps their
+// interface constants in registers (absorption coefficients and soil spectra in shared memory);
+// a WARP owns NU x 32 consecutive bands (66 32-band tiles cover 2101 bands, 99.5% lane efficiency) and walks
+// over the work items (parameter set x geometry).  The NU bands of a thread are independent
 // dependency chains in one instruction stream: the path is bound by the FP64 pipe (DFMA latency 8.6
-// cycles at one warp instruction per 2 cycles per SM sub-partition, measured), and with ~4 resident warps
-// per sub-partition it is this 2-way ILP that keeps the pipe fed.  Rare cases (arguments outside the tau
+// cycles at one warp instruction per 2 cycles per SM sub-partition, measured), and with 3-4 resident warps
+// per sub-partition it is this instruction-level parallelism that keeps the pipe fed.  Rare cases (arguments outside the tau
 // table, zero absorption, the J1 series branch) are flagged in the branch-free fast path and repaired
 // afterwards, so that the hot loop is a handful of large basic blocks the scheduler can interleave.
 // Per-item scalars come from 128-byte records that the prologue kernel packs and that each CTA stages
@@ -35,9 +35,21 @@ namespace pb {
 constexpr int NB = 2101;          // wavelengths 400..2500 nm
 constexpr int NTILES = 66;        // 32-band tiles (unit of the band-mean window map)
 constexpr int NBP = NTILES * 32;  // padded band count (2112)
-constexpr int NT2 = NTILES / 2;   // 64-band double tiles, one per warp
-constexpr int WARPS_PER_CTA = PB_WARPS;
-constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int NT2 = NTILES / 2;   // most tile groups a kernel configuration can have (NU = 2: 33 groups of 64 bands)
+
+// Kernel configuration: NU wavelengths per thread (NU independent dependency chains in one instruction stream) and
+// WARPS warps per CTA (one CTA per SM in fp64; the register file holds WARPS x 32 x (65536 / (WARPS x 32)) registers).
+//   Cfg<2, 16>: 128 registers per thread, 4 warps x 2 chains per SM sub-partition
+//   Cfg<3, 12>: 168 registers per thread, 3 warps x 3 chains per SM sub-partition (22 groups of 96 bands)
+template <int NU_, int WARPS_>
+struct Cfg {
+    static constexpr int NU = NU_;                     // bands per thread: band0 + 32 u
+    static constexpr int WARPS = WARPS_;
+    static constexpr int THREADS = WARPS_ * 32;
+    static constexpr int KSTRIDE = NU_ * THREADS;      // elements per plane of SailSmem::kc: [u][thread]
+    static constexpr int NGROUPS = NTILES / NU_;       // groups of NU 32-band tiles, one per warp
+    static_assert(NTILES % NU_ == 0, "the 66 tiles must split evenly into groups");
+};
 constexpr int CHUNK = PB_CHUNK;   // work items per shared-memory stage (per warp)
 constexpr int REC = 16;           // doubles per record (128 B)
 constexpr int MAX_TILE_SLOTS = 8; // windows that may overlap one 32-band tile
@@ -65,8 +77,8 @@ struct WindowMap {                       // which band-mean windows touch which 
     int nwindows, ntotal;
     int ntiles_active;                       // 32-band tiles touched by at least one window
     int active_tile[NTILES];
-    int ntiles2_active;                      // 64-band double tiles touched by at least one window
-    int active_tile2[NT2];
+    int ngroups_active[2];                   // [NU - 2]: groups of NU tiles touched by at least one window
+    int active_group[2][NT2];
 };
 
 template <typename T>
@@ -78,8 +90,8 @@ struct SailArgs {
     const T* grec;             // [nitems][REC]
     long long nitems;
     int G;                     // geometries per sample (item = s*G + g)
-    int ntile2;                // double tiles visited (33, or the active ones in windows-only mode)
-    int nranges;               // item-chunk ranges: warp gw works on double tile gw % ntile2, chunks gw / ntile2 + i * nranges
+    int ngroups;               // tile groups visited (all NTILES / NU, or the active ones in windows-only mode)
+    int nranges;               // item-chunk ranges: warp gw works on group gw % ngroups, chunks gw / ngroups + i * nranges
     // SAIL-only mode: leaf / soil spectra from memory, row pitch in elements (0 = one spectrum for all samples)
     const T* in_r; const T* in_t; const T* in_rho;
     long long in_pitch_r, in_pitch_t, in_pitch_rho;
@@ -126,14 +138,13 @@ struct alignas(128) Stage {
 };
 
 constexpr int KPLANES = 8;                 // kab kxc kan kbr kw km rs1 rs2: used once per item -> shared memory, not registers
-constexpr int KSTRIDE = 2 * CTA_THREADS;   // elements per plane: [u][thread]
 
-template <typename T>
+template <typename T, typename CF>
 struct alignas(128) SailSmem {
     typename Tables<T>::type mt;           // shared by the CTA, read-only after the prologue
-    Stage<T> stage[WARPS_PER_CTA][2];      // per-warp double-buffered record staging: no CTA-wide barrier in the loop
-    T kc[KPLANES * KSTRIDE];               // conflict-free: consecutive lanes read consecutive elements
-    uint64_t bar[WARPS_PER_CTA][2];
+    Stage<T> stage[CF::WARPS][2];          // per-warp double-buffered record staging: no CTA-wide barrier in the loop
+    T kc[KPLANES * CF::KSTRIDE];           // conflict-free: consecutive lanes read consecutive elements
+    uint64_t bar[CF::WARPS][2];
 };
 
 // issue the two bulk copies of one chunk (called by one thread)
@@ -162,7 +173,7 @@ template <typename T> __device__ __forceinline__ constexpr bool is_f32() { retur
 
 // PROSPECT for one band and one parameter set: leaf reflectance (ks) and transmittance (kt).
 // models.py:949-959 (kall, tau), 1019-1025 (one layer), 1043-1068 (Stokes, N layers).
-template <typename T>
+template <int KSTRIDE, typename T>
 __device__ __forceinline__ T leaf_kall(const T* __restrict__ kc, const T* __restrict__ s) {
     // kall = sum_i C_i K_i / N ; the division by N is folded into the record (C_i / N)      :950-951
     T kall = s[S_CAB] * kc[KC_KAB * KSTRIDE];
@@ -173,7 +184,7 @@ __device__ __forceinline__ T leaf_kall(const T* __restrict__ kc, const T* __rest
     return fma(s[S_CM], kc[KC_KM * KSTRIDE], kall);
 }
 // soil reflectance of the LSM mix, models.py:1917
-template <typename T>
+template <int KSTRIDE, typename T>
 __device__ __forceinline__ T soil_rho(const T* __restrict__ kc, const T* __restrict__ s) {
     return fma(s[S_SOIL1], kc[KC_RS1 * KSTRIDE], s[S_SOIL2] * kc[KC_RS2 * KSTRIDE]);
 }
@@ -196,7 +207,7 @@ __device__ __forceinline__ bool leaf_layers_fast(const BandConst<T>& c, T tau, T
     const T P12 = (p + t) * (p - t);
     const T qmt = q - t;                           // 1 - r - t: <= 0 flags zero absorption
     const T P34 = (q + t) * qmt;
-    const T D = sqrt_pos(P12 * P34);
+    const T D = sqrt_raw(P12 * P34);               // P34 <= 0 only when r + t >= 1: that lane is flagged and recomputed
     const T A = fma(T(-2), r, P12);                // 1 + r^2 - t^2
     const T hD = half * D;
     const T al = fma(half, A, hD);                 // a * r   (a of :1046)
@@ -313,41 +324,44 @@ __device__ __noinline__ void leaf_exact_f32(const BandConst<float>& c, float kal
     refl = (float)(Ra + Ta * Rsub * t / den);
 }
 
-// both bands of a thread: the two chains are independent and written back to back so that they interleave
-template <typename T, typename MT>
-__device__ __forceinline__ void leaf_optics2(const BandConst<T> (&c)[2], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
-                                             T (&refl)[2], T (&tran)[2]) {
-    T kall[2];
-    bool rare[2];
+// all NU bands of a thread: the chains are independent and written back to back so that they interleave
+template <typename CF, typename T, typename MT>
+__device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
+                                            T (&refl)[CF::NU], T (&tran)[CF::NU]) {
+    constexpr int NU = CF::NU;
+    T kall[NU];
+    bool rare[NU];
+    bool any_rare = false;
     const T nm1 = s[S_NM1];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) kall[u] = leaf_kall(kc + u * CTA_THREADS, s);
+    for (int u = 0; u < NU; ++u) kall[u] = leaf_kall<CF::KSTRIDE>(kc + u * CF::THREADS, s);
     if constexpr (std::is_same<T, float>::value) {
-        float omt[2];
+        float omt[NU];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) omt[u] = kall[u] * tau_fast(kall[u], mt.tau, rare[u]);     // 1 - tau = k g(k)
+        for (int u = 0; u < NU; ++u) omt[u] = kall[u] * tau_fast(kall[u], mt.tau, rare[u]);     // 1 - tau = k g(k)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) leaf_layers_f32(c[u], omt[u], nm1, refl[u], tran[u]);
-        if (__builtin_expect(rare[0] | rare[1], 0)) {
+        for (int u = 0; u < NU; ++u) { leaf_layers_f32(c[u], omt[u], nm1, refl[u], tran[u]); any_rare |= rare[u]; }
+        if (__builtin_expect(any_rare, 0)) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < NU; ++u)
                 if (rare[u]) leaf_exact_f32(c[u], kall[u], nm1, refl[u], tran[u]);
         }
     } else {
-        T tau[2];
-        bool zero[2];
+        T tau[NU];
+        bool zero[NU];
+        bool any_zero = false;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) tau[u] = tau_fast(kall[u], mt.tau, rare[u]);               // :953-957
-        if (__builtin_expect(rare[0] | rare[1], 0)) {
+        for (int u = 0; u < NU; ++u) { tau[u] = tau_fast(kall[u], mt.tau, rare[u]); any_rare |= rare[u]; }   // :953-957
+        if (__builtin_expect(any_rare, 0)) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < NU; ++u)
                 if (rare[u]) tau[u] = tau_rare(kall[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) zero[u] = leaf_layers_fast(c[u], tau[u], nm1, mt, refl[u], tran[u]);
-        if (__builtin_expect(zero[0] | zero[1], 0)) {
+        for (int u = 0; u < NU; ++u) { zero[u] = leaf_layers_fast(c[u], tau[u], nm1, mt, refl[u], tran[u]); any_zero |= zero[u]; }
+        if (__builtin_expect(any_zero, 0)) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < NU; ++u)
                 if (zero[u]) leaf_zero_absorption(c[u], tau[u], nm1, refl[u], tran[u]);
         }
     }
@@ -359,13 +373,19 @@ struct Diffuse {
     T m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd;
 };
 
-template <typename T, typename MT>
+// FROM_LEAF: rho, tau come from the PROSPECT stage of the same kernel.  Then 0 < rho, tau and rho + tau < 1 hold by
+// construction (rho >= the interface reflectance, absorption > 0 or the zero-absorption branch), so sigb, sigf are never
+// zero (the 1e-36 floors of models.py:593-598 cannot fire) and att^2 - sigb^2 = (1 - rho - tau)(...) stays positive unless
+// rho + tau rounds to 1, which sqrt_pos still guards.  With spectra supplied by the caller (SAIL mode) the floors are kept.
+template <bool FROM_LEAF, typename T, typename MT>
 __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __restrict__ s, const MT& mt, Diffuse<T>& d) {
     const T one = T(1), tiny = T(1e-36);
     T sigb = fma(s[S_DDB], rho, s[S_DDF] * tau);                      // :590
     T sigf = fma(s[S_DDF], rho, s[S_DDB] * tau);                      // :591
-    sigb = is_zero(sigb) ? tiny : sigb;                               // :594-595 (tests on the integer pipe)
-    sigf = is_zero(sigf) ? tiny : sigf;
+    if (!FROM_LEAF) {
+        sigb = is_zero(sigb) ? tiny : sigb;                           // :594-595 (tests on the integer pipe)
+        sigf = is_zero(sigf) ? tiny : sigf;
+    }
     const T att = one - sigf;                                         // :600
     if constexpr (std::is_same<T, float>::value) {
         // float: m^2 = (att - sigb)(att + sigb) and rinf = sigb/(att + m) avoid the two cancellations of :601, :639
@@ -379,9 +399,13 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
     const T e2 = d.e1 * d.e1;
     const T rinf2 = d.rinf * d.rinf;
     d.re = d.rinf * d.e1;
-    d.invden = rcp(fma(-rinf2, e2, one));                             // :642
     const T omr2 = one - rinf2;
-    d.inv_omr2 = rcp(omr2);
+    {   // 1/(1 - rinf^2 e^2) (:642) and 1/(1 - rinf^2) (:678) from ONE reciprocal of their product: one MUFU less
+        const T den = fma(-rinf2, e2, one);
+        const T r = rcp(den * omr2);
+        d.invden = r * omr2;
+        d.inv_omr2 = r * den;
+    }
     d.tdd = omr2 * d.e1 * d.invden;                                   // :654
     d.rdd = d.rinf * (one - e2) * d.invden;                           // :655
     d.rsrdd = rs * d.rdd;
@@ -450,7 +474,10 @@ __device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const 
     } else {
         // 1/(k-m) and 1/(k+m) from ONE reciprocal of (k-m)(k+m)                             :644-647, 765-789
         const bool rare = !(abs_gt_hi(km, thr_hi) && abs_gt_hi(Km, thr_hi));
-        const T ik = rcp(km * kp), iK = rcp(Km * Kp);
+        // ... and both of those from one reciprocal of (k-m)(k+m)(K-m)(K+m)
+        const T pk = km * kp, pK = Km * Kp;
+        const T rr = rcp(pk * pK);
+        const T ik = rr * pK, iK = rr * pk;
         const T J1ks = (d.e1 - tss) * (ik * kp);
         const T J1ko = (d.e1 - too) * (iK * Kp);
         sail_couple(rho, tau, rs, d, g, J1ks, J1ko, ik * km, iK * Km, need, o);
@@ -517,72 +544,88 @@ enum { MODE_PROSAIL = 0, MODE_SAIL = 1, MODE_PROSPECT = 2, MODE_SOIL = 3 };
 // kernels, where per-item pointer tests, predicated stores and call overhead would cost issue slots.
 constexpr unsigned RUNTIME = 0x80000000u;
 
-template <typename T>
+template <typename T, int NU>
 struct EmitCtx {
     const SailArgs<T>& a;
-    bool valid[2];       // band u of this thread exists (< 2101)
-    int tile[2];         // 32-band tile of band u (index into the window map)
+    bool valid[NU];      // band u of this thread exists (< 2101)
+    int tile0;           // 32-band tile of band 0 (band u is in tile0 + u): index into the window map
     int lane, nt;
-    long long orow;      // item * pitch + band[0]   (band[1] = band[0] + 32)
+    long long orow;      // item * pitch + band[0]   (band[u] = band[0] + 32 u)
     T* pdst;             // partial sums of this item
     int mi;              // running index of the mean plane
 };
 
-template <unsigned PLANES, unsigned MEANS, int PLANE, typename T>
-__device__ __forceinline__ void emit(EmitCtx<T>& e, T v0, T v1) {
+template <unsigned PLANES, unsigned MEANS, int PLANE, typename T, int NU>
+__device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
     if (PLANES == RUNTIME) {
         if (e.a.out[PLANE]) {
-            if (e.valid[0]) __stcs(e.a.out[PLANE] + e.orow, v0);
-            if (e.valid[1]) __stcs(e.a.out[PLANE] + e.orow + 32, v1);
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                if (e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
         }
         if (e.a.mean_mask & (1u << PLANE)) {
-            mean_partials(e.a.win, v0, e.tile[0], e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
-            mean_partials(e.a.win, v1, e.tile[1], e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+#pragma unroll
+            for (int u = 0; u < NU; ++u) mean_partials(e.a.win, v[u], e.tile0 + u, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
             ++e.mi;
         }
     } else {
         if ((PLANES >> PLANE) & 1u) {
-            if (e.valid[0]) __stcs(e.a.out[PLANE] + e.orow, v0);
-            if (e.valid[1]) __stcs(e.a.out[PLANE] + e.orow + 32, v1);
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                if (e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
         }
         if ((MEANS >> PLANE) & 1u) {
-            mean_partials_inl(e.a.win, v0, e.tile[0], e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
-            mean_partials_inl(e.a.win, v1, e.tile[1], e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+#pragma unroll
+            for (int u = 0; u < NU; ++u) mean_partials_inl(e.a.win, v[u], e.tile0 + u, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
             ++e.mi;
         }
     }
 }
+// the same value for every band of the thread (bare-soil constants)
+template <unsigned PLANES, unsigned MEANS, int PLANE, typename T, int NU>
+__device__ __forceinline__ void emit_const(EmitCtx<T, NU>& e, T c) {
+    T v[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) v[u] = c;
+    emit<PLANES, MEANS, PLANE>(e, v);
+}
 
-// resident CTAs per SM the kernel is compiled for: double needs 128 registers (16 warps fill the register file);
-// float fits in 64, so two CTAs share an SM and cover the MUFU / LDS latencies with twice the warps
+// resident CTAs per SM the kernel is compiled for: double needs 65536 / threads registers (one CTA fills the register
+// file); float fits in half of that, so two CTAs share an SM and cover the MUFU / LDS latencies with twice the warps
 template <typename T> __host__ __device__ constexpr int min_ctas() { return std::is_same<T, float>::value ? 2 : PB_MIN_CTAS; }
 
+// per-plane values of all bands of a thread, gathered from the per-band structs
+#define PB_GATHER(dst, arr, field)                       \
+    T dst[NU];                                           \
+    _Pragma("unroll") for (int u = 0; u < NU; ++u) dst[u] = arr[u].field
+
 // ---------------------------------------------------------------------------------------------
-// main kernel.  1-D grid of independent warps: warp gw owns the 64-band double tile gw % ntile2 and walks the item
-// chunks gw / ntile2, + nranges, + 2 nranges, ...  The CTA only shares the read-only math tables.
+// main kernel.  1-D grid of independent warps: warp gw owns the tile group gw % ngroups (NU x 32 consecutive bands) and
+// walks the item chunks gw / ngroups, + nranges, + 2 nranges, ...  The CTA only shares the read-only math tables.
 // ---------------------------------------------------------------------------------------------
 // G1 = true: one geometry per parameter set (the LUT shape) -- every item starts a new parameter set, so nothing
 // is carried between loop iterations and the register allocator sees purely loop-local state.
-template <typename T, int MODE, unsigned PLANES, unsigned MEANS, bool G1>
-__global__ void __launch_bounds__(CTA_THREADS, min_ctas<T>()) k_bands(const SailArgs<T> a) {
+template <typename T, typename CF, int MODE, unsigned PLANES, unsigned MEANS, bool G1>
+__global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const SailArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename Tables<T>::type MT;
-    SailSmem<T>& sm = *reinterpret_cast<SailSmem<T>*>(smem_raw);
+    constexpr int NU = CF::NU;
+    SailSmem<T, CF>& sm = *reinterpret_cast<SailSmem<T, CF>*>(smem_raw);
     const T zero_ = T(0), one = T(1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * WARPS_PER_CTA + warp;                 // global warp id
-    const int range = gw / a.ntile2;
-    const int tslot = gw - range * a.ntile2;
+    const int gw = blockIdx.x * CF::WARPS + warp;                     // global warp id
+    const int range = gw / a.ngroups;
+    const int tslot = gw - range * a.ngroups;
     const bool live = range < a.nranges;
-    const int t2 = !live ? 0 : (a.only_active_tiles ? a.win->active_tile2[tslot] : tslot);
-    const int band0 = t2 * 64 + lane;      // this thread's bands: band0 and band0 + 32
+    const int grp = !live ? 0 : (a.only_active_tiles ? a.win->active_group[NU - 2][tslot] : tslot);
+    const int band0 = grp * (32 * NU) + lane;      // this thread's bands: band0 + 32 u
     Stage<T>* const stage = sm.stage[warp];
     uint64_t* const bar = sm.bar[warp];
 
     {   // math tables -> shared memory
         const uint4* src = reinterpret_cast<const uint4*>(a.tables);
         uint4* dst = reinterpret_cast<uint4*>(&sm.mt);
-        for (int i = threadIdx.x; i < (int)(sizeof(MT) / 16); i += CTA_THREADS) dst[i] = src[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(MT) / 16); i += CF::THREADS) dst[i] = src[i];
     }
     if (lane == 0) {
         mbar_init(&bar[0], 1);
@@ -595,15 +638,16 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas<T>()) k_bands(const Sail
     long long chunk = live ? range : nchunks;
     if (lane == 0 && chunk < nchunks) stage_issue(a, &stage[0], &bar[0], chunk);
 
-    BandConst<T> c[2];
+    BandConst<T> c[NU];
     const T* kc = sm.kc + threadIdx.x;             // this thread's column of the once-per-item constants
+    constexpr int KS = CF::KSTRIDE;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const T* bc = a.bandc + (live ? band0 + 32 * u : 0);          // NBP = 33 * 64: always in range
-        T* k = sm.kc + u * CTA_THREADS + threadIdx.x;                 // only this thread reads these back: no barrier needed
-        k[KC_KAB * KSTRIDE] = bc[C_KAB * NBP]; k[KC_KXC * KSTRIDE] = bc[C_KXC * NBP]; k[KC_KAN * KSTRIDE] = bc[C_KAN * NBP];
-        k[KC_KBR * KSTRIDE] = bc[C_KBR * NBP]; k[KC_KW * KSTRIDE] = bc[C_KW * NBP]; k[KC_KM * KSTRIDE] = bc[C_KM * NBP];
-        k[KC_RS1 * KSTRIDE] = bc[C_RS1 * NBP]; k[KC_RS2 * KSTRIDE] = bc[C_RS2 * NBP];
+    for (int u = 0; u < NU; ++u) {
+        const T* bc = a.bandc + (live ? band0 + 32 * u : 0);          // NBP = 66 * 32: always in range
+        T* k = sm.kc + u * CF::THREADS + threadIdx.x;                 // only this thread reads these back: no barrier needed
+        k[KC_KAB * KS] = bc[C_KAB * NBP]; k[KC_KXC * KS] = bc[C_KXC * NBP]; k[KC_KAN * KS] = bc[C_KAN * NBP];
+        k[KC_KBR * KS] = bc[C_KBR * NBP]; k[KC_KW * KS] = bc[C_KW * NBP]; k[KC_KM * KS] = bc[C_KM * NBP];
+        k[KC_RS1 * KS] = bc[C_RS1 * NBP]; k[KC_RS2 * KS] = bc[C_RS2 * NBP];
         c[u].talf = bc[C_TALF * NBP]; c[u].t12 = bc[C_T12 * NBP]; c[u].t21 = bc[C_T21 * NBP];
         if constexpr (std::is_same<T, float>::value) {      // the complements are uploaded (rounded from float64) instead of being recomputed in float
             c[u].ralf = bc[C_RALF * NBP]; c[u].r12 = bc[C_R12 * NBP]; c[u].r21 = bc[C_R21 * NBP];
@@ -639,48 +683,51 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas<T>()) k_bands(const Sail
             long long s = s0;
             int g = G1 ? 0 : (int)(i0 - s0 * a.G);
             bool fresh = true;
-            T rho[2] = {zero_, zero_}, tau[2] = {zero_, zero_}, rs[2] = {zero_, zero_};
-            Diffuse<T> d[2];
+            T rho[NU], tau[NU], rs[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) rho[u] = tau[u] = rs[u] = zero_;
+            Diffuse<T> d[NU];
             int thr_hi = 0;
             const T* sr = stage[buf].s;
             const T* gr = stage[buf].g;
-            EmitCtx<T> e{a, {band0 < NB, band0 + 32 < NB}, {2 * t2, 2 * t2 + 1}, lane, nt, i0 * a.out_pitch + band0,
-                         ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
+            EmitCtx<T, NU> e{a, {}, NU * grp, lane, nt, i0 * a.out_pitch + band0, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
+#pragma unroll
+            for (int u = 0; u < NU; ++u) e.valid[u] = band0 + 32 * u < NB;
             for (int j = 0; j < n; ++j) {
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) rs[u] = soil_rho(kc + u * CTA_THREADS, sr);
-                    emit<PLANES, MEANS, O_RHO>(e, rs[0], rs[1]);
+                    for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u * CF::THREADS, sr);
+                    emit<PLANES, MEANS, O_RHO>(e, rs);
                 } else if (MODE == MODE_PROSPECT) {
-                    leaf_optics2(c, kc, sr, sm.mt, rho, tau);
-                    emit<PLANES, MEANS, O_LEAF_R>(e, rho[0], rho[1]);
-                    emit<PLANES, MEANS, O_LEAF_T>(e, tau[0], tau[1]);
+                    leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
+                    emit<PLANES, MEANS, O_LEAF_R>(e, rho);
+                    emit<PLANES, MEANS, O_LEAF_T>(e, tau);
                     if (PLANES == RUNTIME && (a.mean_mask & (1u << O_RSOT))) {   // bits 0..2 double as ka / ke / om here
-                        T ka[2], ke[2], om[2];
+                        T ka[NU], ke[NU], om[NU];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {                            // models.py:1066-1068
+                        for (int u = 0; u < NU; ++u) {                           // models.py:1066-1068
                             ka[u] = one - rho[u] - tau[u];
                             ke[u] = rho[u] + ka[u];
                             om[u] = rho[u] / ke[u];
                         }
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            mean_partials(a.win, ka[u], e.tile[u], lane, e.pdst + e.mi * nt, a.f32_means);
-                            mean_partials(a.win, ke[u], e.tile[u], lane, e.pdst + (e.mi + 1) * nt, a.f32_means);
-                            mean_partials(a.win, om[u], e.tile[u], lane, e.pdst + (e.mi + 2) * nt, a.f32_means);
+                        for (int u = 0; u < NU; ++u) {
+                            mean_partials(a.win, ka[u], e.tile0 + u, lane, e.pdst + e.mi * nt, a.f32_means);
+                            mean_partials(a.win, ke[u], e.tile0 + u, lane, e.pdst + (e.mi + 1) * nt, a.f32_means);
+                            mean_partials(a.win, om[u], e.tile0 + u, lane, e.pdst + (e.mi + 2) * nt, a.f32_means);
                         }
                         e.mi += 3;
                     }
                 } else {
                     if (G1 || fresh) {
                         if (MODE == MODE_PROSAIL) {
-                            leaf_optics2(c, kc, sr, sm.mt, rho, tau);
+                            leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) rs[u] = soil_rho(kc + u * CTA_THREADS, sr);
+                            for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u * CF::THREADS, sr);
                         } else {
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
+                            for (int u = 0; u < NU; ++u) {
                                 const int bb = e.valid[u] ? band0 + 32 * u : 0;
                                 rho[u] = a.in_r[s * a.in_pitch_r + bb];
                                 tau[u] = a.in_t[s * a.in_pitch_t + bb];
@@ -688,44 +735,51 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas<T>()) k_bands(const Sail
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) sail_diffuse(rho[u], tau[u], rs[u], sr, sm.mt, d[u]);
+                        for (int u = 0; u < NU; ++u) sail_diffuse<MODE == MODE_PROSAIL>(rho[u], tau[u], rs[u], sr, sm.mt, d[u]);
                         // |k - m| lai <= 1e-3  <=>  |k - m| <= 1e-3 / lai   (threshold on the high word)
                         thr_hi = hi_word(sr[S_THR]);
                         fresh = false;
                     }
                     if (__builtin_expect(sr[S_NOCANOPY] != zero_, 0)) {          // lai <= 0: models.py:609-634
-                        emit<PLANES, MEANS, O_RSOT>(e, rs[0], rs[1]); emit<PLANES, MEANS, O_RDDT>(e, rs[0], rs[1]);
-                        emit<PLANES, MEANS, O_RSDT>(e, rs[0], rs[1]); emit<PLANES, MEANS, O_RDOT>(e, rs[0], rs[1]);
-                        emit<PLANES, MEANS, O_RSO>(e, zero_, zero_); emit<PLANES, MEANS, O_RDD>(e, zero_, zero_);
-                        emit<PLANES, MEANS, O_TDD>(e, one, one); emit<PLANES, MEANS, O_RSD>(e, zero_, zero_);
-                        emit<PLANES, MEANS, O_TSD>(e, zero_, zero_); emit<PLANES, MEANS, O_RDO>(e, zero_, zero_);
-                        emit<PLANES, MEANS, O_TDO>(e, zero_, zero_);
+                        emit<PLANES, MEANS, O_RSOT>(e, rs); emit<PLANES, MEANS, O_RDDT>(e, rs);
+                        emit<PLANES, MEANS, O_RSDT>(e, rs); emit<PLANES, MEANS, O_RDOT>(e, rs);
+                        emit_const<PLANES, MEANS, O_RSO>(e, zero_); emit_const<PLANES, MEANS, O_RDD>(e, zero_);
+                        emit_const<PLANES, MEANS, O_TDD>(e, one); emit_const<PLANES, MEANS, O_RSD>(e, zero_);
+                        emit_const<PLANES, MEANS, O_TSD>(e, zero_); emit_const<PLANES, MEANS, O_RDO>(e, zero_);
+                        emit_const<PLANES, MEANS, O_TDO>(e, zero_);
                     } else {
-                        Canopy<T> o[2];
-                        bool rare[2];
+                        Canopy<T> o[NU];
+                        bool rare[NU];
+                        bool any_rare = false;
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < NU; ++u) {
                             o[u].rddt = o[u].rsdt = o[u].rdot = zero_;
                             rare[u] = sail_directional_fast(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
+                            any_rare |= rare[u];
                         }
                         if constexpr (!std::is_same<T, float>::value) {
-                            if (__builtin_expect(rare[0] | rare[1], 0)) {
+                            if (__builtin_expect(any_rare, 0)) {
 #pragma unroll
-                                for (int u = 0; u < 2; ++u)
+                                for (int u = 0; u < NU; ++u)
                                     if (rare[u]) sail_directional(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
                             }
                         }
-                        emit<PLANES, MEANS, O_RSOT>(e, o[0].rsot, o[1].rsot); emit<PLANES, MEANS, O_RDDT>(e, o[0].rddt, o[1].rddt);
-                        emit<PLANES, MEANS, O_RSDT>(e, o[0].rsdt, o[1].rsdt); emit<PLANES, MEANS, O_RDOT>(e, o[0].rdot, o[1].rdot);
-                        emit<PLANES, MEANS, O_RSO>(e, o[0].rso, o[1].rso); emit<PLANES, MEANS, O_RDD>(e, d[0].rdd, d[1].rdd);
-                        emit<PLANES, MEANS, O_TDD>(e, d[0].tdd, d[1].tdd); emit<PLANES, MEANS, O_RSD>(e, o[0].rsd, o[1].rsd);
-                        emit<PLANES, MEANS, O_TSD>(e, o[0].tsd, o[1].tsd); emit<PLANES, MEANS, O_RDO>(e, o[0].rdo, o[1].rdo);
-                        emit<PLANES, MEANS, O_TDO>(e, o[0].tdo, o[1].tdo);
+                        { PB_GATHER(v, o, rsot); emit<PLANES, MEANS, O_RSOT>(e, v); }
+                        { PB_GATHER(v, o, rddt); emit<PLANES, MEANS, O_RDDT>(e, v); }
+                        { PB_GATHER(v, o, rsdt); emit<PLANES, MEANS, O_RSDT>(e, v); }
+                        { PB_GATHER(v, o, rdot); emit<PLANES, MEANS, O_RDOT>(e, v); }
+                        { PB_GATHER(v, o, rso); emit<PLANES, MEANS, O_RSO>(e, v); }
+                        { PB_GATHER(v, d, rdd); emit<PLANES, MEANS, O_RDD>(e, v); }
+                        { PB_GATHER(v, d, tdd); emit<PLANES, MEANS, O_TDD>(e, v); }
+                        { PB_GATHER(v, o, rsd); emit<PLANES, MEANS, O_RSD>(e, v); }
+                        { PB_GATHER(v, o, tsd); emit<PLANES, MEANS, O_TSD>(e, v); }
+                        { PB_GATHER(v, o, rdo); emit<PLANES, MEANS, O_RDO>(e, v); }
+                        { PB_GATHER(v, o, tdo); emit<PLANES, MEANS, O_TDO>(e, v); }
                     }
-                    emit<PLANES, MEANS, O_KE>(e, d[0].m, d[1].m);
-                    emit<PLANES, MEANS, O_LEAF_R>(e, rho[0], rho[1]);
-                    emit<PLANES, MEANS, O_LEAF_T>(e, tau[0], tau[1]);
-                    emit<PLANES, MEANS, O_RHO>(e, rs[0], rs[1]);
+                    { PB_GATHER(v, d, m); emit<PLANES, MEANS, O_KE>(e, v); }
+                    emit<PLANES, MEANS, O_LEAF_R>(e, rho);
+                    emit<PLANES, MEANS, O_LEAF_T>(e, tau);
+                    emit<PLANES, MEANS, O_RHO>(e, rs);
                 }
                 gr += REC;
                 e.orow += a.out_pitch;
@@ -737,6 +791,7 @@ __global__ void __launch_bounds__(CTA_THREADS, min_ctas<T>()) k_bands(const Sail
         __syncwarp();      // all lanes are done with stage[buf] before lane 0 refills it in the next iteration
     }
 }
+#undef PB_GATHER
 
 // band means = ordered sum of a window's slot partials / band count
 template <typename T>
