@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 NB = 2101
 FLOPS_PER_BAND = 234            # PROSPECT 83 + 4SAIL 151, div/sqrt/exp/E1/pow counted as ONE flop each
 BYTES_PER_SPECTRUM = NB * 8     # one fp64 output plane
-NCU_DRAM_BYTES_PER_SPECTRUM = (4.378456e9 + 91.992576e6) / 262144   # measured, see profiles/r1_k_bands_prosail_brf.txt
+NCU_DRAM_BYTES_PER_SPECTRUM = (4.373978e9 + 89.854720e6) / 262144   # measured, see profiles/r1b_k_bands_prosail_brf_f64.txt
 SEED = 20261019 + 2             # config index 2
 GEOM_DEG = (35.0, 30.0, 50.0)
 
@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=0, help="CPU baseline sample (0 = 4000 per core)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the secondary fp32-mode measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -259,6 +260,32 @@ def main():
         ms = float(t.item())
     value = world * S * args.steps / (ms * 1e-3)
 
+    # ---- the same workload in the fp32 mode of the kernels (north star: <= 1e-5 absolute; a secondary number) ------
+    fp32 = None
+    if not args.no_fp32:
+        out32 = eng.empty((S, NB), np.float32)
+
+        def step32():
+            eng.prosail_device(S, leaf, soil, canopy, {capi.O_RSOT: out32}, pitch=NB, version='5', lidf_type='campbell', n_geom=1,
+                               dtype=np.float32)
+        for _ in range(3):
+            step32()
+        barrier()
+        n32 = max(3, args.steps // 3)
+        eng.timer_begin()
+        for _ in range(n32):
+            step32()
+        ms32 = eng.timer_end()
+        barrier()
+        if dist is not None:
+            t = torch.tensor([ms32], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms32 = float(t.item())
+        fp32 = {"value": world * S * n32 / (ms32 * 1e-3), "unit": "spectra/s", "steps": n32, "ms_per_step": ms32 / n32, "dtype": "f32",
+                "tolerance": "<= 1e-5 absolute vs the float64 reference (tests/test_gpu_fp32.py)",
+                "hbm_write_gbs": world * S * n32 * NB * 4 / (ms32 * 1e-3) / 1e9}
+        out32.free()
+
     # ---- end to end through the host-array API ----------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -311,7 +338,7 @@ def main():
                 "flops_per_band": FLOPS_PER_BAND, "kernel_ms_avg": k_avg, "kernel_launches": int(k_n),
                 "kernel_share_of_step": k_ms / ms if world == 1 else None,
                 # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-                # (profiles/r1_k_bands_prosail_brf.txt: 4.470 GB for 262144 spectra = 17053 B per spectrum), scaled to this launch
+                # (profiles/r1b_k_bands_prosail_brf_f64.txt: 4.464 GB for 262144 spectra = 17028 B per spectrum), scaled to this launch
                 "traffic": spectra_per_launch * NCU_DRAM_BYTES_PER_SPECTRUM,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
@@ -329,7 +356,7 @@ def main():
     line = {"metric": "PROSAIL spectra/s (2101 bands, fp64)", "value": value, "unit": "spectra/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(S, world), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "fp32_mode": fp32,
             "device": eng.device_info()["name"]}
     print(json.dumps(line))
     if dist is not None:

@@ -60,6 +60,9 @@ enum {
     PROSAIL_O_LEAF_R,   /* PROSPECT.ks (leaf reflectance, models.py:1065) */
     PROSAIL_O_LEAF_T,   /* PROSPECT.kt (leaf transmittance, models.py:1064) */
     PROSAIL_O_RHO,      /* LSM.ref (soil reflectance, models.py:1917) */
+    PROSAIL_O_LEAF_KA,  /* PROSPECT.ka = 1 - ks - kt (models.py:1066); prosail_prospect_* only */
+    PROSAIL_O_LEAF_KE,  /* PROSPECT.ke = ks + ka     (models.py:1067) */
+    PROSAIL_O_LEAF_OM,  /* PROSPECT.om = ks / ke     (models.py:1068) */
     PROSAIL_NOUT
 };
 
@@ -128,10 +131,11 @@ int prosail_set_soil_tables(prosail_handle_t* h, const float* rsoil1, const floa
 int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm);
 
 /* ---- the hot path ------------------------------------------------------------------------------------ */
-/* pyrism.PROSPECT(...) for n parameter sets (models.py:900-921): ks -> out ks, kt -> out kt ([n][pitch]).
+/* pyrism.PROSPECT(...) for n parameter sets (models.py:900-921): spectra ks, kt and (optional, NULL = not wanted)
+ * ka, ke, om (models.py:1064-1068), each [n][pitch].
  * means_f32 (optional) = float32 window means of (ks, kt, ka, ke, om), [n][5][n_windows]  (models.py:1071-1195). */
 int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, double* ks, double* kt,
-                         long long pitch, float* means_f32, int on_host, void* stream);
+                         double* ka, double* ke, double* om, long long pitch, float* means_f32, int on_host, void* stream);
 
 /* pyrism.LSM(reflectance, moisture) for n parameter sets (models.py:1908-1920): rho [n][pitch];
  * means_f32 (optional) [n][1][n_windows] float32 (models.py:1918-2006). */
@@ -157,7 +161,7 @@ int prosail_prosail_f64(prosail_handle_t* h, int version, long long n, const pro
 
 /* fp32 mode of the four entry points above: same semantics, float spectra in and out (tolerance 1e-5 absolute). */
 int prosail_prospect_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, float* ks, float* kt,
-                         long long pitch, float* means_f32, int on_host, void* stream);
+                         float* ka, float* ke, float* om, long long pitch, float* means_f32, int on_host, void* stream);
 int prosail_soil_f32(prosail_handle_t* h, long long n, const prosail_soil_t* soil, float* rho, long long pitch,
                      float* means_f32, int on_host, void* stream);
 int prosail_sail_f32(prosail_handle_t* h, long long n, const float* ks, long long pitch_ks, const float* kt,

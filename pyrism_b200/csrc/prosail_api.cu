@@ -65,11 +65,12 @@ struct DevBuf {
 
 struct Work {            // per-stream scratch
     DevBuf srec, grec, partial;
+    DevBuf lidf;         // [samples][18] LIDF workspace (multi-geometry jobs)
     DevBuf in;           // host mode: parameter slices
     DevBuf out;          // host mode: output planes / means / geom of one slab
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    void release() { srec.release(); grec.release(); partial.release(); in.release(); out.release(); }
+    void release() { srec.release(); grec.release(); partial.release(); lidf.release(); in.release(); out.release(); }
 };
 
 struct prosail_handle {
@@ -311,7 +312,14 @@ static int run_device_t(prosail_handle* h, const Job& j, Work& w, cudaStream_t s
         {
             ProfScope ps(h, 1, st);
             if (ni >= h->prologue_thread_min) {     // throughput variant: one thread per item
-                k_prologue_t<T><<<(unsigned)((ni + 127) / 128), 128, 0, st>>>(p, h->d_angles);
+                if (j.has_canopy && G > 1) {        // LIDF once per parameter set, not once per (set, geometry)
+                    if ((rc = w.lidf.reserve((size_t)ns * PROSAIL_NLIDF * 8))) return rc;
+                    k_lidf<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(p, h->d_angles, (double*)w.lidf.p);
+                    h->launches++;
+                    k_prologue_t<T, true><<<(unsigned)((ni + 127) / 128), 128, 0, st>>>(p, h->d_angles, (const double*)w.lidf.p);
+                } else {
+                    k_prologue_t<T, false><<<(unsigned)((ni + 127) / 128), 128, 0, st>>>(p, h->d_angles, nullptr);
+                }
             } else {                                // latency variant: one warp per item, leaf bins across lanes
                 const long long threads = ni * 32;
                 k_prologue<T><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p);
@@ -465,7 +473,6 @@ static int run_host(prosail_handle* h, const Job& j) {
 
 static int run(prosail_handle* h, Job& j, int on_host, void* stream) {
     j.nmean = popcount(j.mean_mask);
-    if (j.mode == MODE_PROSPECT && j.mean_mask) j.nmean = 5;     // ks, kt, ka, ke, om
     int rc = validate(h, j);
     if (rc) return rc;
     DeviceGuard guard(h->device);
@@ -670,7 +677,7 @@ int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, co
 }
 
 static int prospect_impl(prosail_handle_t* h, bool f32, int version, long long n, const prosail_leaf_t* leaf, void* ks, void* kt,
-                         long long pitch, float* means_f32, int on_host, void* stream) {
+                         void* ka, void* ke, void* om, long long pitch, float* means_f32, int on_host, void* stream) {
     if (!leaf) return fail(PROSAIL_E_ARG, "null leaf struct");
     Job j;
     j.f32 = f32;
@@ -681,21 +688,24 @@ static int prospect_impl(prosail_handle_t* h, bool f32, int version, long long n
     j.leaf = *leaf;
     j.plane[O_LEAF_R] = ks;
     j.plane[O_LEAF_T] = kt;
+    j.plane[O_LEAF_KA] = ka;
+    j.plane[O_LEAF_KE] = ke;
+    j.plane[O_LEAF_OM] = om;
     j.pitch = pitch;
     if (means_f32) {
-        j.mean_mask = (1u << O_LEAF_R) | (1u << O_LEAF_T) | (1u << O_RSOT);   // + ka, ke, om
+        j.mean_mask = (1u << O_LEAF_R) | (1u << O_LEAF_T) | (7u << O_LEAF_KA);   // ks, kt, ka, ke, om in this order
         j.means_f32 = means_f32;
         j.f32_means = 1;
     }
     return run(h, j, on_host, stream);
 }
 int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, double* ks, double* kt,
-                         long long pitch, float* means_f32, int on_host, void* stream) {
-    return prospect_impl(h, false, version, n, leaf, ks, kt, pitch, means_f32, on_host, stream);
+                         double* ka, double* ke, double* om, long long pitch, float* means_f32, int on_host, void* stream) {
+    return prospect_impl(h, false, version, n, leaf, ks, kt, ka, ke, om, pitch, means_f32, on_host, stream);
 }
 int prosail_prospect_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, float* ks, float* kt,
-                         long long pitch, float* means_f32, int on_host, void* stream) {
-    return prospect_impl(h, true, version, n, leaf, ks, kt, pitch, means_f32, on_host, stream);
+                         float* ka, float* ke, float* om, long long pitch, float* means_f32, int on_host, void* stream) {
+    return prospect_impl(h, true, version, n, leaf, ks, kt, ka, ke, om, pitch, means_f32, on_host, stream);
 }
 
 static int soil_impl(prosail_handle_t* h, bool f32, long long n, const prosail_soil_t* soil, void* rho, long long pitch, float* means_f32,
@@ -769,6 +779,7 @@ static int sail_impl(prosail_handle_t* h, bool f32, long long n, const void* ks,
     j.in_rho = rho; j.prho = pitch_rho;
     copy_out(j, out);
     if (j.mean_mask & ((1u << O_LEAF_R) | (1u << O_LEAF_T) | (1u << O_RHO))) return fail(PROSAIL_E_ARG, "means of input spectra are not provided by prosail_sail_*");
+    if ((j.mean_mask >> O_LEAF_KA) || j.plane[O_LEAF_KA] || j.plane[O_LEAF_KE] || j.plane[O_LEAF_OM]) return fail(PROSAIL_E_ARG, "ka / ke / om are outputs of prosail_prospect_* only");
     return run(h, j, on_host, stream);
 }
 }

@@ -66,7 +66,8 @@ enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DD
 enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_BF, G_SUMINT, G_ALF };
 
 // output planes (bit index in out_mask / mean_mask)
-enum { O_RSOT = 0, O_RDDT, O_RSDT, O_RDOT, O_RSO, O_RDD, O_TDD, O_RSD, O_TSD, O_RDO, O_TDO, O_KE, O_LEAF_R, O_LEAF_T, O_RHO, NOUT };
+enum { O_RSOT = 0, O_RDDT, O_RSDT, O_RDOT, O_RSO, O_RDD, O_TDD, O_RSD, O_TSD, O_RDO, O_TDO, O_KE, O_LEAF_R, O_LEAF_T, O_RHO,
+       O_LEAF_KA, O_LEAF_KE, O_LEAF_OM, NOUT };   // the last three: PROSPECT's ka, ke, om (models.py:1066-1068), PROSPECT mode only
 
 struct WindowMap {                       // which band-mean windows touch which warp tile
     int nslots[NTILES];
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                     leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
                     emit<PLANES, MEANS, O_LEAF_R>(e, rho);
                     emit<PLANES, MEANS, O_LEAF_T>(e, tau);
-                    if (PLANES == RUNTIME && (a.mean_mask & (1u << O_RSOT))) {   // bits 0..2 double as ka / ke / om here
+                    if (PLANES == RUNTIME && (need & (7u << O_LEAF_KA))) {       // absorptance, extinction, single-scattering albedo
                         T ka[NU], ke[NU], om[NU];
 #pragma unroll
                         for (int u = 0; u < NU; ++u) {                           // models.py:1066-1068
@@ -711,13 +712,9 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                             ke[u] = rho[u] + ka[u];
                             om[u] = rho[u] / ke[u];
                         }
-#pragma unroll
-                        for (int u = 0; u < NU; ++u) {
-                            mean_partials(a.win, ka[u], e.tile0 + u, lane, e.pdst + e.mi * nt, a.f32_means);
-                            mean_partials(a.win, ke[u], e.tile0 + u, lane, e.pdst + (e.mi + 1) * nt, a.f32_means);
-                            mean_partials(a.win, om[u], e.tile0 + u, lane, e.pdst + (e.mi + 2) * nt, a.f32_means);
-                        }
-                        e.mi += 3;
+                        emit<PLANES, MEANS, O_LEAF_KA>(e, ka);
+                        emit<PLANES, MEANS, O_LEAF_KE>(e, ke);
+                        emit<PLANES, MEANS, O_LEAF_OM>(e, om);
                     }
                 } else {
                     if (G1 || fresh) {
@@ -1048,47 +1045,9 @@ struct AngleTables {            // filled on the host by prosail_create with the
     double edge[19];            // the edges in radians as LIDF.verhoef computes them (np.radians(angle), models.py:372)
 };
 
-template <typename T>
-__global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const AngleTables* __restrict__ at) {
-    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nitems = a.nsamples * a.G;
-    if (item >= nitems) return;
-    const long long s = item / a.G;
-    const int g = (int)(item - s * a.G);
-
-    double srec[REC];
-#pragma unroll
-    for (int i = 0; i < REC; ++i) srec[i] = 0.0;
-    if (g == 0) {
-        if (a.has_leaf) {
-            const double N = a.N[s];
-            srec[S_CAB] = a.Cab[s] / N; srec[S_CXC] = a.Cxc[s] / N; srec[S_CAN] = a.Can ? a.Can[s] / N : 0.0;
-            srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
-            srec[S_NM1] = N - 1.0;
-        }
-        if (a.has_soil) {
-            const double sr = a.soil_refl[s], mo = a.soil_moist[s];
-            srec[S_SOIL1] = sr * mo;              // rho = sRef (moisture rsoil1 + (1-moisture) rsoil2), models.py:1917
-            srec[S_SOIL2] = sr * (1.0 - mo);
-        }
-    }
-    if (!a.has_canopy) {
-        if (g == 0) store_rec<T>(a.srec, s, srec);
-        return;
-    }
-
-    const double lai = a.lai[s], hot = a.hot[s];
-    const double la = a.lidf_a[s], lb = a.lidf_b ? a.lidf_b[s] : 0.0;
-    const long long gi = a.geom_per_sample ? s : g;
-    const double tts = a.iza[gi], tto = a.vza[gi], psi = a.raa[gi];
-    double sts, cts, sto, cto, spsi, cpsi;
-    sincos(tts, &sts, &cts);
-    sincos(tto, &sto, &cto);
-    sincos(psi, &spsi, &cpsi);
-
-    // ---- LIDF over 18 bins of 5 degrees ----
-    double lidf[18];
-    if (a.lidf_type == 0) {                       // Campbell, models.py:301-330
+// LIDF over 18 bins of 5 degrees for one parameter set (thread-sequential form; bins in the reference's order)
+__device__ __forceinline__ void lidf_bins(int lidf_type, double la, double lb, const AngleTables* __restrict__ at, double (&lidf)[18]) {
+    if (lidf_type == 0) {                       // Campbell, models.py:301-330
         const double excent = exp(-1.6184e-5 * la * la * la + 2.1145e-3 * la * la - 1.2390e-1 * la + 3.2491);
         const double e2 = excent * excent;
         double sum0 = 0.0;
@@ -1138,6 +1097,66 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
             lidf[i] = Fhi - f;
             Fhi = f;
         }
+    }
+}
+
+// LIDF once per parameter set into a workspace [nsamples][18]: used when several geometries share a set, so that the
+// Verhoef fixed-point solves (the dominant cost of the prologue) are not repeated per geometry
+__global__ void __launch_bounds__(128) k_lidf(const PrologueArgs a, const AngleTables* __restrict__ at, double* __restrict__ ws) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.nsamples) return;
+    double lidf[18];
+    lidf_bins(a.lidf_type, a.lidf_a[s], a.lidf_b ? a.lidf_b[s] : 0.0, at, lidf);
+#pragma unroll 1
+    for (int i = 0; i < 18; ++i) ws[s * 18 + i] = lidf[i];
+}
+
+template <typename T, bool LIDF_WS>
+__global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const AngleTables* __restrict__ at,
+                                                    const double* __restrict__ lidf_ws) {
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nitems = a.nsamples * a.G;
+    if (item >= nitems) return;
+    const long long s = item / a.G;
+    const int g = (int)(item - s * a.G);
+
+    double srec[REC];
+#pragma unroll
+    for (int i = 0; i < REC; ++i) srec[i] = 0.0;
+    if (g == 0) {
+        if (a.has_leaf) {
+            const double N = a.N[s];
+            srec[S_CAB] = a.Cab[s] / N; srec[S_CXC] = a.Cxc[s] / N; srec[S_CAN] = a.Can ? a.Can[s] / N : 0.0;
+            srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
+            srec[S_NM1] = N - 1.0;
+        }
+        if (a.has_soil) {
+            const double sr = a.soil_refl[s], mo = a.soil_moist[s];
+            srec[S_SOIL1] = sr * mo;              // rho = sRef (moisture rsoil1 + (1-moisture) rsoil2), models.py:1917
+            srec[S_SOIL2] = sr * (1.0 - mo);
+        }
+    }
+    if (!a.has_canopy) {
+        if (g == 0) store_rec<T>(a.srec, s, srec);
+        return;
+    }
+
+    const double lai = a.lai[s], hot = a.hot[s];
+    const double la = a.lidf_a[s], lb = a.lidf_b ? a.lidf_b[s] : 0.0;
+    const long long gi = a.geom_per_sample ? s : g;
+    const double tts = a.iza[gi], tto = a.vza[gi], psi = a.raa[gi];
+    double sts, cts, sto, cto, spsi, cpsi;
+    sincos(tts, &sts, &cts);
+    sincos(tto, &sto, &cto);
+    sincos(psi, &spsi, &cpsi);
+
+    // ---- LIDF over 18 bins of 5 degrees: computed here, or read back when k_lidf ran first (several geometries per set) ----
+    double lidf[18];
+    if (LIDF_WS) {
+#pragma unroll 1
+        for (int i = 0; i < 18; ++i) lidf[i] = lidf_ws[s * 18 + i];
+    } else {
+        lidf_bins(a.lidf_type, la, lb, at, lidf);
     }
     if (a.lidf_out && g == 0) {
 #pragma unroll 1

@@ -241,8 +241,12 @@ class Engine(object):
     def _fn(self, name, dt):
         return getattr(self.lib, "%s_%s" % (name, "f32" if dt == np.dtype(_f32) else "f64"))
 
-    def prospect(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=None, version='5', alpha=40, means=False, out=None, dtype=_f64):
-        """Batched PROSPECT.  Returns dict(ks, kt[, means]) with ks/kt dtype[n, 2101]; means float32[n, 5, nw]."""
+    def prospect(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=None, version='5', alpha=40, means=False, out=None, dtype=_f64,
+                 derived=False, spectra=True):
+        """Batched PROSPECT.  Returns dict(ks, kt[, ka, ke, om][, means]) with spectra dtype[n, 2101]; means float32[n, 5, nw].
+
+        derived=True also returns ka, ke, om (models.py:1066-1068); spectra=False skips ks/kt (derived planes / means only).
+        """
         dt = _real(dtype)
         with self._lock:
             self.set_alpha(version, alpha)
@@ -251,17 +255,16 @@ class Engine(object):
             can = _vec(Can, n, 'Can') if (version == 'D') else None
             leaf = self._leaf(v[0], v[1], v[2], v[3], v[4], v[5], can)
             out = out or {}
-            ks = out.get('ks')
-            kt = out.get('kt')
-            if ks is None:
-                ks = PinnedPool.empty((n, K.NBANDS), dt)
-            if kt is None:
-                kt = PinnedPool.empty((n, K.NBANDS), dt)
-            assert ks.dtype == dt and kt.dtype == dt
+            res = {}
+            for name, want in (('ks', spectra), ('kt', spectra), ('ka', derived), ('ke', derived), ('om', derived)):
+                if want:
+                    a = out.get(name)
+                    res[name] = a if a is not None else PinnedPool.empty((n, K.NBANDS), dt)
+                    assert res[name].dtype == dt
             m = PinnedPool.empty((n, 5, len(self.windows)), np.float32) if means else None
-            capi.check(self._fn("prosail_prospect", dt)(self.h, 0 if version == '5' else 1, n, C.byref(leaf), _ptr(ks), _ptr(kt),
+            capi.check(self._fn("prosail_prospect", dt)(self.h, 0 if version == '5' else 1, n, C.byref(leaf), _ptr(res.get('ks')),
+                                                        _ptr(res.get('kt')), _ptr(res.get('ka')), _ptr(res.get('ke')), _ptr(res.get('om')),
                                                         K.NBANDS, _ptr(m), 1, None))
-            res = dict(ks=ks, kt=kt)
             if means:
                 res['means'] = m
             return res
@@ -407,7 +410,8 @@ class Engine(object):
         """Leaf-only batch on DeviceArrays (ks, kt: [n, pitch])."""
         lf = self._leaf(leaf['N'], leaf['Cab'], leaf['Cxc'], leaf['Cbr'], leaf['Cw'], leaf['Cm'], leaf.get('Can'))
         capi.check(self._fn("prosail_prospect", _real(dtype))(self.h, 0 if version == '5' else 1, int(n), C.byref(lf),
-                                                              C.c_void_p(self._addr(ks)), C.c_void_p(self._addr(kt)), int(pitch), None, 0, stream))
+                                                              C.c_void_p(self._addr(ks)), C.c_void_p(self._addr(kt)), None, None, None,
+                                                              int(pitch), None, 0, stream))
 
     @staticmethod
     def _pack(bufs, means, geom, n, G):

@@ -100,24 +100,34 @@ class PROSPECT(_SpectralModel):
 
         self._engine = get_engine(device)
         self._scalar = _is_scalar_call(N, Cab, Cxc, Cbr, Cw, Cm, Can)
+        self._d = None
         res = self._engine.prospect(N, Cab, Cxc, Cbr, Cw, Cm, Can=Can if self.ver == 'D' else None, version=self.ver,
                                     alpha=alpha, means=True, dtype=self.dtype)
         sq = (lambda a: a[0]) if self._scalar else (lambda a: a)
         self.ks, self.kt = sq(res['ks']), sq(res['kt'])
         self.L8, self.ASTER = _band_tuples(sq(res['means']), 'ks kt ka ke omega')
 
-    # ka, ke, om and the float32 table are views derived from ks/kt on first use (models.py:1066-1072)
+    # ka, ke, om (models.py:1066-1068) come from the same kernel; they are evaluated on first use (one more launch that
+    # writes only these three planes) so that large batches which never look at them do not pay 3 x B x 2101 values
+    def _derived(self):
+        if self._d is None:
+            r = self._engine.prospect(self.N, self.Cab, self.Cxc, self.Cbr, self.Cw, self.Cm, Can=self.Can if self.ver == 'D' else None,
+                                      version=self.ver, alpha=self.alpha, dtype=self.dtype, derived=True, spectra=False)
+            sq = (lambda a: a[0]) if self._scalar else (lambda a: a)
+            self._d = {k: sq(r[k]) for k in ('ka', 'ke', 'om')}
+        return self._d
+
     @property
     def ka(self):
-        return 1 - self.ks - self.kt
+        return self._derived()['ka']
 
     @property
     def ke(self):
-        return self.ks + self.ka
+        return self._derived()['ke']
 
     @property
     def om(self):
-        return self.ks / self.ke
+        return self._derived()['om']
 
     @property
     def int(self):

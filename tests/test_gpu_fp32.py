@@ -118,3 +118,17 @@ def test_f32_entry_points_reject_bad_arguments(engine):
     assert lib.prosail_prosail_f32(engine.h, 0, 1, None, None, None, None, 1, None) == -1      # PROSAIL_E_ARG: null structs
     with pytest.raises(ValueError):
         engine.prosail(1.5, 40, 8, 0, 0.01, 0.009, 3.0, 0.1, [0.5], [0.2], [0.3], 1.0, 0.5, dtype=np.float16)
+
+
+def test_prospect_f32_derived_planes_come_from_the_kernel():
+    """ka, ke, om (models.py:1066-1068) are output planes of the PROSPECT kernel in both precisions."""
+    n = 50
+    P = lhs(n)
+    for dt, tol in ((np.float64, 1e-9), (f32, TOL32)):
+        p = pb.PROSPECT(dtype=dt, **P)
+        assert p.ka.dtype == dt and p.ka.shape == (n, 2101)
+        for i in (0, 17, n - 1):
+            o = orc.prospect(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i])
+            for q in ('ka', 'ke', 'om'):
+                assert np.max(np.abs(getattr(p, q)[i] - o[q])) <= tol, (q, i, dt)
+        assert p.int.shape == (n, 2101, 6) and p.int.dtype == f32

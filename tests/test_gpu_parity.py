@@ -388,10 +388,10 @@ def test_custom_windows_and_c_abi_errors(engine):
     finally:
         engine.set_windows(old)
     import ctypes as C
-    rc = engine.lib.prosail_prospect_f64(engine.h, 7, 1, C.byref(capi.Leaf()), None, None, 2101, None, 1, None)
+    rc = engine.lib.prosail_prospect_f64(engine.h, 7, 1, C.byref(capi.Leaf()), None, None, None, None, None, 2101, None, 1, None)
     assert rc == -1 and b"version must be" in engine.lib.prosail_last_error()
-    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, C.byref(capi.Leaf()), None, None, 2101, None, 1, None)
+    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, C.byref(capi.Leaf()), None, None, None, None, None, 2101, None, 1, None)
     assert rc == -1 and b"null leaf" in engine.lib.prosail_last_error()
-    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, None, None, None, 2101, None, 1, None)
+    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, None, None, None, None, None, None, 2101, None, 1, None)
     assert rc == -1
     assert engine.launch_count() > 0
