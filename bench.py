@@ -313,6 +313,7 @@ def main():
             dt = float(t.item())
         e2e = {"value": world * Se * args.e2e_steps / dt, "unit": "spectra/s", "h2d_bytes_per_step": int(Se * len(NAMES) * 8 + 24),
                "d2h_bytes_per_step": int(Se * NB * 8), "samples_per_gpu": int(Se), "steps": args.e2e_steps,
+               "numa_node": eng.numa_node,
                "api": "pyrism_b200.Engine.prosail (prosail_prosail_f64, on_host=1): numpy parameters in, pinned numpy BRF spectra out"}
 
     if rank != 0:

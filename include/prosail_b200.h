@@ -195,6 +195,10 @@ int prosail_profile_read(prosail_handle_t* h, double ms[3], long long count[3]);
 /* name, SM count, HBM bytes of the handle's device */
 int prosail_device_info(prosail_handle_t* h, char* name, int name_len, int* sm_count, long long* mem_bytes);
 
+/* PCI bus id of the handle's device ("0000:1b:00.0"), so that a host process can bind itself and its pinned buffers to
+ * the NUMA node the GPU hangs off before it allocates them (pyrism_b200/engine.py does). */
+int prosail_device_pci_bus_id(prosail_handle_t* h, char* out, int len);
+
 /* ---- calibration / self-test -------------------------------------------------------------------------- */
 /* FP64 roofline denominator: sustained DFMA throughput of the device (TFLOP/s, FMA = 2 flops), measured with a
  * register-resident FMA kernel for about `millis` milliseconds. */

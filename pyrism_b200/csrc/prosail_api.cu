@@ -921,6 +921,12 @@ int prosail_device_info(prosail_handle_t* h, char* name, int name_len, int* sm_c
     return 0;
 }
 
+int prosail_device_pci_bus_id(prosail_handle_t* h, char* out, int len) {
+    if (!h || !out || len < 16) return fail(PROSAIL_E_ARG, "bad argument");
+    CK(cudaDeviceGetPCIBusId(out, len, h->device));
+    return 0;
+}
+
 int prosail_measure_fp64_peak(prosail_handle_t* h, int millis, double* tflops) {
     if (!h || !tflops) return fail(PROSAIL_E_ARG, "bad argument");
     DeviceGuard guard(h->device);

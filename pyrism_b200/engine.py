@@ -121,11 +121,37 @@ class Engine(object):
         self._fin = weakref.finalize(self, self.lib.prosail_destroy, h)
         self._alpha = {}
         self._lock = threading.RLock()
+        self.numa_node = self._bind_to_gpu_numa_node()
         capi.check(self.lib.prosail_set_soil_tables(self.h, _ptr(K.lib.soil.rsoil1), _ptr(K.lib.soil.rsoil2)))
         self.set_alpha('5', alpha)
         self.set_alpha('D', alpha)
         self.windows = None
         self.set_windows(windows)
+
+    def _bind_to_gpu_numa_node(self):
+        """Multi-GPU boxes have two sockets: pin this process to the CPUs of the NUMA node the GPU is attached to, so that
+        the pinned host buffers it allocates afterwards (first touch) and the D2H copies into them stay on that socket.
+        Only done when several ranks share the box (LOCAL_RANK set) or PYRISM_B200_NUMA=1; never fatal."""
+        import os
+        if os.environ.get("PYRISM_B200_NUMA", "1" if "LOCAL_RANK" in os.environ else "0") != "1":
+            return None
+        try:
+            buf = C.create_string_buffer(32)
+            capi.check(self.lib.prosail_device_pci_bus_id(self.h, buf, 32))
+            bus = buf.value.decode().lower()
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+            if node < 0:
+                return None
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+            return node
+        except Exception:
+            return None
 
     # ---- constants -------------------------------------------------------------------------------------
     def set_alpha(self, version, alpha):
