@@ -170,6 +170,18 @@ int prosail_sail_f32(prosail_handle_t* h, long long n, const float* ks, long lon
 int prosail_prosail_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_soil_t* soil,
                         const prosail_canopy_t* canopy, const prosail_out_f32_t* out, int on_host, void* stream);
 
+/* ---- LUT inversion (the consumer of the LUT; BASELINE north star; no counterpart in the reference) ------
+ * For each of n_obs observed feature vectors (e.g. the 15 window means of a pixel) the index of the LUT entry with the smallest
+ *   cost(q, e) = sum_d ( s_d obs[q][d] - s_d lut[e][d] )^2,   s_d = sqrtf(weights[d])  (1 when weights is NULL),
+ * evaluated in float32 in ascending d with fmaf(diff, diff, acc) on pre-scaled features; ties go to the lowest index;
+ * best_index = local index + index_offset (the first LUT row this shard holds; -1 if every cost is NaN/inf).
+ * n_feat <= 32; lut [n_lut][pitch_lut], obs [n_obs][pitch_obs] are float32 (the fp32-mode means of prosail_prosail_f32, or any
+ * other feature table); weights is a HOST array of n_feat values in both modes.  Multi-GPU: every rank inverts against its own
+ * LUT shard and the per-rank (cost, index) pairs are reduced by the caller (pyrism_b200.inversion does it over NCCL). */
+int prosail_invert_f32(prosail_handle_t* h, long long n_lut, int n_feat, const float* lut, long long pitch_lut, long long n_obs,
+                       const float* obs, long long pitch_obs, const float* weights, long long index_offset, long long* best_index,
+                       float* best_cost, int on_host, void* stream);
+
 /* ---- memory / stream helpers (so that a host without torch/cupy can drive the device API) -------------- */
 int prosail_dev_alloc(prosail_handle_t* h, long long bytes, void** out);
 int prosail_dev_free(prosail_handle_t* h, void* p);

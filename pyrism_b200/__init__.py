@@ -13,7 +13,8 @@ from .core import Kernel, SailResult, rad, deg, sec, dB, linear, align_all, asar
 from .models import PROSPECT, LSM, SAIL, PROSAIL, VolScatt, LIDF
 from .engine import Engine, get_engine
 from . import constants
+from . import inversion, lut
 
 __version__ = "0.1.0"
 __all__ = ["PROSPECT", "LSM", "SAIL", "PROSAIL", "VolScatt", "LIDF", "Kernel", "SailResult", "Engine", "get_engine",
-           "rad", "deg", "sec", "dB", "linear", "align_all", "asarrays", "constants"]
+           "rad", "deg", "sec", "dB", "linear", "align_all", "asarrays", "constants", "inversion", "lut"]

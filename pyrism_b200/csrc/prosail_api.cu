@@ -13,6 +13,7 @@
 
 #include "../../include/prosail_b200.h"
 #include "prosail_kernels.cuh"
+#include "invert_kernels.cuh"
 
 using namespace pb;
 
@@ -66,11 +67,12 @@ struct DevBuf {
 struct Work {            // per-stream scratch
     DevBuf srec, grec, partial;
     DevBuf lidf;         // [samples][18] LIDF workspace (multi-geometry jobs)
+    DevBuf inv;          // LUT inversion: per-(observation, chunk) minima + scale vector
     DevBuf in;           // host mode: parameter slices
     DevBuf out;          // host mode: output planes / means / geom of one slab
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    void release() { srec.release(); grec.release(); partial.release(); lidf.release(); in.release(); out.release(); }
+    void release() { srec.release(); grec.release(); partial.release(); lidf.release(); inv.release(); in.release(); out.release(); }
 };
 
 struct prosail_handle {
@@ -918,6 +920,93 @@ int prosail_device_info(prosail_handle_t* h, char* name, int name_len, int* sm_c
     }
     if (sm_count) *sm_count = prop.multiProcessorCount;
     if (mem_bytes) *mem_bytes = (long long)prop.totalGlobalMem;
+    return 0;
+}
+
+}  // extern "C" (templates below)
+
+template <int DP>
+static int launch_invert(prosail_handle* h, InvertArgs& a, long long index_offset, long long* best_index, float* best_cost, Work& w,
+                         const float* h_scale, cudaStream_t st) {
+    typedef InvCfg<DP> IC;
+    const long long obs_tiles = (a.n_obs + IC::OBS_PER_CTA - 1) / IC::OBS_PER_CTA;
+    const long long lut_tiles = (a.n_lut + IC::TILE - 1) / IC::TILE;
+    // enough (observation tile, LUT chunk) pairs for about four CTAs per SM; chunks are whole tiles
+    long long n_chunks = std::max<long long>(1, std::min<long long>(lut_tiles, (4LL * h->sm_count + obs_tiles - 1) / obs_tiles));
+    n_chunks = std::min<long long>(n_chunks, 65535);
+    const long long tiles_per_chunk = (lut_tiles + n_chunks - 1) / n_chunks;
+    n_chunks = (lut_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    a.chunk = tiles_per_chunk * IC::TILE;
+    a.n_chunks = (int)n_chunks;
+    const size_t pc = ((size_t)a.n_obs * n_chunks * sizeof(float) + 255) & ~(size_t)255;
+    const size_t pi = ((size_t)a.n_obs * n_chunks * sizeof(long long) + 255) & ~(size_t)255;
+    int rc;
+    if ((rc = w.inv.reserve(pc + pi + 256))) return rc;
+    a.part_cost = (float*)w.inv.p;
+    a.part_idx = (long long*)((char*)w.inv.p + pc);
+    float* d_scale = (float*)((char*)w.inv.p + pc + pi);
+    CK(cudaMemcpyAsync(d_scale, h_scale, DP * sizeof(float), cudaMemcpyHostToDevice, st));
+    a.scale = d_scale;
+    {
+        ProfScope ps(h, 0, st);
+        k_invert<DP><<<dim3((unsigned)obs_tiles, (unsigned)n_chunks), INV_THREADS, 0, st>>>(a);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    k_invert_reduce<<<(unsigned)((a.n_obs + 255) / 256), 256, 0, st>>>(a.n_obs, a.n_chunks, a.part_cost, a.part_idx, index_offset, best_index, best_cost);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int prosail_invert_f32(prosail_handle_t* h, long long n_lut, int n_feat, const float* lut, long long pitch_lut, long long n_obs,
+                       const float* obs, long long pitch_obs, const float* weights, long long index_offset, long long* best_index,
+                       float* best_cost, int on_host, void* stream) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    if (n_lut < 1 || n_obs < 0) return fail(PROSAIL_E_ARG, "need n_lut >= 1 and n_obs >= 0");
+    if (n_feat < 1 || n_feat > 32) return fail(PROSAIL_E_ARG, "n_feat must be in 1..32");
+    if (pitch_lut < n_feat || pitch_obs < n_feat) return fail(PROSAIL_E_ARG, "pitch smaller than n_feat");
+    if (!lut || !obs || !best_index || !best_cost) return fail(PROSAIL_E_ARG, "null array");
+    if (n_obs == 0) return 0;
+    float scale[32];
+    for (int d = 0; d < 32; ++d) {
+        const float wd = d < n_feat ? (weights ? weights[d] : 1.0f) : 0.0f;      // weights is always a HOST array (n_feat values)
+        if (!(wd >= 0.0f)) return fail(PROSAIL_E_ARG, "weights must be >= 0");
+        scale[d] = std::sqrt(wd);
+    }
+    DeviceGuard guard(h->device);
+    Work& w = h->work;
+    cudaStream_t st = stream && !on_host ? (cudaStream_t)stream : h->stream;
+    InvertArgs a{};
+    a.n_lut = n_lut; a.pitch_lut = pitch_lut; a.n_obs = n_obs; a.pitch_obs = pitch_obs; a.n_feat = n_feat;
+    long long* d_idx = best_index;
+    float* d_cost = best_cost;
+    int rc;
+    if (on_host) {
+        const size_t bl = ((size_t)n_lut * pitch_lut * 4 + 255) & ~(size_t)255, bo = ((size_t)n_obs * pitch_obs * 4 + 255) & ~(size_t)255;
+        const size_t bi = ((size_t)n_obs * 8 + 255) & ~(size_t)255;
+        if ((rc = w.in.reserve(bl + bo)) || (rc = w.out.reserve(bi + (size_t)n_obs * 4 + 256))) return rc;
+        CK(cudaMemcpyAsync(w.in.p, lut, (size_t)n_lut * pitch_lut * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync((char*)w.in.p + bl, obs, (size_t)n_obs * pitch_obs * 4, cudaMemcpyHostToDevice, st));
+        a.lut = (const float*)w.in.p;
+        a.obs = (const float*)((char*)w.in.p + bl);
+        d_idx = (long long*)w.out.p;
+        d_cost = (float*)((char*)w.out.p + bi);
+    } else {
+        a.lut = lut;
+        a.obs = obs;
+    }
+    if (n_feat <= 8) rc = launch_invert<8>(h, a, index_offset, d_idx, d_cost, w, scale, st);
+    else if (n_feat <= 16) rc = launch_invert<16>(h, a, index_offset, d_idx, d_cost, w, scale, st);
+    else rc = launch_invert<32>(h, a, index_offset, d_idx, d_cost, w, scale, st);
+    if (rc) return rc;
+    if (on_host) {
+        CK(cudaMemcpyAsync(best_index, d_idx, (size_t)n_obs * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(best_cost, d_cost, (size_t)n_obs * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return 0;
 }
 

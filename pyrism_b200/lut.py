@@ -76,7 +76,7 @@ def gather_means(local_means, n_total, group=None):
 
 
 def generate_band_lut(engine, params, geometry_deg, version='5', lidf_type='campbell', products=("rsot",), windows_only=True,
-                      rank=0, world=1):
+                      rank=0, world=1, dtype=np.float64):
     """Band-mean PROSAIL LUT for this rank's shard of ``params`` (BASELINE config 5 shape).
 
     ``params``: dict with N, Cab, Cxc, Cbr, Cw, Cm[, Can], lai, hotspot, lidf_a[, lidf_b], soil_reflectance,
@@ -90,5 +90,5 @@ def generate_band_lut(engine, params, geometry_deg, version='5', lidf_type='camp
     res = engine.prosail(local["N"], local["Cab"], local["Cxc"], local["Cbr"], local["Cw"], local["Cm"], local["lai"],
                          local["hotspot"], k.iza, k.vza, k.raa, local["soil_reflectance"], local["soil_moisture"],
                          Can=local.get("Can"), version=version, lidf_type=lidf_type, a=local["lidf_a"], b=local.get("lidf_b", 0.0),
-                         planes=() if windows_only else planes, mean_planes=planes, windows_only=windows_only)
+                         planes=() if windows_only else planes, mean_planes=planes, windows_only=windows_only, dtype=dtype)
     return res["means"], span

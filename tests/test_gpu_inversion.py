@@ -1,0 +1,75 @@
+"""prosail_invert_f32 on the GPU against the contract oracle (oracle/invert_oracle.py): bit-exact indices and costs, ties,
+weights, ragged sizes, and an end-to-end inversion of synthetic observations against a PROSAIL band-mean LUT."""
+import numpy as np
+import pytest
+
+import pyrism_b200 as pb
+from pyrism_b200 import inversion, lut
+from oracle import invert_oracle as inv
+
+pytestmark = pytest.mark.gpu
+rng = np.random.default_rng(20261019 + 41)
+
+
+@pytest.mark.parametrize("m, q, d", [(1, 1, 1), (257, 3, 15), (5000, 1025, 15), (20000, 300, 6), (3001, 700, 32), (4096, 1024, 8), (70000, 64, 15)])
+def test_invert_matches_the_contract_oracle_bitwise(engine, m, q, d):
+    lutf = rng.random((m, d)).astype(np.float32)
+    obs = rng.random((q, d)).astype(np.float32)
+    if m > 300:
+        lutf[m - 1] = lutf[5]                               # duplicates: lowest index wins
+        obs[0] = lutf[5]
+    w = rng.uniform(0.2, 3.0, d).astype(np.float32) if d % 2 else None
+    idx, cost = inversion.invert(engine, lutf, obs, w, index_offset=7)
+    ref_idx, ref_cost = inv.invert(lutf, obs, w, index_offset=7)
+    same = idx == ref_idx
+    if not np.all(same):                                    # only possible on an fmaf double-rounding midpoint: must still be optimal
+        assert np.all(inv.is_optimal(lutf, obs[~same], idx[~same], w, index_offset=7)) and (~same).sum() <= 2
+    assert np.array_equal(cost[same], ref_cost[same])
+    if m > 300:
+        assert idx[0] == 5 + 7 and cost[0] == 0.0
+
+
+def test_invert_edge_cases(engine):
+    lutf = rng.random((100, 15)).astype(np.float32)
+    obs = rng.random((4, 15)).astype(np.float32)
+    obs[1] = np.nan
+    idx, cost = inversion.invert(engine, lutf, obs)
+    assert idx[1] == -1 and np.isinf(cost[1]) and idx[0] >= 0
+    i0, _ = inversion.invert(engine, lutf, obs[:0])
+    assert i0.shape == (0,)
+    with pytest.raises(pb._capi.ProsailError):
+        inversion.invert(engine, rng.random((10, 33)).astype(np.float32), rng.random((2, 33)).astype(np.float32))
+    with pytest.raises(pb._capi.ProsailError):
+        inversion.invert(engine, lutf, obs, weights=-np.ones(15, dtype=np.float32))
+    with pytest.raises(ValueError):
+        inversion.invert(engine, lutf, obs[:, :3])
+
+
+def test_sharded_fold_is_independent_of_the_sharding(engine):
+    m, q = 50001, 500
+    lutf = rng.random((m, 15)).astype(np.float32)
+    obs = rng.random((q, 15)).astype(np.float32)
+    ref = inversion.invert(engine, lutf, obs)
+    for world in (2, 8):
+        parts = [inversion.invert(engine, lutf[b:e], obs, index_offset=b) for b, e in (lut.shard_bounds(m, r, world) for r in range(world))]
+        idx, cost = inversion.reduce_best(np.stack([p[1] for p in parts]), np.stack([p[0] for p in parts]))
+        assert np.array_equal(idx, ref[0]) and np.array_equal(cost, ref[1])
+
+
+def test_end_to_end_band_lut_inversion_recovers_the_generating_entries(engine):
+    """A 40 000-entry PROSAIL band-mean LUT (fp32 mode); observations = LUT rows (must be found exactly, cost 0) and LUT rows
+    with 0.5% noise (the retrieved entry must be at least as close as the generating one)."""
+    n = 40000
+    P = lut.latin_hypercube(n, ("N", "Cab", "Cxc", "Cbr", "Cw", "Cm", "lai", "hotspot", "lidf_a", "soil_reflectance", "soil_moisture"), 20261019 + 5)
+    bi = inversion.BandLutInverter(engine, P, (35.0, 30.0, 50.0))
+    assert bi.features.shape == (n, 15) and bi.features.dtype == np.float32
+    pick = rng.integers(0, n, 200)
+    idx, cost, best = bi.invert(bi.features[pick])
+    assert np.all(cost == 0.0) and np.allclose(best["lai"], P["lai"][idx])
+    assert np.all(inv.costs(bi.features[idx], bi.features[pick]).diagonal() == 0.0)
+    noisy = (bi.features[pick] * (1 + 0.005 * rng.standard_normal((200, 15)))).astype(np.float32)
+    idx2, cost2, _ = bi.invert(noisy)
+    gen_cost = ((noisy.astype(np.float64) - bi.features[pick]) ** 2).sum(axis=1)
+    assert np.all(cost2 <= gen_cost * (1 + 1e-5) + 1e-12)
+    ref_idx, ref_cost = inv.invert(bi.features, noisy)
+    assert np.mean(idx2 == ref_idx) >= 0.99 and np.all(inv.is_optimal(bi.features, noisy, idx2))
