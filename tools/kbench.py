@@ -11,6 +11,7 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 what = sys.argv[3] if len(sys.argv) > 3 else "brf"
 dt = np.float32 if (len(sys.argv) > 4 and sys.argv[4] == "f32") else np.float64
+PITCH = int(sys.argv[5]) if len(sys.argv) > 5 else 2101      # row pitch of the output planes in elements (2112 = 128-byte aligned rows)
 eng = pb.Engine(0)
 P = bench.lhs(S, 123)
 geom = np.deg2rad(np.array(bench.GEOM_DEG))
@@ -20,17 +21,17 @@ soil = {"reflectance": dev["soil_refl"], "moisture": dev["soil_moist"]}
 canopy = {"lidf_a": dev["lidf_a"], "lai": dev["lai"], "hotspot": dev["hotspot"], "iza": eng.to_device(geom[0:1]),
           "vza": eng.to_device(geom[1:2]), "raa": eng.to_device(geom[2:3])}
 if what == "leaf":
-    ks, kt = eng.empty((S, 2101), dt), eng.empty((S, 2101), dt)
-    step = lambda: eng.prospect_device(S, leaf, ks, kt, dtype=dt)
+    ks, kt = eng.empty((S, PITCH), dt), eng.empty((S, PITCH), dt)
+    step = lambda: eng.prospect_device(S, leaf, ks, kt, pitch=PITCH, dtype=dt)
 elif what == "means":
     means = eng.empty((S, 1, len(eng.windows)), dt)
     step = lambda: eng.prosail_device(S, leaf, soil, canopy, None, mean_planes=(capi.O_RSOT,), means=means, windows_only=True, dtype=dt)
 else:
-    planes = {capi.O_RSOT: eng.empty((S, 2101), dt)}
+    planes = {capi.O_RSOT: eng.empty((S, PITCH), dt)}
     if what == "four":
         for p in (capi.O_RDDT, capi.O_RSDT, capi.O_RDOT):
-            planes[p] = eng.empty((S, 2101), dt)
-    step = lambda: eng.prosail_device(S, leaf, soil, canopy, planes, dtype=dt)
+            planes[p] = eng.empty((S, PITCH), dt)
+    step = lambda: eng.prosail_device(S, leaf, soil, canopy, planes, pitch=PITCH, dtype=dt)
 for _ in range(3):
     step()
 eng.sync()
@@ -39,4 +40,4 @@ for _ in range(reps):
     step()
 pr = eng.profile_read()
 ms = pr['bands'][0] / pr['bands'][1]
-print("%s %s lib=%s S=%d kernel %.3f ms  -> %.3e spectra/s   prologue %.3f ms" % (what, np.dtype(dt).name, os.path.basename(capi.LIB_PATH), S, ms, S / ms * 1e3, pr['prologue'][0] / max(pr['prologue'][1], 1)))
+print("%s %s pitch %d lib=%s S=%d kernel %.3f ms  -> %.3e spectra/s   prologue %.3f ms" % (what, np.dtype(dt).name, PITCH, os.path.basename(capi.LIB_PATH), S, ms, S / ms * 1e3, pr['prologue'][0] / max(pr['prologue'][1], 1)))
