@@ -947,10 +947,7 @@ static int launch_invert(prosail_handle* h, InvertArgs& a, long long index_offse
     float* d_scale = (float*)((char*)w.inv.p + pc + pi);
     CK(cudaMemcpyAsync(d_scale, h_scale, DP * sizeof(float), cudaMemcpyHostToDevice, st));
     a.scale = d_scale;
-    {
-        ProfScope ps(h, 0, st);
-        k_invert<DP><<<dim3((unsigned)obs_tiles, (unsigned)n_chunks), INV_THREADS, 0, st>>>(a);
-    }
+    k_invert<DP><<<dim3((unsigned)obs_tiles, (unsigned)n_chunks), INV_THREADS, 0, st>>>(a);
     h->launches++;
     CK(cudaGetLastError());
     k_invert_reduce<<<(unsigned)((a.n_obs + 255) / 256), 256, 0, st>>>(a.n_obs, a.n_chunks, a.part_cost, a.part_idx, index_offset, best_index, best_cost);

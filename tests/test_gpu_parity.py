@@ -395,3 +395,52 @@ def test_custom_windows_and_c_abi_errors(engine):
     rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, None, None, None, None, None, None, 2101, None, 1, None)
     assert rc == -1
     assert engine.launch_count() > 0
+
+
+def test_kernels_write_only_what_they_own_canaries(engine):
+    """No compute-sanitizer on this pool: output buffers are embedded in canary-filled allocations (guard rows before and
+    after, guard columns 2101..2111 of a 2112 pitch) and every guard value must survive, for the fp64 and fp32 band kernels
+    (ragged item count), the window means and the inversion outputs."""
+    from pyrism_b200 import inversion
+    n, G, pitch, guard = 45, 3, 2112, 4
+    P = lhs(n)
+    g = np.radians(np.array([[35.0, 10.0, 60.0], [30.0, 45.0, 0.0], [50.0, 120.0, 180.0]]))
+    dev = {k: engine.to_device(v) for k, v in P.items()}
+    extra = dict(lai=rng.uniform(0.1, 8, n), hotspot=rng.uniform(0.01, 0.5, n), lidf_a=rng.uniform(20, 80, n), sr=rng.uniform(0.3, 1.2, n), sm=rng.uniform(0, 1, n))
+    dv = {k: engine.to_device(v) for k, v in extra.items()}
+    canopy = {"lidf_a": dv["lidf_a"], "lai": dv["lai"], "hotspot": dv["hotspot"], "iza": engine.to_device(g[0]), "vza": engine.to_device(g[1]),
+              "raa": engine.to_device(g[2])}
+    soil = {"reflectance": dv["sr"], "moisture": dv["sm"]}
+    items = n * G
+    nw = len(engine.windows)
+    for dt in (np.float64, np.float32):
+        es = np.dtype(dt).itemsize
+        canary = dt(-777.25)
+        planes_host = np.full((items + 2 * guard, pitch), canary, dtype=dt)
+        means_host = np.full((items + 2 * guard, 2, nw), canary, dtype=dt)
+        bufs = {p: engine.empty(planes_host.shape, dt).upload(planes_host) for p in (capi.O_RSOT, capi.O_RDOT, capi.O_KE)}
+        mbuf = engine.empty(means_host.shape, dt).upload(means_host)
+        inner = {p: b.ptr + guard * pitch * es for p, b in bufs.items()}
+        engine.prosail_device(n, dev, soil, canopy, inner, pitch=pitch, mean_planes=(capi.O_RSOT, capi.O_RDDT), means=mbuf.ptr + guard * 2 * nw * es,
+                              n_geom=G, dtype=dt)
+        engine.sync()
+        for p, b in bufs.items():
+            out = b.download()
+            assert np.all(out[:guard] == canary) and np.all(out[guard + items:] == canary), (p, dt)
+            assert np.all(out[guard:guard + items, 2101:] == canary), (p, dt)                      # pad columns of the pitch
+            assert np.all(np.isfinite(out[guard:guard + items, :2101])) and not np.any(out[guard:guard + items, :2101] == canary)
+        mo = mbuf.download()
+        assert np.all(mo[:guard] == canary) and np.all(mo[guard + items:] == canary) and not np.any(mo[guard:guard + items] == canary)
+    # inversion outputs
+    m, q, d = 700, 1030, 15
+    lutf, obs = rng.random((m, d)).astype(np.float32), rng.random((q, d)).astype(np.float32)
+    dl, do = engine.empty((m, d), np.float32).upload(lutf), engine.empty((q, d), np.float32).upload(obs)
+    hi = np.full(q + 2 * guard, -5, dtype=np.int64)
+    hc = np.full(q + 2 * guard, -777.25, dtype=np.float32)
+    di, dc = engine.empty(hi.shape, np.int64).upload(hi), engine.empty(hc.shape, np.float32).upload(hc)
+    inversion.invert_device(engine, m, d, dl, d, q, do, d, di.ptr + guard * 8, dc.ptr + guard * 4)
+    engine.sync()
+    oi, oc = di.download(), dc.download()
+    assert np.all(oi[:guard] == -5) and np.all(oi[guard + q:] == -5) and np.all(oc[:guard] == np.float32(-777.25)) and np.all(oc[guard + q:] == np.float32(-777.25))
+    ref_i, ref_c = inversion.invert(engine, lutf, obs)
+    assert np.array_equal(oi[guard:guard + q], ref_i) and np.array_equal(oc[guard:guard + q], ref_c)          # device API == host API
