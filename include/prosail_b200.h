@@ -129,6 +129,10 @@ int prosail_set_soil_tables(prosail_handle_t* h, const float* rsoil1, const floa
 /* Inclusive wavelength windows [lo_nm, hi_nm] for the band means.  Replaces the hard-coded L8/ASTER windows of
  * SAIL.__store_L8/__store_aster (models.py:801-809, 836-841) and PROSPECT/LSM.select (models.py:1197-1225). */
 int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm);
+/* The same windows with a spectral response: window w carries one weight per wavelength lo_nm[w]..hi_nm[w] (1 nm steps;
+ * the arrays of all windows concatenated in `weights`), and its "mean" becomes sum(w x) / sum(w) -- a true sensor-band
+ * convolution.  The reference only has the unweighted special case (all weights 1, models.py:811-851); SURVEY.md 8(f)-2. */
+int prosail_set_windows_srf(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm, const double* weights);
 
 /* ---- the hot path ------------------------------------------------------------------------------------ */
 /* pyrism.PROSPECT(...) for n parameter sets (models.py:900-921): spectra ks, kt and (optional, NULL = not wanted)

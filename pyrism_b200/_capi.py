@@ -68,6 +68,7 @@ _SIGNATURES = {
     "prosail_set_leaf_tables": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 9),
     "prosail_set_soil_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "prosail_set_windows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "prosail_set_windows_srf": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prosail_prospect_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.POINTER(Leaf)] + [C.c_void_p] * 5 +
                              [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
     "prosail_soil_f64": (C.c_int, [C.c_void_p, C.c_longlong, C.POINTER(Soil), C.c_void_p, C.c_longlong, C.c_void_p,

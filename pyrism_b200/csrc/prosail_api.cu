@@ -89,6 +89,8 @@ struct prosail_handle {
     AngleTables* d_angles = nullptr;
     long long prologue_thread_min = 2048;   // items from which the thread-per-item prologue is used
     WindowMap* d_win = nullptr;
+    double* d_srf = nullptr;   // [MAX_SLOTS][32] spectral-response weights of the window segments
+    bool have_srf = false;
     WindowMap h_win;
     bool have_win = false;
     Work work;           // device mode (caller's stream)
@@ -335,6 +337,7 @@ static int run_device_t(prosail_handle* h, const Job& j, Work& w, cudaStream_t s
         a.bandc = bandc_of<T>(h, j.has_leaf ? j.version : 0);
         a.tables = tables_of<T>(h);
         a.win = h->d_win;
+        a.srf = h->have_srf ? h->d_srf : nullptr;
         a.srec = (const T*)w.srec.p;
         a.grec = (const T*)w.grec.p;
         a.nitems = ni;
@@ -549,6 +552,8 @@ int prosail_create(int device, prosail_handle_t** out) {
     }
     CK(cudaMalloc(&h->d_win, sizeof(WindowMap)));
     CK(cudaMemset(h->d_win, 0, sizeof(WindowMap)));
+    CK(cudaMalloc(&h->d_srf, sizeof(double) * MAX_SLOTS * 32));
+    CK(cudaMemset(h->d_srf, 0, sizeof(double) * MAX_SLOTS * 32));
     memset(&h->h_win, 0, sizeof(WindowMap));
     *out = h;
     return 0;
@@ -569,6 +574,7 @@ void prosail_destroy(prosail_handle_t* h) {
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_tables_f) cudaFree(h->d_tables_f);
     if (h->d_win) cudaFree(h->d_win);
+    if (h->d_srf) cudaFree(h->d_srf);
     if (h->d_angles) cudaFree(h->d_angles);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
@@ -632,33 +638,45 @@ int prosail_set_soil_tables(prosail_handle_t* h, const float* rsoil1, const floa
     return 0;
 }
 
-int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm) {
+static int set_windows_impl(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm, const double* weights) {
     if (!h) return fail(PROSAIL_E_ARG, "null handle");
     if (n_windows < 1 || n_windows > MAX_WINDOWS) return fail(PROSAIL_E_ARG, "n_windows must be in 1..%d", MAX_WINDOWS);
     if (!lo_nm || !hi_nm) return fail(PROSAIL_E_ARG, "null window array");
     WindowMap m;
     memset(&m, 0, sizeof m);
     m.nwindows = n_windows;
+    std::vector<double> srf((size_t)MAX_SLOTS * 32, 0.0);
     bool touched[NTILES] = {};
     int slot = 0;
+    const double* wp = weights;        // weights of window w: one value per wavelength lo_nm[w]..hi_nm[w] (as given, before clipping)
     for (int w = 0; w < n_windows; ++w) {
         const int lo = std::max(lo_nm[w], 400) - 400, hi = std::min(hi_nm[w], 2500) - 400;   // band indices, inclusive
         if (lo > hi) return fail(PROSAIL_E_ARG, "window %d [%d, %d] nm selects no wavelength in 400..2500", w, lo_nm[w], hi_nm[w]);
         m.wstart[w] = slot;
         m.wcount[w] = hi - lo + 1;
+        double wsum = 0.0;
         for (int t = lo / 32; t <= hi / 32; ++t) {
             if (m.nslots[t] >= MAX_TILE_SLOTS) return fail(PROSAIL_E_ARG, "more than %d windows overlap wavelengths %d..%d nm", MAX_TILE_SLOTS, 400 + t * 32, 431 + t * 32);
             if (slot >= MAX_SLOTS) return fail(PROSAIL_E_ARG, "too many window segments (> %d)", MAX_SLOTS);
             unsigned mask = 0;
             for (int l = 0; l < 32; ++l) {
                 const int b = t * 32 + l;
-                if (b >= lo && b <= hi) mask |= 1u << l;
+                if (b >= lo && b <= hi) {
+                    mask |= 1u << l;
+                    const double wt = weights ? wp[400 + b - lo_nm[w]] : 1.0;
+                    if (!(wt >= 0.0) || !std::isfinite(wt)) return fail(PROSAIL_E_ARG, "response weights must be finite and >= 0 (window %d)", w);
+                    srf[(size_t)slot * 32 + l] = wt;
+                    wsum += wt;
+                }
             }
             m.mask[t][m.nslots[t]] = mask;
             m.slot[t][m.nslots[t]] = slot++;
             m.nslots[t]++;
             touched[t] = true;
         }
+        if (!(wsum > 0.0)) return fail(PROSAIL_E_ARG, "the response weights of window %d sum to zero", w);
+        m.wsum[w] = weights ? wsum : (double)m.wcount[w];
+        if (weights) wp += hi_nm[w] - lo_nm[w] + 1;
     }
     m.wstart[n_windows] = slot;
     m.ntotal = slot;
@@ -673,9 +691,22 @@ int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, co
     DeviceGuard guard(h->device);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h->d_win, &m, sizeof m, cudaMemcpyHostToDevice));
+    if (weights) CK(cudaMemcpy(h->d_srf, srf.data(), srf.size() * 8, cudaMemcpyHostToDevice));
     h->h_win = m;
     h->have_win = true;
+    h->have_srf = weights != nullptr;
     return 0;
+}
+
+int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm) {
+    return set_windows_impl(h, n_windows, lo_nm, hi_nm, nullptr);
+}
+
+int prosail_set_windows_srf(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm, const double* weights) {
+    if (!weights) return fail(PROSAIL_E_ARG, "null weights (use prosail_set_windows for plain means)");
+    for (int w = 0; h && lo_nm && hi_nm && w < n_windows && w < MAX_WINDOWS; ++w)
+        if (hi_nm[w] < lo_nm[w]) return fail(PROSAIL_E_ARG, "window %d: hi < lo", w);
+    return set_windows_impl(h, n_windows, lo_nm, hi_nm, weights);
 }
 
 static int prospect_impl(prosail_handle_t* h, bool f32, int version, long long n, const prosail_leaf_t* leaf, void* ks, void* kt,

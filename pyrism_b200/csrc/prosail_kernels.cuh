@@ -75,6 +75,7 @@ struct WindowMap {                       // which band-mean windows touch which 
     int slot[NTILES][MAX_TILE_SLOTS];        // global slot id (window-major)
     int wstart[MAX_WINDOWS + 1];             // slots of window w: [wstart[w], wstart[w+1])
     int wcount[MAX_WINDOWS];                 // number of bands in window w
+    double wsum[MAX_WINDOWS];                // sum of the spectral-response weights of window w (= wcount when unweighted)
     int nwindows, ntotal;
     int ntiles_active;                       // 32-band tiles touched by at least one window
     int active_tile[NTILES];
@@ -87,6 +88,7 @@ struct SailArgs {
     const T* bandc;            // [NCONST][NBP]
     const void* tables;        // Tables<T>::type image in global memory
     const WindowMap* win;      // band-mean window map (global memory, read uniformly)
+    const double* srf;         // [slots][32] spectral-response weight of each lane of each window segment; NULL = boxcar (the reference)
     const T* srec;             // [nsamples][REC]
     const T* grec;             // [nitems][REC]
     long long nitems;
@@ -523,19 +525,22 @@ __device__ __forceinline__ void sail_directional(T rho, T tau, T rs, const Diffu
 // band-mean partial sums: segmented warp reduction over the windows that touch this tile
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void mean_partials_inl(const WindowMap* __restrict__ win, T v, int tile, int lane,
+__device__ __forceinline__ void mean_partials_inl(const WindowMap* __restrict__ win, const double* __restrict__ srf, T v, int tile, int lane,
                                                   T* __restrict__ dst /* [ntotal] */, bool f32) {
     if (!is_f32<T>() && f32) v = (T)(float)v;
     const int ns = win->nslots[tile];
     for (int j = 0; j < ns; ++j) {
-        const T x = ((win->mask[tile][j] >> lane) & 1u) ? v : T(0);
+        const int slot = win->slot[tile][j];
+        T x = ((win->mask[tile][j] >> lane) & 1u) ? v : T(0);
+        if (srf) x *= (T)srf[slot * 32 + lane];                  // spectral-response weighting (zero outside the window)
         const T sum = warp_sum(x);
-        if (lane == 0) dst[win->slot[tile][j]] = sum;
+        if (lane == 0) dst[slot] = sum;
     }
 }
 template <typename T>
-__device__ __noinline__ void mean_partials(const WindowMap* __restrict__ win, T v, int tile, int lane, T* __restrict__ dst, bool f32) {
-    mean_partials_inl(win, v, tile, lane, dst, f32);
+__device__ __noinline__ void mean_partials(const WindowMap* __restrict__ win, const double* __restrict__ srf, T v, int tile, int lane,
+                                           T* __restrict__ dst, bool f32) {
+    mean_partials_inl(win, srf, v, tile, lane, dst, f32);
 }
 
 enum { MODE_PROSAIL = 0, MODE_SAIL = 1, MODE_PROSPECT = 2, MODE_SOIL = 3 };
@@ -566,7 +571,7 @@ __device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
         }
         if (e.a.mean_mask & (1u << PLANE)) {
 #pragma unroll
-            for (int u = 0; u < NU; ++u) mean_partials(e.a.win, v[u], e.tile0 + u, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+            for (int u = 0; u < NU; ++u) mean_partials(e.a.win, e.a.srf, v[u], e.tile0 + u, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
             ++e.mi;
         }
     } else {
@@ -577,7 +582,7 @@ __device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
         }
         if ((MEANS >> PLANE) & 1u) {
 #pragma unroll
-            for (int u = 0; u < NU; ++u) mean_partials_inl(e.a.win, v[u], e.tile0 + u, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+            for (int u = 0; u < NU; ++u) mean_partials_inl(e.a.win, e.a.srf, v[u], e.tile0 + u, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
             ++e.mi;
         }
     }
@@ -790,7 +795,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
 }
 #undef PB_GATHER
 
-// band means = ordered sum of a window's slot partials / band count
+// band means = ordered sum of a window's slot partials / band count (or / sum of the response weights)
 template <typename T>
 __global__ void k_finalize_means(const WindowMap* __restrict__ win, const T* __restrict__ partial, long long nrows /* nitems*nmean */,
                                  T* __restrict__ means, float* __restrict__ means_f32) {
@@ -801,7 +806,7 @@ __global__ void k_finalize_means(const WindowMap* __restrict__ win, const T* __r
     const int w = (int)(idx - row * nw);
     double acc = 0.0;
     for (int sl = win->wstart[w]; sl < win->wstart[w + 1]; ++sl) acc += (double)partial[row * nt + sl];
-    const double mean = acc / (double)win->wcount[w];
+    const double mean = acc / win->wsum[w];
     if (means) means[idx] = (T)mean;
     if (means_f32) means_f32[idx] = (float)mean;
 }

@@ -126,6 +126,8 @@ class Engine(object):
         self.set_alpha('5', alpha)
         self.set_alpha('D', alpha)
         self.windows = None
+        self.srf = False
+        self._weights = None
         self.set_windows(windows)
 
     def _bind_to_gpu_numa_node(self):
@@ -166,15 +168,32 @@ class Engine(object):
                                                         _ptr(t.Kw), _ptr(t.Km), _ptr(kan), _ptr(talf), _ptr(t12), _ptr(t21)))
             self._alpha[version] = float(alpha)
 
-    def set_windows(self, windows):
-        """Inclusive (lo_nm, hi_nm) windows for the band means (default: 6 Landsat-8 + 9 ASTER windows)."""
+    def set_windows(self, windows, weights=None):
+        """Inclusive (lo_nm, hi_nm) windows for the band means (default: 6 Landsat-8 + 9 ASTER windows).
+
+        weights: None (plain means, the reference's behaviour) or one array per window with hi - lo + 1 spectral-response
+        weights (1 nm steps); the window value is then sum(w x) / sum(w)."""
         with self._lock:
             windows = tuple((int(lo), int(hi)) for lo, hi in windows)
-            if windows == self.windows:
-                return
             lo = np.ascontiguousarray([w[0] for w in windows], dtype=np.int32)
             hi = np.ascontiguousarray([w[1] for w in windows], dtype=np.int32)
-            capi.check(self.lib.prosail_set_windows(self.h, len(windows), _ptr(lo), _ptr(hi)))
+            if weights is None:
+                if windows == self.windows and not self.srf:
+                    return
+                capi.check(self.lib.prosail_set_windows(self.h, len(windows), _ptr(lo), _ptr(hi)))
+                self.srf = False
+                self._weights = None
+            else:
+                if len(weights) != len(windows):
+                    raise ValueError("one weight array per window")
+                ws = [np.asarray(w, dtype=_f64).reshape(-1) for w in weights]
+                for (a, b), w in zip(windows, ws):
+                    if w.size != b - a + 1:
+                        raise ValueError("window (%d, %d) needs %d weights, got %d" % (a, b, b - a + 1, w.size))
+                flat = np.ascontiguousarray(np.concatenate(ws))
+                capi.check(self.lib.prosail_set_windows_srf(self.h, len(windows), _ptr(lo), _ptr(hi), _ptr(flat)))
+                self.srf = True
+                self._weights = ws
             self.windows = windows
 
     # ---- helpers ---------------------------------------------------------------------------------------

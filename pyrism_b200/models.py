@@ -61,12 +61,12 @@ class _SpectralModel(object):
 
     def _with_windows(self, windows, fn):
         eng = self._engine
-        old = eng.windows
+        old, old_w = eng.windows, eng._weights
         try:
             eng.set_windows(windows)
             return fn()
         finally:
-            eng.set_windows(old)
+            eng.set_windows(old, old_w)
 
 
 # ---------------------------------------------------------------------------------------------------------

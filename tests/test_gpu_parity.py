@@ -444,3 +444,48 @@ def test_kernels_write_only_what_they_own_canaries(engine):
     assert np.all(oi[:guard] == -5) and np.all(oi[guard + q:] == -5) and np.all(oc[:guard] == np.float32(-777.25)) and np.all(oc[guard + q:] == np.float32(-777.25))
     ref_i, ref_c = inversion.invert(engine, lutf, obs)
     assert np.array_equal(oi[guard:guard + q], ref_i) and np.array_equal(oc[guard:guard + q], ref_c)          # device API == host API
+
+
+def test_spectral_response_weighted_windows(engine):
+    """prosail_set_windows_srf: window value = sum(w x) / sum(w) (a true sensor-band convolution; all weights 1 is the
+    reference's plain mean, models.py:811-851).  Checked against numpy on the spectra the same launch wrote and against the
+    oracle spectrum; overlapping and tile-crossing windows, fp64 and fp32, then back to the default windows."""
+    n = 300
+    P = lhs(n)
+    args = (P['N'], P['Cab'], P['Cxc'], P['Cbr'], P['Cw'], P['Cm'], rng.uniform(0.1, 8, n), rng.uniform(0.01, 0.5, n), np.radians([35.0]),
+            np.radians([30.0]), np.radians([50.0]), rng.uniform(0.3, 1.2, n), rng.uniform(0, 1, n))
+    kw = dict(lidf_type='campbell', a=rng.uniform(20, 80, n))
+    wins = ((452, 512), (630, 690), (640, 700), (2400, 2500), (400, 400))
+    lam = [np.arange(lo, hi + 1) for lo, hi in wins]
+    wts = [np.exp(-0.5 * ((l - l.mean()) / (0.25 * max(l.size, 2))) ** 2) for l in lam]            # Gaussian responses
+    wts[3] = rng.uniform(0, 1, lam[3].size)
+    default = engine.windows
+    try:
+        engine.set_windows(wins, wts)
+        for dt, tol in ((np.float64, 1e-13), (np.float32, 2e-6)):
+            r = engine.prosail(*args, planes=(capi.O_RSOT, capi.O_RDDT), mean_planes=(capi.O_RSOT, capi.O_RDDT), dtype=dt, **kw)
+            for w, ((lo, hi), wt) in enumerate(zip(wins, wts)):
+                for pi, key in enumerate(('rsot', 'rddt')):
+                    ref = (r[key][:, 0, lo - 400:hi - 400 + 1].astype(np.float64) * wt).sum(axis=1) / wt.sum()
+                    assert np.max(np.abs(r['means'][:, 0, pi, w] - ref)) <= tol, (dt, w, key)
+            wo = engine.prosail(*args, mean_planes=(capi.O_RSOT,), windows_only=True, dtype=dt, **kw)
+            assert np.array_equal(wo['means'][:, 0, 0], r['means'][:, 0, 0])
+        i = 7
+        _, _, o = orc.prosail(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i], args[6][i], args[7][i], 35.0, 30.0, 50.0,
+                              args[11][i], args[12][i], lidf_type='campbell', a=kw['a'][i])
+        r = engine.prosail(*args, mean_planes=(capi.O_RSOT,), **kw)
+        for w, ((lo, hi), wt) in enumerate(zip(wins, wts)):
+            assert abs(r['means'][i, 0, 0, w] - (o['rsot'][lo - 400:hi - 400 + 1] * wt).sum() / wt.sum()) <= TOL
+        # argument checks of the ABI
+        with pytest.raises(ValueError):
+            engine.set_windows(wins, wts[:-1])
+        with pytest.raises(capi.ProsailError):
+            engine.set_windows(((500, 510),), [np.zeros(11)])
+        with pytest.raises(capi.ProsailError):
+            engine.set_windows(((500, 510),), [-np.ones(11)])
+    finally:
+        engine.set_windows(default)
+    assert not engine.srf
+    r = engine.prosail(*args, planes=(capi.O_RSOT,), mean_planes=(capi.O_RSOT,), **kw)
+    lo, hi = default[0]
+    assert np.max(np.abs(r['means'][:, 0, 0, 0] - r['rsot'][:, 0, lo - 400:hi - 400 + 1].mean(axis=1))) <= 1e-14
