@@ -489,3 +489,18 @@ def test_spectral_response_weighted_windows(engine):
     r = engine.prosail(*args, planes=(capi.O_RSOT,), mean_planes=(capi.O_RSOT,), **kw)
     lo, hi = default[0]
     assert np.max(np.abs(r['means'][:, 0, 0, 0] - r['rsot'][:, 0, lo - 400:hi - 400 + 1].mean(axis=1))) <= 1e-14
+
+
+def test_empty_and_single_element_batches(engine):
+    """Empty parameter arrays are legal (a LUT shard may be empty: shard_bounds(5, r, 8)); length-1 arrays keep their batch axis."""
+    e = np.array([])
+    p = pb.PROSPECT(N=e, Cab=e, Cxc=e, Cbr=e, Cw=e, Cm=e)
+    assert p.ks.shape == (0, 2101) and p.kt.shape == (0, 2101)
+    r = engine.prosail(e, e, e, e, e, e, e, e, np.radians([35.0]), np.radians([30.0]), np.radians([50.0]), e, e, lidf_type='campbell', a=e,
+                       planes=(capi.O_RSOT,), mean_planes=(capi.O_RSOT,))
+    assert r['rsot'].shape == (0, 1, 2101) and r['means'].shape[0] == 0
+    one = pb.PROSPECT(N=np.array([1.5]), Cab=np.array([35.0]), Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055)
+    ref = pb.PROSPECT(N=1.5, Cab=35, Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055)
+    assert one.ks.shape == (1, 2101) and ref.ks.shape == (2101,) and np.array_equal(one.ks[0], ref.ks)
+    with pytest.raises(ValueError):
+        pb.PROSPECT(N=np.array([1.5, 2.0]), Cab=np.array([35.0, 36.0, 37.0]), Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055)       # ragged
