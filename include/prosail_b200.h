@@ -30,6 +30,7 @@ extern "C" {
 #define PROSAIL_NBANDS 2101
 #define PROSAIL_NLIDF 18
 #define PROSAIL_MAX_WINDOWS 64
+#define PROSAIL_NGEOM 12 /* per-item scalars of prosail_out_t.geom / prosail_volscatt_f64 */
 
 /* error codes (negative) */
 #define PROSAIL_E_ARG (-1)      /* bad argument */
@@ -63,6 +64,11 @@ enum {
     PROSAIL_O_LEAF_KA,  /* PROSPECT.ka = 1 - ks - kt (models.py:1066); prosail_prospect_* only */
     PROSAIL_O_LEAF_KE,  /* PROSPECT.ke = ks + ka     (models.py:1067) */
     PROSAIL_O_LEAF_OM,  /* PROSPECT.om = ks / ke     (models.py:1068) */
+    PROSAIL_O_LAYER_R,  /* PROSPECT.r, .t, .Ra, .Ta, .denom: the one-plate terms the reference keeps as attributes */
+    PROSAIL_O_LAYER_T,  /*   (models.py:959, 1019-1025); prosail_prospect_* only */
+    PROSAIL_O_LAYER_RA,
+    PROSAIL_O_LAYER_TA,
+    PROSAIL_O_LAYER_DENOM,
     PROSAIL_NOUT
 };
 
@@ -94,7 +100,8 @@ typedef struct prosail_out {
     long long pitch;
     unsigned mean_mask;          /* planes whose window means are wanted (bit = plane index) */
     double* means;               /* [n_items][popcount(mean_mask)][n_windows], planes in bit order */
-    double* geom;                /* optional [n_items][8]: VolScatt ks, ko, bf, Fs, Ft, tss, too, tsstoo */
+    double* geom;                /* optional [n_items][PROSAIL_NGEOM]: VolScatt ks, ko, bf, Fs, Ft; tss, too, tsstoo (models.py:664-
+                                    702); chi_s, chi_o, frho, ftau of the last leaf-inclination bin (what models.py:159 leaves behind) */
     int windows_only;            /* 1: evaluate only the wavelengths inside some window (planes must be NULL) */
 } prosail_out_t;
 
@@ -135,11 +142,12 @@ int prosail_set_windows(prosail_handle_t* h, int n_windows, const int* lo_nm, co
 int prosail_set_windows_srf(prosail_handle_t* h, int n_windows, const int* lo_nm, const int* hi_nm, const double* weights);
 
 /* ---- the hot path ------------------------------------------------------------------------------------ */
-/* pyrism.PROSPECT(...) for n parameter sets (models.py:900-921): spectra ks, kt and (optional, NULL = not wanted)
- * ka, ke, om (models.py:1064-1068), each [n][pitch].
+/* pyrism.PROSPECT(...) for n parameter sets (models.py:900-921).  out->plane[]: PROSAIL_O_LEAF_R (ks), _LEAF_T (kt), _LEAF_KA/KE/OM
+ * (models.py:1064-1068) and _LAYER_R/T/RA/TA/DENOM (the one-plate attributes, models.py:959), each [n][out->pitch], NULL = not
+ * wanted; the other fields of `out` must be zero.
  * means_f32 (optional) = float32 window means of (ks, kt, ka, ke, om), [n][5][n_windows]  (models.py:1071-1195). */
-int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, double* ks, double* kt,
-                         double* ka, double* ke, double* om, long long pitch, float* means_f32, int on_host, void* stream);
+int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_out_t* out,
+                         float* means_f32, int on_host, void* stream);
 
 /* pyrism.LSM(reflectance, moisture) for n parameter sets (models.py:1908-1920): rho [n][pitch];
  * means_f32 (optional) [n][1][n_windows] float32 (models.py:1918-2006). */
@@ -148,7 +156,7 @@ int prosail_soil_f64(prosail_handle_t* h, long long n, const prosail_soil_t* soi
 
 /* pyrism.VolScatt(iza, vza, raa).coef(lidf_type, a, b) + LIDF.campbell/verhoef (models.py:82-175, 283-392),
  * plus the direct transmittances/hotspot terms of SAIL.__calc (models.py:664-702) when lai/hotspot are given.
- * geom [n_items][8] (see prosail_out_t.geom); lidf (optional) [n][18]. */
+ * geom [n_items][PROSAIL_NGEOM] (see prosail_out_t.geom); lidf (optional) [n][18]. */
 int prosail_volscatt_f64(prosail_handle_t* h, long long n, const prosail_canopy_t* canopy, double* geom, double* lidf,
                          int on_host, void* stream);
 
@@ -164,8 +172,8 @@ int prosail_prosail_f64(prosail_handle_t* h, int version, long long n, const pro
                         const prosail_canopy_t* canopy, const prosail_out_t* out, int on_host, void* stream);
 
 /* fp32 mode of the four entry points above: same semantics, float spectra in and out (tolerance 1e-5 absolute). */
-int prosail_prospect_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, float* ks, float* kt,
-                         float* ka, float* ke, float* om, long long pitch, float* means_f32, int on_host, void* stream);
+int prosail_prospect_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_out_f32_t* out,
+                         float* means_f32, int on_host, void* stream);
 int prosail_soil_f32(prosail_handle_t* h, long long n, const prosail_soil_t* soil, float* rho, long long pitch,
                      float* means_f32, int on_host, void* stream);
 int prosail_sail_f32(prosail_handle_t* h, long long n, const float* ks, long long pitch_ks, const float* kt,

@@ -21,9 +21,10 @@ LIDF_CAMPBELL, LIDF_VERHOEF = 0, 1
 
 # output planes (prosail_b200.h: PROSAIL_O_*)
 (O_RSOT, O_RDDT, O_RSDT, O_RDOT, O_RSO, O_RDD, O_TDD, O_RSD, O_TSD, O_RDO, O_TDO, O_KE, O_LEAF_R, O_LEAF_T,
- O_RHO, O_LEAF_KA, O_LEAF_KE, O_LEAF_OM, NOUT) = range(19)
+ O_RHO, O_LEAF_KA, O_LEAF_KE, O_LEAF_OM, O_LAYER_R, O_LAYER_T, O_LAYER_RA, O_LAYER_TA, O_LAYER_DENOM, NOUT) = range(24)
 PLANE_NAMES = ("rsot", "rddt", "rsdt", "rdot", "rso", "rdd", "tdd", "rsd", "tsd", "rdo", "tdo", "ke", "leaf_r",
-               "leaf_t", "rho", "leaf_ka", "leaf_ke", "leaf_om")
+               "leaf_t", "rho", "leaf_ka", "leaf_ke", "leaf_om", "layer_r", "layer_t", "layer_ra", "layer_ta", "layer_denom")
+NGEOM = 12      # prosail_b200.h: PROSAIL_NGEOM
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)
@@ -69,8 +70,8 @@ _SIGNATURES = {
     "prosail_set_soil_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "prosail_set_windows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "prosail_set_windows_srf": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "prosail_prospect_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.POINTER(Leaf)] + [C.c_void_p] * 5 +
-                             [C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
+    "prosail_prospect_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.POINTER(Leaf), C.POINTER(Out), C.c_void_p, C.c_int,
+                                       C.c_void_p]),
     "prosail_soil_f64": (C.c_int, [C.c_void_p, C.c_longlong, C.POINTER(Soil), C.c_void_p, C.c_longlong, C.c_void_p,
                                    C.c_int, C.c_void_p]),
     "prosail_volscatt_f64": (C.c_int, [C.c_void_p, C.c_longlong, C.POINTER(Canopy), C.c_void_p, C.c_void_p, C.c_int,

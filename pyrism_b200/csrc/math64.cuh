@@ -196,6 +196,28 @@ __device__ __noinline__ double tau_rare(double k) {
     return exp(-k) * ((1.0 - k) + k * k / d);
 }
 
+// Table-free tau(k) for any k (plain IEEE arithmetic + libm; absolute error < 2e-15): E1 by its power series below 1 and by
+// the continued fraction above, evaluated bottom-up with a fixed depth (stable: no error accumulation over the levels).
+// Used where no shared-memory table is at hand and speed does not matter (the one-plate attribute planes of PROSPECT).
+__device__ __noinline__ double tau_full(double k) {
+    if (!(k > 0.0)) return 1.0;
+    double e1;
+    if (k < 1.0) {                       // E1(k) = -gamma - ln k + sum_{n>=1} (-1)^(n+1) k^n / (n n!)
+        double term = k, sum = k;
+        for (int n = 2; n <= 24; ++n) {
+            term *= -k / n;
+            sum += term / n;
+        }
+        e1 = -0.57721566490153286061 - log(k) + sum;
+    } else {                             // E1(k) = e^-k / (k + 1 - 1/(k + 3 - 4/(k + 5 - ...))), depth ~ 90/k + 20 levels
+        const int levels = (int)(90.0 / k) + 20;
+        double d = k + (2.0 * levels + 1.0);
+        for (int i = levels; i >= 1; --i) d = k + (2.0 * i - 1.0) - (double)i * (double)i / d;
+        e1 = exp(-k) / d;
+    }
+    return (1.0 - k) * exp(-k) + k * k * e1;
+}
+
 // full-range tau (test kernel, and the reference point for the fast path)
 __device__ __forceinline__ double tau_plate(double k, const double* __restrict__ tab) {
     bool rare;

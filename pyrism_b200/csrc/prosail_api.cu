@@ -19,6 +19,7 @@ using namespace pb;
 
 static_assert((int)PROSAIL_NOUT == (int)NOUT, "plane enums out of sync");
 static_assert(PROSAIL_MAX_WINDOWS == MAX_WINDOWS, "window limit out of sync");
+static_assert(PROSAIL_NGEOM == NGEOM, "geom record out of sync");
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -311,7 +312,7 @@ static int run_device_t(prosail_handle* h, const Job& j, Work& w, cudaStream_t s
         }
         p.srec = w.srec.p;
         p.grec = w.grec.p;
-        p.geom_out = j.geom ? j.geom + i0 * 8 : nullptr;
+        p.geom_out = j.geom ? j.geom + i0 * NGEOM : nullptr;
         p.lidf_out = j.lidf ? j.lidf + s0 * PROSAIL_NLIDF : nullptr;
         {
             ProfScope ps(h, 1, st);
@@ -395,7 +396,7 @@ static int run_host(prosail_handle* h, const Job& j) {
     int nplanes = 0;
     for (int i = 0; i < NOUT; ++i) nplanes += j.plane[i] ? 1 : 0;
     const size_t ES = j.esz();
-    const size_t out_per_item = (size_t)nplanes * j.pitch * ES + (size_t)j.nmean * nw * 8 + 64 + 256;
+    const size_t out_per_item = (size_t)nplanes * j.pitch * ES + (size_t)j.nmean * nw * 8 + NGEOM * 8 + 256;
     size_t in_per_sample = 16 * 8 + (j.mode == MODE_SAIL ? (size_t)(j.pr + j.pt + j.prho) * ES : 0) + PROSAIL_NLIDF * 8;
     const size_t per_sample = out_per_item * G + in_per_sample;
     long long slab = std::max<long long>(1, (long long)((256ull << 20) / per_sample));
@@ -458,7 +459,7 @@ static int run_host(prosail_handle* h, const Job& j) {
         for (int i = 0; i < NOUT; ++i) d.plane[i] = j.plane[i] ? co.take<char>((size_t)ni * j.pitch * ES) : nullptr;
         d.means = j.means ? co.take<char>((size_t)ni * j.nmean * nw * ES) : nullptr;
         d.means_f32 = j.means_f32 ? co.take<float>((size_t)ni * j.nmean * nw) : nullptr;
-        d.geom = j.geom ? co.take<double>((size_t)ni * 8) : nullptr;
+        d.geom = j.geom ? co.take<double>((size_t)ni * NGEOM) : nullptr;
         d.lidf = j.lidf ? co.take<double>((size_t)ns * PROSAIL_NLIDF) : nullptr;
 
         if ((rc = run_device(h, d, w, st))) return rc;
@@ -467,7 +468,7 @@ static int run_host(prosail_handle* h, const Job& j) {
             if (j.plane[i]) CK(cudaMemcpyAsync(offb(j.plane[i], i0 * j.pitch, ES), d.plane[i], (size_t)ni * j.pitch * ES, cudaMemcpyDeviceToHost, st));
         if (j.means) CK(cudaMemcpyAsync(offb(j.means, i0 * j.nmean * nw, ES), d.means, (size_t)ni * j.nmean * nw * ES, cudaMemcpyDeviceToHost, st));
         if (j.means_f32) CK(cudaMemcpyAsync(j.means_f32 + i0 * j.nmean * nw, d.means_f32, (size_t)ni * j.nmean * nw * 4, cudaMemcpyDeviceToHost, st));
-        if (j.geom) CK(cudaMemcpyAsync(j.geom + i0 * 8, d.geom, (size_t)ni * 8 * 8, cudaMemcpyDeviceToHost, st));
+        if (j.geom) CK(cudaMemcpyAsync(j.geom + i0 * NGEOM, d.geom, (size_t)ni * NGEOM * 8, cudaMemcpyDeviceToHost, st));
         if (j.lidf) CK(cudaMemcpyAsync(j.lidf + s0 * PROSAIL_NLIDF, d.lidf, (size_t)ns * PROSAIL_NLIDF * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(w.done, st));
     }
@@ -709,9 +710,11 @@ int prosail_set_windows_srf(prosail_handle_t* h, int n_windows, const int* lo_nm
     return set_windows_impl(h, n_windows, lo_nm, hi_nm, weights);
 }
 
-static int prospect_impl(prosail_handle_t* h, bool f32, int version, long long n, const prosail_leaf_t* leaf, void* ks, void* kt,
-                         void* ka, void* ke, void* om, long long pitch, float* means_f32, int on_host, void* stream) {
-    if (!leaf) return fail(PROSAIL_E_ARG, "null leaf struct");
+extern "C++" {
+template <class OUT>
+static int prospect_impl(prosail_handle_t* h, bool f32, int version, long long n, const prosail_leaf_t* leaf, const OUT* out,
+                         float* means_f32, int on_host, void* stream) {
+    if (!leaf || !out) return fail(PROSAIL_E_ARG, "null leaf / out struct");
     Job j;
     j.f32 = f32;
     j.mode = MODE_PROSPECT;
@@ -719,12 +722,14 @@ static int prospect_impl(prosail_handle_t* h, bool f32, int version, long long n
     j.n = n;
     j.has_leaf = true;
     j.leaf = *leaf;
-    j.plane[O_LEAF_R] = ks;
-    j.plane[O_LEAF_T] = kt;
-    j.plane[O_LEAF_KA] = ka;
-    j.plane[O_LEAF_KE] = ke;
-    j.plane[O_LEAF_OM] = om;
-    j.pitch = pitch;
+    constexpr unsigned ALLOWED = (1u << O_LEAF_R) | (1u << O_LEAF_T) | (7u << O_LEAF_KA) | (31u << O_LAYER_R);
+    for (int i = 0; i < NOUT; ++i) {
+        if (out->plane[i] && !((ALLOWED >> i) & 1u)) return fail(PROSAIL_E_ARG, "plane %d is not an output of prosail_prospect_*", i);
+        j.plane[i] = out->plane[i];
+    }
+    if (out->mean_mask || out->means || out->geom || out->windows_only)
+        return fail(PROSAIL_E_ARG, "prosail_prospect_* takes its window means through means_f32 (float32, as the reference)");
+    j.pitch = out->pitch;
     if (means_f32) {
         j.mean_mask = (1u << O_LEAF_R) | (1u << O_LEAF_T) | (7u << O_LEAF_KA);   // ks, kt, ka, ke, om in this order
         j.means_f32 = means_f32;
@@ -732,13 +737,14 @@ static int prospect_impl(prosail_handle_t* h, bool f32, int version, long long n
     }
     return run(h, j, on_host, stream);
 }
-int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, double* ks, double* kt,
-                         double* ka, double* ke, double* om, long long pitch, float* means_f32, int on_host, void* stream) {
-    return prospect_impl(h, false, version, n, leaf, ks, kt, ka, ke, om, pitch, means_f32, on_host, stream);
 }
-int prosail_prospect_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, float* ks, float* kt,
-                         float* ka, float* ke, float* om, long long pitch, float* means_f32, int on_host, void* stream) {
-    return prospect_impl(h, true, version, n, leaf, ks, kt, ka, ke, om, pitch, means_f32, on_host, stream);
+int prosail_prospect_f64(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_out_t* out,
+                         float* means_f32, int on_host, void* stream) {
+    return prospect_impl(h, false, version, n, leaf, out, means_f32, on_host, stream);
+}
+int prosail_prospect_f32(prosail_handle_t* h, int version, long long n, const prosail_leaf_t* leaf, const prosail_out_f32_t* out,
+                         float* means_f32, int on_host, void* stream) {
+    return prospect_impl(h, true, version, n, leaf, out, means_f32, on_host, stream);
 }
 
 static int soil_impl(prosail_handle_t* h, bool f32, long long n, const prosail_soil_t* soil, void* rho, long long pitch, float* means_f32,
@@ -812,7 +818,8 @@ static int sail_impl(prosail_handle_t* h, bool f32, long long n, const void* ks,
     j.in_rho = rho; j.prho = pitch_rho;
     copy_out(j, out);
     if (j.mean_mask & ((1u << O_LEAF_R) | (1u << O_LEAF_T) | (1u << O_RHO))) return fail(PROSAIL_E_ARG, "means of input spectra are not provided by prosail_sail_*");
-    if ((j.mean_mask >> O_LEAF_KA) || j.plane[O_LEAF_KA] || j.plane[O_LEAF_KE] || j.plane[O_LEAF_OM]) return fail(PROSAIL_E_ARG, "ka / ke / om are outputs of prosail_prospect_* only");
+    for (int i = O_LEAF_KA; i < NOUT; ++i)
+        if (j.plane[i] || ((j.mean_mask >> i) & 1u)) return fail(PROSAIL_E_ARG, "planes %d.. (ka, ke, om, one-plate terms) are outputs of prosail_prospect_* only", O_LEAF_KA);
     return run(h, j, on_host, stream);
 }
 }

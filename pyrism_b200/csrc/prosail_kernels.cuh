@@ -67,7 +67,10 @@ enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TS
 
 // output planes (bit index in out_mask / mean_mask)
 enum { O_RSOT = 0, O_RDDT, O_RSDT, O_RDOT, O_RSO, O_RDD, O_TDD, O_RSD, O_TSD, O_RDO, O_TDO, O_KE, O_LEAF_R, O_LEAF_T, O_RHO,
-       O_LEAF_KA, O_LEAF_KE, O_LEAF_OM, NOUT };   // the last three: PROSPECT's ka, ke, om (models.py:1066-1068), PROSPECT mode only
+       O_LEAF_KA, O_LEAF_KE, O_LEAF_OM,           // PROSPECT's ka, ke, om (models.py:1066-1068), PROSPECT mode only
+       O_LAYER_R, O_LAYER_T, O_LAYER_RA, O_LAYER_TA, O_LAYER_DENOM,   // one-plate r, t, Ra, Ta, denom (models.py:959, 1019-1025), idem
+       NOUT };
+constexpr int NGEOM = 12;         // per-item scalars returned to the host: ks ko bf Fs Ft tss too tsstoo + chi_s chi_o frho ftau (last leaf bin)
 
 struct WindowMap {                       // which band-mean windows touch which warp tile
     int nslots[NTILES];
@@ -325,6 +328,20 @@ __device__ __noinline__ void leaf_exact_f32(const BandConst<float>& c, float kal
     const double den = 1.0 - Rsub * r;
     tran = (float)(Ta * Tsub / den);                              // :1062-1065
     refl = (float)(Ra + Ta * Rsub * t / den);
+}
+
+// One-plate quantities exactly as models.py:1019-1025 (IEEE divisions), for the attributes PROSPECT.r/t/Ra/Ta/denom that the
+// reference leaves behind (:959).  Only the run-time-selected PROSPECT instance calls this, when one of those planes is wanted.
+template <typename T>
+__device__ __noinline__ void leaf_one_layer(const BandConst<T>& c, T kall, T (&out)[5]) {
+    const double tau = tau_full((double)kall);
+    const double r21 = (double)c.r21, t21 = (double)c.t21;
+    const double denom = 1.0 - r21 * r21 * tau * tau;
+    const double Ta = (double)c.talf * tau * t21 / denom;
+    const double Ra = (double)c.ralf + r21 * tau * Ta;
+    const double t = (double)c.t12 * tau * t21 / denom;
+    const double r = (double)c.r12 + r21 * tau * t;
+    out[0] = (T)r; out[1] = (T)t; out[2] = (T)Ra; out[3] = (T)Ta; out[4] = (T)denom;
 }
 
 // all NU bands of a thread: the chains are independent and written back to back so that they interleave
@@ -603,7 +620,7 @@ template <typename T> __host__ __device__ constexpr int min_ctas() { return std:
 // per-plane values of all bands of a thread, gathered from the per-band structs
 #define PB_GATHER(dst, arr, field)                       \
     T dst[NU];                                           \
-    _Pragma("unroll") for (int u = 0; u < NU; ++u) dst[u] = arr[u].field
+    _Pragma("unroll") for (int u = 0; u < NU; ++u) dst[u] = arr[u] field
 
 // ---------------------------------------------------------------------------------------------
 // main kernel.  1-D grid of independent warps: warp gw owns the tile group gw % ngroups (NU x 32 consecutive bands) and
@@ -721,6 +738,16 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         emit<PLANES, MEANS, O_LEAF_KE>(e, ke);
                         emit<PLANES, MEANS, O_LEAF_OM>(e, om);
                     }
+                    if (PLANES == RUNTIME && (need & (31u << O_LAYER_R))) {      // PROSPECT.r, t, Ra, Ta, denom (models.py:959)
+                        T q[NU][5];
+#pragma unroll
+                        for (int u = 0; u < NU; ++u) leaf_one_layer(c[u], leaf_kall<KS>(kc + u * CF::THREADS, sr), q[u]);
+                        { PB_GATHER(v, q, [0]); emit<PLANES, MEANS, O_LAYER_R>(e, v); }
+                        { PB_GATHER(v, q, [1]); emit<PLANES, MEANS, O_LAYER_T>(e, v); }
+                        { PB_GATHER(v, q, [2]); emit<PLANES, MEANS, O_LAYER_RA>(e, v); }
+                        { PB_GATHER(v, q, [3]); emit<PLANES, MEANS, O_LAYER_TA>(e, v); }
+                        { PB_GATHER(v, q, [4]); emit<PLANES, MEANS, O_LAYER_DENOM>(e, v); }
+                    }
                 } else {
                     if (G1 || fresh) {
                         if (MODE == MODE_PROSAIL) {
@@ -766,19 +793,19 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                                     if (rare[u]) sail_directional(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
                             }
                         }
-                        { PB_GATHER(v, o, rsot); emit<PLANES, MEANS, O_RSOT>(e, v); }
-                        { PB_GATHER(v, o, rddt); emit<PLANES, MEANS, O_RDDT>(e, v); }
-                        { PB_GATHER(v, o, rsdt); emit<PLANES, MEANS, O_RSDT>(e, v); }
-                        { PB_GATHER(v, o, rdot); emit<PLANES, MEANS, O_RDOT>(e, v); }
-                        { PB_GATHER(v, o, rso); emit<PLANES, MEANS, O_RSO>(e, v); }
-                        { PB_GATHER(v, d, rdd); emit<PLANES, MEANS, O_RDD>(e, v); }
-                        { PB_GATHER(v, d, tdd); emit<PLANES, MEANS, O_TDD>(e, v); }
-                        { PB_GATHER(v, o, rsd); emit<PLANES, MEANS, O_RSD>(e, v); }
-                        { PB_GATHER(v, o, tsd); emit<PLANES, MEANS, O_TSD>(e, v); }
-                        { PB_GATHER(v, o, rdo); emit<PLANES, MEANS, O_RDO>(e, v); }
-                        { PB_GATHER(v, o, tdo); emit<PLANES, MEANS, O_TDO>(e, v); }
+                        { PB_GATHER(v, o, .rsot); emit<PLANES, MEANS, O_RSOT>(e, v); }
+                        { PB_GATHER(v, o, .rddt); emit<PLANES, MEANS, O_RDDT>(e, v); }
+                        { PB_GATHER(v, o, .rsdt); emit<PLANES, MEANS, O_RSDT>(e, v); }
+                        { PB_GATHER(v, o, .rdot); emit<PLANES, MEANS, O_RDOT>(e, v); }
+                        { PB_GATHER(v, o, .rso); emit<PLANES, MEANS, O_RSO>(e, v); }
+                        { PB_GATHER(v, d, .rdd); emit<PLANES, MEANS, O_RDD>(e, v); }
+                        { PB_GATHER(v, d, .tdd); emit<PLANES, MEANS, O_TDD>(e, v); }
+                        { PB_GATHER(v, o, .rsd); emit<PLANES, MEANS, O_RSD>(e, v); }
+                        { PB_GATHER(v, o, .tsd); emit<PLANES, MEANS, O_TSD>(e, v); }
+                        { PB_GATHER(v, o, .rdo); emit<PLANES, MEANS, O_RDO>(e, v); }
+                        { PB_GATHER(v, o, .tdo); emit<PLANES, MEANS, O_TDO>(e, v); }
                     }
-                    { PB_GATHER(v, d, m); emit<PLANES, MEANS, O_KE>(e, v); }
+                    { PB_GATHER(v, d, .m); emit<PLANES, MEANS, O_KE>(e, v); }
                     emit<PLANES, MEANS, O_LEAF_R>(e, rho);
                     emit<PLANES, MEANS, O_LEAF_T>(e, tau);
                     emit<PLANES, MEANS, O_RHO>(e, rs);
@@ -827,7 +854,7 @@ struct PrologueArgs {
     const double *iza, *vza, *raa;   // radians, already normalised like core/_core.py:136-146
     void* srec;            // [nsamples][REC] of T (the kernel's template type: double, or float for the fp32 mode)
     void* grec;            // [nitems][REC] of T
-    double* geom_out;      // optional [nitems][8]: VolScatt ks, ko, bf, Fs, Ft and tss, too, tsstoo
+    double* geom_out;      // optional [nitems][NGEOM]: VolScatt ks, ko, bf, Fs, Ft; tss, too, tsstoo; chi_s, chi_o, frho, ftau of the last leaf bin
     double* lidf_out;      // optional [nsamples][18]
 };
 
@@ -967,6 +994,7 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
     // ---- LIDF-weighted volume-scattering sums, models.py:144-175 ----
     double ksli = 0.0, koli = 0.0, bfli = 0.0, sobli = 0.0, sofli = 0.0;
     const double cts = cos(tts), cto = cos(tto);
+    double last[4] = {0.0, 0.0, 0.0, 0.0};        // chi_s, chi_o, frho, ftau of this lane's bin; lane 17 = the last bin (models.py:159)
     if (lane < 18) {
         const double ttl = lane * 5.0 + 2.5;
         double chi_s, chi_o, frho, ftau;
@@ -977,6 +1005,11 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         bfli = cttl * cttl * lidf;
         sobli = frho * PB_PI / (cts * cto) * lidf;
         sofli = ftau * PB_PI / (cts * cto) * lidf;
+        last[0] = chi_s; last[1] = chi_o; last[2] = frho; last[3] = ftau;
+    }
+    if (a.geom_out) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) last[i] = __shfl_sync(0xffffffffu, last[i], 17);
     }
     const double k = warp_sum(ksli), K = warp_sum(koli), bf = warp_sum(bfli), Fs = warp_sum(sobli), Ft = warp_sum(sofli);
 
@@ -1029,8 +1062,9 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
             store_rec<T>(a.srec, s, srec);
         }
         if (a.geom_out) {
-            double* o = a.geom_out + item * 8;
+            double* o = a.geom_out + item * NGEOM;
             o[0] = k; o[1] = K; o[2] = bf; o[3] = Fs; o[4] = Ft; o[5] = tss; o[6] = too; o[7] = tsstoo;
+            o[8] = last[0]; o[9] = last[1]; o[10] = last[2]; o[11] = last[3];
         }
     }
 }
@@ -1170,6 +1204,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
 
     // ---- LIDF-weighted volume-scattering sums, models.py:144-258 ----
     double k = 0.0, K = 0.0, bf = 0.0, Fs = 0.0, Ft = 0.0;
+    double last_chi_s = 0.0, last_chi_o = 0.0, last_frho = 0.0, last_ftau = 0.0;
     const double ctscto = cts * cto;
     const bool view_up = tto < 90.0 * PB_PI / 180.0;
 #pragma unroll 1
@@ -1203,6 +1238,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
         const double frho = fmax(((PB_PI - bt2) * t1 + t2) / denom, 0.0);
         const double ftau = fmax((-bt2 * t1 + t2) / denom, 0.0);
         const double w = lidf[i];
+        last_chi_s = chi_s; last_chi_o = chi_o; last_frho = frho; last_ftau = ftau;
         k += chi_s / cts * w;
         K += chi_o / cto * w;
         bf += clza * clza * w;
@@ -1255,15 +1291,16 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
         store_rec<T>(a.srec, s, srec);
     }
     if (a.geom_out) {
-        double* o = a.geom_out + item * 8;
+        double* o = a.geom_out + item * NGEOM;
         o[0] = k; o[1] = K; o[2] = bf; o[3] = Fs; o[4] = Ft; o[5] = tss; o[6] = too; o[7] = tsstoo;
+        o[8] = last_chi_s; o[9] = last_chi_o; o[10] = last_frho; o[11] = last_ftau;      // as left behind by models.py:159
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // test / calibration kernels
 // ---------------------------------------------------------------------------------------------
-// op: 0 rcp, 1 sqrt_pos, 2 exp_neg, 3 log2_pos, 4 exp2_any, 5 tau_plate
+// op: 0 rcp, 1 sqrt_pos, 2 exp_neg, 3 log2_pos, 4 exp2_any, 5 tau_plate, 6 tau_full
 __global__ void k_test_math(int op, long long n, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ tables) {
     __shared__ MathTables mt;
     for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 8); i += blockDim.x) reinterpret_cast<double*>(&mt)[i] = tables[i];
@@ -1278,6 +1315,7 @@ __global__ void k_test_math(int op, long long n, const double* __restrict__ in, 
         case 2: y = exp_neg(x, mt.exp2t); break;
         case 3: y = log2_pos(x, mt.logt); break;
         case 4: y = exp2_any(x, mt.exp2t); break;
+        case 6: y = tau_full(x); break;
         default: y = tau_plate(x, mt.tau); break;
     }
     out[i] = y;

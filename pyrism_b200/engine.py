@@ -286,11 +286,14 @@ class Engine(object):
     def _fn(self, name, dt):
         return getattr(self.lib, "%s_%s" % (name, "f32" if dt == np.dtype(_f32) else "f64"))
 
-    def prospect(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=None, version='5', alpha=40, means=False, out=None, dtype=_f64,
-                 derived=False, spectra=True):
-        """Batched PROSPECT.  Returns dict(ks, kt[, ka, ke, om][, means]) with spectra dtype[n, 2101]; means float32[n, 5, nw].
+    _LEAF_PLANES = {'ks': capi.O_LEAF_R, 'kt': capi.O_LEAF_T, 'ka': capi.O_LEAF_KA, 'ke': capi.O_LEAF_KE, 'om': capi.O_LEAF_OM,
+                    'r': capi.O_LAYER_R, 't': capi.O_LAYER_T, 'Ra': capi.O_LAYER_RA, 'Ta': capi.O_LAYER_TA, 'denom': capi.O_LAYER_DENOM}
 
-        derived=True also returns ka, ke, om (models.py:1066-1068); spectra=False skips ks/kt (derived planes / means only).
+    def prospect(self, N, Cab, Cxc, Cbr, Cw, Cm, Can=None, version='5', alpha=40, means=False, out=None, dtype=_f64,
+                 derived=False, spectra=True, layer=False):
+        """Batched PROSPECT.  Returns dict of spectra dtype[n, 2101] (+ 'means' float32[n, 5, nw]).
+
+        spectra: ks, kt; derived: ka, ke, om (models.py:1066-1068); layer: the one-plate r, t, Ra, Ta, denom (models.py:959).
         """
         dt = _real(dtype)
         with self._lock:
@@ -301,15 +304,14 @@ class Engine(object):
             leaf = self._leaf(v[0], v[1], v[2], v[3], v[4], v[5], can)
             out = out or {}
             res = {}
-            for name, want in (('ks', spectra), ('kt', spectra), ('ka', derived), ('ke', derived), ('om', derived)):
-                if want:
-                    a = out.get(name)
-                    res[name] = a if a is not None else PinnedPool.empty((n, K.NBANDS), dt)
-                    assert res[name].dtype == dt
+            want = (('ks', 'kt') if spectra else ()) + (('ka', 'ke', 'om') if derived else ()) + (('r', 't', 'Ra', 'Ta', 'denom') if layer else ())
+            for name in want:
+                a = out.get(name)
+                res[name] = a if a is not None else PinnedPool.empty((n, K.NBANDS), dt)
+                assert res[name].dtype == dt
             m = PinnedPool.empty((n, 5, len(self.windows)), np.float32) if means else None
-            capi.check(self._fn("prosail_prospect", dt)(self.h, 0 if version == '5' else 1, n, C.byref(leaf), _ptr(res.get('ks')),
-                                                        _ptr(res.get('kt')), _ptr(res.get('ka')), _ptr(res.get('ke')), _ptr(res.get('om')),
-                                                        K.NBANDS, _ptr(m), 1, None))
+            o = self._out({self._LEAF_PLANES[k]: a for k, a in res.items()}, K.NBANDS, 0, None, None, 0)
+            capi.check(self._fn("prosail_prospect", dt)(self.h, 0 if version == '5' else 1, n, C.byref(leaf), C.byref(o), _ptr(m), 1, None))
             if means:
                 res['means'] = m
             return res
@@ -348,11 +350,12 @@ class Engine(object):
         return can, G, keep
 
     def volscatt(self, iza, vza, raa, lidf_type='campbell', a=57, b=0, lai=0.0, hotspot=0.0, geom_per_sample=False):
-        """Batched VolScatt.coef: returns (geom float64[n, G, 8], lidf float64[n, 18]); angles in normalised radians."""
+        """Batched VolScatt.coef: returns (geom float64[n, G, 12], lidf float64[n, 18]); angles in normalised radians.
+        geom[..., :] = ks, ko, bf, Fs, Ft, tss, too, tsstoo, chi_s, chi_o, frho, ftau (the last four at the last leaf bin)."""
         with self._lock:
             n = batch_size(a, b, lai, hotspot) if not geom_per_sample else max(batch_size(a, b, lai, hotspot), np.size(iza))
             can, G, keep = self._canopy_host(n, iza, vza, raa, lai, hotspot, lidf_type, a, b, geom_per_sample)
-            geom = np.empty((n, G, 8), dtype=_f64)
+            geom = np.empty((n, G, capi.NGEOM), dtype=_f64)
             lidf = np.empty((n, capi.NLIDF), dtype=_f64)
             capi.check(self.lib.prosail_volscatt_f64(self.h, n, C.byref(can), _ptr(geom), _ptr(lidf), 1, None))
             return geom, lidf
@@ -370,14 +373,14 @@ class Engine(object):
         nmean = bin(mask).count("1")
         means = (out.get('means') if out.get('means') is not None else
                  PinnedPool.empty((n_items, nmean, len(self.windows)), dt)) if nmean else None
-        geom = np.empty((n_items, 8), dtype=_f64) if want_geom else None
+        geom = np.empty((n_items, capi.NGEOM), dtype=_f64) if want_geom else None
         return bufs, mask, means, geom
 
     def sail(self, ks, kt, rho, iza, vza, raa, lai, hotspot, lidf_type='campbell', a=57, b=0, planes=(capi.O_RSOT,),
              mean_planes=(), geom_per_sample=False, want_geom=True, out=None, dtype=_f64):
         """Batched SAIL with leaf/soil spectra given as arrays ([2101] broadcast or [n, 2101]).
 
-        Returns dict: plane name -> dtype[n, G, 2101]; 'means' dtype[n, G, nmean, nw]; 'geom' float64[n, G, 8].
+        Returns dict: plane name -> dtype[n, G, 2101]; 'means' dtype[n, G, nmean, nw]; 'geom' float64[n, G, 12].
         """
         dt = _real(dtype)
         with self._lock:
@@ -454,9 +457,8 @@ class Engine(object):
     def prospect_device(self, n, leaf, ks, kt, pitch=K.NBANDS, version='5', stream=None, dtype=_f64):
         """Leaf-only batch on DeviceArrays (ks, kt: [n, pitch])."""
         lf = self._leaf(leaf['N'], leaf['Cab'], leaf['Cxc'], leaf['Cbr'], leaf['Cw'], leaf['Cm'], leaf.get('Can'))
-        capi.check(self._fn("prosail_prospect", _real(dtype))(self.h, 0 if version == '5' else 1, int(n), C.byref(lf),
-                                                              C.c_void_p(self._addr(ks)), C.c_void_p(self._addr(kt)), None, None, None,
-                                                              int(pitch), None, 0, stream))
+        o = self._out({capi.O_LEAF_R: ks, capi.O_LEAF_T: kt}, pitch, 0, None, None, 0)
+        capi.check(self._fn("prosail_prospect", _real(dtype))(self.h, 0 if version == '5' else 1, int(n), C.byref(lf), C.byref(o), None, 0, stream))
 
     @staticmethod
     def _pack(bufs, means, geom, n, G):
@@ -466,7 +468,7 @@ class Engine(object):
         if means is not None:
             res['means'] = means.reshape(n, G, means.shape[-2], means.shape[-1])
         if geom is not None:
-            res['geom'] = geom.reshape(n, G, 8)
+            res['geom'] = geom.reshape(n, G, capi.NGEOM)
         return res
 
 

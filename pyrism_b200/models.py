@@ -101,6 +101,7 @@ class PROSPECT(_SpectralModel):
         self._engine = get_engine(device)
         self._scalar = _is_scalar_call(N, Cab, Cxc, Cbr, Cw, Cm, Can)
         self._d = None
+        self._l = None
         res = self._engine.prospect(N, Cab, Cxc, Cbr, Cw, Cm, Can=Can if self.ver == 'D' else None, version=self.ver,
                                     alpha=alpha, means=True, dtype=self.dtype)
         sq = (lambda a: a[0]) if self._scalar else (lambda a: a)
@@ -128,6 +129,21 @@ class PROSPECT(_SpectralModel):
     @property
     def om(self):
         return self._derived()['om']
+
+    # the one-plate terms the reference keeps as attributes (models.py:959): same lazy scheme
+    def _layer(self):
+        if self._l is None:
+            r = self._engine.prospect(self.N, self.Cab, self.Cxc, self.Cbr, self.Cw, self.Cm, Can=self.Can if self.ver == 'D' else None,
+                                      version=self.ver, alpha=self.alpha, dtype=self.dtype, layer=True, spectra=False)
+            sq = (lambda a: a[0]) if self._scalar else (lambda a: a)
+            self._l = {k: sq(r[k]) for k in ('r', 't', 'Ra', 'Ta', 'denom')}
+        return self._l
+
+    r = property(lambda self: self._layer()['r'])
+    t = property(lambda self: self._layer()['t'])
+    Ra = property(lambda self: self._layer()['Ra'])
+    Ta = property(lambda self: self._layer()['Ta'])
+    denom = property(lambda self: self._layer()['denom'])
 
     @property
     def int(self):
@@ -240,6 +256,8 @@ class VolScatt(Kernel):
         bf = g[..., 2]
         self.bf = bf[..., 0][()] if scalar else bf[..., 0]    # bf does not depend on the geometry
         self.Fst = self.Fs + self.Ft
+        # values of the last leaf-inclination bin (87.5 deg), which the reference's loop leaves behind (models.py:159)
+        self.chi_s, self.chi_o, self.frho, self.ftau = g[..., 8], g[..., 9], g[..., 10], g[..., 11]
 
 
 # ---------------------------------------------------------------------------------------------------------

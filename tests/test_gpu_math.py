@@ -62,3 +62,16 @@ def test_tau_against_scipy_expi(engine):
     k = 10.0 ** rng.uniform(-6, 1.7, 20000)
     want = (1 - k) * np.exp(-k) + k ** 2 * (-expi(-k))
     assert np.max(np.abs(engine.test_math(5, k) - want)) < 2e-15
+
+
+def test_table_free_tau_against_mpmath(engine):
+    """tau_full (op 6): the table-free evaluation behind the one-plate attribute planes."""
+    import mpmath as mp
+    rng = np.random.default_rng(5)
+    k = np.concatenate([10.0 ** rng.uniform(-10, 2.3, 1500), rng.uniform(1.5, 2.5, 200), [1e-300, 2.0, 1.9999999, 50.0, 200.0]])
+    ref = np.array([float((1 - mp.mpf(v)) * mp.exp(-mp.mpf(v)) + mp.mpf(v) ** 2 * mp.e1(mp.mpf(v))) for v in k])
+    got = engine.test_math(6, k)
+    assert np.max(np.abs(got - ref)) < 2e-15                       # absolute: what r, t, Ra, Ta see
+    m = k <= 20.0                                                   # (1-k)e^-k + k^2 E1(k) cancels ~k^2/2 digits (in the reference too)
+    assert np.max(np.abs(got[m] - ref[m]) / ref[m]) < 3e-13
+    assert np.array_equal(engine.test_math(6, np.array([0.0, -2.0])), [1.0, 1.0])

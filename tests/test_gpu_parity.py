@@ -338,7 +338,7 @@ def test_both_prologue_mappings_vs_oracle(engine, lidf_type):
             o = orc.sail(izad[g], vzad[g], raad[g], ks, ks, lai[i], hot[i], ks, lidf_type=lidf_type, a=a[i], b=b[i])
             want = np.array([o['vol_ks'], o['vol_ko'], o['bf'], o['Fs'], o['Ft'], o['tss'], o['too'], o['tsstoo']], dtype=np.float64)
             for name in ('thread', 'warp'):
-                assert np.max(np.abs(out[name][0][i, g] - want)) <= 1e-12, (name, i, g)
+                assert np.max(np.abs(out[name][0][i, g, :8] - want)) <= 1e-12, (name, i, g)
 
 
 def test_device_resident_api_matches_host_api(engine):
@@ -388,11 +388,16 @@ def test_custom_windows_and_c_abi_errors(engine):
     finally:
         engine.set_windows(old)
     import ctypes as C
-    rc = engine.lib.prosail_prospect_f64(engine.h, 7, 1, C.byref(capi.Leaf()), None, None, None, None, None, 2101, None, 1, None)
+    o = capi.Out()
+    o.pitch = 2101
+    rc = engine.lib.prosail_prospect_f64(engine.h, 7, 1, C.byref(capi.Leaf()), C.byref(o), None, 1, None)
     assert rc == -1 and b"version must be" in engine.lib.prosail_last_error()
-    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, C.byref(capi.Leaf()), None, None, None, None, None, 2101, None, 1, None)
+    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, C.byref(capi.Leaf()), C.byref(o), None, 1, None)
     assert rc == -1 and b"null leaf" in engine.lib.prosail_last_error()
-    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, None, None, None, None, None, None, 2101, None, 1, None)
+    o.plane[capi.O_RSOT] = 1
+    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, C.byref(capi.Leaf()), C.byref(o), None, 1, None)
+    assert rc == -1 and b"not an output of prosail_prospect" in engine.lib.prosail_last_error()
+    rc = engine.lib.prosail_prospect_f64(engine.h, 0, 1, None, None, None, 1, None)
     assert rc == -1
     assert engine.launch_count() > 0
 
@@ -504,3 +509,32 @@ def test_empty_and_single_element_batches(engine):
     assert one.ks.shape == (1, 2101) and ref.ks.shape == (2101,) and np.array_equal(one.ks[0], ref.ks)
     with pytest.raises(ValueError):
         pb.PROSPECT(N=np.array([1.5, 2.0]), Cab=np.array([35.0, 36.0, 37.0]), Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055)       # ragged
+
+
+def test_leftover_attributes_of_the_reference(engine):
+    """the reference leaves PROSPECT.r/t/Ra/Ta/denom (models.py:959) and VolScatt.chi_s/chi_o/frho/ftau of the LAST
+    leaf-inclination bin (models.py:159) behind as attributes; both come from the kernels here."""
+    n = 40
+    P = lhs(n)
+    for dt, tol in ((np.float64, TOL), (np.float32, 1e-5)):
+        p = pb.PROSPECT(dtype=dt, **P)
+        for i in (0, 13, n - 1):
+            o = orc.prospect(P['N'][i], P['Cab'][i], P['Cxc'][i], P['Cbr'][i], P['Cw'][i], P['Cm'][i])
+            for q in ('r', 't', 'Ra', 'Ta', 'denom'):
+                got = getattr(p, q)
+                assert got.shape == (n, 2101) and got.dtype == dt and np.max(np.abs(got[i] - o[q])) <= tol, (q, i, dt)
+    one = pb.PROSPECT(N=1.5, Cab=35, Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055, Can=1.0, version='D')
+    o = orc.prospect(np.float64(1.5), np.float64(35), np.float64(5), np.float64(0.15), np.float64(0.003), np.float64(0.0055), Can=np.float64(1.0), version='D')
+    assert one.r.shape == (2101,) and np.max(np.abs(one.r - o['r'])) <= TOL and np.max(np.abs(one.denom - o['denom'])) <= TOL
+    # volume scattering terms of the last bin, both prologue mappings
+    iza, vza, raa = np.array([35.0, 10.0, 60.0, 0.0]), np.array([30.0, 45.0, 0.0, 0.0]), np.array([50.0, 120.0, 180.0, 0.0])
+    for thr in (2048, 0):
+        engine.set_prologue_threshold(thr)
+        try:
+            v = pb.VolScatt(iza, vza, raa)
+            v.coef(lidf_type='campbell', a=57)
+        finally:
+            engine.set_prologue_threshold(2048)
+        for g in range(4):
+            cs, co, fr, ft = orc.volscatt_volume(np.radians(iza[g]), np.radians(vza[g]), np.radians(raa[g]), 87.5)
+            assert max(abs(v.chi_s[g] - cs), abs(v.chi_o[g] - co), abs(v.frho[g] - fr), abs(v.ftau[g] - ft)) <= 1e-12, (thr, g)

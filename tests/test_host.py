@@ -149,9 +149,9 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(capi.Leaf) == 7 * 8 and ctypes.sizeof(capi.Soil) == 2 * 8
     assert capi.Canopy.lidf_a.offset == 8 and capi.Canopy.n_geom.offset == 40 and capi.Canopy.iza.offset == 48
     assert ctypes.sizeof(capi.Canopy) == 72
-    assert capi.Out.pitch.offset == 18 * 8 and capi.Out.mean_mask.offset == 19 * 8 and capi.Out.means.offset == 20 * 8
-    assert ctypes.sizeof(capi.Out) == 23 * 8
-    assert capi.NOUT == 18 and len(capi.PLANE_NAMES) == 18
+    assert capi.Out.pitch.offset == 23 * 8 and capi.Out.mean_mask.offset == 24 * 8 and capi.Out.means.offset == 25 * 8
+    assert ctypes.sizeof(capi.Out) == 28 * 8
+    assert capi.NOUT == 23 and len(capi.PLANE_NAMES) == 23 and capi.NGEOM == 12
 
 
 @pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a GPU")
