@@ -74,9 +74,9 @@ __device__ __forceinline__ float tau_fast(float k, const float* __restrict__ tab
     const int E = min(max(E0, TAU_EMIN), TAU_EMAX);
     rare = E != E0;
     const int e1 = max(E, 1);
-    const int j = (bits & 0x007FFFFF) >> (22 - e1);
-    const int idx = (TAU_NA - 4) + j + (E <= 0 ? (E << 2) : (2 << E));
-    const float S = __int_as_float((130 - min(E, 1)) << 23);        // 2^(3 - min(E, 1))
+    const int j = (bits & 0x007FFFFF) >> (24 - TAU_SB - e1);
+    const int idx = (TAU_NA - (1 << TAU_SB)) + j + (E <= 0 ? (E << TAU_SB) : ((1 << (TAU_SB - 1)) << E));
+    const float S = __int_as_float((128 + TAU_SB - min(E, 1)) << 23);   // 2^(TAU_SB + 1 - min(E, 1))
     const float4* row = reinterpret_cast<const float4*>(tab + idx * TAU_ROW_F);
     const float4 a = row[0], b = row[1];                            // O c0 c1 c2 | c3 c4 c5 pad
     const float u = fmaf(k, S, -a.x);

@@ -20,19 +20,18 @@ namespace pb {
 // Polynomial / range-reduction constants live in constant memory so that DFMA takes them straight from the
 // constant bank (operand c[3][..]); as literals they would each cost two UMOV issue slots per use.
 // (Values whose low 32 bits are zero -- 0.5, 1.0, 256.0, the rounding magic -- are encodable as immediates.)
-enum { M_L2E256 = 0, M_LN2H, M_LN2L, M_E4, M_E3, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P4, M_P3, M_P2, M_P1, M_COUNT };
+enum { M_L2EN = 0, M_LN2H, M_LN2L, M_E3, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P3, M_P2, M_P1, M_COUNT };
+static_assert(EXP2_BITS == 11, "the range-reduction constants below are for a 2048-entry 2^(j/2048) table");
 __constant__ double c_m[M_COUNT] = {
-    369.32993046757462751,       // 256 log2(e)
-    -0x1.62e42fe000000p-9,       // -(ln2/256) high part (29 significant bits: n * hi is exact for |n| < 2^24)
-    -0x1.f473de6af278fp-38,      // -(ln2/256) low part
-    0x1.5555555555555p-5,        // 1/24
+    2954.6394437405970201,       // 2048 log2(e)
+    -0x1.62e42fe000000p-12,      // -(ln2/2048) high part (29 significant bits: n * hi is exact for |n| < 2^24)
+    -0x1.f473de6af278fp-41,      // -(ln2/2048) low part
     0x1.5555555555555p-3,        // 1/6
     -0x1.71547652b82fep-2,       // -1/(4 ln2)
     0x1.ec709dc3a03fdp-2,        // 1/(3 ln2)
     -0x1.71547652b82fep-1,       // -1/(2 ln2)
     0x1.71547652b82fep+0,        // 1/ln2
     4503601774854144.0,          // 2^52 + 2^31
-    0x1.3b2ab6fba4e77p-7,        // ln2^4/24
     0x1.c6b08d704a0c0p-5,        // ln2^3/6
     0x1.ebfbdff82c58fp-3,        // ln2^2/2
     0x1.62e42fefa39efp-1,        // ln2
@@ -41,7 +40,7 @@ __constant__ double c_m[M_COUNT] = {
 // ---- shared-memory image of the lookup tables (copied once per CTA) ----
 struct alignas(16) MathTables {
     double tau[TAU_NROWS * TAU_ROW];   // piecewise polynomials of tau(k), see tools/gen_math_tables.py
-    double exp2t[256];                 // 2^(j/256)
+    double exp2t[1 << EXP2_BITS];      // 2^(j/2048)
     double logt[512];                  // pairs (1/c_i, log2 c_i), c_i = 1 + (i+.5)/256
 };
 
@@ -79,22 +78,21 @@ __device__ __forceinline__ double sqrt_pos(double x) {
     return is_pos(x) ? g : 0.0;
 }
 
-// exp(x) for x <= 0 (clamped at about -700; positive x is outside the contract): n = rint(256 x log2 e); exp = 2^(n>>8) * T[n&255] * P4(r), |r| <= ln2/512.
-// 9 FP64 ops + one table load.
+// exp(x) for x <= 0 (clamped at about -700; positive x is outside the contract): n = rint(2048 x log2 e);
+// exp = 2^(n>>11) * T[n&2047] * P3(r), |r| <= ln2/4096 (the cubic truncates at r^4/24 < 4e-17).  8 FP64 ops + one table load.
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ exp2t) {
     // clamp at about -700: for x <= 0 the high word grows (as an unsigned integer) with |x|, so ONE integer min does it
     x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC085E000u), __double2loint(x));
-    const double t = fma(x, c_m[M_L2E256], PB_MAGIC);
+    const double t = fma(x, c_m[M_L2EN], PB_MAGIC);
     const int n = __double2loint(t);
     const double nd = t - PB_MAGIC;
     double r = fma(nd, c_m[M_LN2H], x);
     r = fma(nd, c_m[M_LN2L], r);
-    double p = fma(r, c_m[M_E4], c_m[M_E3]);
-    p = fma(r, p, 0.5);
+    double p = fma(r, c_m[M_E3], 0.5);
     p = fma(r, p, 1.0);
     p = fma(r, p, 1.0);
-    const double v = exp2t[n & 255] * p;
-    return __hiloint2double(__double2hiint(v) + ((n >> 8) << 20), __double2loint(v));
+    const double v = exp2t[n & ((1 << EXP2_BITS) - 1)] * p;
+    return __hiloint2double(__double2hiint(v) + ((n >> EXP2_BITS) << 20), __double2loint(v));
 }
 
 // log2(b) for normal b > 0: b = 2^E m, m in [1,2); i = top 8 mantissa bits; r = m/c_i - 1, |r| <= 2^-9;
@@ -115,21 +113,20 @@ __device__ __forceinline__ double log2_pos(double b, const double* __restrict__ 
     return fma(r, q, Ed + tc.y);
 }
 
-// 2^y (clamped at about 500): n = rint(256 y); r = y - n/256 (exact); 2^y = 2^(n>>8) T[n&255] P4(r ln2).
-// 8 FP64 ops + one table load.
+// 2^y (clamped at about 500): n = rint(2048 y); r = y - n/2048 (exact); 2^y = 2^(n>>11) T[n&2047] P3(r ln2).
+// 7 FP64 ops + one table load.
 __device__ __forceinline__ double exp2_any(double y, const double* __restrict__ exp2t) {
     // clamp at about 500: one signed integer min on the high word (negative y has a negative high word and passes)
     y = __hiloint2double(min(__double2hiint(y), 0x407F4000), __double2loint(y));
-    const double t = fma(y, 256.0, PB_MAGIC);
+    const double t = fma(y, (double)(1 << EXP2_BITS), PB_MAGIC);
     const int n = __double2loint(t);
     const double nd = t - PB_MAGIC;
-    const double r = fma(nd, -0.00390625, y);
-    double p = fma(r, c_m[M_P4], c_m[M_P3]);
-    p = fma(r, p, c_m[M_P2]);
+    const double r = fma(nd, -1.0 / (1 << EXP2_BITS), y);
+    double p = fma(r, c_m[M_P3], c_m[M_P2]);
     p = fma(r, p, c_m[M_P1]);
     p = fma(r, p, 1.0);
-    const double v = exp2t[n & 255] * p;
-    return __hiloint2double(__double2hiint(v) + ((n >> 8) << 20), __double2loint(v));
+    const double v = exp2t[n & ((1 << EXP2_BITS) - 1)] * p;
+    return __hiloint2double(__double2hiint(v) + ((n >> EXP2_BITS) << 20), __double2loint(v));
 }
 
 // type-generic spellings used by the kernel template (the float twins are in math32.cuh)
@@ -148,10 +145,10 @@ __device__ __forceinline__ double tau_fast(double k, const double* __restrict__ 
     const int E0 = (hi >> 20) - 1023;
     const int E = min(max(E0, TAU_EMIN), TAU_EMAX);
     rare = E != E0;
-    const int e1 = max(E, 1);                                      // sub-interval bits: 2 below k = 2, E + 1 above
-    const int j = (hi & 0x000FFFFF) >> (19 - e1);
-    const int idx = (TAU_NA - 4) + j + (E <= 0 ? (E << 2) : (2 << E));
-    const double S = __hiloint2double((1026 - min(E, 1)) << 20, 0);   // 2^(3 - min(E, 1))
+    const int e1 = max(E, 1);                                      // sub-interval bits: TAU_SB below k = 2, E + TAU_SB - 1 above
+    const int j = (hi & 0x000FFFFF) >> (21 - TAU_SB - e1);
+    const int idx = (TAU_NA - (1 << TAU_SB)) + j + (E <= 0 ? (E << TAU_SB) : ((1 << (TAU_SB - 1)) << E));
+    const double S = __hiloint2double((1024 + TAU_SB - min(E, 1)) << 20, 0);   // 2^(TAU_SB + 1 - min(E, 1))
     const double2* row = reinterpret_cast<const double2*>(tab + idx * TAU_ROW);
     const double2 c01 = row[0];                                    // O, c0
     const double u = fma(k, S, -c01.x);

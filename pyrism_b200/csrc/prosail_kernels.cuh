@@ -635,7 +635,9 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     constexpr int NU = CF::NU;
     SailSmem<T, CF>& sm = *reinterpret_cast<SailSmem<T, CF>*>(smem_raw);
     const T zero_ = T(0), one = T(1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: tells the compiler it is warp-uniform (uniform registers / uniform addressing of
+    // the per-warp staging buffers and of everything derived from the tile group)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int gw = blockIdx.x * CF::WARPS + warp;                     // global warp id
     const int range = gw / a.ngroups;
     const int tslot = gw - range * a.ngroups;

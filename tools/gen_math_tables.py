@@ -3,13 +3,14 @@
 
 1. TAU table -- piecewise polynomials for the plate transmissivity of PROSPECT,
        tau(k) = (1-k) exp(-k) + k^2 E1(k)  ( = 2 E3(k) ),        reference models.py:953-957,
-   on 120 intervals that are addressed with integer operations on the exponent/mantissa bits of k
-   (so that the FP64 pipe only sees one FMA for the local variable plus the Horner chain):
-     region A, k in [2^-14, 2):  4 equal sub-intervals per binade            (60 intervals)
-     region B, k in [2, 32):     sub-intervals of width 0.5 (2^(E+1) per binade E=1..4)  (60 intervals)
+   on intervals that are addressed with integer operations on the exponent/mantissa bits of k
+   (so that the FP64 pipe only sees one FMA for the local variable plus the Horner chain); with SB = TAU_SB:
+     region A, k in [2^-14, 2):  2^SB equal sub-intervals per binade                       (15 * 2^SB intervals)
+     region B, k in [2, 32):     sub-intervals of width 2^(1-SB) (2^(E+SB-1) per binade E=1..4)  (15 * 2^SB intervals)
+   SB = 3 and degree 8 (240 rows of 10 doubles) replaced SB = 2 and degree 10: two three-register DFMAs less per evaluation.
    Row layout: [O, c0, c1, ..., cD] with u = k*S - O in [-1, 1], S a power of two, tau ~= sum c_i u^i.
    Outside (rare path of the kernel): k < 2^-14 -> series with log(k);  k >= 32 -> continued fraction of E1.
-2. EXP2 table -- 2^(j/256), j = 0..255.
+2. EXP2 table -- 2^(j/2^EXP2_BITS), j = 0..2^EXP2_BITS - 1 (2048 entries: a cubic in the reduced argument is then exact to 4e-17).
 3. LOG table  -- for c_i = 1 + (i + 0.5)/256, i = 0..255:  1/c_i (rounded) and -log2(1/c_i) paired.
 
 Coefficients are fitted with mpmath (50 digits) at Chebyshev nodes, converted to the monomial basis in u
@@ -24,11 +25,13 @@ import mpmath as mp
 import numpy as np
 
 mp.mp.dps = 60
-DEG = int(os.environ.get("TAU_DEG", "10"))
+DEG = int(os.environ.get("TAU_DEG", "8"))
+SB = int(os.environ.get("TAU_SB", "3"))
+EXP2_BITS = int(os.environ.get("EXP2_BITS", "11"))
 EMIN = -14
 EMAX = 4
-NA = (0 - EMIN + 1) * 4          # 60
-NB = sum(2 ** (E + 1) for E in range(1, EMAX + 1))   # 60
+NA = (0 - EMIN + 1) * 2 ** SB
+NB = sum(2 ** (E + SB - 1) for E in range(1, EMAX + 1))
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "pyrism_b200", "csrc", "math_tables.inc")
 
 
@@ -41,15 +44,15 @@ def intervals():
     """(lo, hi, S, O) per interval in table order."""
     rows = []
     for E in range(EMIN, 1):
-        for j in range(4):
-            lo = mp.mpf(2) ** E * (1 + mp.mpf(j) / 4)
-            h = mp.mpf(2) ** (E - 3)
-            rows.append((lo, lo + 2 * h, mp.mpf(2) ** (3 - E), 9 + 2 * j))
+        for j in range(2 ** SB):
+            lo = mp.mpf(2) ** E * (1 + mp.mpf(j) / 2 ** SB)
+            w = mp.mpf(2) ** (E - SB)
+            rows.append((lo, lo + w, mp.mpf(2) ** (SB + 1 - E), 2 ** (SB + 1) + 2 * j + 1))
+    w = mp.mpf(2) ** (1 - SB)
     for E in range(1, EMAX + 1):
-        sb = E + 1
-        for j in range(2 ** sb):
-            lo = mp.mpf(2) ** E + mp.mpf(j) / 2
-            rows.append((lo, lo + mp.mpf(1) / 2, mp.mpf(4), 2 ** (E + 2) + 2 * j + 1))
+        for j in range(2 ** (E + SB - 1)):
+            lo = mp.mpf(2) ** E + j * w
+            rows.append((lo, lo + w, mp.mpf(2) ** SB, 2 ** (E + SB) + 2 * j + 1))
     return rows
 
 
@@ -131,7 +134,7 @@ def main():
     if worst_f > 4e-7:
         sys.exit("float table misses the 4e-7 relative target")
 
-    exp2t = [float(mp.mpf(2) ** (mp.mpf(j) / 256)) for j in range(256)]
+    exp2t = [float(mp.mpf(2) ** (mp.mpf(j) / 2 ** EXP2_BITS)) for j in range(2 ** EXP2_BITS)]
     logt = []
     for i in range(256):
         c = 1 + (mp.mpf(i) + mp.mpf(1) / 2) / 256
@@ -143,7 +146,7 @@ def main():
         fh.write("// tau(k) = (1-k)exp(-k) + k^2 E1(k): degree-%d piecewise polynomials; worst abs %.2e, worst rel %.2e (vs mpmath).\n"
                  % (DEG, worst_abs, worst_rel))
         fh.write("#define TAU_DEG %d\n#define TAU_ROW %d\n#define TAU_NROWS %d\n#define TAU_NA %d\n#define TAU_EMIN (%d)\n#define TAU_EMAX (%d)\n"
-                 % (DEG, DEG + 2, len(rows), NA, EMIN, EMAX))
+                 "#define TAU_SB %d\n#define EXP2_BITS %d\n" % (DEG, DEG + 2, len(rows), NA, EMIN, EMAX, SB, EXP2_BITS))
         fh.write("static const double h_tau_table[TAU_NROWS * TAU_ROW] = {\n")
         for r in range(len(rows)):
             fh.write("  " + ", ".join(float(v).hex() for v in table[r]) + ",\n")
@@ -153,7 +156,7 @@ def main():
         for r in range(len(rows)):
             fh.write("  " + ", ".join("%sf" % float(v).hex() for v in table_f[r]) + ",\n")
         fh.write("};\n")
-        fh.write("static const double h_exp2_table[256] = {\n  " + ",\n  ".join(v.hex() for v in exp2t) + "\n};\n")
+        fh.write("static const double h_exp2_table[1 << EXP2_BITS] = {\n  " + ",\n  ".join(v.hex() for v in exp2t) + "\n};\n")
         fh.write("static const double h_log_table[512] = {\n  " + ",\n  ".join("%s, %s" % (a.hex(), b.hex()) for a, b in logt) + "\n};\n")
     print("wrote", os.path.normpath(OUT))
 
