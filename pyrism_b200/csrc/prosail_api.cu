@@ -210,14 +210,19 @@ static inline const void* offb(const void* p, long long n, size_t esz) { return 
 #define PB_NU 2          /* bands per thread of the fp64 band kernel (2 or 3) */
 #endif
 // kernel configuration per real type: see struct Cfg in prosail_kernels.cuh
-template <typename T> struct CfgOf { typedef Cfg<PB_NU, PB_NU == 3 ? 12 : PB_WARPS> type; };
-template <> struct CfgOf<float> { typedef Cfg<2, PB_WARPS> type; };
+#ifndef PB_MULTI_WARPS
+#define PB_MULTI_WARPS 12   /* warps per CTA of the fp64 instances that loop over several geometries per set: the state carried
+                               across the geometry loop (leaf + diffuse terms of both bands) needs 168 registers to stay out of local memory */
+#endif
+// kernel configuration per real type and loop shape (G1 = one geometry per set): see struct Cfg in prosail_kernels.cuh
+template <typename T, bool G1> struct CfgOf { typedef Cfg<PB_NU, PB_NU == 3 ? 12 : (G1 ? PB_WARPS : PB_MULTI_WARPS)> type; };
+template <bool G1> struct CfgOf<float, G1> { typedef Cfg<2, PB_WARPS> type; };
 
-template <typename T, int MODE, unsigned PLANES, unsigned MEANS>
-static int launch_bands(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
-    typedef typename CfgOf<T>::type CF;
+template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS>
+static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
+    typedef typename CfgOf<T, G1>::type CF;
     const size_t smem = sizeof(SailSmem<T, CF>);
-    auto kern = a.G == 1 ? k_bands<T, CF, MODE, PLANES, MEANS, true> : k_bands<T, CF, MODE, PLANES, MEANS, false>;
+    auto kern = k_bands<T, CF, MODE, PLANES, MEANS, G1>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CF::THREADS, smem));
@@ -239,6 +244,10 @@ static int launch_bands(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStr
     h->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+template <typename T, int MODE, unsigned PLANES, unsigned MEANS>
+static int launch_bands(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
+    return a.G == 1 ? launch_bands_g<T, true, MODE, PLANES, MEANS>(h, j, a, st) : launch_bands_g<T, false, MODE, PLANES, MEANS>(h, j, a, st);
 }
 
 // pick the kernel instance: compile-time plane sets for the LUT shapes, run-time selection otherwise
