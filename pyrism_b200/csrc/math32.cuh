@@ -87,4 +87,41 @@ __device__ __forceinline__ float tau_fast(float k, const float* __restrict__ tab
     return fmaf(u, acc, a.y);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2, PTX add/mul/fma.f32x2): one instruction works on the two bands of a thread.
+// Measured on B200 (tools/micro/ffma2.cu, profiles/r1c_micro_ffma2.txt): a packed instruction occupies the FP32 pipes for
+// two cycles (same lane throughput as two scalar ones) but ONE issue slot, and the fp32 band kernel is issue-bound; a
+// scalar register can be broadcast to both halves as an operand (R.F32) and immediates are splatted, so per-item scalars
+// cost nothing extra; negations fold into operand modifiers.  Like DFMA, a three-register-pair FFMA2 takes 3 cycles.
+// MUFU seeds (rcp, rsq, ex2, lg2), table look-ups, guards and stores stay scalar per half.
+// ---------------------------------------------------------------------------------------------------------------
+typedef float2 f2;
+using ::fma;      // keep the scalar overloads visible next to the packed ones declared below
+__device__ __forceinline__ f2 F2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ f2 F2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ f2 neg(f2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ f2 add(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub(f2 a, f2 b) { return __fadd2_rn(a, neg(b)); }
+__device__ __forceinline__ f2 mul(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 add(f2 a, float s) { return __fadd2_rn(a, F2(s)); }
+__device__ __forceinline__ f2 mul(f2 a, float s) { return __fmul2_rn(a, F2(s)); }
+__device__ __forceinline__ f2 fma(float s, f2 b, f2 c) { return __ffma2_rn(F2(s), b, c); }
+__device__ __forceinline__ f2 fma(f2 a, f2 b, float c) { return __ffma2_rn(a, b, F2(c)); }
+__device__ __forceinline__ f2 rcp(f2 a) { return F2(rcp(a.x), rcp(a.y)); }
+__device__ __forceinline__ f2 sqrt_pos(f2 a) { return F2(sqrt_pos(a.x), sqrt_pos(a.y)); }
+__device__ __forceinline__ f2 exp2_fast(f2 a) { return F2(exp2_fast(a.x), exp2_fast(a.y)); }
+__device__ __forceinline__ f2 log2_fast(f2 a) { return F2(log2_fast(a.x), log2_fast(a.y)); }
+// expm1(x)/x for both halves: packed degree-6 series, direct form per half where |x| >= 0.25
+__device__ __forceinline__ f2 expm1_over_x(f2 x) {
+    f2 p = fma(x, F2(1.0f / 5040.0f), 1.0f / 720.0f);
+    p = fma(x, p, 1.0f / 120.0f);
+    p = fma(x, p, 1.0f / 24.0f);
+    p = fma(x, p, 1.0f / 6.0f);
+    p = fma(x, p, 0.5f);
+    p = fma(x, p, 1.0f);
+    const f2 q = mul(add(exp2_fast(mul(x, 1.4426950408889634f)), -1.0f), rcp(x));
+    return F2(fabsf(x.x) < 0.25f ? p.x : q.x, fabsf(x.y) < 0.25f ? p.y : q.y);
+}
+
 }  // namespace pb

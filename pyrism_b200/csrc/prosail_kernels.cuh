@@ -286,6 +286,37 @@ __device__ __forceinline__ void leaf_layers_f32(const BandConst<float>& c, float
     refl = fmaf(TaI * bm1, (t * al) * r, Ra);
 }
 
+// the same for the two bands of a thread at once, in packed FP32 (see math32.cuh)
+__device__ __forceinline__ void leaf_layers_f32x2(const BandConst<f2>& c, f2 omt, float nm1, f2& refl, f2& tran) {
+    const f2 tau = sub(F2(1.0f), omt);
+    const f2 x = mul(c.r21, tau);
+    const f2 inv = rcp(fma(neg(x), x, 1.0f));
+    const f2 tt = mul(mul(tau, c.t21), inv);
+    const f2 Ta = mul(c.talf, tt);
+    const f2 t = mul(c.t12, tt);
+    const f2 Ra = fma(x, Ta, c.ralf);
+    const f2 r = fma(x, t, c.r12);
+    const f2 p = add(r, 1.0f), q = sub(F2(1.0f), r);
+    const f2 qmt = mul(mul(c.t12, omt), fma(x, inv, inv));        // t12 (1 - tau) (1 + x)/(1 - x^2)
+    const f2 pmt = sub(p, t);
+    const f2 P12 = mul(add(p, t), pmt);
+    const f2 P34 = mul(add(q, t), qmt);
+    const f2 D = sqrt_pos(mul(P12, P34));
+    const f2 da = mul(add(P34, D), 0.5f);
+    const f2 al = add(r, da);
+    const f2 db = mul(fma(qmt, pmt, D), 0.5f);
+    const f2 b = fma(db, rcp(t), 1.0f);
+    const f2 lb = mul(log2_fast(b), nm1);
+    const f2 bNm1 = exp2_fast(F2(fminf(lb.x, 60.0f), fminf(lb.y, 60.0f)));   // opaque plates: b^(N-1) saturates
+    const f2 bN2 = mul(bNm1, bNm1);
+    const f2 bm1 = add(bN2, -1.0f);
+    const f2 dal = mul(da, add(al, r));                           // (a r)^2 - r^2
+    const f2 X = fma(mul(al, bm1), fma(neg(r), r, al), dal);
+    const f2 TaI = mul(Ta, rcp(X));
+    tran = mul(TaI, mul(bNm1, dal));
+    refl = fma(mul(TaI, bm1), mul(mul(t, al), r), Ra);
+}
+
 // rare lanes of the float path (k outside [2^-14, 32)): the whole plate + Stokes stage in float64 with IEEE divisions and
 // libm, exactly as models.py:953-957, 1019-1025, 1043-1065 (zero-absorption branch included)
 __device__ __noinline__ void leaf_exact_f32(const BandConst<float>& c, float kall, float nm1f, float& refl, float& tran) {
@@ -383,6 +414,28 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
 #pragma unroll
             for (int u = 0; u < NU; ++u)
                 if (zero[u]) leaf_zero_absorption(c[u], tau[u], nm1, refl[u], tran[u]);
+        }
+    }
+}
+
+// fp32 mode, two bands per thread: kall and the table look-ups per band (scalar), plate + Stokes stage packed
+template <typename CF, typename MT>
+__device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const float* __restrict__ kc, const float* __restrict__ s, const MT& mt,
+                                               f2& refl, f2& tran) {
+    static_assert(CF::NU == 2, "the packed path pairs the two bands of a thread");
+    const float nm1 = s[S_NM1];
+    const float k0 = leaf_kall<CF::KSTRIDE>(kc, s), k1 = leaf_kall<CF::KSTRIDE>(kc + CF::THREADS, s);
+    bool rare0, rare1;
+    const float g0 = tau_fast(k0, mt.tau, rare0), g1 = tau_fast(k1, mt.tau, rare1);
+    leaf_layers_f32x2(c2, F2(k0 * g0, k1 * g1), nm1, refl, tran);                  // 1 - tau = k g(k)
+    if (__builtin_expect(rare0 | rare1, 0)) {
+        if (rare0) {
+            const BandConst<float> c{c2.talf.x, c2.ralf.x, c2.t12.x, c2.r12.x, c2.t21.x, c2.r21.x};
+            leaf_exact_f32(c, k0, nm1, refl.x, tran.x);
+        }
+        if (rare1) {
+            const BandConst<float> c{c2.talf.y, c2.ralf.y, c2.t12.y, c2.r12.y, c2.t21.y, c2.r21.y};
+            leaf_exact_f32(c, k1, nm1, refl.y, tran.y);
         }
     }
 }
@@ -539,6 +592,75 @@ __device__ __forceinline__ void sail_directional(T rho, T tau, T rs, const Diffu
 }
 
 // ---------------------------------------------------------------------------------------------
+// 4SAIL for the two bands of a thread in packed FP32 (fp32 mode).  Same formulas as sail_diffuse<float>,
+// sail_directional_fast<float> and sail_couple<float>; per-item scalars enter as broadcast operands.
+// ---------------------------------------------------------------------------------------------
+template <bool FROM_LEAF>
+__device__ __forceinline__ void sail_diffuse_f32x2(f2 rho, f2 tau, f2 rs, const float* __restrict__ s, Diffuse<f2>& d) {
+    f2 sigb = fma(s[S_DDB], rho, mul(tau, s[S_DDF]));                 // :590
+    f2 sigf = fma(s[S_DDF], rho, mul(tau, s[S_DDB]));                 // :591
+    if (!FROM_LEAF) {
+        sigb = F2(is_zero(sigb.x) ? 1e-36f : sigb.x, is_zero(sigb.y) ? 1e-36f : sigb.y);      // :594-595
+        sigf = F2(is_zero(sigf.x) ? 1e-36f : sigf.x, is_zero(sigf.y) ? 1e-36f : sigf.y);
+    }
+    const f2 att = sub(F2(1.0f), sigf);                               // :600
+    d.m = sqrt_pos(mul(sub(att, sigb), add(att, sigb)));              // :601 without the cancellation
+    d.rinf = mul(sigb, rcp(add(att, d.m)));                           // :639 as sigb / (att + m)
+    d.e1 = exp2_fast(mul(d.m, s[S_NEGLAI] * 1.4426950408889634f));    // :637
+    const f2 e2 = mul(d.e1, d.e1);
+    const f2 rinf2 = mul(d.rinf, d.rinf);
+    d.re = mul(d.rinf, d.e1);
+    const f2 omr2 = sub(F2(1.0f), rinf2);
+    const f2 den = fma(neg(rinf2), e2, 1.0f);                         // :642
+    const f2 r = rcp(mul(den, omr2));
+    d.invden = mul(r, omr2);
+    d.inv_omr2 = mul(r, den);
+    d.tdd = mul(mul(omr2, d.e1), d.invden);                           // :654
+    d.rdd = mul(mul(d.rinf, sub(F2(1.0f), e2)), d.invden);            // :655
+    d.rsrdd = mul(rs, d.rdd);
+    f2 dn = sub(F2(1.0f), d.rsrdd);                                   // :714-719
+    dn = F2(below_tiny(dn.x) ? 1e-36f : dn.x, below_tiny(dn.y) ? 1e-36f : dn.y);
+    d.rs_invdn = mul(rs, rcp(dn));
+}
+
+__device__ __forceinline__ void sail_directional_f32x2(f2 rho, f2 tau, f2 rs, const Diffuse<f2>& d, const float* __restrict__ s,
+                                                       const float* __restrict__ g, unsigned need, Canopy<f2>& o) {
+    const float k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO], lai = s[S_LAI];
+    const f2 km = sub(F2(k), d.m), kp = add(d.m, k), Km = sub(F2(K), d.m), Kp = add(d.m, K);
+    // J1(k,m) = e^{-k t} t expm1(d)/d, d = (k - m) t: no cancellation, no series branch                  :765-785
+    const f2 J1ks = mul(expm1_over_x(mul(km, lai)), tss * lai);
+    const f2 J1ko = mul(expm1_over_x(mul(Km, lai)), too * lai);
+    const f2 inv_kp = rcp(kp), inv_Kp = rcp(Kp);
+    const f2 sb = fma(g[G_SDB], rho, mul(tau, g[G_SDF]));             // :603-607
+    const f2 sf = fma(g[G_SDF], rho, mul(tau, g[G_SDB]));
+    const f2 vb = fma(g[G_DOB], rho, mul(tau, g[G_DOF]));
+    const f2 vf = fma(g[G_DOF], rho, mul(tau, g[G_DOB]));
+    const f2 w = fma(g[G_FS], rho, mul(tau, g[G_FT]));
+    const f2 J2ks = mul(fma(neg(d.e1), F2(tss), 1.0f), inv_kp);       // :787-789
+    const f2 J2ko = mul(fma(neg(d.e1), F2(too), 1.0f), inv_Kp);
+    const f2 u1 = fma(sb, d.rinf, sf), u2 = fma(sf, d.rinf, sb);      // :649-652
+    const f2 v1 = fma(vb, d.rinf, vf), v2 = fma(vf, d.rinf, vb);
+    const f2 Pss = mul(u1, J1ks), Qss = mul(u2, J2ks), Pv = mul(v1, J1ko), Qv = mul(v2, J2ko);
+    const f2 nre = neg(d.re);
+    o.tsd = mul(fma(nre, Qss, Pss), d.invden);                        // :656-659
+    o.rsd = mul(fma(nre, Pss, Qss), d.invden);
+    o.tdo = mul(fma(nre, Qv, Pv), d.invden);
+    o.rdo = mul(fma(nre, Pv, Qv), d.invden);
+    const f2 g1 = mul(fma(neg(J1ks), F2(too), F2(g[G_Z])), inv_Kp);   // :668-669
+    const f2 g2 = mul(fma(neg(J1ko), F2(tss), F2(g[G_Z])), inv_kp);
+    const f2 T1 = mul(mul(v2, g1), u1), T2 = mul(mul(v1, g2), u2);    // :671-675
+    const f2 T3 = mul(fma(o.rdo, Qss, mul(o.tdo, Pss)), d.rinf);
+    const f2 rsod = mul(sub(add(T1, T2), T3), d.inv_omr2);            // :678
+    o.rso = fma(g[G_LAISUM], w, rsod);                                // :706, :710
+    // soil coupling                                                                        :721-726
+    const f2 rsodt = mul(fma(add(o.tsd, tss), o.tdo, mul(fma(tss, d.rsrdd, o.tsd), too)), d.rs_invdn);
+    o.rsot = add(fma(g[G_TSSTOO], rs, o.rso), rsodt);
+    if (need & (1u << O_RDDT)) o.rddt = fma(mul(d.tdd, d.tdd), d.rs_invdn, d.rdd);
+    if (need & (1u << O_RSDT)) o.rsdt = fma(mul(add(o.tsd, tss), d.tdd), d.rs_invdn, o.rsd);
+    if (need & (1u << O_RDOT)) o.rdot = fma(mul(d.tdd, add(o.tdo, too)), d.rs_invdn, o.rdo);
+}
+
+// ---------------------------------------------------------------------------------------------
 // band-mean partial sums: segmented warp reduction over the windows that touch this tile
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -680,6 +802,13 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             c[u].ralf = one - c[u].talf; c[u].r12 = one - c[u].t12; c[u].r21 = one - c[u].t21;     // models.py:1012-1016
         }
     }
+    // fp32 mode with two bands per thread: the arithmetic of the item loop runs in packed FP32 (FFMA2 ...), both bands per instruction
+    constexpr bool PACKED = std::is_same<T, float>::value && NU == 2;
+    BandConst<f2> c2;
+    if constexpr (PACKED) {
+        c2.talf = F2(c[0].talf, c[1].talf); c2.ralf = F2(c[0].ralf, c[1].ralf); c2.t12 = F2(c[0].t12, c[1].t12);
+        c2.r12 = F2(c[0].r12, c[1].r12); c2.t21 = F2(c[0].t21, c[1].t21); c2.r21 = F2(c[0].r21, c[1].r21);
+    }
     unsigned need;
     if (PLANES == RUNTIME) {
         need = a.mean_mask;
@@ -712,6 +841,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
 #pragma unroll
             for (int u = 0; u < NU; ++u) rho[u] = tau[u] = rs[u] = zero_;
             Diffuse<T> d[NU];
+            Diffuse<f2> dp;          // packed twin of d[] (fp32 mode)
             int thr_hi = 0;
             const T* sr = stage[buf].s;
             const T* gr = stage[buf].g;
@@ -725,7 +855,13 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                     for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u * CF::THREADS, sr);
                     emit<PLANES, MEANS, O_RHO>(e, rs);
                 } else if (MODE == MODE_PROSPECT) {
-                    leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
+                    if constexpr (PACKED) {
+                        f2 r2, t2;
+                        leaf_optics_x2<CF>(c2, kc, sr, sm.mt, r2, t2);
+                        rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
+                    } else {
+                        leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
+                    }
                     emit<PLANES, MEANS, O_LEAF_R>(e, rho);
                     emit<PLANES, MEANS, O_LEAF_T>(e, tau);
                     if (PLANES == RUNTIME && (need & (7u << O_LEAF_KA))) {       // absorptance, extinction, single-scattering albedo
@@ -753,7 +889,13 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                 } else {
                     if (G1 || fresh) {
                         if (MODE == MODE_PROSAIL) {
-                            leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
+                            if constexpr (PACKED) {
+                                f2 r2, t2;
+                                leaf_optics_x2<CF>(c2, kc, sr, sm.mt, r2, t2);
+                                rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
+                            } else {
+                                leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
+                            }
 #pragma unroll
                             for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u * CF::THREADS, sr);
                         } else {
@@ -765,8 +907,12 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                                 rs[u] = a.in_rho[s * a.in_pitch_rho + bb];
                             }
                         }
+                        if constexpr (PACKED) {
+                            sail_diffuse_f32x2<MODE == MODE_PROSAIL>(F2(rho[0], rho[1]), F2(tau[0], tau[1]), F2(rs[0], rs[1]), sr, dp);
+                        } else {
 #pragma unroll
-                        for (int u = 0; u < NU; ++u) sail_diffuse<MODE == MODE_PROSAIL>(rho[u], tau[u], rs[u], sr, sm.mt, d[u]);
+                            for (int u = 0; u < NU; ++u) sail_diffuse<MODE == MODE_PROSAIL>(rho[u], tau[u], rs[u], sr, sm.mt, d[u]);
+                        }
                         // |k - m| lai <= 1e-3  <=>  |k - m| <= 1e-3 / lai   (threshold on the high word)
                         thr_hi = hi_word(sr[S_THR]);
                         fresh = false;
@@ -780,20 +926,31 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         emit_const<PLANES, MEANS, O_TDO>(e, zero_);
                     } else {
                         Canopy<T> o[NU];
-                        bool rare[NU];
-                        bool any_rare = false;
+                        if constexpr (PACKED) {
+                            Canopy<f2> op;
+                            op.rddt = op.rsdt = op.rdot = F2(0.0f);
+                            sail_directional_f32x2(F2(rho[0], rho[1]), F2(tau[0], tau[1]), F2(rs[0], rs[1]), dp, sr, gr, need, op);
+                            o[0] = Canopy<T>{op.rsot.x, op.rddt.x, op.rsdt.x, op.rdot.x, op.rso.x, op.rsd.x, op.tsd.x, op.rdo.x, op.tdo.x};
+                            o[1] = Canopy<T>{op.rsot.y, op.rddt.y, op.rsdt.y, op.rdot.y, op.rso.y, op.rsd.y, op.tsd.y, op.rdo.y, op.tdo.y};
+                        } else {
+                            bool rare[NU];
+                            bool any_rare = false;
 #pragma unroll
-                        for (int u = 0; u < NU; ++u) {
-                            o[u].rddt = o[u].rsdt = o[u].rdot = zero_;
-                            rare[u] = sail_directional_fast(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
-                            any_rare |= rare[u];
-                        }
-                        if constexpr (!std::is_same<T, float>::value) {
-                            if (__builtin_expect(any_rare, 0)) {
-#pragma unroll
-                                for (int u = 0; u < NU; ++u)
-                                    if (rare[u]) sail_directional(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
+                            for (int u = 0; u < NU; ++u) {
+                                o[u].rddt = o[u].rsdt = o[u].rdot = zero_;
+                                rare[u] = sail_directional_fast(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
+                                any_rare |= rare[u];
                             }
+                            if constexpr (!std::is_same<T, float>::value) {
+                                if (__builtin_expect(any_rare, 0)) {
+#pragma unroll
+                                    for (int u = 0; u < NU; ++u)
+                                        if (rare[u]) sail_directional(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
+                                }
+                            }
+                        }
+                        if constexpr (PACKED) {      // the diffuse planes come from the packed state
+                            d[0].rdd = dp.rdd.x; d[1].rdd = dp.rdd.y; d[0].tdd = dp.tdd.x; d[1].tdd = dp.tdd.y;
                         }
                         { PB_GATHER(v, o, .rsot); emit<PLANES, MEANS, O_RSOT>(e, v); }
                         { PB_GATHER(v, o, .rddt); emit<PLANES, MEANS, O_RDDT>(e, v); }
@@ -807,6 +964,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         { PB_GATHER(v, o, .rdo); emit<PLANES, MEANS, O_RDO>(e, v); }
                         { PB_GATHER(v, o, .tdo); emit<PLANES, MEANS, O_TDO>(e, v); }
                     }
+                    if constexpr (PACKED) { d[0].m = dp.m.x; d[1].m = dp.m.y; }
                     { PB_GATHER(v, d, .m); emit<PLANES, MEANS, O_KE>(e, v); }
                     emit<PLANES, MEANS, O_LEAF_R>(e, rho);
                     emit<PLANES, MEANS, O_LEAF_T>(e, tau);
