@@ -63,7 +63,8 @@ enum { C_KAB = 0, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RS1, 
 // sample record (per parameter set)
 enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DDB, S_DDF, S_NEGLAI, S_LAI, S_NOCANOPY, S_THR };
 // geometry record (per parameter set x geometry)
-enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_BF, G_SUMINT, G_ALF };
+enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_ITSS, G_ITOO, G_ALF };
+// (G_ITSS, G_ITOO = 1/tss, 1/too: exp((k - m) lai) = e1 / tss without another exponential in the packed fp32 path)
 
 // output planes (bit index in out_mask / mean_mask)
 enum { O_RSOT = 0, O_RDDT, O_RSDT, O_RDOT, O_RSO, O_RDD, O_TDD, O_RSD, O_TSD, O_RDO, O_TDO, O_KE, O_LEAF_R, O_LEAF_T, O_RHO,
@@ -424,10 +425,17 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
                                                f2& refl, f2& tran) {
     static_assert(CF::NU == 2, "the packed path pairs the two bands of a thread");
     const float nm1 = s[S_NM1];
-    const float k0 = leaf_kall<CF::KSTRIDE>(kc, s), k1 = leaf_kall<CF::KSTRIDE>(kc + CF::THREADS, s);
+    constexpr int KS = CF::KSTRIDE, TH = CF::THREADS;
+    f2 kall = mul(F2(kc[KC_KAB * KS], kc[KC_KAB * KS + TH]), s[S_CAB]);           // :950-951, both bands per instruction
+    kall = fma(s[S_CXC], F2(kc[KC_KXC * KS], kc[KC_KXC * KS + TH]), kall);
+    kall = fma(s[S_CAN], F2(kc[KC_KAN * KS], kc[KC_KAN * KS + TH]), kall);
+    kall = fma(s[S_CBR], F2(kc[KC_KBR * KS], kc[KC_KBR * KS + TH]), kall);
+    kall = fma(s[S_CW], F2(kc[KC_KW * KS], kc[KC_KW * KS + TH]), kall);
+    kall = fma(s[S_CM], F2(kc[KC_KM * KS], kc[KC_KM * KS + TH]), kall);
+    const float k0 = kall.x, k1 = kall.y;
     bool rare0, rare1;
     const float g0 = tau_fast(k0, mt.tau, rare0), g1 = tau_fast(k1, mt.tau, rare1);
-    leaf_layers_f32x2(c2, F2(k0 * g0, k1 * g1), nm1, refl, tran);                  // 1 - tau = k g(k)
+    leaf_layers_f32x2(c2, mul(kall, F2(g0, g1)), nm1, refl, tran);                 // 1 - tau = k g(k)
     if (__builtin_expect(rare0 | rare1, 0)) {
         if (rare0) {
             const BandConst<float> c{c2.talf.x, c2.ralf.x, c2.t12.x, c2.r12.x, c2.t21.x, c2.r21.x};
@@ -628,9 +636,11 @@ __device__ __forceinline__ void sail_directional_f32x2(f2 rho, f2 tau, f2 rs, co
     const float k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO], lai = s[S_LAI];
     const f2 km = sub(F2(k), d.m), kp = add(d.m, k), Km = sub(F2(K), d.m), Kp = add(d.m, K);
     // J1(k,m) = e^{-k t} t expm1(d)/d, d = (k - m) t: no cancellation, no series branch                  :765-785
-    const f2 J1ks = mul(expm1_over_x(mul(km, lai)), tss * lai);
-    const f2 J1ko = mul(expm1_over_x(mul(Km, lai)), too * lai);
-    const f2 inv_kp = rcp(kp), inv_Kp = rcp(Kp);
+    // expm1(d) = e1 / tss - 1 needs no further exponential (1/tss comes with the record); below |d| = 0.25 the series takes over
+    const f2 J1ks = mul(expm1_over_x(mul(km, lai), fma(d.e1, F2(g[G_ITSS]), -1.0f)), tss * lai);
+    const f2 J1ko = mul(expm1_over_x(mul(Km, lai), fma(d.e1, F2(g[G_ITOO]), -1.0f)), too * lai);
+    const f2 rkK = rcp(mul(kp, Kp));                                  // 1/(k+m) and 1/(K+m) from one reciprocal (both > 0)
+    const f2 inv_kp = mul(rkK, Kp), inv_Kp = mul(rkK, kp);
     const f2 sb = fma(g[G_SDB], rho, mul(tau, g[G_SDF]));             // :603-607
     const f2 sf = fma(g[G_SDF], rho, mul(tau, g[G_SDB]));
     const f2 vb = fma(g[G_DOB], rho, mul(tau, g[G_DOF]));
@@ -1213,7 +1223,7 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         r[G_DOB] = 0.5 * (K + bf); r[G_DOF] = 0.5 * (K - bf);
         r[G_FS] = Fs; r[G_FT] = Ft;
         r[G_TSS] = tss; r[G_TOO] = too; r[G_TSSTOO] = tsstoo;
-        r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_BF] = bf; r[G_SUMINT] = sumint; r[G_ALF] = alf;
+        r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_ITSS] = 1.0 / tss; r[G_ITOO] = 1.0 / too; r[G_ALF] = alf;
         store_rec<T>(a.grec, item, r);
         if (g == 0) {
             srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
@@ -1442,7 +1452,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
     grec[G_DOB] = 0.5 * (K + bf); grec[G_DOF] = 0.5 * (K - bf);
     grec[G_FS] = Fs; grec[G_FT] = Ft;
     grec[G_TSS] = tss; grec[G_TOO] = too; grec[G_TSSTOO] = tsstoo;
-    grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_BF] = bf; grec[G_SUMINT] = sumint; grec[G_ALF] = alf;
+    grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_ITSS] = 1.0 / tss; grec[G_ITOO] = 1.0 / too; grec[G_ALF] = alf;
     store_rec<T>(a.grec, item, grec);
     if (g == 0) {
         srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
