@@ -89,7 +89,7 @@ __device__ __forceinline__ float tau_fast(float k, const float* __restrict__ tab
 
 // ---------------------------------------------------------------------------------------------------------------
 // Packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2, PTX add/mul/fma.f32x2): one instruction works on the two bands of a thread.
-// Measured on B200 (tools/micro/ffma2.cu, profiles/r1c_micro_ffma2.txt): a packed instruction occupies the FP32 pipes for
+// Measured on B200 (tools/micro/ffma2.cu, profiles/r1d_micro_ffma2.txt): a packed instruction occupies the FP32 pipes for
 // two cycles (same lane throughput as two scalar ones) but ONE issue slot, and the fp32 band kernel is issue-bound; a
 // scalar register can be broadcast to both halves as an operand (R.F32) and immediates are splatted, so per-item scalars
 // cost nothing extra; negations fold into operand modifiers.  Like DFMA, a three-register-pair FFMA2 takes 3 cycles.
