@@ -160,6 +160,11 @@ int prosail_soil_f64(prosail_handle_t* h, long long n, const prosail_soil_t* soi
 int prosail_volscatt_f64(prosail_handle_t* h, long long n, const prosail_canopy_t* canopy, double* geom, double* lidf,
                          int on_host, void* stream);
 
+/* pyrism.VolScatt(iza, vza, raa).volume(lza) (models.py:177-258): interception and bidirectional scattering terms of ONE leaf
+ * zenith angle lza_deg (degrees) for n_geom geometries (radians, normalised); out [n_geom][4] = chi_s, chi_o, frho, ftau. */
+int prosail_volume_f64(prosail_handle_t* h, int n_geom, const double* iza, const double* vza, const double* raa, double lza_deg,
+                       double* out, int on_host, void* stream);
+
 /* pyrism.SAIL(...) for n parameter sets x n_geom geometries (models.py:528-729) with leaf and soil spectra
  * supplied as arrays: ks, kt, rho are [n][pitch_*] or a single spectrum broadcast to all sets (pitch_* = 0). */
 int prosail_sail_f64(prosail_handle_t* h, long long n, const double* ks, long long pitch_ks, const double* kt,

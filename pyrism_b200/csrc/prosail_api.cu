@@ -1054,6 +1054,35 @@ int prosail_invert_f32(prosail_handle_t* h, long long n_lut, int n_feat, const f
     return 0;
 }
 
+int prosail_volume_f64(prosail_handle_t* h, int n_geom, const double* iza, const double* vza, const double* raa, double lza_deg,
+                       double* out, int on_host, void* stream) {
+    if (!h || !iza || !vza || !raa || !out || n_geom < 0) return fail(PROSAIL_E_ARG, "bad argument");
+    if (n_geom == 0) return 0;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = stream && !on_host ? (cudaStream_t)stream : h->stream;
+    const double *di = iza, *dv = vza, *dr = raa;
+    double* dout = out;
+    const size_t nb = ((size_t)n_geom * 8 + 255) & ~(size_t)255;
+    if (on_host) {
+        int rc;
+        if ((rc = h->work.in.reserve(3 * nb)) || (rc = h->work.out.reserve((size_t)n_geom * 32 + 256))) return rc;
+        char* base = (char*)h->work.in.p;
+        CK(cudaMemcpyAsync(base, iza, (size_t)n_geom * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(base + nb, vza, (size_t)n_geom * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(base + 2 * nb, raa, (size_t)n_geom * 8, cudaMemcpyHostToDevice, st));
+        di = (const double*)base; dv = (const double*)(base + nb); dr = (const double*)(base + 2 * nb);
+        dout = (double*)h->work.out.p;
+    }
+    k_volume<<<(unsigned)((n_geom + 127) / 128), 128, 0, st>>>(n_geom, di, dv, dr, lza_deg, dout);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (on_host) {
+        CK(cudaMemcpyAsync(out, dout, (size_t)n_geom * 32, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
 int prosail_device_pci_bus_id(prosail_handle_t* h, char* out, int len) {
     if (!h || !out || len < 16) return fail(PROSAIL_E_ARG, "bad argument");
     CK(cudaDeviceGetPCIBusId(out, len, h->device));

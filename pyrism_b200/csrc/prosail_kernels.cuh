@@ -1063,6 +1063,16 @@ __device__ __forceinline__ void volscatt_volume(double tts, double tto, double p
     ftau = fmax((-bt2 * t1 + t2) / denom, 0.0);
 }
 
+// VolScatt.volume(lza) for n geometries and one leaf zenith angle (degrees): out [n][4] = chi_s, chi_o, frho, ftau (models.py:177-258)
+__global__ void k_volume(int n, const double* __restrict__ iza, const double* __restrict__ vza, const double* __restrict__ raa, double lza_deg,
+                         double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double chi_s, chi_o, frho, ftau;
+    volscatt_volume(iza[i], vza[i], raa[i], lza_deg, chi_s, chi_o, frho, ftau);
+    out[4 * i] = chi_s; out[4 * i + 1] = chi_o; out[4 * i + 2] = frho; out[4 * i + 3] = ftau;
+}
+
 // write one 16-element record as T (double: 128 B, float: 64 B) with 16-byte stores
 template <typename T>
 __device__ __forceinline__ void store_rec(void* base, long long idx, const double (&rec)[REC]) {

@@ -360,6 +360,16 @@ class Engine(object):
             capi.check(self.lib.prosail_volscatt_f64(self.h, n, C.byref(can), _ptr(geom), _ptr(lidf), 1, None))
             return geom, lidf
 
+    def volume(self, iza, vza, raa, lza_deg):
+        """VolScatt.volume for one leaf zenith angle (degrees): float64 [G, 4] = chi_s, chi_o, frho, ftau; angles in normalised radians."""
+        with self._lock:
+            a = [np.ascontiguousarray(np.asarray(x, dtype=_f64).reshape(-1)) for x in (iza, vza, raa)]
+            if not (a[0].size == a[1].size == a[2].size):
+                raise ValueError("iza, vza, raa must have the same length")
+            out = np.empty((a[0].size, 4), dtype=_f64)
+            capi.check(self.lib.prosail_volume_f64(self.h, a[0].size, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), float(lza_deg), _ptr(out), 1, None))
+            return out
+
     def _alloc_out(self, n_items, planes, mean_planes, want_geom, out, dt=np.dtype(_f64)):
         out = out or {}
         bufs = {}

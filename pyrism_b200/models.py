@@ -250,8 +250,13 @@ class VolScatt(Kernel):
         self._set(geom, _is_scalar_call(a, b))
         self.lidf = lidf[0] if _is_scalar_call(a, b) else lidf
 
+    def volume(self, lza):
+        """chi_s, chi_o, frho, ftau for the leaf zenith angle ``lza`` [deg], arrays over the geometries (models.py:177-258)."""
+        v = get_engine().volume(self.iza, self.vza, self.raa, lza)
+        return v[:, 0], v[:, 1], v[:, 2], v[:, 3]
+
     def _set(self, geom, scalar):
-        g = geom[0] if scalar else geom                       # [G, 8] or [B, G, 8]
+        g = geom[0] if scalar else geom                       # [G, 12] or [B, G, 12]
         self.ks, self.ko, self.Fs, self.Ft = g[..., 0], g[..., 1], g[..., 3], g[..., 4]
         bf = g[..., 2]
         self.bf = bf[..., 0][()] if scalar else bf[..., 0]    # bf does not depend on the geometry

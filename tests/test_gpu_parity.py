@@ -538,3 +538,14 @@ def test_leftover_attributes_of_the_reference(engine):
         for g in range(4):
             cs, co, fr, ft = orc.volscatt_volume(np.radians(iza[g]), np.radians(vza[g]), np.radians(raa[g]), 87.5)
             assert max(abs(v.chi_s[g] - cs), abs(v.chi_o[g] - co), abs(v.frho[g] - fr), abs(v.ftau[g] - ft)) <= 1e-12, (thr, g)
+
+
+def test_volscatt_volume_method():
+    """VolScatt.volume(lza) (models.py:177-258) for arbitrary leaf angles, including the branches |cos beta| >= 1."""
+    iza, vza, raa = np.array([35.0, 10.0, 60.0, 0.0, 70.0, 89.0]), np.array([30.0, 45.0, 0.0, 0.0, 60.0, 5.0]), np.array([50.0, 120.0, 180.0, 0.0, 10.0, 90.0])
+    v = pb.VolScatt(iza, vza, raa)
+    for lza in (2.5, 17.5, 45.0, 62.5, 87.5, 0.0, 90.0):
+        got = v.volume(lza)
+        for g in range(iza.size):
+            want = orc.volscatt_volume(np.radians(iza[g]), np.radians(vza[g]), np.radians(raa[g]), lza)
+            assert max(abs(got[q][g] - want[q]) for q in range(4)) <= 1e-13, (lza, g)
