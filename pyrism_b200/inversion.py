@@ -71,15 +71,13 @@ def reduce_best(costs, indices):
     return idx, best
 
 
-def invert_sharded(engine, lut_local, index_offset, observations, weights=None, group=None):
-    """This rank's shard ``lut_local`` starts at global row ``index_offset``; every rank passes the same observations and
-    receives the global result.  Without an initialised process group it is the single-GPU :func:`invert`."""
-    idx, cost = invert(engine, lut_local, observations, weights, index_offset)
-    try:
-        import torch
-        import torch.distributed as dist
-    except ImportError:
+def _fold_over_ranks(idx, cost, group=None):
+    """all_gather the per-rank (index, cost) pairs and fold them; identity without an initialised process group."""
+    import sys
+    torch = sys.modules.get("torch")          # a process group can only exist if the caller imported torch: never import it here (~2 s)
+    if torch is None:
         return idx, cost
+    import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized():
         return idx, cost
     world = dist.get_world_size(group)
@@ -94,9 +92,17 @@ def invert_sharded(engine, lut_local, index_offset, observations, weights=None, 
     return reduce_best(np.stack([t.cpu().numpy() for t in gc]), np.stack([t.cpu().numpy() for t in gi]))
 
 
+def invert_sharded(engine, lut_local, index_offset, observations, weights=None, group=None):
+    """This rank's shard ``lut_local`` starts at global row ``index_offset``; every rank passes the same observations and
+    receives the global result.  Without an initialised process group it is the single-GPU :func:`invert`."""
+    idx, cost = invert(engine, lut_local, observations, weights, index_offset)
+    return _fold_over_ranks(idx, cost, group)
+
+
 class BandLutInverter(object):
     """Generate a band-mean PROSAIL LUT for this rank's shard of ``params`` (fp32 mode, only the wavelengths inside a
-    window are evaluated) and invert observations against it.
+    window are evaluated) and invert observations against it.  The LUT features are produced on the GPU and STAY there
+    (``features_dev``, float32 [n_local, n_windows]); an inversion call moves only the observations and the results.
 
     params: dict with N, Cab, Cxc, Cbr, Cw, Cm[, Can], lai, hotspot, lidf_a[, lidf_b], soil_reflectance, soil_moisture -- arrays of
     one common length (the GLOBAL LUT; each rank keeps only its shard).  geometry_deg = (iza, vza, raa) of the observations.
@@ -104,16 +110,61 @@ class BandLutInverter(object):
 
     def __init__(self, engine, params, geometry_deg, version='5', lidf_type='campbell', rank=0, world=1):
         from . import lut as lutmod
+        from .core import Kernel
         self.engine = engine
         self.params = {k: np.asarray(v) for k, v in params.items()}
-        means, (self.begin, self.end) = lutmod.generate_band_lut(engine, params, geometry_deg, version=version, lidf_type=lidf_type,
-                                                                 products=("rsot",), windows_only=True, rank=rank, world=world,
-                                                                 dtype=np.float32)
-        self.features = np.ascontiguousarray(means.reshape(means.shape[0], -1), dtype=np.float32)      # [n_local, n_windows]
+        local, (self.begin, self.end) = lutmod.shard(params, rank, world)
+        n = self.end - self.begin
+        self.n_local, self.n_feat = n, len(engine.windows)
+        self.features_dev = engine.empty((max(n, 1), self.n_feat), np.float32)
+        self._features = None
+        if n > 0:
+            k = Kernel(*geometry_deg)
+            if k.iza.size != 1:
+                raise ValueError("BandLutInverter takes one sun/view geometry")
+            dev = lambda name, default=None: engine.to_device(np.broadcast_to(np.asarray(local.get(name, default), dtype=np.float64), (n,)))
+            leaf = {q: dev(q) for q in ("N", "Cab", "Cxc", "Cbr", "Cw", "Cm")}
+            if version == 'D':
+                leaf["Can"] = dev("Can")
+            soil = {"reflectance": dev("soil_reflectance"), "moisture": dev("soil_moisture")}
+            canopy = {"lidf_a": dev("lidf_a"), "lidf_b": dev("lidf_b", 0.0), "lai": dev("lai"), "hotspot": dev("hotspot"),
+                      "iza": engine.to_device(k.iza), "vza": engine.to_device(k.vza), "raa": engine.to_device(k.raa)}
+            with engine._lock:
+                engine.set_alpha(version, 40)
+                engine.prosail_device(n, leaf, soil, canopy, None, mean_planes=(capi.O_RSOT,), means=self.features_dev, version=version,
+                                      lidf_type=lidf_type, windows_only=True, dtype=np.float32)
+                engine.sync()
+
+    @property
+    def features(self):
+        """Host copy of the LUT features (float32 [n_local, n_windows]), downloaded on first use."""
+        if self._features is None:
+            self._features = self.features_dev.download()[:self.n_local]
+        return self._features
+
+    def invert_local(self, observations, weights=None):
+        """Best entry of THIS rank's shard: (global index [Q], cost [Q]); only the observations travel to the GPU."""
+        obs = _f32c(observations)
+        if obs.ndim != 2 or obs.shape[1] != self.n_feat:
+            raise ValueError("observations must be [Q, %d]" % self.n_feat)
+        q = obs.shape[0]
+        idx, cost = np.full(q, -1, dtype=np.int64), np.full(q, np.inf, dtype=np.float32)
+        if q == 0 or self.n_local == 0:
+            return idx, cost
+        eng = self.engine
+        with eng._lock:
+            d_obs = eng.empty(obs.shape, np.float32).upload(obs)
+            d_idx, d_cost = eng.empty((q,), np.int64), eng.empty((q,), np.float32)
+            invert_device(eng, self.n_local, self.n_feat, self.features_dev, self.n_feat, q, d_obs, self.n_feat, d_idx, d_cost, weights, self.begin)
+            idx, cost = d_idx.download(), d_cost.download()
+            for b in (d_obs, d_idx, d_cost):
+                b.free()
+        return idx, cost
 
     def invert(self, observations, weights=None, group=None):
-        """-> (global index [Q], cost [Q], {parameter name: value of the best entry [Q]})"""
-        idx, cost = invert_sharded(self.engine, self.features, self.begin, observations, weights, group)
+        """-> (global index [Q], cost [Q], {parameter name: value of the best entry [Q]}); folds over the ranks of ``group``."""
+        idx, cost = self.invert_local(observations, weights)
+        idx, cost = _fold_over_ranks(idx, cost, group)
         n = max(np.size(v) for v in self.params.values())
         best = {k: (v[np.clip(idx, 0, n - 1)] if np.size(v) == n else v) for k, v in self.params.items()}
         return idx, cost, best

@@ -73,3 +73,20 @@ def test_end_to_end_band_lut_inversion_recovers_the_generating_entries(engine):
     assert np.all(cost2 <= gen_cost * (1 + 1e-5) + 1e-12)
     ref_idx, ref_cost = inv.invert(bi.features, noisy)
     assert np.mean(idx2 == ref_idx) >= 0.99 and np.all(inv.is_optimal(bi.features, noisy, idx2))
+
+
+def test_band_lut_inverter_shards_fold_to_the_single_gpu_result(engine):
+    """Two BandLutInverter shards (rank 0 / rank 1 of a world of 2, both on this GPU) folded with reduce_best == one inverter."""
+    n = 30001
+    P = lut.latin_hypercube(n, ("N", "Cab", "Cxc", "Cbr", "Cw", "Cm", "lai", "hotspot", "lidf_a", "soil_reflectance", "soil_moisture"), 20261019 + 6)
+    full = inversion.BandLutInverter(engine, P, (35.0, 30.0, 50.0))
+    obs = (full.features[rng.integers(0, n, 300)] * (1 + 0.01 * rng.standard_normal((300, 15)))).astype(np.float32)
+    ref_idx, ref_cost = full.invert_local(obs)
+    parts = [inversion.BandLutInverter(engine, P, (35.0, 30.0, 50.0), rank=r, world=2) for r in range(2)]
+    assert parts[0].end == parts[1].begin and np.array_equal(np.concatenate([p.features for p in parts]), full.features)
+    res = [p.invert_local(obs) for p in parts]
+    idx, cost = inversion.reduce_best(np.stack([r[1] for r in res]), np.stack([r[0] for r in res]))
+    assert np.array_equal(idx, ref_idx) and np.array_equal(cost, ref_cost)
+    assert np.array_equal(inv.invert(full.features, obs)[1], ref_cost)
+    w = np.linspace(0.5, 2.0, 15).astype(np.float32)
+    assert np.array_equal(full.invert_local(obs, w)[1], inv.invert(full.features, obs, w)[1])
