@@ -199,6 +199,13 @@ int prosail_invert_f32(prosail_handle_t* h, long long n_lut, int n_feat, const f
                        const float* obs, long long pitch_obs, const float* weights, long long index_offset, long long* best_index,
                        float* best_cost, int on_host, void* stream);
 
+/* The k best entries per observation (1 <= k <= 16), for estimators that average the parameters of the k closest entries:
+ * best_index / best_cost are [n_obs][k], ascending cost, equal costs by ascending index; -1 / +inf pad when fewer than k
+ * entries have a finite cost.  Same cost definition and evaluation order as prosail_invert_f32 (k = 1 gives the same result). */
+int prosail_invert_topk_f32(prosail_handle_t* h, int k, long long n_lut, int n_feat, const float* lut, long long pitch_lut,
+                            long long n_obs, const float* obs, long long pitch_obs, const float* weights, long long index_offset,
+                            long long* best_index, float* best_cost, int on_host, void* stream);
+
 /* ---- memory / stream helpers (so that a host without torch/cupy can drive the device API) -------------- */
 int prosail_dev_alloc(prosail_handle_t* h, long long bytes, void** out);
 int prosail_dev_free(prosail_handle_t* h, void* p);

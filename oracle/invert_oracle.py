@@ -38,6 +38,21 @@ def invert(lut, obs, weights=None, index_offset=0):
     return idx, best
 
 
+def invert_topk(lut, obs, k, weights=None, index_offset=0):
+    """(index int64 [Q, k], cost float32 [Q, k]): ascending cost, equal costs by ascending index, -1 / inf padding."""
+    c = costs(lut, obs, weights)
+    c = np.where(np.isfinite(c), c, np.float32(np.inf))
+    order = np.argsort(c, axis=1, kind='stable')[:, :k]          # stable: equal costs keep index order
+    if order.shape[1] < k:
+        order = np.pad(order, ((0, 0), (0, k - order.shape[1])), constant_values=0)
+    rows = np.arange(c.shape[0])[:, None]
+    best = c[rows, order]
+    if lut.shape[0] < k:
+        best[:, lut.shape[0]:] = np.inf
+    idx = np.where(np.isfinite(best), order + index_offset, -1)
+    return idx, best
+
+
 def is_optimal(lut, obs, idx, weights=None, index_offset=0, rel=4e-7):
     """True per observation if ``idx`` is a minimiser of the float64 cost up to float32 rounding of the accumulation."""
     lut64, obs64 = np.asarray(lut, dtype=np.float64), np.asarray(obs, dtype=np.float64)

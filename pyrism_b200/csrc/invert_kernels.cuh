@@ -131,4 +131,120 @@ __global__ void k_invert_reduce(long long n_obs, int n_chunks, const float* __re
     best_cost[q] = best;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k best entries per observation (k <= INV_KMAX): the usual LUT inversion takes the mean / median of the parameters of the k
+// closest entries.  One observation per thread (features + a sorted list of k (cost, index) pairs in registers); the same LUT
+// streaming as k_invert.  An entry enters the list only if it beats the current k-th cost, which after the first few tiles is
+// rare, so the inner loop is the distance evaluation plus one compare.  Order: ascending cost, equal costs by ascending index.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int INV_KMAX = 16;
+
+__device__ __forceinline__ bool inv_before(float c, long long i, float c2, long long i2) { return c < c2 || (c == c2 && i < i2); }
+
+template <int DP>
+__global__ void __launch_bounds__(INV_THREADS) k_invert_topk(const InvertArgs a, int kk) {
+    constexpr int TILE = InvCfg<DP>::TILE;
+    __shared__ __align__(16) float tile[2][INV_TILE_FLOATS];
+    __shared__ float s_scale[DP];
+    const int tid = threadIdx.x;
+    if (tid < DP) s_scale[tid] = a.scale[tid];
+    __syncthreads();
+    const long long q = (long long)blockIdx.x * INV_THREADS + tid;
+    const long long row = q < a.n_obs ? q : 0;
+    float o[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) o[d] = d < a.n_feat ? a.obs[row * a.pitch_obs + d] * s_scale[d] : 0.0f;
+    float bc[INV_KMAX];
+    long long bi[INV_KMAX];
+#pragma unroll
+    for (int j = 0; j < INV_KMAX; ++j) { bc[j] = __int_as_float(0x7f800000); bi[j] = -1; }
+    float worst = __int_as_float(0x7f800000);      // cost of the current k-th entry (bc[kk - 1], kept in its own register)
+
+    const long long e0 = (long long)blockIdx.y * a.chunk;
+    const long long e1 = min(e0 + a.chunk, a.n_lut);
+    const int ntiles = (int)((e1 - e0 + TILE - 1) / TILE);
+    auto load_tile = [&](int t, int buf) {
+        const long long base = e0 + (long long)t * TILE;
+        for (int i = tid; i < TILE * DP; i += INV_THREADS) {
+            const int e = i / DP, d = i - e * DP;
+            const long long r = base + e;
+            float v = 0.0f;
+            if (d < a.n_feat && r < e1) v = __ldg(a.lut + r * a.pitch_lut + d) * s_scale[d];
+            tile[buf][i] = v;
+        }
+    };
+    if (ntiles > 0) load_tile(0, 0);
+    __syncthreads();
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) load_tile(t + 1, buf ^ 1);
+        const long long base = e0 + (long long)t * TILE;
+        const int n = (int)min((long long)TILE, e1 - base);
+        const float4* tp = reinterpret_cast<const float4*>(tile[buf]);
+        for (int e = 0; e < n; ++e) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int d4 = 0; d4 < DP / 4; ++d4) {
+                const float4 l = tp[e * (DP / 4) + d4];
+                float df = o[4 * d4 + 0] - l.x; acc = fmaf(df, df, acc);
+                df = o[4 * d4 + 1] - l.y; acc = fmaf(df, df, acc);
+                df = o[4 * d4 + 2] - l.z; acc = fmaf(df, df, acc);
+                df = o[4 * d4 + 3] - l.w; acc = fmaf(df, df, acc);
+            }
+            if (acc < worst) {
+                // sorted insertion (indices ascend while scanning, so among equal costs the earlier entry stays in front)
+                float c = acc;
+                long long id = base + e;
+#pragma unroll
+                for (int j = 0; j < INV_KMAX; ++j) {
+                    const bool sw = j < kk && c < bc[j];
+                    const float tc = bc[j];
+                    const long long ti = bi[j];
+                    bc[j] = sw ? c : tc;
+                    bi[j] = sw ? id : ti;
+                    c = sw ? tc : c;
+                    id = sw ? ti : id;
+                    if (j == kk - 1) worst = bc[j];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (q < a.n_obs) {
+        float* pc = a.part_cost + (q * a.n_chunks + blockIdx.y) * kk;
+        long long* pi = a.part_idx + (q * a.n_chunks + blockIdx.y) * kk;
+#pragma unroll
+        for (int j = 0; j < INV_KMAX; ++j)
+            if (j < kk) { pc[j] = bc[j]; pi[j] = bi[j]; }
+    }
+}
+
+// merge the chunk lists of one observation (each sorted): k rounds of "smallest head", ties to the lower index
+__global__ void k_invert_topk_reduce(long long n_obs, int n_chunks, int kk, const float* __restrict__ part_cost,
+                                     const long long* __restrict__ part_idx, long long index_offset, long long* __restrict__ best_idx,
+                                     float* __restrict__ best_cost) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_obs) return;
+    const float* pc = part_cost + q * n_chunks * kk;
+    const long long* pi = part_idx + q * n_chunks * kk;
+    float lastc = -1.0f;
+    long long lasti = -1;
+    for (int j = 0; j < kk; ++j) {
+        // smallest (cost, index) strictly after the previous pick: lists are short, a full scan per pick is cheap enough
+        float bc = __int_as_float(0x7f800000);
+        long long bi = -1;
+        for (int i = 0; i < n_chunks * kk; ++i) {
+            const float c = pc[i];
+            const long long id = pi[i];
+            if (id < 0) continue;
+            const bool after = c > lastc || (c == lastc && id > lasti);
+            if (after && (bi < 0 || inv_before(c, id, bc, bi))) { bc = c; bi = id; }
+        }
+        best_idx[q * kk + j] = bi < 0 ? -1 : bi + index_offset;
+        best_cost[q * kk + j] = bc;
+        if (bi >= 0) { lastc = bc; lasti = bi; }
+        else { lastc = __int_as_float(0x7f800000); lasti = 0x7fffffffffffffffLL; }
+    }
+}
+
 }  // namespace pb

@@ -1003,11 +1003,61 @@ static int launch_invert(prosail_handle* h, InvertArgs& a, long long index_offse
     return 0;
 }
 
+template <int DP>
+static int launch_invert_topk(prosail_handle* h, InvertArgs& a, int k, long long index_offset, long long* best_index, float* best_cost, Work& w,
+                              const float* h_scale, cudaStream_t st) {
+    typedef InvCfg<DP> IC;
+    const long long obs_tiles = (a.n_obs + INV_THREADS - 1) / INV_THREADS;
+    const long long lut_tiles = (a.n_lut + IC::TILE - 1) / IC::TILE;
+    long long n_chunks = std::max<long long>(1, std::min<long long>(lut_tiles, (4LL * h->sm_count + obs_tiles - 1) / obs_tiles));
+    n_chunks = std::min<long long>(n_chunks, 65535);
+    const long long tiles_per_chunk = (lut_tiles + n_chunks - 1) / n_chunks;
+    n_chunks = (lut_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    a.chunk = tiles_per_chunk * IC::TILE;
+    a.n_chunks = (int)n_chunks;
+    const size_t pc = ((size_t)a.n_obs * n_chunks * k * sizeof(float) + 255) & ~(size_t)255;
+    const size_t pi = ((size_t)a.n_obs * n_chunks * k * sizeof(long long) + 255) & ~(size_t)255;
+    int rc;
+    if ((rc = w.inv.reserve(pc + pi + 256))) return rc;
+    a.part_cost = (float*)w.inv.p;
+    a.part_idx = (long long*)((char*)w.inv.p + pc);
+    float* d_scale = (float*)((char*)w.inv.p + pc + pi);
+    CK(cudaMemcpyAsync(d_scale, h_scale, DP * sizeof(float), cudaMemcpyHostToDevice, st));
+    a.scale = d_scale;
+    k_invert_topk<DP><<<dim3((unsigned)obs_tiles, (unsigned)n_chunks), INV_THREADS, 0, st>>>(a, k);
+    h->launches++;
+    CK(cudaGetLastError());
+    k_invert_topk_reduce<<<(unsigned)((a.n_obs + 127) / 128), 128, 0, st>>>(a.n_obs, a.n_chunks, k, a.part_cost, a.part_idx, index_offset, best_index,
+                                                                          best_cost);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" {
+
+static int invert_impl(prosail_handle_t* h, int k, long long n_lut, int n_feat, const float* lut, long long pitch_lut, long long n_obs,
+                       const float* obs, long long pitch_obs, const float* weights, long long index_offset, long long* best_index,
+                       float* best_cost, int on_host, void* stream);
+
+int prosail_invert_topk_f32(prosail_handle_t* h, int k, long long n_lut, int n_feat, const float* lut, long long pitch_lut, long long n_obs,
+                            const float* obs, long long pitch_obs, const float* weights, long long index_offset, long long* best_index,
+                            float* best_cost, int on_host, void* stream) {
+    if (k < 1 || k > INV_KMAX) return fail(PROSAIL_E_ARG, "k must be in 1..%d", INV_KMAX);
+    return invert_impl(h, k, n_lut, n_feat, lut, pitch_lut, n_obs, obs, pitch_obs, weights, index_offset, best_index, best_cost, on_host, stream);
+}
 
 int prosail_invert_f32(prosail_handle_t* h, long long n_lut, int n_feat, const float* lut, long long pitch_lut, long long n_obs,
                        const float* obs, long long pitch_obs, const float* weights, long long index_offset, long long* best_index,
                        float* best_cost, int on_host, void* stream) {
+    return invert_impl(h, 0, n_lut, n_feat, lut, pitch_lut, n_obs, obs, pitch_obs, weights, index_offset, best_index, best_cost, on_host, stream);
+}
+
+// k = 0: the single-best kernel (four observations per thread); k >= 1: the k-best kernel
+static int invert_impl(prosail_handle_t* h, int k, long long n_lut, int n_feat, const float* lut, long long pitch_lut, long long n_obs,
+                       const float* obs, long long pitch_obs, const float* weights, long long index_offset, long long* best_index,
+                       float* best_cost, int on_host, void* stream) {
+    const long long nres = n_obs * std::max(k, 1);
     if (!h) return fail(PROSAIL_E_ARG, "null handle");
     if (n_lut < 1 || n_obs < 0) return fail(PROSAIL_E_ARG, "need n_lut >= 1 and n_obs >= 0");
     if (n_feat < 1 || n_feat > 32) return fail(PROSAIL_E_ARG, "n_feat must be in 1..32");
@@ -1030,8 +1080,8 @@ int prosail_invert_f32(prosail_handle_t* h, long long n_lut, int n_feat, const f
     int rc;
     if (on_host) {
         const size_t bl = ((size_t)n_lut * pitch_lut * 4 + 255) & ~(size_t)255, bo = ((size_t)n_obs * pitch_obs * 4 + 255) & ~(size_t)255;
-        const size_t bi = ((size_t)n_obs * 8 + 255) & ~(size_t)255;
-        if ((rc = w.in.reserve(bl + bo)) || (rc = w.out.reserve(bi + (size_t)n_obs * 4 + 256))) return rc;
+        const size_t bi = ((size_t)nres * 8 + 255) & ~(size_t)255;
+        if ((rc = w.in.reserve(bl + bo)) || (rc = w.out.reserve(bi + (size_t)nres * 4 + 256))) return rc;
         CK(cudaMemcpyAsync(w.in.p, lut, (size_t)n_lut * pitch_lut * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync((char*)w.in.p + bl, obs, (size_t)n_obs * pitch_obs * 4, cudaMemcpyHostToDevice, st));
         a.lut = (const float*)w.in.p;
@@ -1042,13 +1092,19 @@ int prosail_invert_f32(prosail_handle_t* h, long long n_lut, int n_feat, const f
         a.lut = lut;
         a.obs = obs;
     }
-    if (n_feat <= 8) rc = launch_invert<8>(h, a, index_offset, d_idx, d_cost, w, scale, st);
-    else if (n_feat <= 16) rc = launch_invert<16>(h, a, index_offset, d_idx, d_cost, w, scale, st);
-    else rc = launch_invert<32>(h, a, index_offset, d_idx, d_cost, w, scale, st);
+    if (k == 0) {
+        if (n_feat <= 8) rc = launch_invert<8>(h, a, index_offset, d_idx, d_cost, w, scale, st);
+        else if (n_feat <= 16) rc = launch_invert<16>(h, a, index_offset, d_idx, d_cost, w, scale, st);
+        else rc = launch_invert<32>(h, a, index_offset, d_idx, d_cost, w, scale, st);
+    } else {
+        if (n_feat <= 8) rc = launch_invert_topk<8>(h, a, k, index_offset, d_idx, d_cost, w, scale, st);
+        else if (n_feat <= 16) rc = launch_invert_topk<16>(h, a, k, index_offset, d_idx, d_cost, w, scale, st);
+        else rc = launch_invert_topk<32>(h, a, k, index_offset, d_idx, d_cost, w, scale, st);
+    }
     if (rc) return rc;
     if (on_host) {
-        CK(cudaMemcpyAsync(best_index, d_idx, (size_t)n_obs * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(best_cost, d_cost, (size_t)n_obs * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(best_index, d_idx, (size_t)nres * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(best_cost, d_cost, (size_t)nres * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
     return 0;

@@ -45,6 +45,42 @@ def invert(engine, lut_features, observations, weights=None, index_offset=0):
     return idx, cost
 
 
+def invert_topk(engine, lut_features, observations, k, weights=None, index_offset=0):
+    """The k best LUT rows per observation (1 <= k <= 16): (index int64 [Q, k], cost float32 [Q, k]), ascending cost, equal costs
+    by ascending index; -1 / inf pad when fewer than k rows have a finite cost."""
+    lut_features, observations = _f32c(lut_features), _f32c(observations)
+    if lut_features.ndim != 2 or observations.ndim != 2 or lut_features.shape[1] != observations.shape[1]:
+        raise ValueError("lut_features [M, D] and observations [Q, D] must share D")
+    m, d = lut_features.shape
+    q = observations.shape[0]
+    w = None if weights is None else _f32c(weights).reshape(-1)
+    if w is not None and w.size != d:
+        raise ValueError("weights must have D = %d values" % d)
+    idx = np.empty((q, int(k)), dtype=np.int64)
+    cost = np.empty((q, int(k)), dtype=np.float32)
+    with engine._lock:
+        capi.check(engine.lib.prosail_invert_topk_f32(engine.h, int(k), m, d, lut_features.ctypes.data, d, q, observations.ctypes.data, d,
+                                                      None if w is None else w.ctypes.data, int(index_offset), idx.ctypes.data,
+                                                      cost.ctypes.data, 1, None))
+    return idx, cost
+
+
+def reduce_topk(costs, indices, k):
+    """Fold per-shard k-best lists: costs [W, Q, k], indices [W, Q, k] (global, -1 = none) -> (index [Q, k], cost [Q, k]) with
+    the kernel's order (ascending cost, equal costs by ascending index)."""
+    costs = np.asarray(costs, dtype=np.float32)
+    indices = np.asarray(indices, dtype=np.int64)
+    w, q, kk = costs.shape
+    c = np.moveaxis(costs, 0, 1).reshape(q, w * kk)
+    i = np.moveaxis(indices, 0, 1).reshape(q, w * kk)
+    c = np.where(i >= 0, c, np.float32(np.inf))
+    key_i = np.where(i >= 0, i, np.iinfo(np.int64).max)
+    order = np.lexsort((key_i, c), axis=1)[:, :k]
+    rows = np.arange(q)[:, None]
+    out_i, out_c = i[rows, order], c[rows, order]
+    return np.where(np.isfinite(out_c), out_i, -1), out_c
+
+
 def invert_device(engine, n_lut, n_feat, lut, pitch_lut, n_obs, obs, pitch_obs, best_index, best_cost, weights=None,
                   index_offset=0, stream=None):
     """Device-resident variant: ``lut``, ``obs``, ``best_index`` (int64) and ``best_cost`` (float32) are DeviceArrays or raw
@@ -160,6 +196,26 @@ class BandLutInverter(object):
             for b in (d_obs, d_idx, d_cost):
                 b.free()
         return idx, cost
+
+    def invert_topk(self, observations, k, weights=None):
+        """k best entries of THIS rank's shard: (global index [Q, k], cost [Q, k], {parameter name: [Q, k] values});
+        fold several ranks with :func:`reduce_topk`."""
+        obs = _f32c(observations)
+        eng = self.engine
+        q = obs.shape[0]
+        with eng._lock:
+            d_obs = eng.empty(obs.shape, np.float32).upload(obs)
+            d_idx, d_cost = eng.empty((q, int(k)), np.int64), eng.empty((q, int(k)), np.float32)
+            w = None if weights is None else _f32c(weights).reshape(-1)
+            capi.check(eng.lib.prosail_invert_topk_f32(eng.h, int(k), self.n_local, self.n_feat, C.c_void_p(self.features_dev.ptr), self.n_feat, q,
+                                                       C.c_void_p(d_obs.ptr), self.n_feat, None if w is None else w.ctypes.data, self.begin,
+                                                       C.c_void_p(d_idx.ptr), C.c_void_p(d_cost.ptr), 0, None))
+            idx, cost = d_idx.download(), d_cost.download()
+            for b in (d_obs, d_idx, d_cost):
+                b.free()
+        n = max(np.size(v) for v in self.params.values())
+        best = {kk: (v[np.clip(idx, 0, n - 1)] if np.size(v) == n else v) for kk, v in self.params.items()}
+        return idx, cost, best
 
     def invert(self, observations, weights=None, group=None):
         """-> (global index [Q], cost [Q], {parameter name: value of the best entry [Q]}); folds over the ranks of ``group``."""

@@ -90,3 +90,45 @@ def test_band_lut_inverter_shards_fold_to_the_single_gpu_result(engine):
     assert np.array_equal(inv.invert(full.features, obs)[1], ref_cost)
     w = np.linspace(0.5, 2.0, 15).astype(np.float32)
     assert np.array_equal(full.invert_local(obs, w)[1], inv.invert(full.features, obs, w)[1])
+
+
+@pytest.mark.parametrize("m, q, d, k", [(5, 3, 15, 8), (300, 257, 15, 1), (5000, 300, 15, 16), (20000, 100, 6, 5), (3001, 70, 32, 10), (70000, 33, 15, 16)])
+def test_topk_matches_the_contract_oracle(engine, m, q, d, k):
+    lutf = rng.random((m, d)).astype(np.float32)
+    obs = rng.random((q, d)).astype(np.float32)
+    if m > 100:
+        lutf[m - 1] = lutf[7]                               # duplicate rows: equal costs, ascending index order
+        lutf[m // 2] = lutf[7]
+        obs[0] = lutf[7]
+    w = rng.uniform(0.2, 3.0, d).astype(np.float32) if d == 6 else None
+    idx, cost = inversion.invert_topk(engine, lutf, obs, k, w, index_offset=3)
+    ref_idx, ref_cost = inv.invert_topk(lutf, obs, k, w, index_offset=3)
+    assert idx.shape == (q, k)
+    same = np.all(idx == ref_idx, axis=1)
+    assert same.mean() >= 0.98 and np.array_equal(cost[same], ref_cost[same])           # the rest: fmaf double-rounding near-ties
+    assert np.all(cost[:, :-1] <= cost[:, 1:])
+    if m > 100 and k >= 3:
+        assert idx[0, :3].tolist() == [7 + 3, m // 2 + 3, m - 1 + 3] and np.all(cost[0, :3] == 0)
+    if m < k:
+        assert np.all(idx[:, m:] == -1) and np.all(np.isinf(cost[:, m:]))
+    if k == 1:
+        i1, c1 = inversion.invert(engine, lutf, obs, w, index_offset=3)
+        assert np.array_equal(i1, idx[:, 0]) and np.array_equal(c1, cost[:, 0])
+
+
+def test_topk_shard_fold_and_band_lut_inverter(engine):
+    m, q, k = 40001, 200, 8
+    lutf = rng.random((m, 15)).astype(np.float32)
+    obs = rng.random((q, 15)).astype(np.float32)
+    ref = inversion.invert_topk(engine, lutf, obs, k)
+    parts = [inversion.invert_topk(engine, lutf[b:e], obs, k, index_offset=b) for b, e in (lut.shard_bounds(m, r, 4) for r in range(4))]
+    idx, cost = inversion.reduce_topk(np.stack([p[1] for p in parts]), np.stack([p[0] for p in parts]), k)
+    assert np.array_equal(idx, ref[0]) and np.array_equal(cost, ref[1])
+    n = 20000
+    P = lut.latin_hypercube(n, ("N", "Cab", "Cxc", "Cbr", "Cw", "Cm", "lai", "hotspot", "lidf_a", "soil_reflectance", "soil_moisture"), 20261019 + 8)
+    bi = inversion.BandLutInverter(engine, P, (35.0, 30.0, 50.0))
+    pick = rng.integers(0, n, 50)
+    i2, c2, best = bi.invert_topk(bi.features[pick], 4)
+    assert np.array_equal(i2[:, 0], pick) and np.all(c2[:, 0] == 0) and best["lai"].shape == (50, 4) and np.allclose(best["lai"][:, 0], P["lai"][pick])
+    with pytest.raises(pb._capi.ProsailError):
+        inversion.invert_topk(engine, lutf, obs, 17)

@@ -52,6 +52,21 @@ def test_fold_of_shards_equals_the_unsharded_result(world):
     assert np.all((idx2 >= lut.shard_bounds(m, 0, world)[1]) | (world == 1) | (idx2 == -1))
 
 
+def test_topk_oracle_and_fold():
+    m, q, k = 2000, 40, 6
+    lutf = rng.random((m, 9)).astype(np.float32)
+    lutf[1500] = lutf[3]
+    obs = np.concatenate([lutf[[3]], rng.random((q - 1, 9)).astype(np.float32)])
+    ref_i, ref_c = inv.invert_topk(lutf, obs, k)
+    assert ref_i[0, :2].tolist() == [3, 1500] and np.all(np.diff(ref_c, axis=1) >= 0)
+    assert np.array_equal(ref_i[:, 0], inv.invert(lutf, obs)[0])
+    parts = [inv.invert_topk(lutf[b:e], obs, k, index_offset=b) for b, e in (lut.shard_bounds(m, r, 3) for r in range(3))]
+    idx, cost = inversion.reduce_topk(np.stack([p[1] for p in parts]), np.stack([p[0] for p in parts]), k)
+    assert np.array_equal(idx, ref_i) and np.array_equal(cost, ref_c)
+    small_i, small_c = inv.invert_topk(lutf[:4], obs, k)
+    assert np.all(small_i[:, 4:] == -1) and np.all(np.isinf(small_c[:, 4:]))
+
+
 def _gloo_worker(rank, world, port, lutf, obs, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
