@@ -9,7 +9,7 @@
 // Mapping: a CTA owns 256 threads x 4 observations (features in registers) and one chunk of the LUT, which it
 // streams through shared memory in tiles; every LUT entry is read as 128-bit shared-memory broadcasts and reused by the four
 // observations of each thread (4 x DP FMAs per DP / 4 LDS.128).  Per-(observation, chunk) minima go to a small partial buffer;
-// k_invert_reduce folds the chunks in index order.  Bound: FP32 FMA issue (2 DP flops per pair), not HBM: the LUT is re-read
+// k_invert_reduce folds the chunks in index order.  Bound: the FP32 lanes (packed FADD2 / FFMA2 on pairs of observations), not HBM: the LUT is re-read
 // once per 1024 observations and stays in the 126 MB L2 for LUT shards up to ~2e6 entries x 16 features.
 #pragma once
 #include <cuda_runtime.h>
@@ -48,15 +48,21 @@ __global__ void __launch_bounds__(INV_THREADS) k_invert(const InvertArgs a) {
     if (tid < DP) s_scale[tid] = a.scale[tid];
     __syncthreads();
 
-    // this thread's observations, pre-scaled (invalid rows replicate row 0 and are not written back)
-    float o[INV_OPT][DP];
+    // this thread's observations, pre-scaled (invalid rows replicate row 0 and are not written back), held as PAIRS of
+    // observations per feature: the distance update runs in packed FP32 (FADD2 with the LUT value as a broadcast operand,
+    // FFMA2), i.e. half the issue slots of the scalar form for the same arithmetic, bit for bit
+    static_assert(INV_OPT % 2 == 0, "observations are processed in pairs");
+    float2 o2[INV_OPT / 2][DP];
     long long q[INV_OPT];
 #pragma unroll
     for (int j = 0; j < INV_OPT; ++j) {
         q[j] = (long long)blockIdx.x * INV_OBS_PER_CTA + j * INV_THREADS + tid;
         const long long row = q[j] < a.n_obs ? q[j] : 0;
 #pragma unroll
-        for (int d = 0; d < DP; ++d) o[j][d] = d < a.n_feat ? a.obs[row * a.pitch_obs + d] * s_scale[d] : 0.0f;
+        for (int d = 0; d < DP; ++d) {
+            const float v = d < a.n_feat ? a.obs[row * a.pitch_obs + d] * s_scale[d] : 0.0f;
+            if (j & 1) o2[j / 2][d].y = v; else o2[j / 2][d].x = v;
+        }
     }
     float best[INV_OPT];
     long long bidx[INV_OPT];
@@ -88,23 +94,25 @@ __global__ void __launch_bounds__(INV_THREADS) k_invert(const InvertArgs a) {
         const float4* tp = reinterpret_cast<const float4*>(tile[buf]);
 #pragma unroll 2
         for (int e = 0; e < n; ++e) {
-            float acc[INV_OPT];
+            float2 acc[INV_OPT / 2];
 #pragma unroll
-            for (int j = 0; j < INV_OPT; ++j) acc[j] = 0.0f;
+            for (int j = 0; j < INV_OPT / 2; ++j) acc[j] = make_float2(0.0f, 0.0f);
 #pragma unroll
             for (int d4 = 0; d4 < DP / 4; ++d4) {
                 const float4 l = tp[e * (DP / 4) + d4];          // broadcast: all lanes read the same 16 bytes
 #pragma unroll
-                for (int j = 0; j < INV_OPT; ++j) {
-                    float df = o[j][4 * d4 + 0] - l.x; acc[j] = fmaf(df, df, acc[j]);
-                    df = o[j][4 * d4 + 1] - l.y; acc[j] = fmaf(df, df, acc[j]);
-                    df = o[j][4 * d4 + 2] - l.z; acc[j] = fmaf(df, df, acc[j]);
-                    df = o[j][4 * d4 + 3] - l.w; acc[j] = fmaf(df, df, acc[j]);
+                for (int j = 0; j < INV_OPT / 2; ++j) {
+                    float2 df = __fadd2_rn(o2[j][4 * d4 + 0], make_float2(-l.x, -l.x)); acc[j] = __ffma2_rn(df, df, acc[j]);
+                    df = __fadd2_rn(o2[j][4 * d4 + 1], make_float2(-l.y, -l.y)); acc[j] = __ffma2_rn(df, df, acc[j]);
+                    df = __fadd2_rn(o2[j][4 * d4 + 2], make_float2(-l.z, -l.z)); acc[j] = __ffma2_rn(df, df, acc[j]);
+                    df = __fadd2_rn(o2[j][4 * d4 + 3], make_float2(-l.w, -l.w)); acc[j] = __ffma2_rn(df, df, acc[j]);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < INV_OPT; ++j)
-                if (acc[j] < best[j]) { best[j] = acc[j]; bidx[j] = base + e; }
+            for (int j = 0; j < INV_OPT / 2; ++j) {
+                if (acc[j].x < best[2 * j]) { best[2 * j] = acc[j].x; bidx[2 * j] = base + e; }
+                if (acc[j].y < best[2 * j + 1]) { best[2 * j + 1] = acc[j].y; bidx[2 * j + 1] = base + e; }
+            }
         }
         __syncthreads();
     }
