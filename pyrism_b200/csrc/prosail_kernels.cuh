@@ -452,6 +452,7 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
 template <typename T>
 struct Diffuse {
     T m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd;
+    T a1, a2;      // rho + tau rinf, tau + rho rinf: the leaf-dependent factors of (sf + sb rinf), (sf rinf + sb), ... (:649-652)
 };
 
 // FROM_LEAF: rho, tau come from the PROSPECT stage of the same kernel.  Then 0 < rho, tau and rho + tau < 1 hold by
@@ -493,6 +494,8 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
     T dn = one - d.rsrdd;                                             // :714-719
     dn = below_tiny(dn) ? tiny : dn;                                  // dn < 1e-36 (integer-pipe test; negatives too)
     d.rs_invdn = rs * rcp(dn);
+    d.a1 = fma(tau, d.rinf, rho);
+    d.a2 = fma(rho, d.rinf, tau);
 }
 
 template <typename T>
@@ -508,15 +511,14 @@ __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>
                                             T inv_Kp, unsigned need, Canopy<T>& o) {
     const T one = T(1);
     const T tss = g[G_TSS], too = g[G_TOO];
-    const T sb = fma(g[G_SDB], rho, g[G_SDF] * tau);                  // :603-607
-    const T sf = fma(g[G_SDF], rho, g[G_SDB] * tau);
-    const T vb = fma(g[G_DOB], rho, g[G_DOF] * tau);
-    const T vf = fma(g[G_DOF], rho, g[G_DOB] * tau);
-    const T w = fma(g[G_FS], rho, g[G_FT] * tau);
+    // sb, sf, vb, vf (:603-606) only ever appear as sf + sb rinf, sf rinf + sb, vf + vb rinf, vf rinf + vb (:649-652).  With
+    // a1 = rho + tau rinf and a2 = tau + rho rinf (geometry independent, computed once per parameter set):
+    //   sf + sb rinf = sdf a1 + sdb a2,   sf rinf + sb = sdf a2 + sdb a1,   and the same with (dof, dob) for the view direction
+    const T w = fma(g[G_FS], rho, g[G_FT] * tau);                     // :607
     const T J2ks = fma(-d.e1, tss, one) * inv_kp;
     const T J2ko = fma(-d.e1, too, one) * inv_Kp;
-    const T u1 = fma(sb, d.rinf, sf), u2 = fma(sf, d.rinf, sb);       // :649-652
-    const T v1 = fma(vb, d.rinf, vf), v2 = fma(vf, d.rinf, vb);
+    const T u1 = fma(g[G_SDF], d.a1, g[G_SDB] * d.a2), u2 = fma(g[G_SDF], d.a2, g[G_SDB] * d.a1);
+    const T v1 = fma(g[G_DOF], d.a1, g[G_DOB] * d.a2), v2 = fma(g[G_DOF], d.a2, g[G_DOB] * d.a1);
     const T Pss = u1 * J1ks, Qss = u2 * J2ks, Pv = v1 * J1ko, Qv = v2 * J2ko;
     o.tsd = fma(-d.re, Qss, Pss) * d.invden;                          // :656-659
     o.rsd = fma(-d.re, Pss, Qss) * d.invden;
@@ -629,6 +631,8 @@ __device__ __forceinline__ void sail_diffuse_f32x2(f2 rho, f2 tau, f2 rs, const 
     f2 dn = sub(F2(1.0f), d.rsrdd);                                   // :714-719
     dn = F2(below_tiny(dn.x) ? 1e-36f : dn.x, below_tiny(dn.y) ? 1e-36f : dn.y);
     d.rs_invdn = mul(rs, rcp(dn));
+    d.a1 = fma(tau, d.rinf, rho);
+    d.a2 = fma(rho, d.rinf, tau);
 }
 
 __device__ __forceinline__ void sail_directional_f32x2(f2 rho, f2 tau, f2 rs, const Diffuse<f2>& d, const float* __restrict__ s,
@@ -641,15 +645,11 @@ __device__ __forceinline__ void sail_directional_f32x2(f2 rho, f2 tau, f2 rs, co
     const f2 J1ko = mul(expm1_over_x(mul(Km, lai), fma(d.e1, F2(g[G_ITOO]), -1.0f)), too * lai);
     const f2 rkK = rcp(mul(kp, Kp));                                  // 1/(k+m) and 1/(K+m) from one reciprocal (both > 0)
     const f2 inv_kp = mul(rkK, Kp), inv_Kp = mul(rkK, kp);
-    const f2 sb = fma(g[G_SDB], rho, mul(tau, g[G_SDF]));             // :603-607
-    const f2 sf = fma(g[G_SDF], rho, mul(tau, g[G_SDB]));
-    const f2 vb = fma(g[G_DOB], rho, mul(tau, g[G_DOF]));
-    const f2 vf = fma(g[G_DOF], rho, mul(tau, g[G_DOB]));
-    const f2 w = fma(g[G_FS], rho, mul(tau, g[G_FT]));
+    const f2 w = fma(g[G_FS], rho, mul(tau, g[G_FT]));               // :607
     const f2 J2ks = mul(fma(neg(d.e1), F2(tss), 1.0f), inv_kp);       // :787-789
     const f2 J2ko = mul(fma(neg(d.e1), F2(too), 1.0f), inv_Kp);
-    const f2 u1 = fma(sb, d.rinf, sf), u2 = fma(sf, d.rinf, sb);      // :649-652
-    const f2 v1 = fma(vb, d.rinf, vf), v2 = fma(vf, d.rinf, vb);
+    const f2 u1 = fma(g[G_SDF], d.a1, mul(d.a2, g[G_SDB])), u2 = fma(g[G_SDF], d.a2, mul(d.a1, g[G_SDB]));   // :603-606, 649-652 via a1, a2
+    const f2 v1 = fma(g[G_DOF], d.a1, mul(d.a2, g[G_DOB])), v2 = fma(g[G_DOF], d.a2, mul(d.a1, g[G_DOB]));
     const f2 Pss = mul(u1, J1ks), Qss = mul(u2, J2ks), Pv = mul(v1, J1ko), Qv = mul(v2, J2ko);
     const f2 nre = neg(d.re);
     o.tsd = mul(fma(nre, Qss, Pss), d.invden);                        // :656-659
