@@ -1191,7 +1191,8 @@ int prosail_test_math(prosail_handle_t* h, int op, long long n, const double* in
         din = (const double*)bi.p;
         dout = (double*)bo.p;
     }
-    k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(op, n, din, dout, h->d_tables);
+    CK(cudaFuncSetAttribute(k_test_math, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MathTables)));
+    k_test_math<<<(unsigned)((n + 255) / 256), 256, sizeof(MathTables), h->stream>>>(op, n, din, dout, h->d_tables);
     h->launches++;
     CK(cudaGetLastError());
     if (on_host) {

@@ -1482,7 +1482,8 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
 // ---------------------------------------------------------------------------------------------
 // op: 0 rcp, 1 sqrt_pos, 2 exp_neg, 3 log2_pos, 4 exp2_any, 5 tau_plate, 6 tau_full
 __global__ void k_test_math(int op, long long n, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ tables) {
-    __shared__ MathTables mt;
+    extern __shared__ __align__(16) unsigned char test_smem[];              // sizeof(MathTables) bytes of dynamic shared memory
+    MathTables& mt = *reinterpret_cast<MathTables*>(test_smem);
     for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 8); i += blockDim.x) reinterpret_cast<double*>(&mt)[i] = tables[i];
     __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
