@@ -9,6 +9,8 @@
 // per sub-partition it is this instruction-level parallelism that keeps the pipe fed.  Rare cases (arguments outside the tau
 // table, zero absorption, the J1 series branch) are flagged in the branch-free fast path and repaired
 // afterwards, so that the hot loop is a handful of large basic blocks the scheduler can interleave.
+// The kernel is a template over the real type: double is the parity path (<= 1e-9 against the reference), float the
+// fp32 mode (<= 1e-5), whose item loop runs in packed FP32 (FFMA2 / FMUL2 / FADD2: the two bands of a thread per instruction).
 // Per-item scalars come from 128-byte records that the prologue kernel packs and that each CTA stages
 // into shared memory with bulk async copies (cp.async.bulk + mbarrier, double buffered), so the inner
 // loop touches HBM only for the coalesced 256-byte-per-warp stores of the output spectra.
@@ -51,12 +53,12 @@ struct Cfg {
     static_assert(NTILES % NU_ == 0, "the 66 tiles must split evenly into groups");
 };
 constexpr int CHUNK = PB_CHUNK;   // work items per shared-memory stage (per warp)
-constexpr int REC = 16;           // doubles per record (128 B)
+constexpr int REC = 16;           // values per record (128 B in double, 64 B in float)
 constexpr int MAX_TILE_SLOTS = 8; // windows that may overlap one 32-band tile
 constexpr int MAX_WINDOWS = 64;
 constexpr int MAX_SLOTS = 256;
 
-// planes of the per-band constant array  double[NCONST][NBP]
+// planes of the per-band constant array  T[NCONST][NBP]
 enum { C_KAB = 0, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RS1, C_RS2, C_RALF, C_R12, C_R21, NCONST };
 // (C_RALF.. = 1 - talf, 1 - t12, 1 - t21: only the float image carries them, rounded once from the float64 values)
 
