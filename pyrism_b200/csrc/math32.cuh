@@ -112,17 +112,14 @@ __device__ __forceinline__ f2 rcp(f2 a) { return F2(rcp(a.x), rcp(a.y)); }
 __device__ __forceinline__ f2 sqrt_pos(f2 a) { return F2(sqrt_pos(a.x), sqrt_pos(a.y)); }
 __device__ __forceinline__ f2 exp2_fast(f2 a) { return F2(exp2_fast(a.x), exp2_fast(a.y)); }
 __device__ __forceinline__ f2 log2_fast(f2 a) { return F2(log2_fast(a.x), log2_fast(a.y)); }
-// expm1(x)/x for both halves given em1 = expm1(x) from elsewhere (accurate where |x| >= 0.25): packed degree-6 series
-// below 0.25, em1 / x above
-__device__ __forceinline__ f2 expm1_over_x(f2 x, f2 em1) {
+// expm1(x)/x for |x| < 0.25, both halves: packed degree-6 series (truncation 0.25^7/40320 < 2e-9)
+__device__ __forceinline__ f2 expm1_over_x_small(f2 x) {
     f2 p = fma(x, F2(1.0f / 5040.0f), 1.0f / 720.0f);
     p = fma(x, p, 1.0f / 120.0f);
     p = fma(x, p, 1.0f / 24.0f);
     p = fma(x, p, 1.0f / 6.0f);
     p = fma(x, p, 0.5f);
-    p = fma(x, p, 1.0f);
-    const f2 q = mul(em1, rcp(x));
-    return F2(fabsf(x.x) < 0.25f ? p.x : q.x, fabsf(x.y) < 0.25f ? p.y : q.y);
+    return fma(x, p, 1.0f);
 }
 
 }  // namespace pb

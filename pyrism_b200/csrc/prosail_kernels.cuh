@@ -65,8 +65,7 @@ enum { C_KAB = 0, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RS1, 
 // sample record (per parameter set)
 enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DDB, S_DDF, S_NEGLAI, S_LAI, S_NOCANOPY, S_THR };
 // geometry record (per parameter set x geometry)
-enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_ITSS, G_ITOO, G_ALF };
-// (G_ITSS, G_ITOO = 1/tss, 1/too: exp((k - m) lai) = e1 / tss without another exponential in the packed fp32 path)
+enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_BF, G_SUMINT, G_ALF };
 
 // output planes (bit index in out_mask / mean_mask)
 enum { O_RSOT = 0, O_RDDT, O_RSDT, O_RDOT, O_RSO, O_RDD, O_TDD, O_RSD, O_TSD, O_RDO, O_TDO, O_KE, O_LEAF_R, O_LEAF_T, O_RHO,
@@ -552,8 +551,10 @@ __device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const 
     const T km = k - d.m, kp = k + d.m, Km = K - d.m, Kp = K + d.m;
     if constexpr (std::is_same<T, float>::value) {
         const T lai = s[S_LAI];
-        const T J1ks = (tss * lai) * expm1_over_x(km * lai);
-        const T J1ko = (too * lai) * expm1_over_x(Km * lai);
+        // direct difference where |d| >= 0.25 (at most two bits lost), series below: see sail_directional_f32x2
+        const T xk = km * lai, xK = Km * lai;
+        const T J1ks = fabsf(xk) < 0.25f ? (tss * lai) * expm1_over_x(xk) : (d.e1 - tss) * rcp(km);
+        const T J1ko = fabsf(xK) < 0.25f ? (too * lai) * expm1_over_x(xK) : (d.e1 - too) * rcp(Km);
         sail_couple(rho, tau, rs, d, g, J1ks, J1ko, rcp(kp), rcp(Kp), need, o);
         return false;
     } else {
@@ -641,10 +642,14 @@ __device__ __forceinline__ void sail_directional_f32x2(f2 rho, f2 tau, f2 rs, co
                                                        const float* __restrict__ g, unsigned need, Canopy<f2>& o) {
     const float k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO], lai = s[S_LAI];
     const f2 km = sub(F2(k), d.m), kp = add(d.m, k), Km = sub(F2(K), d.m), Kp = add(d.m, K);
-    // J1(k,m) = e^{-k t} t expm1(d)/d, d = (k - m) t: no cancellation, no series branch                  :765-785
-    // expm1(d) = e1 / tss - 1 needs no further exponential (1/tss comes with the record); below |d| = 0.25 the series takes over
-    const f2 J1ks = mul(expm1_over_x(mul(km, lai), fma(d.e1, F2(g[G_ITSS]), -1.0f)), tss * lai);
-    const f2 J1ko = mul(expm1_over_x(mul(Km, lai), fma(d.e1, F2(g[G_ITOO]), -1.0f)), too * lai);
+    // J1(k,m) = (e^{-m t} - e^{-k t})/(k - m)  (:765-785).  Where |d| = |k - m| t >= 0.25 the difference loses at most two bits
+    // and is taken directly; below, J1 = e^{-k t} t expm1(d)/d with a series: no cancellation anywhere, no repair path, and no
+    // intermediate can overflow or turn 0 * inf into NaN when tss or e1 underflow (lai of hundreds, grazing sun).
+    const f2 xk = mul(km, lai), xK = mul(Km, lai);
+    const f2 sk = mul(expm1_over_x_small(xk), tss * lai), sK = mul(expm1_over_x_small(xK), too * lai);
+    const f2 dk = mul(add(d.e1, -tss), rcp(km)), dK = mul(add(d.e1, -too), rcp(Km));
+    const f2 J1ks = F2(fabsf(xk.x) < 0.25f ? sk.x : dk.x, fabsf(xk.y) < 0.25f ? sk.y : dk.y);
+    const f2 J1ko = F2(fabsf(xK.x) < 0.25f ? sK.x : dK.x, fabsf(xK.y) < 0.25f ? sK.y : dK.y);
     const f2 rkK = rcp(mul(kp, Kp));                                  // 1/(k+m) and 1/(K+m) from one reciprocal (both > 0)
     const f2 inv_kp = mul(rkK, Kp), inv_Kp = mul(rkK, kp);
     const f2 w = fma(g[G_FS], rho, mul(tau, g[G_FT]));               // :607
@@ -1235,7 +1240,7 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         r[G_DOB] = 0.5 * (K + bf); r[G_DOF] = 0.5 * (K - bf);
         r[G_FS] = Fs; r[G_FT] = Ft;
         r[G_TSS] = tss; r[G_TOO] = too; r[G_TSSTOO] = tsstoo;
-        r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_ITSS] = 1.0 / tss; r[G_ITOO] = 1.0 / too; r[G_ALF] = alf;
+        r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_BF] = bf; r[G_SUMINT] = sumint; r[G_ALF] = alf;
         store_rec<T>(a.grec, item, r);
         if (g == 0) {
             srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
@@ -1464,7 +1469,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
     grec[G_DOB] = 0.5 * (K + bf); grec[G_DOF] = 0.5 * (K - bf);
     grec[G_FS] = Fs; grec[G_FT] = Ft;
     grec[G_TSS] = tss; grec[G_TOO] = too; grec[G_TSSTOO] = tsstoo;
-    grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_ITSS] = 1.0 / tss; grec[G_ITOO] = 1.0 / too; grec[G_ALF] = alf;
+    grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_BF] = bf; grec[G_SUMINT] = sumint; grec[G_ALF] = alf;
     store_rec<T>(a.grec, item, grec);
     if (g == 0) {
         srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);

@@ -132,3 +132,17 @@ def test_prospect_f32_derived_planes_come_from_the_kernel():
             for q in ('ka', 'ke', 'om'):
                 assert np.max(np.abs(getattr(p, q)[i] - o[q])) <= tol, (q, i, dt)
         assert p.int.shape == (n, 2101, 6) and p.int.dtype == f32
+
+
+@pytest.mark.parametrize("over", [dict(lai=300.0), dict(iza=89.9), dict(lai=50.0, hotspot=1e-9), dict(vza=89.0, lai=8.0), dict(lai=1e-6)])
+def test_f32_underflowing_transmittances_stay_finite(over):
+    """tss = exp(-k lai) and e1 underflow in float for lai of hundreds or a grazing sun: no 0 * inf may appear (the J1 term is
+    taken as a direct difference there), and the result stays within the fp32 tolerance of the float64 oracle."""
+    p = dict(N=1.5, Cab=40.0, Cxc=8.0, Cbr=0.1, Cw=0.01, Cm=0.009, lai=3.0, hotspot=0.1, iza=35.0, vza=30.0, raa=50.0)
+    p.update(over)
+    _, _, o = orc.prosail(p['N'], p['Cab'], p['Cxc'], p['Cbr'], p['Cw'], p['Cm'], p['lai'], p['hotspot'], p['iza'], p['vza'], p['raa'], 1.0, 0.5)
+    for dt, tol in ((np.float64, 1e-9), (f32, TOL32)):
+        m = pb.PROSAIL(N=p['N'], Cab=p['Cab'], Cxc=p['Cxc'], Cbr=p['Cbr'], Cw=p['Cw'], Cm=p['Cm'], lai=p['lai'], hotspot=p['hotspot'], iza=p['iza'],
+                       vza=p['vza'], raa=p['raa'], soil_reflectance=1.0, soil_moisture=0.5, dtype=dt)
+        for got, key in ((m.BRF.ref, 'rsot'), (m.BHR.ref, 'rddt'), (m.DHR.ref, 'rsdt'), (m.HDR.ref, 'rdot')):
+            assert np.all(np.isfinite(got)) and np.max(np.abs(got - o[key])) <= tol, (over, key, dt)
