@@ -341,6 +341,9 @@ def main():
                 # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
                 # (profiles/r1e_k_bands_prosail_brf_f64.txt: 4.466 GB for 262144 spectra = 17037 B per spectrum), scaled to this launch
                 "traffic": spectra_per_launch * NCU_DRAM_BYTES_PER_SPECTRUM,
+                # lower bounds of one launch from each roofline; the larger one binds (fp64 by ~5x)
+                "t_fp64_min_ms": spectra_per_launch * NB * FLOPS_PER_BAND / (fp64_peak * 1e12) * 1e3,
+                "t_hbm_min_ms": spectra_per_launch * BYTES_PER_SPECTRUM / (hbm_peak * 1e9) * 1e3,
                 "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                         "algorithmic_bytes_per_spectrum": BYTES_PER_SPECTRUM}}
