@@ -48,7 +48,7 @@ struct Cfg {
     static constexpr int NU = NU_;                     // bands per thread: band0 + 32 u
     static constexpr int WARPS = WARPS_;
     static constexpr int THREADS = WARPS_ * 32;
-    static constexpr int KSTRIDE = NU_ * THREADS;      // elements per plane of SailSmem::kc: [u][thread]
+    static constexpr int KSTRIDE = NU_ * THREADS;      // elements per plane of SailSmem::kc: [thread][u]
     static constexpr int NGROUPS = NTILES / NU_;       // groups of NU 32-band tiles, one per warp
     static_assert(NTILES % NU_ == 0, "the 66 tiles must split evenly into groups");
 };
@@ -151,7 +151,7 @@ template <typename T, typename CF>
 struct alignas(128) SailSmem {
     typename Tables<T>::type mt;           // shared by the CTA, read-only after the prologue
     Stage<T> stage[CF::WARPS][2];          // per-warp double-buffered record staging: no CTA-wide barrier in the loop
-    T kc[KPLANES * CF::KSTRIDE];           // conflict-free: consecutive lanes read consecutive elements
+    T kc[KPLANES * CF::KSTRIDE];           // [plane][thread][u]: a thread's bands are adjacent (vector loads), lanes consecutive
     uint64_t bar[CF::WARPS][2];
 };
 
@@ -387,7 +387,7 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
     bool any_rare = false;
     const T nm1 = s[S_NM1];
 #pragma unroll
-    for (int u = 0; u < NU; ++u) kall[u] = leaf_kall<CF::KSTRIDE>(kc + u * CF::THREADS, s);
+    for (int u = 0; u < NU; ++u) kall[u] = leaf_kall<CF::KSTRIDE>(kc + u, s);
     if constexpr (std::is_same<T, float>::value) {
         float omt[NU];
 #pragma unroll
@@ -426,7 +426,7 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
                                                f2& refl, f2& tran) {
     static_assert(CF::NU == 2, "the packed path pairs the two bands of a thread");
     const float nm1 = s[S_NM1];
-    constexpr int KS = CF::KSTRIDE, TH = CF::THREADS;
+    constexpr int KS = CF::KSTRIDE, TH = 1;        // the two bands of a thread are adjacent in SailSmem::kc: one 64-bit load per pair
     f2 kall = mul(F2(kc[KC_KAB * KS], kc[KC_KAB * KS + TH]), s[S_CAB]);           // :950-951, both bands per instruction
     kall = fma(s[S_CXC], F2(kc[KC_KXC * KS], kc[KC_KXC * KS + TH]), kall);
     kall = fma(s[S_CAN], F2(kc[KC_KAN * KS], kc[KC_KAN * KS + TH]), kall);
@@ -803,12 +803,12 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     if (lane == 0 && chunk < nchunks) stage_issue(a, &stage[0], &bar[0], chunk);
 
     BandConst<T> c[NU];
-    const T* kc = sm.kc + threadIdx.x;             // this thread's column of the once-per-item constants
+    const T* kc = sm.kc + threadIdx.x * NU;        // this thread's NU adjacent columns of the once-per-item constants
     constexpr int KS = CF::KSTRIDE;
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         const T* bc = a.bandc + (live ? band0 + 32 * u : 0);          // NBP = 66 * 32: always in range
-        T* k = sm.kc + u * CF::THREADS + threadIdx.x;                 // only this thread reads these back: no barrier needed
+        T* k = sm.kc + threadIdx.x * NU + u;                          // only this thread reads these back: no barrier needed
         k[KC_KAB * KS] = bc[C_KAB * NBP]; k[KC_KXC * KS] = bc[C_KXC * NBP]; k[KC_KAN * KS] = bc[C_KAN * NBP];
         k[KC_KBR * KS] = bc[C_KBR * NBP]; k[KC_KW * KS] = bc[C_KW * NBP]; k[KC_KM * KS] = bc[C_KM * NBP];
         k[KC_RS1 * KS] = bc[C_RS1 * NBP]; k[KC_RS2 * KS] = bc[C_RS2 * NBP];
@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {
 #pragma unroll
-                    for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u * CF::THREADS, sr);
+                    for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u, sr);
                     emit<PLANES, MEANS, O_RHO>(e, rs);
                 } else if (MODE == MODE_PROSPECT) {
                     if constexpr (PACKED) {
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                     if (PLANES == RUNTIME && (need & (31u << O_LAYER_R))) {      // PROSPECT.r, t, Ra, Ta, denom (models.py:959)
                         T q[NU][5];
 #pragma unroll
-                        for (int u = 0; u < NU; ++u) leaf_one_layer(c[u], leaf_kall<KS>(kc + u * CF::THREADS, sr), q[u]);
+                        for (int u = 0; u < NU; ++u) leaf_one_layer(c[u], leaf_kall<KS>(kc + u, sr), q[u]);
                         { PB_GATHER(v, q, [0]); emit<PLANES, MEANS, O_LAYER_R>(e, v); }
                         { PB_GATHER(v, q, [1]); emit<PLANES, MEANS, O_LAYER_T>(e, v); }
                         { PB_GATHER(v, q, [2]); emit<PLANES, MEANS, O_LAYER_RA>(e, v); }
@@ -914,7 +914,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                                 leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
                             }
 #pragma unroll
-                            for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u * CF::THREADS, sr);
+                            for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u, sr);
                         } else {
 #pragma unroll
                             for (int u = 0; u < NU; ++u) {
