@@ -69,11 +69,12 @@ struct Work {            // per-stream scratch
     DevBuf srec, grec, partial;
     DevBuf lidf;         // [samples][18] LIDF workspace (multi-geometry jobs)
     DevBuf inv;          // LUT inversion: per-(observation, chunk) minima + scale vector
+    DevBuf geomtab;      // [G][18][8] geometry-only volume-scattering bin terms (shared-geometry batches)
     DevBuf in;           // host mode: parameter slices
     DevBuf out;          // host mode: output planes / means / geom of one slab
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    void release() { srec.release(); grec.release(); partial.release(); lidf.release(); inv.release(); in.release(); out.release(); }
+    void release() { srec.release(); grec.release(); partial.release(); lidf.release(); inv.release(); geomtab.release(); in.release(); out.release(); }
 };
 
 struct prosail_handle {
@@ -326,13 +327,23 @@ static int run_device_t(prosail_handle* h, const Job& j, Work& w, cudaStream_t s
         {
             ProfScope ps(h, 1, st);
             if (ni >= h->prologue_thread_min) {     // throughput variant: one thread per item
+                const unsigned pgrid = (unsigned)((ni + 127) / 128);
+                const double* gt = nullptr;
+                if (j.has_canopy && !j.can.geom_per_sample) {   // shared geometry list: the bin terms once per (geometry, bin)
+                    if ((rc = w.geomtab.reserve((size_t)G * 18 * 8 * 8))) return rc;
+                    k_geom_bins<<<(unsigned)((G * 18 + 127) / 128), 128, 0, st>>>(G, p.iza, p.vza, p.raa, h->d_angles, (double*)w.geomtab.p);
+                    h->launches++;
+                    gt = (const double*)w.geomtab.p;
+                }
                 if (j.has_canopy && G > 1) {        // LIDF once per parameter set, not once per (set, geometry)
                     if ((rc = w.lidf.reserve((size_t)ns * PROSAIL_NLIDF * 8))) return rc;
                     k_lidf<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(p, h->d_angles, (double*)w.lidf.p);
                     h->launches++;
-                    k_prologue_t<T, true><<<(unsigned)((ni + 127) / 128), 128, 0, st>>>(p, h->d_angles, (const double*)w.lidf.p);
+                    if (gt) k_prologue_t<T, true, true><<<pgrid, 128, 0, st>>>(p, h->d_angles, (const double*)w.lidf.p, gt);
+                    else k_prologue_t<T, true, false><<<pgrid, 128, 0, st>>>(p, h->d_angles, (const double*)w.lidf.p, nullptr);
                 } else {
-                    k_prologue_t<T, false><<<(unsigned)((ni + 127) / 128), 128, 0, st>>>(p, h->d_angles, nullptr);
+                    if (gt) k_prologue_t<T, false, true><<<pgrid, 128, 0, st>>>(p, h->d_angles, nullptr, gt);
+                    else k_prologue_t<T, false, false><<<pgrid, 128, 0, st>>>(p, h->d_angles, nullptr, nullptr);
                 }
             } else {                                // latency variant: one warp per item, leaf bins across lanes
                 const long long threads = ni * 32;

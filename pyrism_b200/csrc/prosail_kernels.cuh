@@ -1271,6 +1271,62 @@ struct AngleTables {            // filled on the host by prosail_create with the
     double edge[19];            // the edges in radians as LIDF.verhoef computes them (np.radians(angle), models.py:372)
 };
 
+// One leaf-inclination bin of VolScatt.volume / coef (models.py:154-173, 177-258) for one geometry:
+// b = { chi_s/cos(tts), chi_o/cos(tto), frho pi/(cos cos), ftau pi/(cos cos), chi_s, chi_o, frho, ftau }.
+// The trigonometry is reduced to two acos per bin with angle-addition identities (see k_prologue_t).
+__device__ __forceinline__ void volscatt_bin(const AngleTables* __restrict__ at, int i, double tto, double sts, double cts, double sto,
+                                             double cto, double spsi, double cpsi, double psi, double (&b)[8]) {
+    const double ctscto = cts * cto;
+    const bool view_up = tto < 90.0 * PB_PI / 180.0;
+    const double clza = at->cl[i], slza = at->sl[i];
+    const double cs = clza * cts, co = clza * cto, ss = slza * sts, so = slza * sto;
+    double cbs = 5.0, cbo = 5.0;
+    if (fabs(ss) > 1e-6) cbs = -cs / ss;
+    if (fabs(so) > 1e-6) cbo = -co / so;
+    double bts, ds, sbs, bto, do_, sbo;
+    if (fabs(cbs) < 1.0) { bts = acos(cbs); ds = ss; sbs = sqrt(1.0 - cbs * cbs); }
+    else { bts = PB_PI; ds = cs; cbs = -1.0; sbs = 0.0; }
+    const double chi_s = 2.0 / PB_PI * ((bts - PB_PI * 0.5) * cs + sbs * ss);
+    if (fabs(cbo) < 1.0) { bto = acos(cbo); do_ = so; sbo = sqrt(1.0 - cbo * cbo); }
+    else if (view_up) { bto = PB_PI; do_ = co; cbo = -1.0; sbo = 0.0; }
+    else { bto = 0.0; do_ = -co; cbo = 1.0; sbo = 0.0; }
+    const double chi_o = 2.0 / PB_PI * ((bto - PB_PI * 0.5) * co + sbo * so);
+    const double btran1 = fabs(bts - bto);
+    const double btran2 = PB_PI - fabs(bts + bto - PB_PI);
+    const double cc = cbs * cbo, sscp = sbs * sbo, sc = sbs * cbo, cs_ = cbs * sbo;
+    const double cos1 = cc + sscp, sin1 = fabs(sc - cs_);        // btran1
+    const double cos2 = cc - sscp, sin2 = fabs(sc + cs_);        // btran2
+    double bt2, sin_bt2, cos_bt1, cos_bt3;
+    if (psi <= btran1) { bt2 = btran1; sin_bt2 = sin1; cos_bt1 = cpsi; cos_bt3 = cos2; }
+    else if (psi <= btran2) { bt2 = psi; sin_bt2 = spsi; cos_bt1 = cos1; cos_bt3 = cos2; }
+    else { bt2 = btran2; sin_bt2 = sin2; cos_bt1 = cos1; cos_bt3 = cpsi; }
+    const double t1 = 2.0 * cs * co + ss * so * cpsi;
+    double t2 = 0.0;
+    if (bt2 > 0.0) t2 = sin_bt2 * (2.0 * ds * do_ + ss * so * cos_bt1 * cos_bt3);
+    const double denom = 2.0 * PB_PI * PB_PI;
+    const double frho = fmax(((PB_PI - bt2) * t1 + t2) / denom, 0.0);
+    const double ftau = fmax((-bt2 * t1 + t2) / denom, 0.0);
+    b[0] = chi_s / cts; b[1] = chi_o / cto; b[2] = frho * PB_PI / ctscto; b[3] = ftau * PB_PI / ctscto;
+    b[4] = chi_s; b[5] = chi_o; b[6] = frho; b[7] = ftau;
+}
+
+// The bin terms depend on the geometry only: when a batch shares its geometry list (LUT shapes), they are computed once per
+// (geometry, bin) into a table [G][18][8] and every (parameter set, geometry) item just weights them with its LIDF.
+__global__ void __launch_bounds__(128) k_geom_bins(int G, const double* __restrict__ iza, const double* __restrict__ vza,
+                                                   const double* __restrict__ raa, const AngleTables* __restrict__ at, double* __restrict__ ws) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * 18) return;
+    const int g = t / 18, i = t - g * 18;
+    double sts, cts, sto, cto, spsi, cpsi;
+    sincos(iza[g], &sts, &cts);
+    sincos(vza[g], &sto, &cto);
+    sincos(raa[g], &spsi, &cpsi);
+    double b[8];
+    volscatt_bin(at, i, vza[g], sts, cts, sto, cto, spsi, cpsi, raa[g], b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ws[(long long)t * 8 + j] = b[j];
+}
+
 // LIDF over 18 bins of 5 degrees for one parameter set (thread-sequential form; bins in the reference's order)
 __device__ __forceinline__ void lidf_bins(int lidf_type, double la, double lb, const AngleTables* __restrict__ at, double (&lidf)[18]) {
     if (lidf_type == 0) {                       // Campbell, models.py:301-330
@@ -1337,9 +1393,9 @@ __global__ void __launch_bounds__(128) k_lidf(const PrologueArgs a, const AngleT
     for (int i = 0; i < 18; ++i) ws[s * 18 + i] = lidf[i];
 }
 
-template <typename T, bool LIDF_WS>
+template <typename T, bool LIDF_WS, bool GEOM_WS>
 __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const AngleTables* __restrict__ at,
-                                                    const double* __restrict__ lidf_ws) {
+                                                    const double* __restrict__ lidf_ws, const double* __restrict__ geom_ws) {
     const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nitems = a.nsamples * a.G;
     if (item >= nitems) return;
@@ -1392,45 +1448,25 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
     // ---- LIDF-weighted volume-scattering sums, models.py:144-258 ----
     double k = 0.0, K = 0.0, bf = 0.0, Fs = 0.0, Ft = 0.0;
     double last_chi_s = 0.0, last_chi_o = 0.0, last_frho = 0.0, last_ftau = 0.0;
-    const double ctscto = cts * cto;
-    const bool view_up = tto < 90.0 * PB_PI / 180.0;
 #pragma unroll 1
     for (int i = 0; i < 18; ++i) {
-        const double clza = at->cl[i], slza = at->sl[i];
-        const double cs = clza * cts, co = clza * cto, ss = slza * sts, so = slza * sto;
-        double cbs = 5.0, cbo = 5.0;
-        if (fabs(ss) > 1e-6) cbs = -cs / ss;
-        if (fabs(so) > 1e-6) cbo = -co / so;
-        double bts, ds, sbs, bto, do_, sbo;
-        if (fabs(cbs) < 1.0) { bts = acos(cbs); ds = ss; sbs = sqrt(1.0 - cbs * cbs); }
-        else { bts = PB_PI; ds = cs; cbs = -1.0; sbs = 0.0; }
-        const double chi_s = 2.0 / PB_PI * ((bts - PB_PI * 0.5) * cs + sbs * ss);
-        if (fabs(cbo) < 1.0) { bto = acos(cbo); do_ = so; sbo = sqrt(1.0 - cbo * cbo); }
-        else if (view_up) { bto = PB_PI; do_ = co; cbo = -1.0; sbo = 0.0; }
-        else { bto = 0.0; do_ = -co; cbo = 1.0; sbo = 0.0; }
-        const double chi_o = 2.0 / PB_PI * ((bto - PB_PI * 0.5) * co + sbo * so);
-        const double btran1 = fabs(bts - bto);
-        const double btran2 = PB_PI - fabs(bts + bto - PB_PI);
-        const double cc = cbs * cbo, sscp = sbs * sbo, sc = sbs * cbo, cs_ = cbs * sbo;
-        const double cos1 = cc + sscp, sin1 = fabs(sc - cs_);        // btran1
-        const double cos2 = cc - sscp, sin2 = fabs(sc + cs_);        // btran2
-        double bt2, sin_bt2, cos_bt1, cos_bt3;
-        if (psi <= btran1) { bt2 = btran1; sin_bt2 = sin1; cos_bt1 = cpsi; cos_bt3 = cos2; }
-        else if (psi <= btran2) { bt2 = psi; sin_bt2 = spsi; cos_bt1 = cos1; cos_bt3 = cos2; }
-        else { bt2 = btran2; sin_bt2 = sin2; cos_bt1 = cos1; cos_bt3 = cpsi; }
-        const double t1 = 2.0 * cs * co + ss * so * cpsi;
-        double t2 = 0.0;
-        if (bt2 > 0.0) t2 = sin_bt2 * (2.0 * ds * do_ + ss * so * cos_bt1 * cos_bt3);
-        const double denom = 2.0 * PB_PI * PB_PI;
-        const double frho = fmax(((PB_PI - bt2) * t1 + t2) / denom, 0.0);
-        const double ftau = fmax((-bt2 * t1 + t2) / denom, 0.0);
+        double b[8];                                  // ws wo wr wt chi_s chi_o frho ftau of this bin
+        if (GEOM_WS) {
+            const double4* row = reinterpret_cast<const double4*>(geom_ws + ((long long)gi * 18 + i) * 8);
+            const double4 r0 = row[0];
+            b[0] = r0.x; b[1] = r0.y; b[2] = r0.z; b[3] = r0.w;
+            if (i == 17) { const double4 r1 = row[1]; b[4] = r1.x; b[5] = r1.y; b[6] = r1.z; b[7] = r1.w; }
+        } else {
+            volscatt_bin(at, i, tto, sts, cts, sto, cto, spsi, cpsi, psi, b);
+        }
+        const double clza = at->cl[i];
         const double w = lidf[i];
-        last_chi_s = chi_s; last_chi_o = chi_o; last_frho = frho; last_ftau = ftau;
-        k += chi_s / cts * w;
-        K += chi_o / cto * w;
+        if (i == 17) { last_chi_s = b[4]; last_chi_o = b[5]; last_frho = b[6]; last_ftau = b[7]; }
+        k += b[0] * w;
+        K += b[1] * w;
         bf += clza * clza * w;
-        Fs += frho * PB_PI / ctscto * w;
-        Ft += ftau * PB_PI / ctscto * w;
+        Fs += b[2] * w;
+        Ft += b[3] * w;
     }
 
     // ---- direct transmittances and the hotspot integral, models.py:664-666, 687-702, 731-763 ----
