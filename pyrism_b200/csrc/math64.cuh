@@ -20,12 +20,11 @@ namespace pb {
 // Polynomial / range-reduction constants live in constant memory so that DFMA takes them straight from the
 // constant bank (operand c[3][..]); as literals they would each cost two UMOV issue slots per use.
 // (Values whose low 32 bits are zero -- 0.5, 1.0, 256.0, the rounding magic -- are encodable as immediates.)
-enum { M_L2EN = 0, M_LN2H, M_LN2L, M_E3, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P3, M_P2, M_P1, M_COUNT };
+enum { M_L2EN = 0, M_NLN2S, M_E3, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P3, M_P2, M_P1, M_COUNT };
 static_assert(EXP2_BITS == 11, "the range-reduction constants below are for a 2048-entry 2^(j/2048) table");
 __constant__ double c_m[M_COUNT] = {
     2954.6394437405970201,       // 2048 log2(e)
-    -0x1.62e42fe000000p-12,      // -(ln2/2048) high part (29 significant bits: n * hi is exact for |n| < 2^24)
-    -0x1.f473de6af278fp-41,      // -(ln2/2048) low part
+    -0x1.62e42fefa39efp-12,      // -ln2/2048
     0x1.5555555555555p-3,        // 1/6
     -0x1.71547652b82fep-2,       // -1/(4 ln2)
     0x1.ec709dc3a03fdp-2,        // 1/(3 ln2)
@@ -78,16 +77,58 @@ __device__ __forceinline__ double sqrt_pos(double x) {
     return is_pos(x) ? g : 0.0;
 }
 
+// ---- Newton steps of second order: the build variant -DPB_QUADRATIC=1 (NOT the default) ----
+// The MUFU seeds are good to about 2^-20 (they read the upper 32 bits of the argument), so ONE quadratic step leaves
+// e^2 ~ 9.2e-13 relative (measured: tests/test_gpu_math.py) where the cubic steps above reach 1 ulp: 2 FP64-pipe instructions
+// per reciprocal instead of 3, 3 per square root instead of 5, and the merged reciprocals of sail_diffuse /
+// sail_directional_fast undone (a reciprocal is then cheaper than the multiplications that merge it): 365 instead of 395
+// FP64-pipe instructions per pair of bands and item.  Measured on B200 (profiles/r1g_variants.txt): the kernel is only
+// 1.4-1.9% faster (the FP64 instruction count is not what binds it), while the deviation from
+// the oracle grows from 1.3e-13 to 1.3e-10 (60 000-set sweep) and to 3e-6 in the degenerate all-zero-pigment leaf, where
+// 1 - r - t ~ 1e-16 amplifies every relative error by 1e8.  Not worth three digits of parity margin: kept as an experiment.
+#ifndef PB_QUADRATIC
+#define PB_QUADRATIC 0
+#endif
+// x * 2^-1 on the integer pipe (x normal and not within one binade of the subnormals)
+__device__ __forceinline__ double half_of(double x) { return __hiloint2double(__double2hiint(x) - 0x00100000, __double2loint(x)); }
+
+__device__ __forceinline__ double rcp_q(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+// sqrt(x), x > 0 normal: t = x y, e = 1 - t y, sqrt = t (1 + e/2) + O(3 e^2 / 8); the half of t is an exponent decrement
+__device__ __forceinline__ double sqrt_q_raw(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    return fma(half_of(t), e, t);
+}
+#if PB_QUADRATIC
+__device__ __forceinline__ double rcp_k(double x) { return rcp_q(x); }
+__device__ __forceinline__ double sqrt_k_raw(double x) { return sqrt_q_raw(x); }
+#else
+__device__ __forceinline__ double rcp_k(double x) { return rcp(x); }
+__device__ __forceinline__ double sqrt_k_raw(double x) { return sqrt_raw(x); }
+#endif
+__device__ __forceinline__ double sqrt_k_pos(double x) {
+    const double g = sqrt_k_raw(x);
+    return is_pos(x) ? g : 0.0;
+}
+
 // exp(x) for x <= 0 (clamped at about -700; positive x is outside the contract): n = rint(2048 x log2 e);
-// exp = 2^(n>>11) * T[n&2047] * P3(r), |r| <= ln2/4096 (the cubic truncates at r^4/24 < 4e-17).  8 FP64 ops + one table load.
+// exp = 2^(n>>11) * T[n&2047] * P3(r), |r| <= ln2/4096 (the cubic truncates at r^4/24 < 4e-17).  7 FP64 ops + one table load.
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ exp2t) {
     // clamp at about -700: for x <= 0 the high word grows (as an unsigned integer) with |x|, so ONE integer min does it
     x = __hiloint2double((int)min((unsigned)__double2hiint(x), 0xC085E000u), __double2loint(x));
     const double t = fma(x, c_m[M_L2EN], PB_MAGIC);
     const int n = __double2loint(t);
     const double nd = t - PB_MAGIC;
-    double r = fma(nd, c_m[M_LN2H], x);
-    r = fma(nd, c_m[M_LN2L], r);
+    // ONE fused step: nd * (-ln2/2048) + x is rounded once, so the only reduction error is that of the constant,
+    // |x| 2^-53 relative to exp(x) -- at most 4e-17 of absolute error after the multiplication by exp(x) <= 1
+    const double r = fma(nd, c_m[M_NLN2S], x);
     double p = fma(r, c_m[M_E3], 0.5);
     p = fma(r, p, 1.0);
     p = fma(r, p, 1.0);

@@ -222,7 +222,7 @@ template <bool G1> struct CfgOf<float, G1> { typedef Cfg<2, PB_WARPS> type; };
 template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS>
 static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
     typedef typename CfgOf<T, G1>::type CF;
-    const size_t smem = sizeof(SailSmem<T, CF>);
+    const size_t smem = sizeof(SailSmem<T, CF, MODE>);
     auto kern = k_bands<T, CF, MODE, PLANES, MEANS, G1>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

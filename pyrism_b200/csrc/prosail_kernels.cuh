@@ -145,13 +145,18 @@ struct alignas(128) Stage {
     T g[CHUNK * REC];        // geometry records of the chunk
 };
 
-constexpr int KPLANES = 8;                 // kab kxc kan kbr kw km rs1 rs2: used once per item -> shared memory, not registers
+// once-per-item band constants live in shared memory, not registers: kab kxc kan kbr kw km rs1 rs2, and in the double kernels
+// also the five (folded) interface terms.  Every one of them is read once per item, and 20 registers less per thread are what
+// keeps the fp64 item loop free of local-memory spills (with 200+ KB of the SM's L1 configured as shared memory, spill
+// reloads miss L1 and show up as long-scoreboard stalls: 4-12% of the warp time in the ncu captures of the spilling builds).
+template <typename T, int MODE> __host__ __device__ constexpr bool consts_in_smem() { return !std::is_same<T, float>::value && MODE == 0 /* MODE_PROSAIL */; }
+template <typename T, int MODE> __host__ __device__ constexpr int kplanes() { return consts_in_smem<T, MODE>() ? 13 : 8; }
 
-template <typename T, typename CF>
+template <typename T, typename CF, int MODE>
 struct alignas(128) SailSmem {
     typename Tables<T>::type mt;           // shared by the CTA, read-only after the prologue
     Stage<T> stage[CF::WARPS][2];          // per-warp double-buffered record staging: no CTA-wide barrier in the loop
-    T kc[KPLANES * CF::KSTRIDE];           // [plane][thread][u]: a thread's bands are adjacent (vector loads), lanes consecutive
+    T kc[kplanes<T, MODE>() * CF::KSTRIDE];   // [plane][thread][u]: a thread's bands are adjacent (vector loads), lanes consecutive
     uint64_t bar[CF::WARPS][2];
 };
 
@@ -173,9 +178,25 @@ __device__ __forceinline__ void stage_issue(const SailArgs<T>& a, Stage<T>* st, 
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 struct BandConst {
-    T talf, ralf, t12, r12, t21, r21;  // interface terms (models.py:1011-1016), register resident
+    T talf, ralf, t12, r12, t21, r21;  // interface terms (models.py:1011-1016)
+    T ta21, t1221;                     // talf t21, t12 t21: the folded factors of the double fast path (leaf_layers_fast)
 };
-enum { KC_KAB = 0, KC_KXC, KC_KAN, KC_KBR, KC_KW, KC_KM, KC_RS1, KC_RS2 };   // planes of SailSmem::kc
+enum { KC_KAB = 0, KC_KXC, KC_KAN, KC_KBR, KC_KW, KC_KM, KC_RS1, KC_RS2,     // planes of SailSmem::kc
+       KC_TA21, KC_RALF, KC_T1221, KC_R12, KC_R21 };                          // double only: talf t21, 1 - talf, t12 t21, 1 - t12, 1 - t21
+
+// interface constants of one band from the constant array (bc = bandc + band)
+template <typename T>
+__device__ __forceinline__ BandConst<T> load_band_const(const T* __restrict__ bc) {
+    BandConst<T> c;
+    c.talf = bc[C_TALF * NBP]; c.t12 = bc[C_T12 * NBP]; c.t21 = bc[C_T21 * NBP];
+    if constexpr (std::is_same<T, float>::value) {      // the complements are uploaded (rounded from float64) instead of being recomputed in float
+        c.ralf = bc[C_RALF * NBP]; c.r12 = bc[C_R12 * NBP]; c.r21 = bc[C_R21 * NBP];
+    } else {
+        c.ralf = T(1) - c.talf; c.r12 = T(1) - c.t12; c.r21 = T(1) - c.t21;                          // models.py:1012-1016
+    }
+    c.ta21 = c.talf * c.t21; c.t1221 = c.t12 * c.t21;
+    return c;
+}
 
 template <typename T> __device__ __forceinline__ constexpr bool is_f32() { return std::is_same<T, float>::value; }
 
@@ -199,28 +220,29 @@ __device__ __forceinline__ T soil_rho(const T* __restrict__ kc, const T* __restr
 
 // Branch-free plate + Stokes stage.  Returns true when r + t >= 1 (zero absorption, models.py:1057-1059); the
 // values written are then meaningless and leaf_zero_absorption() must be called for that band.
+// The interface constants enter in FOLDED form (ta21 = talf t21, t1221 = t12 t21), so that Ta = ta21 tau/(1 - x^2) and
+// t = t1221 tau/(1 - x^2) cost one multiplication each.
 template <typename T, typename MT>
-__device__ __forceinline__ bool leaf_layers_fast(const BandConst<T>& c, T tau, T nm1, const MT& mt, T& refl, T& tran) {
+__device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf, T r12, T tau, T nm1, const MT& mt, T& refl, T& tran) {
     const T one = T(1), half = T(0.5);
     // one layer                                                                              :1019-1025
-    const T x = c.r21 * tau;
-    const T inv = rcp(fma(-x, x, one));
-    const T tt = tau * c.t21 * inv;
-    const T Ta = c.talf * tt;
-    const T t = c.t12 * tt;
-    const T Ra = fma(x, Ta, c.ralf);
-    const T r = fma(x, t, c.r12);
+    const T x = r21 * tau;
+    const T tq = tau * rcp_k(fma(-x, x, one));
+    const T Ta = ta21 * tq;
+    const T t = t1221 * tq;
+    const T Ra = fma(x, Ta, ralf);
+    const T r = fma(x, t, r12);
     // Stokes: D^2 = (1+r+t)(1+r-t)(1-r+t)(1-r-t)                                             :1043
     const T p = one + r, q = one - r;
     const T P12 = (p + t) * (p - t);
     const T qmt = q - t;                           // 1 - r - t: <= 0 flags zero absorption
     const T P34 = (q + t) * qmt;
-    const T D = sqrt_raw(P12 * P34);               // P34 <= 0 only when r + t >= 1: that lane is flagged and recomputed
+    const T D = sqrt_k_raw(P12 * P34);             // P34 <= 0 only when r + t >= 1: that lane is flagged and recomputed
     const T A = fma(T(-2), r, P12);                // 1 + r^2 - t^2
-    const T hD = half * D;
+    const T hD = half_of(D);                       // D / 2 as an exponent decrement (integer pipe); D > 0 on every lane that is kept
     const T al = fma(half, A, hD);                 // a * r   (a of :1046)
     const T be = fma(-half, A, one + hD);          // b * t   (b of :1047), using 1 - r^2 + t^2 = 2 - A
-    const T b = be * rcp(t);
+    const T b = be * rcp_k(t);
     // b^(N-1) = 2^((N-1) log2 b)                                                             :1049
     const T bNm1 = pow_pos(b, nm1, mt);
     const T bN2 = bNm1 * bNm1;
@@ -229,12 +251,11 @@ __device__ __forceinline__ bool leaf_layers_fast(const BandConst<T>& c, T tau, T
     const T bm1 = bN2 - one;
     const T al2 = al * al, r2 = r * r;
     const T X = fma(-(al * r2), bm1, fma(al2, bN2, -r2));
-    const T TaI = Ta * rcp(X);
+    const T TaI = Ta * rcp_k(X);
     tran = TaI * (bNm1 * (al2 - r2));
     refl = fma(TaI * bm1, (t * al) * r, Ra);
     return !is_pos(qmt);                           // r + t >= 1, tested on the sign of 1 - r - t (integer pipe)
 }
-
 // zero-absorption case (r + t >= 1), exactly as models.py:1057-1065 with IEEE divisions (rare path)
 template <typename T>
 __device__ __forceinline__ void leaf_zero_absorption(const BandConst<T>& c, T tau, T nm1, T& refl, T& tran) {
@@ -377,17 +398,20 @@ __device__ __noinline__ void leaf_one_layer(const BandConst<T>& c, T kall, T (&o
     out[0] = (T)r; out[1] = (T)t; out[2] = (T)Ra; out[3] = (T)Ta; out[4] = (T)denom;
 }
 
-// all NU bands of a thread: the chains are independent and written back to back so that they interleave
-template <typename CF, typename T, typename MT>
+// all NU bands of a thread: the chains are independent and written back to back so that they interleave.
+// CSMEM (double, fused PROSAIL instances): the interface constants are read from the thread's columns of SailSmem::kc instead of
+// c[] -- 20 registers less across the item loop; the rare zero-absorption path rebuilds the plain constants from the complements.
+template <typename CF, bool CSMEM, typename T, typename MT>
 __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
                                             T (&refl)[CF::NU], T (&tran)[CF::NU]) {
     constexpr int NU = CF::NU;
+    constexpr int KS = CF::KSTRIDE;
     T kall[NU];
     bool rare[NU];
     bool any_rare = false;
     const T nm1 = s[S_NM1];
 #pragma unroll
-    for (int u = 0; u < NU; ++u) kall[u] = leaf_kall<CF::KSTRIDE>(kc + u, s);
+    for (int u = 0; u < NU; ++u) kall[u] = leaf_kall<KS>(kc + u, s);
     if constexpr (std::is_same<T, float>::value) {
         float omt[NU];
 #pragma unroll
@@ -411,11 +435,27 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
                 if (rare[u]) tau[u] = tau_rare(kall[u]);
         }
 #pragma unroll
-        for (int u = 0; u < NU; ++u) { zero[u] = leaf_layers_fast(c[u], tau[u], nm1, mt, refl[u], tran[u]); any_zero |= zero[u]; }
+        for (int u = 0; u < NU; ++u) {
+            if constexpr (CSMEM)
+                zero[u] = leaf_layers_fast(kc[u + KC_R21 * KS], kc[u + KC_TA21 * KS], kc[u + KC_T1221 * KS], kc[u + KC_RALF * KS], kc[u + KC_R12 * KS],
+                                           tau[u], nm1, mt, refl[u], tran[u]);
+            else
+                zero[u] = leaf_layers_fast(c[u].r21, c[u].ta21, c[u].t1221, c[u].ralf, c[u].r12, tau[u], nm1, mt, refl[u], tran[u]);
+            any_zero |= zero[u];
+        }
         if (__builtin_expect(any_zero, 0)) {
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-                if (zero[u]) leaf_zero_absorption(c[u], tau[u], nm1, refl[u], tran[u]);
+                if (zero[u]) {
+                    if constexpr (CSMEM) {       // talf = 1 - (1 - talf) etc.: within an ulp of the uploaded constants
+                        BandConst<T> cc;
+                        cc.ralf = kc[u + KC_RALF * KS]; cc.r12 = kc[u + KC_R12 * KS]; cc.r21 = kc[u + KC_R21 * KS];
+                        cc.talf = T(1) - cc.ralf; cc.t12 = T(1) - cc.r12; cc.t21 = T(1) - cc.r21;
+                        leaf_zero_absorption(cc, tau[u], nm1, refl[u], tran[u]);
+                    } else {
+                        leaf_zero_absorption(c[u], tau[u], nm1, refl[u], tran[u]);
+                    }
+                }
         }
     }
 }
@@ -475,26 +515,30 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
         d.m = sqrt_pos((att - sigb) * (att + sigb));
         d.rinf = sigb * rcp(att + d.m);
     } else {
-        d.m = sqrt_pos(fma(att, att, -(sigb * sigb)));                // :601
-        d.rinf = (att - d.m) * rcp(sigb);                             // :639
+        d.m = sqrt_k_pos(fma(att, att, -(sigb * sigb)));              // :601
+        d.rinf = (att - d.m) * rcp_k(sigb);                           // :639
     }
     d.e1 = exp_neg(d.m * s[S_NEGLAI], mt);                            // :637
     const T e2 = d.e1 * d.e1;
     const T rinf2 = d.rinf * d.rinf;
     d.re = d.rinf * d.e1;
     const T omr2 = one - rinf2;
-    {   // 1/(1 - rinf^2 e^2) (:642) and 1/(1 - rinf^2) (:678) from ONE reciprocal of their product: one MUFU less
-        const T den = fma(-rinf2, e2, one);
+    const T den = fma(-rinf2, e2, one);
+    if constexpr (is_f32<T>() || !PB_QUADRATIC) {
+        // 1/(1 - rinf^2 e^2) (:642) and 1/(1 - rinf^2) (:678) from ONE reciprocal of their product: one MUFU less
         const T r = rcp(den * omr2);
         d.invden = r * omr2;
         d.inv_omr2 = r * den;
+    } else {                                                          // two 2-instruction reciprocals beat the merged form (6 -> 4)
+        d.invden = rcp_k(den);
+        d.inv_omr2 = rcp_k(omr2);
     }
     d.tdd = omr2 * d.e1 * d.invden;                                   // :654
     d.rdd = d.rinf * (one - e2) * d.invden;                           // :655
     d.rsrdd = rs * d.rdd;
     T dn = one - d.rsrdd;                                             // :714-719
     dn = below_tiny(dn) ? tiny : dn;                                  // dn < 1e-36 (integer-pipe test; negatives too)
-    d.rs_invdn = rs * rcp(dn);
+    d.rs_invdn = rs * rcp_k(dn);
     d.a1 = fma(tau, d.rinf, rho);
     d.a2 = fma(rho, d.rinf, tau);
 }
@@ -560,6 +604,12 @@ __device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const 
     } else {
         // 1/(k-m) and 1/(k+m) from ONE reciprocal of (k-m)(k+m)                             :644-647, 765-789
         const bool rare = !(abs_gt_hi(km, thr_hi) && abs_gt_hi(Km, thr_hi));
+#if PB_QUADRATIC
+        // four 2-instruction reciprocals (8 FP64-pipe instructions + 4 MUFU) instead of the merged form below (12 + 1 MUFU)
+        const T J1ks = (d.e1 - tss) * rcp_k(km);
+        const T J1ko = (d.e1 - too) * rcp_k(Km);
+        sail_couple(rho, tau, rs, d, g, J1ks, J1ko, rcp_k(kp), rcp_k(Kp), need, o);
+#else
         // ... and both of those from one reciprocal of (k-m)(k+m)(K-m)(K+m)
         const T pk = km * kp, pK = Km * Kp;
         const T rr = rcp(pk * pK);
@@ -567,6 +617,7 @@ __device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const 
         const T J1ks = (d.e1 - tss) * (ik * kp);
         const T J1ko = (d.e1 - too) * (iK * Kp);
         sail_couple(rho, tau, rs, d, g, J1ks, J1ko, ik * km, iK * Km, need, o);
+#endif
         return rare;
     }
 }
@@ -709,7 +760,8 @@ constexpr unsigned RUNTIME = 0x80000000u;
 template <typename T, int NU>
 struct EmitCtx {
     const SailArgs<T>& a;
-    bool valid[NU];      // band u of this thread exists (< 2101)
+    bool tail;           // warp-uniform: this warp owns the last tile group, the only one with bands >= 2101
+    bool valid[NU];      // band u of this thread exists (< 2101); only consulted when tail
     int tile0;           // 32-band tile of band 0 (band u is in tile0 + u): index into the window map
     int lane, nt;
     long long orow;      // item * pitch + band[0]   (band[u] = band[0] + 32 u)
@@ -723,7 +775,7 @@ __device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
         if (e.a.out[PLANE]) {
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-                if (e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
+                if (!e.tail || e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
         }
         if (e.a.mean_mask & (1u << PLANE)) {
 #pragma unroll
@@ -734,7 +786,7 @@ __device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
         if ((PLANES >> PLANE) & 1u) {
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-                if (e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
+                if (!e.tail || e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
         }
         if ((MEANS >> PLANE) & 1u) {
 #pragma unroll
@@ -772,7 +824,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename Tables<T>::type MT;
     constexpr int NU = CF::NU;
-    SailSmem<T, CF>& sm = *reinterpret_cast<SailSmem<T, CF>*>(smem_raw);
+    SailSmem<T, CF, MODE>& sm = *reinterpret_cast<SailSmem<T, CF, MODE>*>(smem_raw);
     const T zero_ = T(0), one = T(1);
     // the warp index through a shuffle: tells the compiler it is warp-uniform (uniform registers / uniform addressing of
     // the per-warp staging buffers and of everything derived from the tile group)
@@ -783,6 +835,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     const bool live = range < a.nranges;
     const int grp = !live ? 0 : (a.only_active_tiles ? a.win->active_group[NU - 2][tslot] : tslot);
     const int band0 = grp * (32 * NU) + lane;      // this thread's bands: band0 + 32 u
+    const bool tail = (grp + 1) * (32 * NU) > NB;    // warp-uniform
     Stage<T>* const stage = sm.stage[warp];
     uint64_t* const bar = sm.bar[warp];
 
@@ -803,6 +856,8 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     if (lane == 0 && chunk < nchunks) stage_issue(a, &stage[0], &bar[0], chunk);
 
     BandConst<T> c[NU];
+    // fused fp64 instances keep the interface constants in shared memory (register pressure); everything else in registers
+    constexpr bool CSMEM = consts_in_smem<T, MODE>();
     const T* kc = sm.kc + threadIdx.x * NU;        // this thread's NU adjacent columns of the once-per-item constants
     constexpr int KS = CF::KSTRIDE;
 #pragma unroll
@@ -812,11 +867,10 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
         k[KC_KAB * KS] = bc[C_KAB * NBP]; k[KC_KXC * KS] = bc[C_KXC * NBP]; k[KC_KAN * KS] = bc[C_KAN * NBP];
         k[KC_KBR * KS] = bc[C_KBR * NBP]; k[KC_KW * KS] = bc[C_KW * NBP]; k[KC_KM * KS] = bc[C_KM * NBP];
         k[KC_RS1 * KS] = bc[C_RS1 * NBP]; k[KC_RS2 * KS] = bc[C_RS2 * NBP];
-        c[u].talf = bc[C_TALF * NBP]; c[u].t12 = bc[C_T12 * NBP]; c[u].t21 = bc[C_T21 * NBP];
-        if constexpr (std::is_same<T, float>::value) {      // the complements are uploaded (rounded from float64) instead of being recomputed in float
-            c[u].ralf = bc[C_RALF * NBP]; c[u].r12 = bc[C_R12 * NBP]; c[u].r21 = bc[C_R21 * NBP];
-        } else {
-            c[u].ralf = one - c[u].talf; c[u].r12 = one - c[u].t12; c[u].r21 = one - c[u].t21;     // models.py:1012-1016
+        c[u] = load_band_const(bc);
+        if constexpr (CSMEM) {                               // the fast path reads the folded terms from shared memory; c[] is dead in the loop
+            k[KC_TA21 * KS] = c[u].ta21; k[KC_RALF * KS] = c[u].ralf; k[KC_T1221 * KS] = c[u].t1221;
+            k[KC_R12 * KS] = c[u].r12; k[KC_R21 * KS] = c[u].r21;
         }
     }
     // fp32 mode with two bands per thread: the arithmetic of the item loop runs in packed FP32 (FFMA2 ...), both bands per instruction
@@ -862,7 +916,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             int thr_hi = 0;
             const T* sr = stage[buf].s;
             const T* gr = stage[buf].g;
-            EmitCtx<T, NU> e{a, {}, NU * grp, lane, nt, i0 * a.out_pitch + band0, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
+            EmitCtx<T, NU> e{a, tail, {}, NU * grp, lane, nt, i0 * a.out_pitch + band0, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
 #pragma unroll
             for (int u = 0; u < NU; ++u) e.valid[u] = band0 + 32 * u < NB;
             for (int j = 0; j < n; ++j) {
@@ -877,7 +931,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         leaf_optics_x2<CF>(c2, kc, sr, sm.mt, r2, t2);
                         rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
                     } else {
-                        leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
+                        leaf_optics<CF, CSMEM>(c, kc, sr, sm.mt, rho, tau);
                     }
                     emit<PLANES, MEANS, O_LEAF_R>(e, rho);
                     emit<PLANES, MEANS, O_LEAF_T>(e, tau);
@@ -911,7 +965,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                                 leaf_optics_x2<CF>(c2, kc, sr, sm.mt, r2, t2);
                                 rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
                             } else {
-                                leaf_optics<CF>(c, kc, sr, sm.mt, rho, tau);
+                                leaf_optics<CF, CSMEM>(c, kc, sr, sm.mt, rho, tau);
                             }
 #pragma unroll
                             for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u, sr);
@@ -1523,7 +1577,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
 // ---------------------------------------------------------------------------------------------
 // test / calibration kernels
 // ---------------------------------------------------------------------------------------------
-// op: 0 rcp, 1 sqrt_pos, 2 exp_neg, 3 log2_pos, 4 exp2_any, 5 tau_plate, 6 tau_full
+// op: 0 rcp, 1 sqrt_pos, 2 exp_neg, 3 log2_pos, 4 exp2_any, 5 tau_plate, 6 tau_full, 7 rcp_q, 8 sqrt_q_raw (x > 0)
 __global__ void k_test_math(int op, long long n, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ tables) {
     extern __shared__ __align__(16) unsigned char test_smem[];              // sizeof(MathTables) bytes of dynamic shared memory
     MathTables& mt = *reinterpret_cast<MathTables*>(test_smem);
@@ -1540,6 +1594,8 @@ __global__ void k_test_math(int op, long long n, const double* __restrict__ in, 
         case 3: y = log2_pos(x, mt.logt); break;
         case 4: y = exp2_any(x, mt.exp2t); break;
         case 6: y = tau_full(x); break;
+        case 7: y = rcp_q(x); break;
+        case 8: y = sqrt_q_raw(x); break;
         default: y = tau_plate(x, mt.tau); break;
     }
     out[i] = y;
