@@ -43,10 +43,12 @@ def max_length(data):
 
 def align_all(data, constant_values='default'):
     """Pad every 1-D array to the longest one, repeating its last value (auxiliary.py:332-340)."""
-    n = max_length(data)
-    if constant_values == 'default':
-        return np.asarray([np.pad(item, (0, n - len(item)), 'constant', constant_values=item[-1]) for item in data])
-    return np.asarray([np.pad(item, (0, n - len(item)), 'constant', constant_values=constant_values) for item in data])
+    n = max(len(item) for item in data)
+    out = np.empty((len(data), n), dtype=np.result_type(*data))
+    for k, item in enumerate(data):
+        out[k, :len(item)] = item
+        out[k, len(item):] = item[-1] if isinstance(constant_values, str) and constant_values == 'default' else constant_values
+    return out
 
 
 class SailResult(dict):

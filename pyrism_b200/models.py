@@ -34,15 +34,21 @@ def _is_scalar_call(*params):
     return all(np.ndim(p) == 0 for p in params if p is not None)
 
 
+_FIELD_TUPLES = {}      # namedtuple classes per field list, created once (the reference re-creates them per call: SURVEY 8a, a7)
+
+
 def _band_tuples(means, fields=None):
     """means[..., 15] (or [..., F, 15] with named fields) -> (L8 namedtuple, ASTER namedtuple)."""
-    names = fields.split() if fields else None
+    T = None
+    if fields:
+        T = _FIELD_TUPLES.get(fields)
+        if T is None:
+            T = _FIELD_TUPLES[fields] = namedtuple('B', fields.split())
 
     def pick(w):
-        if names is None:
+        if T is None:
             return means[..., w][()]
-        T = namedtuple('B', names)
-        return T(*(means[..., f, w][()] for f in range(len(names))))
+        return T(*(means[..., f, w][()] for f in range(len(T._fields))))
     l8 = _L8(*(pick(w) for w in range(_NL8)))
     aster = _ASTER(*(pick(_NL8 + w) for w in range(len(K.ASTER_BANDS))))
     return l8, aster
