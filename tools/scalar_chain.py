@@ -1,3 +1,5 @@
+"""Latency of the README call chain PROSPECT -> LSM -> SAIL through the scalar drop-in API (BASELINE config 1), with a cProfile
+breakdown of the host side.  usage (GPU box): python tools/scalar_chain.py"""
 import sys, os, time, cProfile, pstats
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
