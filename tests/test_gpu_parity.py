@@ -549,3 +549,22 @@ def test_volscatt_volume_method():
         for g in range(iza.size):
             want = orc.volscatt_volume(np.radians(iza[g]), np.radians(vza[g]), np.radians(raa[g]), lza)
             assert max(abs(got[q][g] - want[q]) for q in range(4)) <= 1e-13, (lza, g)
+
+
+def test_fused_kernel_rare_leaf_paths_agree_with_the_leaf_only_kernel():
+    """The fused fp64 instances read the plate's interface constants from shared memory and rebuild the plain ones from their
+    complements on the zero-absorption path (models.py:1057-1059); the leaf-only kernel keeps them in registers.  Same leaf
+    spectra from both for: no absorption at all (k = 0), arguments of tau() below / above the table range, an ordinary leaf, and
+    bands >= 2101 - 64 (the last, partly empty tile group)."""
+    leaves = [dict(N=1.5, Cab=0.0, Cxc=0.0, Cbr=0.0, Cw=0.0, Cm=0.0), dict(N=1.0, Cab=1e-3, Cxc=0.0, Cbr=0.0, Cw=1e-6, Cm=1e-6),
+              dict(N=3.0, Cab=200.0, Cxc=60.0, Cbr=3.0, Cw=0.3, Cm=0.1), dict(N=1.0, Cab=0.0, Cxc=0.0, Cbr=0.0, Cw=1.0, Cm=0.0),
+              dict(N=1.7, Cab=40.0, Cxc=8.0, Cbr=0.1, Cw=0.01, Cm=0.008)]
+    P = {k: np.array([l[k] for l in leaves]) for k in leaves[0]}
+    leaf = pb.PROSPECT(**P)
+    fused = pb.PROSAIL(lai=2.0, hotspot=0.1, iza=30.0, vza=20.0, raa=40.0, soil_reflectance=0.8, soil_moisture=0.3, keep_leaf=True, **P)
+    assert np.all(np.isfinite(fused.leaf_ks)) and np.all(np.isfinite(fused.BRF.ref[1:]))     # row 0: a conservative canopy, 1 - rinf^2 = 0
+    # rows 1..4: identical arithmetic up to the last bit of the rebuilt constants; row 0 is the 0/0 limit of the Stokes system
+    assert np.max(np.abs(fused.leaf_ks[1:] - leaf.ks[1:])) <= 1e-14 and np.max(np.abs(fused.leaf_kt[1:] - leaf.kt[1:])) <= 1e-14
+    assert np.max(np.abs(fused.leaf_ks[0] - leaf.ks[0])) <= 1e-7 and np.max(np.abs(fused.leaf_kt[0] - leaf.kt[0])) <= 1e-7
+    o = orc.prosail(1.7, 40.0, 8.0, 0.1, 0.01, 0.008, 2.0, 0.1, 30.0, 20.0, 40.0, 0.8, 0.3, lidf_type='campbell', a=57)[2]
+    assert np.max(np.abs(fused.BRF.ref[4, 0] - o['rsot'])) <= TOL
