@@ -234,9 +234,9 @@ __device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf,
     const T r = fma(x, t, r12);
     // Stokes: D^2 = (1+r+t)(1+r-t)(1-r+t)(1-r-t)                                             :1043
     const T p = one + r, q = one - r;
-    const T P12 = (p + t) * (p - t);
+    const T P12 = fma(-t, t, p * p);               // (1+r+t)(1+r-t): >= 1, no cancellation in this form
     const T qmt = q - t;                           // 1 - r - t: <= 0 flags zero absorption
-    const T P34 = (q + t) * qmt;
+    const T P34 = (q + t) * qmt;                   // the small factor keeps its product form
     const T D = sqrt_k_raw(P12 * P34);             // P34 <= 0 only when r + t >= 1: that lane is flagged and recomputed
     const T A = fma(T(-2), r, P12);                // 1 + r^2 - t^2
     const T hD = half_of(D);                       // D / 2 as an exponent decrement (integer pipe); D > 0 on every lane that is kept
@@ -492,7 +492,7 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
 // geometry-independent part of 4SAIL for one band (models.py:590-601, 637-642, 654-655, 714-719)
 template <typename T>
 struct Diffuse {
-    T m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd;
+    T m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd, rinf_invden;
     T a1, a2;      // rho + tau rinf, tau + rho rinf: the leaf-dependent factors of (sf + sb rinf), (sf rinf + sb), ... (:649-652)
 };
 
@@ -534,7 +534,8 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
         d.inv_omr2 = rcp_k(omr2);
     }
     d.tdd = omr2 * d.e1 * d.invden;                                   // :654
-    d.rdd = d.rinf * (one - e2) * d.invden;                           // :655
+    d.rinf_invden = d.rinf * d.invden;                                // shared by rdd and by T3 of the directional stage
+    d.rdd = d.rinf_invden * (one - e2);                               // :655
     d.rsrdd = rs * d.rdd;
     T dn = one - d.rsrdd;                                             // :714-719
     dn = below_tiny(dn) ? tiny : dn;                                  // dn < 1e-36 (integer-pipe test; negatives too)
@@ -560,19 +561,21 @@ __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>
     // a1 = rho + tau rinf and a2 = tau + rho rinf (geometry independent, computed once per parameter set):
     //   sf + sb rinf = sdf a1 + sdb a2,   sf rinf + sb = sdf a2 + sdb a1,   and the same with (dof, dob) for the view direction
     const T w = fma(g[G_FS], rho, g[G_FT] * tau);                     // :607
-    const T J2ks = fma(-d.e1, tss, one) * inv_kp;
-    const T J2ko = fma(-d.e1, too, one) * inv_Kp;
     const T u1 = fma(g[G_SDF], d.a1, g[G_SDB] * d.a2), u2 = fma(g[G_SDF], d.a2, g[G_SDB] * d.a1);
     const T v1 = fma(g[G_DOF], d.a1, g[G_DOB] * d.a2), v2 = fma(g[G_DOF], d.a2, g[G_DOB] * d.a1);
-    const T Pss = u1 * J1ks, Qss = u2 * J2ks, Pv = v1 * J1ko, Qv = v2 * J2ko;
-    o.tsd = fma(-d.re, Qss, Pss) * d.invden;                          // :656-659
+    // J2(k,m) = (1 - e1 tss)/(k+m), J2(K,m) = (1 - e1 too)/(K+m) (:646-647) only appear multiplied by u2 resp. v2, and so do the
+    // 1/(k+m), 1/(K+m) of g2, g1 (:668-669): ck = u2/(k+m) and cK = v2/(K+m) are formed once
+    const T ck = u2 * inv_kp, cK = v2 * inv_Kp;
+    const T Pss = u1 * J1ks, Qss = ck * fma(-d.e1, tss, one), Pv = v1 * J1ko, Qv = cK * fma(-d.e1, too, one);
+    // tsd, rsd, tdo, rdo (:656-659) before their common factor 1/(1 - rinf^2 e^2): T3 takes it together with rinf
+    const T tsd_u = fma(-d.re, Qss, Pss), tdo_u = fma(-d.re, Qv, Pv), rdo_u = fma(-d.re, Pv, Qv);
+    o.tsd = tsd_u * d.invden;
     o.rsd = fma(-d.re, Pss, Qss) * d.invden;
-    o.tdo = fma(-d.re, Qv, Pv) * d.invden;
-    o.rdo = fma(-d.re, Pv, Qv) * d.invden;
-    const T g1 = fma(-J1ks, too, g[G_Z]) * inv_Kp;                    // :668-669
-    const T g2 = fma(-J1ko, tss, g[G_Z]) * inv_kp;
-    const T T1 = (v2 * g1) * u1, T2 = (v1 * g2) * u2;                 // :671-675
-    const T T3 = fma(o.rdo, Qss, o.tdo * Pss) * d.rinf;
+    o.tdo = tdo_u * d.invden;
+    o.rdo = rdo_u * d.invden;
+    const T T1 = (cK * u1) * fma(-J1ks, too, g[G_Z]);                 // v2 g1 u1, g1 = (z - J1(k,m) too)/(K+m)   :668-675
+    const T T2 = (ck * v1) * fma(-J1ko, tss, g[G_Z]);                 // v1 g2 u2
+    const T T3 = fma(rdo_u, Qss, tdo_u * Pss) * d.rinf_invden;        // (rdo Qss + tdo Pss) rinf
     const T rsod = (T1 + T2 - T3) * d.inv_omr2;                       // :678
     o.rso = fma(w, g[G_LAISUM], rsod);                                // :706, :710
     // soil coupling                                                                        :721-726
