@@ -683,7 +683,8 @@ __device__ __forceinline__ void sail_diffuse_f32x2(f2 rho, f2 tau, f2 rs, const 
     d.invden = mul(r, omr2);
     d.inv_omr2 = mul(r, den);
     d.tdd = mul(mul(omr2, d.e1), d.invden);                           // :654
-    d.rdd = mul(mul(d.rinf, sub(F2(1.0f), e2)), d.invden);            // :655
+    d.rinf_invden = mul(d.rinf, d.invden);
+    d.rdd = mul(d.rinf_invden, sub(F2(1.0f), e2));                    // :655
     d.rsrdd = mul(rs, d.rdd);
     f2 dn = sub(F2(1.0f), d.rsrdd);                                   // :714-719
     dn = F2(below_tiny(dn.x) ? 1e-36f : dn.x, below_tiny(dn.y) ? 1e-36f : dn.y);
@@ -707,20 +708,19 @@ __device__ __forceinline__ void sail_directional_f32x2(f2 rho, f2 tau, f2 rs, co
     const f2 rkK = rcp(mul(kp, Kp));                                  // 1/(k+m) and 1/(K+m) from one reciprocal (both > 0)
     const f2 inv_kp = mul(rkK, Kp), inv_Kp = mul(rkK, kp);
     const f2 w = fma(g[G_FS], rho, mul(tau, g[G_FT]));               // :607
-    const f2 J2ks = mul(fma(neg(d.e1), F2(tss), 1.0f), inv_kp);       // :787-789
-    const f2 J2ko = mul(fma(neg(d.e1), F2(too), 1.0f), inv_Kp);
     const f2 u1 = fma(g[G_SDF], d.a1, mul(d.a2, g[G_SDB])), u2 = fma(g[G_SDF], d.a2, mul(d.a1, g[G_SDB]));   // :603-606, 649-652 via a1, a2
     const f2 v1 = fma(g[G_DOF], d.a1, mul(d.a2, g[G_DOB])), v2 = fma(g[G_DOF], d.a2, mul(d.a1, g[G_DOB]));
-    const f2 Pss = mul(u1, J1ks), Qss = mul(u2, J2ks), Pv = mul(v1, J1ko), Qv = mul(v2, J2ko);
+    const f2 ck = mul(u2, inv_kp), cK = mul(v2, inv_Kp);             // u2/(k+m), v2/(K+m): shared by Q (J2, :787-789) and T2, T1
+    const f2 Pss = mul(u1, J1ks), Qss = mul(ck, fma(neg(d.e1), F2(tss), 1.0f)), Pv = mul(v1, J1ko), Qv = mul(cK, fma(neg(d.e1), F2(too), 1.0f));
     const f2 nre = neg(d.re);
+    const f2 tdo_u = fma(nre, Qv, Pv), rdo_u = fma(nre, Pv, Qv);     // before the common factor 1/(1 - rinf^2 e^2)
     o.tsd = mul(fma(nre, Qss, Pss), d.invden);                        // :656-659
     o.rsd = mul(fma(nre, Pss, Qss), d.invden);
-    o.tdo = mul(fma(nre, Qv, Pv), d.invden);
-    o.rdo = mul(fma(nre, Pv, Qv), d.invden);
-    const f2 g1 = mul(fma(neg(J1ks), F2(too), F2(g[G_Z])), inv_Kp);   // :668-669
-    const f2 g2 = mul(fma(neg(J1ko), F2(tss), F2(g[G_Z])), inv_kp);
-    const f2 T1 = mul(mul(v2, g1), u1), T2 = mul(mul(v1, g2), u2);    // :671-675
-    const f2 T3 = mul(fma(o.rdo, Qss, mul(o.tdo, Pss)), d.rinf);
+    o.tdo = mul(tdo_u, d.invden);
+    o.rdo = mul(rdo_u, d.invden);
+    const f2 T1 = mul(mul(cK, u1), fma(neg(J1ks), F2(too), F2(g[G_Z])));   // :668-675
+    const f2 T2 = mul(mul(ck, v1), fma(neg(J1ko), F2(tss), F2(g[G_Z])));
+    const f2 T3 = mul(fma(rdo_u, Qss, mul(tdo_u, Pss)), d.rinf_invden);
     const f2 rsod = mul(sub(add(T1, T2), T3), d.inv_omr2);            // :678
     o.rso = fma(g[G_LAISUM], w, rsod);                                // :706, :710
     // soil coupling                                                                        :721-726
