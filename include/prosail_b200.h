@@ -160,6 +160,15 @@ int prosail_soil_f64(prosail_handle_t* h, long long n, const prosail_soil_t* soi
 int prosail_volscatt_f64(prosail_handle_t* h, long long n, const prosail_canopy_t* canopy, double* geom, double* lidf,
                          int on_host, void* stream);
 
+/* LIDF.campbell(a, n_elements) / LIDF.verhoef(a, b, n_elements) and VolScatt(...).coef(lidf_type, n_elements, a, b) for a number
+ * of leaf-inclination classes other than SAIL's 18 (the reference's n_elements argument, models.py:82-175, 283-392).
+ * lidf_a, lidf_b [n] (lidf_b may be NULL for Campbell); iza, vza, raa [n_geom] radians, normalised (unused when geom is NULL);
+ * lidf [n][n_elements] is always written; geom (optional) [n][n_geom][PROSAIL_NGEOM]: ks, ko, bf, Fs, Ft in slots 0-4,
+ * chi_s, chi_o, frho, ftau of the last class in slots 8-11, slots 5-7 zero.  1 <= n_elements <= 4096. */
+int prosail_volscatt_bins_f64(prosail_handle_t* h, long long n, int lidf_type, const double* lidf_a, const double* lidf_b, int n_geom,
+                              const double* iza, const double* vza, const double* raa, int n_elements, double* geom, double* lidf,
+                              int on_host, void* stream);
+
 /* pyrism.VolScatt(iza, vza, raa).volume(lza) (models.py:177-258): interception and bidirectional scattering terms of ONE leaf
  * zenith angle lza_deg (degrees) for n_geom geometries (radians, normalised); out [n_geom][4] = chi_s, chi_o, frho, ftau. */
 int prosail_volume_f64(prosail_handle_t* h, int n_geom, const double* iza, const double* vza, const double* raa, double lza_deg,

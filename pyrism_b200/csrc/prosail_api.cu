@@ -1121,6 +1121,50 @@ static int invert_impl(prosail_handle_t* h, int k, long long n_lut, int n_feat, 
     return 0;
 }
 
+int prosail_volscatt_bins_f64(prosail_handle_t* h, long long n, int lidf_type, const double* lidf_a, const double* lidf_b, int n_geom,
+                              const double* iza, const double* vza, const double* raa, int n_elements, double* geom, double* lidf,
+                              int on_host, void* stream) {
+    if (!h || !lidf_a || !lidf || n < 0 || n_elements < 1 || n_elements > 4096 || (lidf_type != PROSAIL_LIDF_CAMPBELL && lidf_type != PROSAIL_LIDF_VERHOEF))
+        return fail(PROSAIL_E_ARG, "bad argument");
+    if (lidf_type == PROSAIL_LIDF_VERHOEF && !lidf_b) return fail(PROSAIL_E_ARG, "the Verhoef LIDF needs lidf_b");
+    if (geom && (n_geom < 1 || !iza || !vza || !raa)) return fail(PROSAIL_E_ARG, "geom needs n_geom >= 1 angles");
+    if (n == 0) return 0;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = stream && !on_host ? (cudaStream_t)stream : h->stream;
+    const double *da = lidf_a, *db = lidf_b, *di = iza, *dv = vza, *dr = raa;
+    double *dgeom = geom, *dlidf = lidf;
+    const size_t G = geom ? (size_t)n_geom : 0;
+    if (on_host) {
+        int rc;
+        const size_t nb = ((size_t)n * 8 + 255) & ~(size_t)255, gb = (G * 8 + 255) & ~(size_t)255;
+        const size_t lb = ((size_t)n * n_elements * 8 + 255) & ~(size_t)255;
+        if ((rc = h->work.in.reserve(2 * nb + 3 * gb)) || (rc = h->work.out.reserve(lb + (size_t)n * G * NGEOM * 8 + 256))) return rc;
+        char* base = (char*)h->work.in.p;
+        CK(cudaMemcpyAsync(base, lidf_a, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        da = (const double*)base;
+        if (lidf_b) { CK(cudaMemcpyAsync(base + nb, lidf_b, (size_t)n * 8, cudaMemcpyHostToDevice, st)); db = (const double*)(base + nb); }
+        if (geom) {
+            char* gp = base + 2 * nb;
+            CK(cudaMemcpyAsync(gp, iza, G * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(gp + gb, vza, G * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(gp + 2 * gb, raa, G * 8, cudaMemcpyHostToDevice, st));
+            di = (const double*)gp; dv = (const double*)(gp + gb); dr = (const double*)(gp + 2 * gb);
+        }
+        dlidf = (double*)h->work.out.p;
+        dgeom = geom ? (double*)((char*)h->work.out.p + lb) : nullptr;
+    }
+    k_volscatt_general<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, (int)G, lidf_type == PROSAIL_LIDF_VERHOEF ? 1 : 0, da, db, di, dv, dr,
+                                                                     n_elements, dgeom, dlidf);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (on_host) {
+        CK(cudaMemcpyAsync(lidf, dlidf, (size_t)n * n_elements * 8, cudaMemcpyDeviceToHost, st));
+        if (geom) CK(cudaMemcpyAsync(geom, dgeom, (size_t)n * G * NGEOM * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
 int prosail_volume_f64(prosail_handle_t* h, int n_geom, const double* iza, const double* vza, const double* raa, double lza_deg,
                        double* out, int on_host, void* stream) {
     if (!h || !iza || !vza || !raa || !out || n_geom < 0) return fail(PROSAIL_E_ARG, "bad argument");

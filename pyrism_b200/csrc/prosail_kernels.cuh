@@ -1127,6 +1127,83 @@ __device__ __forceinline__ void volscatt_volume(double tts, double tto, double p
     ftau = fmax((-bt2 * t1 + t2) / denom, 0.0);
 }
 
+// LIDF.campbell / LIDF.verhoef / VolScatt.coef for an arbitrary number of leaf-inclination classes `ne` (the reference's
+// `n_elements` argument, models.py:82-175, 283-392; SAIL itself always uses 18, which is what the prologue kernels are built
+// for).  One thread per parameter set: lidf [n][ne] (always written), geom (optional) [n][G][NGEOM] with ks, ko, bf, Fs, Ft in
+// slots 0-4 and chi_s, chi_o, frho, ftau of the last class in slots 8-11 (the rest zero).  Plain libm arithmetic in the
+// reference's order; not on the hot path.
+__global__ void __launch_bounds__(128) k_volscatt_general(long long n, int G, int lidf_type, const double* __restrict__ la_,
+                                                          const double* __restrict__ lb_, const double* __restrict__ iza,
+                                                          const double* __restrict__ vza, const double* __restrict__ raa, int ne,
+                                                          double* __restrict__ geom, double* __restrict__ lidf) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const double la = la_[s], lb = lb_ ? lb_[s] : 0.0;
+    double* L = lidf + s * ne;
+    const double step = 90.0 / ne;
+    if (lidf_type == 0) {                                             // Campbell, models.py:299-330
+        const double excent = exp(-1.6184e-5 * la * la * la + 2.1145e-3 * la * la - 1.2390e-1 * la + 3.2491);
+        const double e2 = excent * excent;
+        const double alph = excent / sqrt(fabs(1.0 - e2)), alph2 = alph * alph;
+        double sum0 = 0.0, Fprev = 0.0;
+        for (int i = 0; i <= ne; ++i) {                               // F at the ne + 1 class edges; freq_i = |F_i - F_{i+1}|
+            const double tl = (i * step) * (PB_PI / 180.0);
+            double F;
+            if (excent == 1.0) {
+                F = cos(tl);
+            } else {
+                const double tn = tan(tl);
+                const double x = excent / sqrt(1.0 + e2 * tn * tn), x2 = x * x;
+                if (excent > 1.0) { const double p = sqrt(alph2 + x2); F = x * p + alph2 * log(x + p); }
+                else { const double q = sqrt(alph2 - x2); F = x * q + alph2 * asin(x / alph); }
+            }
+            if (i > 0) { L[i - 1] = fabs(Fprev - F); sum0 += L[i - 1]; }
+            Fprev = F;
+        }
+        for (int i = 0; i < ne; ++i) L[i] = L[i] / sum0;
+    } else {                                                          // Verhoef, models.py:366-390: from the last class edge down to 0
+        double Fhi = 1.0;
+        for (int i = ne - 1; i >= 0; --i) {
+            const double tl1 = (i * step) * (PB_PI / 180.0);
+            double f;
+            if (la > 1.0) {
+                f = 1.0 - cos(tl1);
+            } else {
+                double x = 2.0 * tl1, y = 0.0, dx;
+                const double p = x;
+                int itn = 0;
+                do {
+                    y = la * sin(x) + 0.5 * lb * sin(2.0 * x);
+                    dx = 0.5 * (y - x + p);
+                    x += dx;
+                } while (fabs(dx) >= 1e-8 && ++itn < 4096);
+                f = (2.0 * y + p) / PB_PI;
+            }
+            L[i] = Fhi - f;
+            Fhi = f;
+        }
+    }
+    if (!geom) return;
+    for (int g = 0; g < G; ++g) {                                     // VolScatt.coef, models.py:144-175
+        const double tts = iza[g], tto = vza[g], psi = raa[g];
+        const double cts = cos(tts), cto = cos(tto);
+        double ks = 0.0, ko = 0.0, bf = 0.0, Fs = 0.0, Ft = 0.0, chi_s = 0.0, chi_o = 0.0, frho = 0.0, ftau = 0.0;
+        for (int i = 0; i < ne; ++i) {
+            const double ttl = i * step + step * 0.5;
+            const double cttl = cos(ttl * (PB_PI / 180.0));
+            volscatt_volume(tts, tto, psi, ttl, chi_s, chi_o, frho, ftau);
+            ks += chi_s / cts * L[i];
+            ko += chi_o / cto * L[i];
+            bf += cttl * cttl * L[i];
+            Fs += frho * PB_PI / (cts * cto) * L[i];
+            Ft += ftau * PB_PI / (cts * cto) * L[i];
+        }
+        double* o = geom + (s * G + g) * NGEOM;
+        o[0] = ks; o[1] = ko; o[2] = bf; o[3] = Fs; o[4] = Ft; o[5] = 0.0; o[6] = 0.0; o[7] = 0.0;
+        o[8] = chi_s; o[9] = chi_o; o[10] = frho; o[11] = ftau;
+    }
+}
+
 // VolScatt.volume(lza) for n geometries and one leaf zenith angle (degrees): out [n][4] = chi_s, chi_o, frho, ftau (models.py:177-258)
 __global__ void k_volume(int n, const double* __restrict__ iza, const double* __restrict__ vza, const double* __restrict__ raa, double lza_deg,
                          double* __restrict__ out) {

@@ -360,6 +360,25 @@ class Engine(object):
             capi.check(self.lib.prosail_volscatt_f64(self.h, n, C.byref(can), _ptr(geom), _ptr(lidf), 1, None))
             return geom, lidf
 
+    def volscatt_bins(self, n_elements, lidf_type, a, b=0.0, iza=None, vza=None, raa=None):
+        """LIDF / VolScatt.coef with ``n_elements`` leaf-inclination classes instead of SAIL's 18 (the reference's n_elements
+        argument).  Returns (geom float64[n, G, 12] or None when no angles are given, lidf float64[n, n_elements])."""
+        with self._lock:
+            n = batch_size(a, b)
+            av, bv = _vec(a, n, 'a'), _vec(0.0 if b is None else b, n, 'b')
+            lt = {'campbell': capi.LIDF_CAMPBELL, 'verhoef': capi.LIDF_VERHOEF}[lidf_type]
+            lidf = np.empty((n, int(n_elements)), dtype=_f64)
+            geom, G, ang = None, 0, [None, None, None]
+            if iza is not None:
+                ang = [np.ascontiguousarray(np.asarray(x, dtype=_f64).reshape(-1)) for x in (iza, vza, raa)]
+                if not (ang[0].size == ang[1].size == ang[2].size):
+                    raise ValueError("iza, vza, raa must have the same length")
+                G = ang[0].size
+                geom = np.empty((n, G, capi.NGEOM), dtype=_f64)
+            capi.check(self.lib.prosail_volscatt_bins_f64(self.h, n, lt, _ptr(av), _ptr(bv), G, _ptr(ang[0]), _ptr(ang[1]), _ptr(ang[2]),
+                                                          int(n_elements), _ptr(geom), _ptr(lidf), 1, None))
+            return geom, lidf
+
     def volume(self, iza, vza, raa, lza_deg):
         """VolScatt.volume for one leaf zenith angle (degrees): float64 [G, 4] = chi_s, chi_o, frho, ftau; angles in normalised radians."""
         with self._lock:

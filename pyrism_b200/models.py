@@ -211,10 +211,11 @@ class LIDF(object):
 
     @staticmethod
     def _run(lidf_type, a, b, n_elements):
-        if n_elements != capi.NLIDF:
-            raise NotImplementedError("the GPU kernels use the reference's 18 leaf-inclination bins")
         scalar = _is_scalar_call(a, b)
-        _, lidf = get_engine().volscatt(0.0, 0.0, 0.0, lidf_type=lidf_type, a=a, b=b)
+        if n_elements != capi.NLIDF:      # any other resolution than SAIL's 18 classes: the general (slower) kernel
+            _, lidf = get_engine().volscatt_bins(n_elements, lidf_type, a, b)
+        else:
+            _, lidf = get_engine().volscatt(0.0, 0.0, 0.0, lidf_type=lidf_type, a=a, b=b)
         return lidf[0] if scalar else lidf
 
     @staticmethod
@@ -250,9 +251,10 @@ class VolScatt(Kernel):
             b = 0.0
         else:
             raise AttributeError("lad_method must be verhoef, nilson or campbell")
-        if n_elements != capi.NLIDF:
-            raise NotImplementedError("the GPU kernels use the reference's 18 leaf-inclination bins")
-        geom, lidf = get_engine().volscatt(self.iza, self.vza, self.raa, lidf_type=lidf_type, a=a, b=b)
+        if n_elements != capi.NLIDF:      # any other resolution than SAIL's 18 classes: the general (slower) kernel
+            geom, lidf = get_engine().volscatt_bins(n_elements, lidf_type, a, b, self.iza, self.vza, self.raa)
+        else:
+            geom, lidf = get_engine().volscatt(self.iza, self.vza, self.raa, lidf_type=lidf_type, a=a, b=b)
         self._set(geom, _is_scalar_call(a, b))
         self.lidf = lidf[0] if _is_scalar_call(a, b) else lidf
 

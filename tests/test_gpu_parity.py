@@ -568,3 +568,32 @@ def test_fused_kernel_rare_leaf_paths_agree_with_the_leaf_only_kernel():
     assert np.max(np.abs(fused.leaf_ks[0] - leaf.ks[0])) <= 1e-7 and np.max(np.abs(fused.leaf_kt[0] - leaf.kt[0])) <= 1e-7
     o = orc.prosail(1.7, 40.0, 8.0, 0.1, 0.01, 0.008, 2.0, 0.1, 30.0, 20.0, 40.0, 0.8, 0.3, lidf_type='campbell', a=57)[2]
     assert np.max(np.abs(fused.BRF.ref[4, 0] - o['rsot'])) <= TOL
+
+
+@pytest.mark.parametrize("ne", [1, 9, 36, 90])
+def test_lidf_and_volscatt_with_other_numbers_of_leaf_classes(ne):
+    """LIDF.campbell / LIDF.verhoef / VolScatt.coef with the reference's n_elements argument (models.py:82-175, 283-392);
+    SAIL itself always uses 18 classes."""
+    for a in (57.0, 20.0, 80.0, 30.0):
+        assert np.max(np.abs(pb.LIDF.campbell(a, n_elements=ne) - orc.lidf_campbell(a, ne))) <= 1e-12
+    for a, b in ((-0.35, -0.15), (0.0, 0.0), (0.5, -0.3), (1.2, 0.0)):
+        assert np.max(np.abs(pb.LIDF.verhoef(a, b, n_elements=ne) - orc.lidf_verhoef(a, b, ne))) <= 1e-12
+    la = np.array([-0.35, 0.2, 0.6])
+    lb = np.array([-0.15, 0.1, -0.3])
+    got = pb.LIDF.verhoef(la, lb, n_elements=ne)
+    assert got.shape == (3, ne)
+    for i in range(3):
+        assert np.max(np.abs(got[i] - orc.lidf_verhoef(la[i], lb[i], ne))) <= 1e-12
+    iza, vza, raa = [35.0, 10.0, 60.0], [30.0, 45.0, 0.0], [50.0, 120.0, 180.0]
+    v = pb.VolScatt(iza, vza, raa)
+    v.coef(lidf_type='campbell', n_elements=ne, a=45.0)
+    lidf = orc.lidf_campbell(45.0, ne)
+    assert v.lidf.shape == (ne,) and np.max(np.abs(v.lidf - lidf)) <= 1e-12
+    for g in range(3):
+        want = orc.volscatt_coef(np.radians(iza[g]), np.radians(vza[g]), np.radians(raa[g]), lidf)
+        got = (v.ks[g], v.ko[g], v.bf, v.Fs[g], v.Ft[g])
+        assert np.allclose(got, want, atol=1e-12), (ne, g)
+        last = orc.volscatt_volume(np.radians(iza[g]), np.radians(vza[g]), np.radians(raa[g]), 90.0 - 45.0 / ne)
+        assert np.allclose((v.chi_s[g], v.chi_o[g], v.frho[g], v.ftau[g]), last, atol=1e-12)
+    with pytest.raises(capi.ProsailError):
+        pb.LIDF.campbell(57.0, n_elements=0)
