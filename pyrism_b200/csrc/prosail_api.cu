@@ -97,6 +97,10 @@ struct prosail_handle {
     bool have_win = false;
     Work work;           // device mode (caller's stream)
     Work slot[2];        // host mode pipeline
+    // small host-mode jobs (the scalar drop-in calls): every input goes up and every result comes back in ONE copy each,
+    // through these page-locked staging buffers, instead of one pageable cudaMemcpyAsync per array (20-30 per call)
+    char* stage_in = nullptr;
+    char* stage_out = nullptr;
     long long launches = 0;
     // optional per-kernel timing (CUDA events on the launching stream), see prosail_profile_*
     bool profiling = false;
@@ -410,6 +414,8 @@ struct Carver {          // carve typed sub-buffers out of one device allocation
     }
 };
 
+constexpr size_t SMALL_STAGE = 1u << 20;     // bytes of each staging buffer: jobs whose inputs and outputs both fit take the staged path
+
 static int run_host(prosail_handle* h, const Job& j) {
     const int G = j.G();
     const int nw = h->have_win ? h->h_win.nwindows : 0;
@@ -435,15 +441,26 @@ static int run_host(prosail_handle* h, const Job& j) {
         if (j.mode == MODE_SAIL)
             for (long long p : {j.pr, j.pt, j.prho}) in_bytes += (((size_t)(p ? ns * p : NB) * ES + 255) & ~(size_t)255);
         if ((rc = w.in.reserve(in_bytes))) return rc;
+        const size_t out_bytes = out_per_item * (size_t)ni + (size_t)ns * PROSAIL_NLIDF * 8 + 8192;
+        const bool staged = in_bytes <= SMALL_STAGE && out_bytes <= SMALL_STAGE;
+        if (staged && !h->stage_in) {
+            CK(cudaHostAlloc((void**)&h->stage_in, SMALL_STAGE, cudaHostAllocPortable));
+            CK(cudaHostAlloc((void**)&h->stage_out, SMALL_STAGE, cudaHostAllocPortable));
+        }
         Carver ci(w.in.p);
         Job d = j;
         d.n = ns;
+        // host -> device: directly (large slabs), or via the staging buffer at the same offsets followed by one copy
+        auto h2d = [&](void* dst, const void* src, size_t bytes) -> int {
+            if (staged) memcpy(h->stage_in + ((char*)dst - (char*)w.in.p), src, bytes);
+            else CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+            return 0;
+        };
         auto up = [&](const double* src, size_t count, const double** dst) -> int {
             if (!src) { *dst = nullptr; return 0; }
             double* p = ci.take<double>(count);
-            CK(cudaMemcpyAsync(p, src, count * 8, cudaMemcpyHostToDevice, st));
             *dst = p;
-            return 0;
+            return h2d(p, src, count * 8);
         };
         if (j.has_leaf) {
             if ((rc = up(j.leaf.N + s0, ns, &d.leaf.N)) || (rc = up(j.leaf.Cab + s0, ns, &d.leaf.Cab)) ||
@@ -467,14 +484,14 @@ static int run_host(prosail_handle* h, const Job& j) {
             auto upspec = [&](const void* src, long long pitch, const void** dst) -> int {
                 const size_t count = pitch == 0 ? (size_t)NB : (size_t)ns * pitch;
                 char* p = ci.take<char>(count * ES);
-                CK(cudaMemcpyAsync(p, offb(src, s0 * pitch, ES), count * ES, cudaMemcpyHostToDevice, st));
                 *dst = p;
-                return 0;
+                return h2d(p, offb(src, s0 * pitch, ES), count * ES);
             };
             if ((rc = upspec(j.in_r, j.pr, &d.in_r)) || (rc = upspec(j.in_t, j.pt, &d.in_t)) || (rc = upspec(j.in_rho, j.prho, &d.in_rho))) return rc;
         }
+        if (staged) CK(cudaMemcpyAsync(w.in.p, h->stage_in, ci.off, cudaMemcpyHostToDevice, st));
         // ---- outputs ----
-        if ((rc = w.out.reserve(out_per_item * (size_t)ni + (size_t)ns * PROSAIL_NLIDF * 8 + 8192))) return rc;
+        if ((rc = w.out.reserve(out_bytes))) return rc;
         Carver co(w.out.p);
         for (int i = 0; i < NOUT; ++i) d.plane[i] = j.plane[i] ? co.take<char>((size_t)ni * j.pitch * ES) : nullptr;
         d.means = j.means ? co.take<char>((size_t)ni * j.nmean * nw * ES) : nullptr;
@@ -484,12 +501,22 @@ static int run_host(prosail_handle* h, const Job& j) {
 
         if ((rc = run_device(h, d, w, st))) return rc;
 
+        // device -> host: directly (large slabs), or one copy of everything carved into the staging buffer, then host copies
+        if (staged) {
+            CK(cudaMemcpyAsync(h->stage_out, w.out.p, co.off, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
+            if (staged) memcpy(dst, h->stage_out + ((const char*)src - (const char*)w.out.p), bytes);
+            else CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+            return 0;
+        };
         for (int i = 0; i < NOUT; ++i)
-            if (j.plane[i]) CK(cudaMemcpyAsync(offb(j.plane[i], i0 * j.pitch, ES), d.plane[i], (size_t)ni * j.pitch * ES, cudaMemcpyDeviceToHost, st));
-        if (j.means) CK(cudaMemcpyAsync(offb(j.means, i0 * j.nmean * nw, ES), d.means, (size_t)ni * j.nmean * nw * ES, cudaMemcpyDeviceToHost, st));
-        if (j.means_f32) CK(cudaMemcpyAsync(j.means_f32 + i0 * j.nmean * nw, d.means_f32, (size_t)ni * j.nmean * nw * 4, cudaMemcpyDeviceToHost, st));
-        if (j.geom) CK(cudaMemcpyAsync(j.geom + i0 * NGEOM, d.geom, (size_t)ni * NGEOM * 8, cudaMemcpyDeviceToHost, st));
-        if (j.lidf) CK(cudaMemcpyAsync(j.lidf + s0 * PROSAIL_NLIDF, d.lidf, (size_t)ns * PROSAIL_NLIDF * 8, cudaMemcpyDeviceToHost, st));
+            if (j.plane[i] && (rc = d2h(offb(j.plane[i], i0 * j.pitch, ES), d.plane[i], (size_t)ni * j.pitch * ES))) return rc;
+        if (j.means && (rc = d2h(offb(j.means, i0 * j.nmean * nw, ES), d.means, (size_t)ni * j.nmean * nw * ES))) return rc;
+        if (j.means_f32 && (rc = d2h(j.means_f32 + i0 * j.nmean * nw, d.means_f32, (size_t)ni * j.nmean * nw * 4))) return rc;
+        if (j.geom && (rc = d2h(j.geom + i0 * NGEOM, d.geom, (size_t)ni * NGEOM * 8))) return rc;
+        if (j.lidf && (rc = d2h(j.lidf + s0 * PROSAIL_NLIDF, d.lidf, (size_t)ns * PROSAIL_NLIDF * 8))) return rc;
         CK(cudaEventRecord(w.done, st));
     }
     CK(cudaStreamSynchronize(h->slot[0].stream));
@@ -597,6 +624,8 @@ void prosail_destroy(prosail_handle_t* h) {
     if (h->d_win) cudaFree(h->d_win);
     if (h->d_srf) cudaFree(h->d_srf);
     if (h->d_angles) cudaFree(h->d_angles);
+    if (h->stage_in) cudaFreeHost(h->stage_in);
+    if (h->stage_out) cudaFreeHost(h->stage_out);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->stream) cudaStreamDestroy(h->stream);
