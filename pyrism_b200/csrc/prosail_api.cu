@@ -443,10 +443,8 @@ static int run_host(prosail_handle* h, const Job& j) {
         if ((rc = w.in.reserve(in_bytes))) return rc;
         const size_t out_bytes = out_per_item * (size_t)ni + (size_t)ns * PROSAIL_NLIDF * 8 + 8192;
         const bool staged = in_bytes <= SMALL_STAGE && out_bytes <= SMALL_STAGE;
-        if (staged && !h->stage_in) {
-            CK(cudaHostAlloc((void**)&h->stage_in, SMALL_STAGE, cudaHostAllocPortable));
-            CK(cudaHostAlloc((void**)&h->stage_out, SMALL_STAGE, cudaHostAllocPortable));
-        }
+        if (staged && !h->stage_in) CK(cudaHostAlloc((void**)&h->stage_in, SMALL_STAGE, cudaHostAllocPortable));
+        if (staged && !h->stage_out) CK(cudaHostAlloc((void**)&h->stage_out, SMALL_STAGE, cudaHostAllocPortable));
         Carver ci(w.in.p);
         Job d = j;
         d.n = ns;
