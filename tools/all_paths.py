@@ -40,6 +40,8 @@ for dt in (np.float64, np.float32):
         vs = pb.VolScatt([35.0, 10.0], [30.0, 45.0], [50.0, 120.0])
         vs.coef(lidf_type='campbell', a=57)
         acc += float(vs.ks.sum() + pb.LIDF.verhoef(-0.35, -0.15).sum())
+        vs.coef(lidf_type='verhoef', n_elements=36, a=-0.35, b=-0.15)      # the general leaf-class kernel
+        acc += float(vs.ks.sum() + pb.LIDF.campbell(57.0, n_elements=7).sum())
 eng.set_prologue_threshold(2048)
 for m_, q_, d_ in ((1, 1, 1), (700, 1030, 15), (513, 5, 32), (300, 9, 6)):
     lutf = rng.random((m_, d_)).astype(np.float32)
