@@ -1,6 +1,7 @@
 # Builds libprosail_b200.so (sm_100a only) in-tree.  `make` here or __graft_entry__.build().
 NVCC ?= nvcc
-NVFLAGS ?= -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC
+# --register-usage-level=3: ptxas' default (5) costs the multi-geometry instances 4% and the fp32 / four-plane ones 1% (profiles/r1g_variants.txt)
+NVFLAGS ?= -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xptxas --register-usage-level=3 -Xcompiler -fPIC
 # tuning experiments: make variant NAME=nu3 EXTRA=-DPB_NU=3  ->  pyrism_b200/lib/variants/libprosail_nu3.so (PYRISM_B200_LIB selects it)
 EXTRA ?=
 SRC := pyrism_b200/csrc/prosail_api.cu
