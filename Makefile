@@ -10,7 +10,7 @@ LIB := pyrism_b200/lib/libprosail_b200.so
 
 all: $(LIB)
 
-$(LIB): $(SRC) $(HDR)
+$(LIB): $(SRC) $(HDR) Makefile
 	mkdir -p pyrism_b200/lib
 	$(NVCC) $(NVFLAGS) $(EXTRA) -shared -o $@ $(SRC)
 
