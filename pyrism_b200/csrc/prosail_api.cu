@@ -228,10 +228,15 @@ static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaS
     typedef typename CfgOf<T, G1>::type CF;
     const size_t smem = sizeof(SailSmem<T, CF, MODE>);
     auto kern = k_bands<T, CF, MODE, PLANES, MEANS, G1>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CF::THREADS, smem));
-    occ = std::max(occ, 1);
+    // shared-memory opt-in and resident CTAs per SM: once per kernel instance and device (a benign race: idempotent values)
+    static int occ_of_device[64] = {0};
+    int occ = h->device < 64 ? occ_of_device[h->device] : 0;
+    if (occ == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CF::THREADS, smem));
+        occ = std::max(occ, 1);
+        if (h->device < 64) occ_of_device[h->device] = occ;
+    }
     a.ngroups = j.windows_only ? h->h_win.ngroups_active[CF::NU - 2] : CF::NGROUPS;
     if (a.ngroups == 0) return 0;
     const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
