@@ -270,7 +270,7 @@ static int dispatch_bands(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaS
         case MODE_PROSAIL:
             if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, BRF, 0>(h, j, a, st);
             if (planes == FOUR && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, FOUR, 0>(h, j, a, st);
-            if (planes == 0 && j.mean_mask == BRF && !j.f32_means) return launch_bands<T, MODE_PROSAIL, 0, BRF>(h, j, a, st);
+            if (planes == 0 && j.mean_mask == BRF && !j.f32_means && !h->have_srf) return launch_bands<T, MODE_PROSAIL, 0, BRF>(h, j, a, st);
             return launch_bands<T, MODE_PROSAIL, RUNTIME, 0>(h, j, a, st);
         case MODE_SAIL:
             if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_SAIL, BRF, 0>(h, j, a, st);
