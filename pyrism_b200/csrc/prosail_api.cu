@@ -239,6 +239,7 @@ static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaS
     }
     a.ngroups = j.windows_only ? h->h_win.ngroups_active[CF::NU - 2] : CF::NGROUPS;
     if (a.ngroups == 0) return 0;
+    if (a.nitems >= (1LL << 31)) return fail(PROSAIL_E_ARG, "more than 2^31 items in one launch");   // the kernel indexes items of a launch in 32 bits
     const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
     // persistent grid, exactly one wave: as many warps as can be resident, split into ranges of ngroups warps
     const long long resident_warps = (long long)occ * h->sm_count * CF::WARPS;

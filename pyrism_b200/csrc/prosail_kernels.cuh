@@ -165,7 +165,8 @@ template <typename T>
 __device__ __forceinline__ void stage_issue(const SailArgs<T>& a, Stage<T>* st, uint64_t* bar, long long chunk) {
     const long long i0 = chunk * CHUNK;
     const long long i1 = min(i0 + (long long)CHUNK, a.nitems);
-    const long long s0 = i0 / a.G, s1 = (i1 - 1) / a.G;
+    // item indices of one launch fit in 32 bits (run_device_t slabs: <= 2^20 items): no 64-bit division in the loop
+    const long long s0 = (unsigned)i0 / (unsigned)a.G, s1 = (unsigned)(i1 - 1) / (unsigned)a.G;
     const uint32_t gbytes = (uint32_t)(i1 - i0) * REC * (uint32_t)sizeof(T);
     const uint32_t sbytes = (uint32_t)(s1 - s0 + 1) * REC * (uint32_t)sizeof(T);
     mbar_expect_tx(bar, gbytes + sbytes);
@@ -935,7 +936,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
         {
             const long long i0 = chunk * CHUNK;
             const int n = (int)min((long long)CHUNK, a.nitems - i0);
-            const long long s0 = G1 ? i0 : i0 / a.G;
+            const long long s0 = G1 ? i0 : (long long)((unsigned)i0 / (unsigned)a.G);
             long long s = s0;
             int g = G1 ? 0 : (int)(i0 - s0 * a.G);
             bool fresh = true;
