@@ -950,7 +950,8 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             const T* gr = stage[buf].g;
             EmitCtx<T, NU> e{a, tail, {}, NU * grp, lane, nt, i0 * a.out_pitch + band0, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
 #pragma unroll
-            for (int u = 0; u < NU; ++u) e.valid[u] = band0 + 32 * u < NB;
+            for (int u = 0; u < NU; ++u)      // only the last tile group has bands >= 2101: there the answer depends on the lane alone
+                e.valid[u] = !tail || lane < NB - (NTILES / NU - 1) * (32 * NU) - 32 * u;
             for (int j = 0; j < n; ++j) {
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {
