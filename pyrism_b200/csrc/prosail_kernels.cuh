@@ -946,6 +946,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             Diffuse<T> d[NU];
             Diffuse<f2> dp;          // packed twin of d[] (fp32 mode)
             int thr_hi = 0;
+            bool nocanopy = false;
             const T* sr = stage[buf].s;
             const T* gr = stage[buf].g;
             EmitCtx<T, NU> e{a, tail, {}, NU * grp, lane, nt, i0 * a.out_pitch + band0, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
@@ -1019,9 +1020,10 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         }
                         // |k - m| lai <= 1e-3  <=>  |k - m| <= 1e-3 / lai   (threshold on the high word)
                         thr_hi = hi_word(sr[S_THR]);
+                        nocanopy = hi_word(sr[S_NOCANOPY]) != 0;                 // the flag is 0 or 1: an integer test on its high word, once per set
                         fresh = false;
                     }
-                    if (__builtin_expect(sr[S_NOCANOPY] != zero_, 0)) {          // lai <= 0: models.py:609-634
+                    if (__builtin_expect(nocanopy, 0)) {                         // lai <= 0: models.py:609-634
                         emit<PLANES, MEANS, O_RSOT>(e, rs); emit<PLANES, MEANS, O_RDDT>(e, rs);
                         emit<PLANES, MEANS, O_RSDT>(e, rs); emit<PLANES, MEANS, O_RDOT>(e, rs);
                         emit_const<PLANES, MEANS, O_RSO>(e, zero_); emit_const<PLANES, MEANS, O_RDD>(e, zero_);
