@@ -223,9 +223,18 @@ static inline const void* offb(const void* p, long long n, size_t esz) { return 
 template <typename T, bool G1> struct CfgOf { typedef Cfg<PB_NU, PB_NU == 3 ? 12 : (G1 ? PB_WARPS : PB_MULTI_WARPS)> type; };
 template <bool G1> struct CfgOf<float, G1> { typedef Cfg<2, PB_WARPS> type; };
 
+// Three bands per thread (12 warps x 168 registers: 3 warps x 3 chains per sub-partition) for the two fp64 LUT instances that
+// measure faster that way -- BRF plane (+1.6%) and leaf-only (+1.3%); the four-plane instance (-1.3%), the band-mean instance
+// (-18%: more wavelengths outside any window are evaluated) and the multi-geometry instances (-29%: spills) keep two.
+template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS> struct CfgFor { typedef typename CfgOf<T, G1>::type type; };
+#if PB_NU == 2 && !defined(PB_NO_NU3)
+template <> struct CfgFor<double, true, MODE_PROSAIL, 1u << O_RSOT, 0u> { typedef Cfg<3, 12> type; };
+template <> struct CfgFor<double, true, MODE_PROSPECT, (1u << O_LEAF_R) | (1u << O_LEAF_T), 0u> { typedef Cfg<3, 12> type; };
+#endif
+
 template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS>
 static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
-    typedef typename CfgOf<T, G1>::type CF;
+    typedef typename CfgFor<T, G1, MODE, PLANES, MEANS>::type CF;
     const size_t smem = sizeof(SailSmem<T, CF, MODE>);
     auto kern = k_bands<T, CF, MODE, PLANES, MEANS, G1>;
     // shared-memory opt-in and resident CTAs per SM: once per kernel instance and device (a benign race: idempotent values)
