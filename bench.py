@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 NB = 2101
 FLOPS_PER_BAND = 234            # PROSPECT 83 + 4SAIL 151, div/sqrt/exp/E1/pow counted as ONE flop each
 BYTES_PER_SPECTRUM = NB * 8     # one fp64 output plane
-NCU_DRAM_BYTES_PER_SPECTRUM = (4.371877e9 + 91.775744e6) / 262144   # measured, see profiles/r1j_k_bands_prosail_brf_f64.txt
+NCU_DRAM_BYTES_PER_SPECTRUM = (4.361098e9 + 80.665344e6) / 262144   # measured, see profiles/r1k_k_bands_prosail_brf_f64.txt
 SEED = 20261019 + 2             # config index 2
 GEOM_DEG = (35.0, 30.0, 50.0)
 
@@ -339,7 +339,7 @@ def main():
                 "flops_per_band": FLOPS_PER_BAND, "kernel_ms_avg": k_avg, "kernel_launches": int(k_n),
                 "kernel_share_of_step": k_ms / ms if world == 1 else None,
                 # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-                # (profiles/r1j_k_bands_prosail_brf_f64.txt: 4.464 GB for 262144 spectra = 17027 B per spectrum), scaled to this launch
+                # (profiles/r1k_k_bands_prosail_brf_f64.txt: 4.442 GB for 262144 spectra = 16944 B per spectrum), scaled to this launch
                 "traffic": spectra_per_launch * NCU_DRAM_BYTES_PER_SPECTRUM,
                 # lower bounds of one launch from each roofline; the larger one binds (fp64 by ~5x)
                 "t_fp64_min_ms": spectra_per_launch * NB * FLOPS_PER_BAND / (fp64_peak * 1e12) * 1e3,
