@@ -24,7 +24,7 @@ ptxas: $(SRC) $(HDR)
 # pipe microbenchmarks (results: profiles/r1b_micro_*.txt): make micro && tools/micro/bin/<name> on the GPU box
 micro:
 	mkdir -p tools/micro/bin
-	for f in dfma_lat issue_mix fp64_flavours fp64_operands; do $(NVCC) -O3 -gencode arch=compute_100a,code=sm_100a -o tools/micro/bin/$$f tools/micro/$$f.cu; done
+	for f in dfma_lat issue_mix fp64_flavours fp64_operands conv_mix; do $(NVCC) -O3 -gencode arch=compute_100a,code=sm_100a -o tools/micro/bin/$$f tools/micro/$$f.cu; done
 
 clean:
 	rm -f $(LIB)

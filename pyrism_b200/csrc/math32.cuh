@@ -39,7 +39,8 @@ __device__ __forceinline__ float sqrt_raw(float x) {
     return y;
 }
 __device__ __forceinline__ float sqrt_pos(float x) { return is_pos(x) ? sqrt_raw(x) : 0.0f; }
-__device__ __forceinline__ float rcp_k(float x) { return rcp(x); }      // float twin of the band kernel's reciprocal (math64.cuh)
+__device__ __forceinline__ float rcp_k(float x) { return rcp(x); }      // float twins of the band kernel's reciprocals (math64.cuh)
+__device__ __forceinline__ float rcp_b(float x) { return rcp(x); }
 __device__ __forceinline__ float exp2_fast(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

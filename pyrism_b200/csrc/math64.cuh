@@ -36,9 +36,29 @@ __constant__ double c_m[M_COUNT] = {
     0x1.62e42fefa39efp-1,        // ln2
 };
 
+// Round 2: the band kernel is bound by the FP64 pipe INCLUDING its operand reads (a DFMA with three distinct register
+// operands takes three pipe cycles), and the Horner steps of the tau polynomial are exactly such
+// instructions (coefficients come from a per-lane table row).  PB_TAU_F32TAIL = 1 (default) evaluates the terms of degree
+// >= 4 on the FP32 pipe: with |u| <= 1 and |c4| <= 1.7e-6 over the whole table, float rounding (6e-8 relative) leaves
+// <= 2e-13 absolute in tau, where the parity bar is 1e-9.  The two conversions (F2F.F32.F64 of u, F2F.F64.F32 of the tail)
+// run on the SFU pipe (8 cycles per warp instruction, measured: profiles/r2a_conv_mix.txt), which this kernel leaves
+// 80% idle.  FP64-pipe instructions per tau: 5 instead of 9.
+#ifndef PB_TAU_F32TAIL
+#define PB_TAU_F32TAIL 1
+#endif
+struct alignas(16) TauRow {            // 64 bytes: four 128-bit shared-memory loads
+    double O, c0, c1, c2, c3;          // u = k S - O;  tau = c0 + u (c1 + u (c2 + u (c3 + u T4(u))))
+    float f4, f5, f6, f7, f8, pad;     // T4(u) = f4 + u (f5 + u (f6 + u (f7 + u f8))) in float
+};
+static_assert(sizeof(TauRow) == 64, "TauRow layout");
+
 // ---- shared-memory image of the lookup tables (copied once per CTA) ----
 struct alignas(16) MathTables {
+#if PB_TAU_F32TAIL
+    TauRow tau[TAU_NROWS];             // piecewise polynomials of tau(k), see tools/gen_math_tables.py (degree 8, tail in float)
+#else
     double tau[TAU_NROWS * TAU_ROW];   // piecewise polynomials of tau(k), see tools/gen_math_tables.py
+#endif
     double exp2t[1 << EXP2_BITS];      // 2^(j/2048)
     double logt[512];                  // pairs (1/c_i, log2 c_i), c_i = 1 + (i+.5)/256
 };
@@ -105,6 +125,29 @@ __device__ __forceinline__ double sqrt_q_raw(double x) {
     const double t = x * y;
     const double e = fma(-t, y, 1.0);
     return fma(half_of(t), e, t);
+}
+// ---- round 2: per-site error budget ----
+// The parity bar is 1e-9 absolute; round 1 held every primitive to 4e-16.  A second-order Newton step leaves e^2 ~ 9e-13
+// RELATIVE.  That is harmless wherever the result only scales an output or enters as the small quantity itself
+// ("benign" sites: 1/(1 - x^2), 1/X of the Stokes stage, D = sqrt(...), m, 1/(att + m), 1/den, 1/(1 - rinf^2), 1/dn,
+// 1/(k -+ m), 1/(K -+ m)), and it is not where a value close to 1 is later differenced (b = (b t)/t feeds b^(2(N-1)) - 1):
+// that one keeps the third-order step.  rcp_b / sqrt_b_raw are the benign-site spellings.
+#ifndef PB_BENIGN_Q
+#define PB_BENIGN_Q 1
+#endif
+#ifndef PB_UNMERGE
+#define PB_UNMERGE 0      /* 1: one reciprocal per denominator instead of merged products (experiment; slower) */
+#endif
+#if PB_BENIGN_Q
+__device__ __forceinline__ double rcp_b(double x) { return rcp_q(x); }
+__device__ __forceinline__ double sqrt_b_raw(double x) { return sqrt_q_raw(x); }
+#else
+__device__ __forceinline__ double rcp_b(double x) { return rcp(x); }
+__device__ __forceinline__ double sqrt_b_raw(double x) { return sqrt_raw(x); }
+#endif
+__device__ __forceinline__ double sqrt_b_pos(double x) {
+    const double g = sqrt_b_raw(x);
+    return is_pos(x) ? g : 0.0;
 }
 #if PB_QUADRATIC
 __device__ __forceinline__ double rcp_k(double x) { return rcp_q(x); }
@@ -181,6 +224,30 @@ __device__ __forceinline__ double exp_neg(double x, const MathTables& mt) { retu
 // sees 1 FMA (local variable) + TAU_DEG FMAs (Horner).  Arguments outside the range are clamped to a valid row
 // (the value is then meaningless) and flagged in `rare`; the caller repairs flagged lanes with tau_rare() after
 // both evaluations of a thread have been issued.
+#if PB_TAU_F32TAIL
+__device__ __forceinline__ double tau_fast(double k, const TauRow* __restrict__ tab, bool& rare) {
+    const int hi = __double2hiint(k);
+    const int E0 = (hi >> 20) - 1023;
+    const int E = min(max(E0, TAU_EMIN), TAU_EMAX);
+    rare = E != E0;
+    const int e1 = max(E, 1);                                      // sub-interval bits: TAU_SB below k = 2, E + TAU_SB - 1 above
+    const int j = (hi & 0x000FFFFF) >> (21 - TAU_SB - e1);
+    const int idx = (TAU_NA - (1 << TAU_SB)) + j + (E <= 0 ? (E << TAU_SB) : ((1 << (TAU_SB - 1)) << E));
+    const double S = __hiloint2double((1024 + TAU_SB - min(E, 1)) << 20, 0);   // 2^(TAU_SB + 1 - min(E, 1))
+    const uint4* row = reinterpret_cast<const uint4*>(tab + idx);
+    const uint4 q0 = row[0], q3 = row[3], q2 = row[2], q1 = row[1];
+    const double u = fma(k, S, -__hiloint2double((int)q0.y, (int)q0.x));
+    const float uf = (float)u;                                     // F2F.F32.F64 (SFU pipe)
+    float t = fmaf(uf, __uint_as_float(q3.z), __uint_as_float(q3.y));          // f7 + u f8
+    t = fmaf(uf, t, __uint_as_float(q3.x));                        // f6
+    t = fmaf(uf, t, __uint_as_float(q2.w));                        // f5
+    t = fmaf(uf, t, __uint_as_float(q2.z));                        // f4
+    double acc = fma(u, (double)t, __hiloint2double((int)q2.y, (int)q2.x));    // c3 + u T4   (F2F.F64.F32)
+    acc = fma(u, acc, __hiloint2double((int)q1.w, (int)q1.z));    // c2
+    acc = fma(u, acc, __hiloint2double((int)q1.y, (int)q1.x));    // c1
+    return fma(u, acc, __hiloint2double((int)q0.w, (int)q0.z));   // c0
+}
+#else
 __device__ __forceinline__ double tau_fast(double k, const double* __restrict__ tab, bool& rare) {
     const int hi = __double2hiint(k);
     const int E0 = (hi >> 20) - 1023;
@@ -220,6 +287,8 @@ __device__ __forceinline__ double tau_fast(double k, const double* __restrict__ 
 #endif
 }
 
+#endif
+
 // Rare path (never taken for realistic leaves, k in [6e-4, 16]): k <= 0, k < 2^-14, k >= 32.  Plain IEEE arithmetic.
 __device__ __noinline__ double tau_rare(double k) {
     if (!(k > 0.0)) return 1.0;                                    // k <= 0 (or NaN): the reference leaves tau = 1
@@ -257,7 +326,12 @@ __device__ __noinline__ double tau_full(double k) {
 }
 
 // full-range tau (test kernel, and the reference point for the fast path)
-__device__ __forceinline__ double tau_plate(double k, const double* __restrict__ tab) {
+#if PB_TAU_F32TAIL
+typedef TauRow TauTab;
+#else
+typedef double TauTab;
+#endif
+__device__ __forceinline__ double tau_plate(double k, const TauTab* __restrict__ tab) {
     bool rare;
     const double t = tau_fast(k, tab, rare);
     return rare ? tau_rare(k) : t;

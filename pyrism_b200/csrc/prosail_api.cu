@@ -91,6 +91,9 @@ struct prosail_handle {
     AngleTables* d_angles = nullptr;
     long long prologue_thread_min = 2048;   // items from which the thread-per-item prologue is used
     WindowMap* d_win = nullptr;
+    WindowMap* d_winp = nullptr;               // packed map (in-window wavelengths only), see WindowMap::packed
+    WindowMap h_winp;
+    bool have_winp = false;
     double* d_srf = nullptr;   // [MAX_SLOTS][32] spectral-response weights of the window segments
     bool have_srf = false;
     WindowMap h_win;
@@ -211,6 +214,9 @@ template <typename T> static inline T* off(void* p, long long n) { return static
 static inline void* offb(void* p, long long n, size_t esz) { return static_cast<char*>(p) + n * (long long)esz; }
 static inline const void* offb(const void* p, long long n, size_t esz) { return static_cast<const char*>(p) + n * (long long)esz; }
 
+#ifndef PB_PACKED_WINDOWS
+#define PB_PACKED_WINDOWS 1   /* band-mean-only LUTs evaluate only the in-window wavelengths (packed window map) */
+#endif
 #ifndef PB_NU
 #define PB_NU 2          /* bands per thread of the fp64 band kernel (2 or 3) */
 #endif
@@ -246,7 +252,7 @@ static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaS
         occ = std::max(occ, 1);
         if (h->device < 64) occ_of_device[h->device] = occ;
     }
-    a.ngroups = j.windows_only ? h->h_win.ngroups_active[CF::NU - 2] : CF::NGROUPS;
+    a.ngroups = j.windows_only ? (a.packed ? h->h_winp : h->h_win).ngroups_active[CF::NU - 2] : CF::NGROUPS;
     if (a.ngroups == 0) return 0;
     if (a.nitems >= (1LL << 31)) return fail(PROSAIL_E_ARG, "more than 2^31 items in one launch");   // the kernel indexes items of a launch in 32 bits
     const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
@@ -307,8 +313,14 @@ static int run_device_t(prosail_handle* h, const Job& j, Work& w, cudaStream_t s
     const int G = j.G();
     const long long nitems_total = j.n * G;
     if (nitems_total == 0) return 0;
-    const int nw = h->have_win ? h->h_win.nwindows : 0;
-    const int nt = h->have_win ? h->h_win.ntotal : 0;
+    // band-mean-only PROSAIL jobs with plain boxcar windows run on the packed window map (only in-window wavelengths exist)
+    bool any_plane = false;
+    for (int i = 0; i < NOUT; ++i) any_plane = any_plane || j.plane[i];
+    const bool packed = PB_PACKED_WINDOWS && j.windows_only && j.mode == MODE_PROSAIL && !any_plane && h->have_winp && !h->have_srf;
+    const WindowMap& hw = packed ? h->h_winp : h->h_win;
+    const WindowMap* dw = packed ? h->d_winp : h->d_win;
+    const int nw = h->have_win ? hw.nwindows : 0;
+    const int nt = h->have_win ? hw.ntotal : 0;
     // slab = bounded workspace
     long long cap_items = 1LL << 20;
     if (j.nmean > 0) cap_items = std::min<long long>(cap_items, std::max<long long>(4096, (1LL << 30) / ((long long)j.nmean * std::max(nt, 1) * (long long)ES)));
@@ -376,7 +388,8 @@ static int run_device_t(prosail_handle* h, const Job& j, Work& w, cudaStream_t s
         SailArgs<T> a{};
         a.bandc = bandc_of<T>(h, j.has_leaf ? j.version : 0);
         a.tables = tables_of<T>(h);
-        a.win = h->d_win;
+        a.win = dw;
+        a.packed = packed ? 1 : 0;
         a.srf = h->have_srf ? h->d_srf : nullptr;
         a.srec = (const T*)w.srec.p;
         a.grec = (const T*)w.grec.p;
@@ -399,7 +412,7 @@ static int run_device_t(prosail_handle* h, const Job& j, Work& w, cudaStream_t s
             const unsigned blocks = (unsigned)((total + 255) / 256);
             {
                 ProfScope ps(h, 2, st);
-                k_finalize_means<T><<<blocks, 256, 0, st>>>(h->d_win, (const T*)w.partial.p, rows,
+                k_finalize_means<T><<<blocks, 256, 0, st>>>(dw, (const T*)w.partial.p, rows,
                                                          j.means ? off<T>(j.means, i0 * j.nmean * nw) : nullptr,
                                                          j.means_f32 ? j.means_f32 + i0 * j.nmean * nw : nullptr);
             }
@@ -585,7 +598,18 @@ int prosail_create(int device, prosail_handle_t** out) {
     {
         std::vector<double> img(sizeof(MathTables) / 8);
         MathTables* mt = reinterpret_cast<MathTables*>(img.data());
+#if PB_TAU_F32TAIL
+        for (int r = 0; r < TAU_NROWS; ++r) {                 // [O, c0..c8] -> O, c0..c3 in double, c4..c8 rounded to float
+            const double* src = h_tau_table + r * TAU_ROW;
+            TauRow& t = mt->tau[r];
+            t.O = src[0]; t.c0 = src[1]; t.c1 = src[2]; t.c2 = src[3]; t.c3 = src[4];
+            t.f4 = (float)src[5]; t.f5 = (float)src[6]; t.f6 = (float)src[7]; t.f7 = (float)src[8]; t.f8 = (float)src[9];
+            t.pad = 0.0f;
+        }
+        static_assert(TAU_DEG == 8, "TauRow holds a degree-8 polynomial");
+#else
         memcpy(mt->tau, h_tau_table, sizeof(mt->tau));
+#endif
         memcpy(mt->exp2t, h_exp2_table, sizeof(mt->exp2t));
         memcpy(mt->logt, h_log_table, sizeof(mt->logt));
         CK(cudaMalloc(&h->d_tables, sizeof(MathTables)));
@@ -613,9 +637,12 @@ int prosail_create(int device, prosail_handle_t** out) {
     }
     CK(cudaMalloc(&h->d_win, sizeof(WindowMap)));
     CK(cudaMemset(h->d_win, 0, sizeof(WindowMap)));
+    CK(cudaMalloc(&h->d_winp, sizeof(WindowMap)));
+    CK(cudaMemset(h->d_winp, 0, sizeof(WindowMap)));
     CK(cudaMalloc(&h->d_srf, sizeof(double) * MAX_SLOTS * 32));
     CK(cudaMemset(h->d_srf, 0, sizeof(double) * MAX_SLOTS * 32));
     memset(&h->h_win, 0, sizeof(WindowMap));
+    memset(&h->h_winp, 0, sizeof(WindowMap));
     *out = h;
     return 0;
 }
@@ -635,6 +662,7 @@ void prosail_destroy(prosail_handle_t* h) {
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_tables_f) cudaFree(h->d_tables_f);
     if (h->d_win) cudaFree(h->d_win);
+    if (h->d_winp) cudaFree(h->d_winp);
     if (h->d_srf) cudaFree(h->d_srf);
     if (h->d_angles) cudaFree(h->d_angles);
     if (h->stage_in) cudaFreeHost(h->stage_in);
@@ -751,12 +779,56 @@ static int set_windows_impl(prosail_handle_t* h, int n_windows, const int* lo_nm
             for (int u = 0; u < nu; ++u) any = any || touched[nu * g + u];
             if (any) m.active_group[nu - 2][m.ngroups_active[nu - 2]++] = g;
         }
+    // ---- packed map: only the wavelengths inside at least one window, ascending; same slot construction in lane space ----
+    WindowMap mp;
+    memset(&mp, 0, sizeof mp);
+    bool have_packed = false;
+    if (!weights) {
+        int pidx[NB];                       // wavelength index -> packed lane (or -1)
+        bool in_win[NB] = {};
+        for (int w = 0; w < n_windows; ++w)
+            for (int b = std::max(lo_nm[w], 400) - 400; b <= std::min(hi_nm[w], 2500) - 400; ++b) in_win[b] = true;
+        int np = 0;
+        for (int b = 0; b < NB; ++b) { pidx[b] = in_win[b] ? np : -1; if (in_win[b]) mp.band[np++] = b; }
+        mp.packed = 1;
+        mp.nbands_packed = np;
+        mp.nwindows = n_windows;
+        const int ptiles = (np + 31) / 32;
+        int pslot = 0;
+        have_packed = true;
+        for (int w = 0; w < n_windows && have_packed; ++w) {
+            const int lo = pidx[std::max(lo_nm[w], 400) - 400], hi = pidx[std::min(hi_nm[w], 2500) - 400];   // a window is a run of lanes
+            mp.wstart[w] = pslot;
+            mp.wcount[w] = m.wcount[w];
+            mp.wsum[w] = m.wsum[w];
+            for (int t = lo / 32; t <= hi / 32; ++t) {
+                if (mp.nslots[t] >= MAX_TILE_SLOTS || pslot >= MAX_SLOTS) { have_packed = false; break; }   // fall back to the unpacked map
+                unsigned mask = 0;
+                for (int l = 0; l < 32; ++l)
+                    if (t * 32 + l >= lo && t * 32 + l <= hi) mask |= 1u << l;
+                mp.mask[t][mp.nslots[t]] = mask;
+                mp.slot[t][mp.nslots[t]] = pslot++;
+                mp.nslots[t]++;
+            }
+        }
+        mp.wstart[n_windows] = pslot;
+        mp.ntotal = pslot;
+        mp.ntiles_active = ptiles;
+        for (int t = 0; t < ptiles; ++t) mp.active_tile[t] = t;
+        for (int nu = 2; nu <= 3; ++nu) {
+            mp.ngroups_active[nu - 2] = (ptiles + nu - 1) / nu;
+            for (int g = 0; g < mp.ngroups_active[nu - 2]; ++g) mp.active_group[nu - 2][g] = g;
+        }
+    }
     DeviceGuard guard(h->device);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h->d_win, &m, sizeof m, cudaMemcpyHostToDevice));
+    if (have_packed) CK(cudaMemcpy(h->d_winp, &mp, sizeof mp, cudaMemcpyHostToDevice));
     if (weights) CK(cudaMemcpy(h->d_srf, srf.data(), srf.size() * 8, cudaMemcpyHostToDevice));
     h->h_win = m;
+    h->h_winp = mp;
     h->have_win = true;
+    h->have_winp = have_packed;
     h->have_srf = weights != nullptr;
     return 0;
 }

@@ -86,6 +86,14 @@ struct WindowMap {                       // which band-mean windows touch which 
     int active_tile[NTILES];
     int ngroups_active[2];                   // [NU - 2]: groups of NU tiles touched by at least one window
     int active_group[2][NT2];
+    // Packed variant of the map (band-mean-only LUTs, plain boxcar windows): the wavelengths that lie inside at least one
+    // window, in ascending order, are the ONLY lanes that exist -- 782 of 2101 for the reference's 6 L8 + 9 ASTER windows
+    // (25 tiles instead of the 38 tiles = 19 two-tile groups the unpacked map touches).  A window is still a run of
+    // consecutive lanes (the list is sorted), so the segmented warp reduction is unchanged; `band` maps a packed lane back to
+    // its wavelength index for the gather of the per-band constants (lanes past `nbands_packed`: band 0, in no mask).
+    int packed;                              // 1: tiles / masks / slots of this map are in packed-lane space
+    int nbands_packed;
+    int band[NBP];
 };
 
 template <typename T>
@@ -109,6 +117,7 @@ struct SailArgs {
     T* partial;                // [nitems][nmean][ntotal slots]
     int nmean;
     int only_active_tiles;     // 1: visit only tiles touched by a window (band-mean-only LUTs)
+    int packed;                // 1: `win` is the packed map (lanes = in-window wavelengths only); implies only_active_tiles, no planes
     int f32_means;             // 1: round values to float before averaging (PROSPECT/LSM convention, models.py:1071)
 };
 
@@ -208,7 +217,9 @@ __device__ __forceinline__ T leaf_kall(const T* __restrict__ kc, const T* __rest
     // kall = sum_i C_i K_i / N ; the division by N is folded into the record (C_i / N)      :950-951
     T kall = s[S_CAB] * kc[KC_KAB * KSTRIDE];
     kall = fma(s[S_CXC], kc[KC_KXC * KSTRIDE], kall);
-    kall = fma(s[S_CAN], kc[KC_KAN * KSTRIDE], kall);
+    // PROSPECT-5 has no anthocyanin term (Kan = zeros, models.py:935): the record carries Can/N = +0.0 and the FMA is
+    // predicated off by an integer test on that (warp-uniform) value -- one three-register DFMA less per band and item
+    if (!is_zero(s[S_CAN])) kall = fma(s[S_CAN], kc[KC_KAN * KSTRIDE], kall);
     kall = fma(s[S_CBR], kc[KC_KBR * KSTRIDE], kall);
     kall = fma(s[S_CW], kc[KC_KW * KSTRIDE], kall);
     return fma(s[S_CM], kc[KC_KM * KSTRIDE], kall);
@@ -228,7 +239,7 @@ __device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf,
     const T one = T(1), half = T(0.5);
     // one layer                                                                              :1019-1025
     const T x = r21 * tau;
-    const T tq = tau * rcp_k(fma(-x, x, one));
+    const T tq = tau * rcp_b(fma(-x, x, one));     // benign: scales r - r12, t, Ta, Ra - ralf consistently (a slightly different plate)
     const T Ta = ta21 * tq;
     const T t = t1221 * tq;
     const T Ra = fma(x, Ta, ralf);
@@ -238,22 +249,24 @@ __device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf,
     const T P12 = fma(-t, t, p * p);               // (1+r+t)(1+r-t): >= 1, no cancellation in this form
     const T qmt = q - t;                           // 1 - r - t: <= 0 flags zero absorption
     const T P34 = (q + t) * qmt;                   // the small factor keeps its product form
-    const T D = sqrt_k_raw(P12 * P34);             // P34 <= 0 only when r + t >= 1: that lane is flagged and recomputed
+    const T D = sqrt_b_raw(P12 * P34);             // benign: D is itself the small quantity (a - 1/a = D/r).  P34 <= 0 only when r + t >= 1: that lane is flagged and recomputed
     const T A = fma(T(-2), r, P12);                // 1 + r^2 - t^2
     const T hD = half_of(D);                       // D / 2 as an exponent decrement (integer pipe); D > 0 on every lane that is kept
     const T al = fma(half, A, hD);                 // a * r   (a of :1046)
     const T be = fma(-half, A, one + hD);          // b * t   (b of :1047), using 1 - r^2 + t^2 = 2 - A
-    const T b = be * rcp_k(t);
+    const T b = be * rcp_k(t);                     // NOT benign: b^(2(N-1)) - 1 differences it against 1 (third-order step)
     // b^(N-1) = 2^((N-1) log2 b)                                                             :1049
     const T bNm1 = pow_pos(b, nm1, mt);
     const T bN2 = bNm1 * bNm1;
     // With a = al/r:  kt = Ta bNm1 (al^2 - r^2)/X,  ks = Ra + Ta t al r (bN2 - 1)/X,
     //                 X = al^2 bN2 - r^2 - al r^2 (bN2 - 1)      (algebraically :1052-1065, one division)
+    //                   = (al^2 - r^2) + (bN2 - 1) al (al - r^2)
     const T bm1 = bN2 - one;
-    const T al2 = al * al, r2 = r * r;
-    const T X = fma(-(al * r2), bm1, fma(al2, bN2, -r2));
-    const T TaI = Ta * rcp_k(X);
-    tran = TaI * (bNm1 * (al2 - r2));
+    const T r2 = r * r;
+    const T dal = fma(al, al, -r2);                // al^2 - r^2 = r^2 (a^2 - 1)
+    const T X = fma(bm1, al * (al - r2), dal);
+    const T TaI = Ta * rcp_b(X);                   // benign: scales kt and ks - Ra
+    tran = TaI * (bNm1 * dal);
     refl = fma(TaI * bm1, (t * al) * r, Ra);
     return !is_pos(qmt);                           // r + t >= 1, tested on the sign of 1 - r - t (integer pipe)
 }
@@ -516,8 +529,14 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
         d.m = sqrt_pos((att - sigb) * (att + sigb));
         d.rinf = sigb * rcp(att + d.m);
     } else {
-        d.m = sqrt_k_pos(fma(att, att, -(sigb * sigb)));              // :601
+        d.m = sqrt_b_pos(fma(att, att, -(sigb * sigb)));              // :601
+#if PB_BENIGN_Q
+        // :639 as sigb / (att + m) (= (att - m)/sigb because m^2 = att^2 - sigb^2): a relative error of m then reaches rinf
+        // divided by (att + m) >= 1 instead of multiplied by m/sigb -- what makes the second-order sqrt benign here
+        d.rinf = sigb * rcp_b(att + d.m);
+#else
         d.rinf = (att - d.m) * rcp_k(sigb);                           // :639
+#endif
     }
     d.e1 = exp_neg(d.m * s[S_NEGLAI], mt);                            // :637
     const T e2 = d.e1 * d.e1;
@@ -525,14 +544,16 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
     d.re = d.rinf * d.e1;
     const T omr2 = one - rinf2;
     const T den = fma(-rinf2, e2, one);
-    if constexpr (is_f32<T>() || !PB_QUADRATIC) {
-        // 1/(1 - rinf^2 e^2) (:642) and 1/(1 - rinf^2) (:678) from ONE reciprocal of their product: one MUFU less
-        const T r = rcp(den * omr2);
+    if constexpr (is_f32<T>() || !(PB_QUADRATIC || PB_UNMERGE)) {
+        // 1/(1 - rinf^2 e^2) (:642) and 1/(1 - rinf^2) (:678) from ONE reciprocal of their product: one MUFU less (an SFU
+        // instruction next to a busy FP64 pipe costs about as much as the two multiplications that replace it, and the
+        // unmerged build measured 5% slower: profiles/r2b_variants.txt).  Both results only scale outputs: benign.
+        const T r = rcp_b(den * omr2);
         d.invden = r * omr2;
         d.inv_omr2 = r * den;
-    } else {                                                          // two 2-instruction reciprocals beat the merged form (6 -> 4)
-        d.invden = rcp_k(den);
-        d.inv_omr2 = rcp_k(omr2);
+    } else {                                                          // two 2-instruction reciprocals (experiment)
+        d.invden = rcp_b(den);
+        d.inv_omr2 = rcp_b(omr2);
     }
     d.tdd = omr2 * d.e1 * d.invden;                                   // :654
     d.rinf_invden = d.rinf * d.invden;                                // shared by rdd and by T3 of the directional stage
@@ -540,7 +561,7 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
     d.rsrdd = rs * d.rdd;
     T dn = one - d.rsrdd;                                             // :714-719
     dn = below_tiny(dn) ? tiny : dn;                                  // dn < 1e-36 (integer-pipe test; negatives too)
-    d.rs_invdn = rs * rcp_k(dn);
+    d.rs_invdn = rs * rcp_b(dn);
     d.a1 = fma(tau, d.rinf, rho);
     d.a2 = fma(rho, d.rinf, tau);
 }
@@ -608,15 +629,17 @@ __device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const 
     } else {
         // 1/(k-m) and 1/(k+m) from ONE reciprocal of (k-m)(k+m)                             :644-647, 765-789
         const bool rare = !(abs_gt_hi(km, thr_hi) && abs_gt_hi(Km, thr_hi));
-#if PB_QUADRATIC
-        // four 2-instruction reciprocals (8 FP64-pipe instructions + 4 MUFU) instead of the merged form below (12 + 1 MUFU)
-        const T J1ks = (d.e1 - tss) * rcp_k(km);
-        const T J1ko = (d.e1 - too) * rcp_k(Km);
-        sail_couple(rho, tau, rs, d, g, J1ks, J1ko, rcp_k(kp), rcp_k(Kp), need, o);
+#if PB_QUADRATIC || PB_UNMERGE
+        // four 2-instruction reciprocals (8 FP64-pipe instructions + 4 MUFU) instead of the merged form below (11 + 1 MUFU):
+        // measured SLOWER (round 2b) -- the three extra SFU instructions cost more than the three FP64 instructions saved
+        const T J1ks = (d.e1 - tss) * rcp_b(km);
+        const T J1ko = (d.e1 - too) * rcp_b(Km);
+        sail_couple(rho, tau, rs, d, g, J1ks, J1ko, rcp_b(kp), rcp_b(Kp), need, o);
 #else
         // ... and both of those from one reciprocal of (k-m)(k+m)(K-m)(K+m)
+        // all four reciprocals only scale their numerators (the difference e1 - tss is not touched): benign
         const T pk = km * kp, pK = Km * Kp;
-        const T rr = rcp(pk * pK);
+        const T rr = rcp_b(pk * pK);
         const T ik = rr * pK, iK = rr * pk;
         const T J1ks = (d.e1 - tss) * (ik * kp);
         const T J1ko = (d.e1 - too) * (iK * Kp);
@@ -866,8 +889,8 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     const int tslot = gw - range * a.ngroups;
     const bool live = range < a.nranges;
     const int grp = !live ? 0 : (a.only_active_tiles ? a.win->active_group[NU - 2][tslot] : tslot);
-    const int band0 = grp * (32 * NU) + lane;      // this thread's bands: band0 + 32 u
-    const bool tail = (grp + 1) * (32 * NU) > NB;    // warp-uniform
+    const int band0 = grp * (32 * NU) + lane;      // this thread's bands (packed map: lanes): band0 + 32 u
+    const bool tail = !a.packed && (grp + 1) * (32 * NU) > NB;    // warp-uniform; the packed map has no out-of-range stores (no planes)
     Stage<T>* const stage = sm.stage[warp];
     uint64_t* const bar = sm.bar[warp];
 
@@ -894,7 +917,8 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     constexpr int KS = CF::KSTRIDE;
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
-        const T* bc = a.bandc + (live ? band0 + 32 * u : 0);          // NBP = 66 * 32: always in range
+        const int lane_u = live ? band0 + 32 * u : 0;                 // NBP = 66 * 32: always in range
+        const T* bc = a.bandc + (a.packed ? a.win->band[lane_u] : lane_u);   // packed map: gather through the lane -> wavelength list
         T* k = sm.kc + threadIdx.x * NU + u;                          // only this thread reads these back: no barrier needed
         k[KC_KAB * KS] = bc[C_KAB * NBP]; k[KC_KXC * KS] = bc[C_KXC * NBP]; k[KC_KAN * KS] = bc[C_KAN * NBP];
         k[KC_KBR * KS] = bc[C_KBR * NBP]; k[KC_KW * KS] = bc[C_KW * NBP]; k[KC_KM * KS] = bc[C_KM * NBP];

@@ -56,6 +56,7 @@ class PinnedPool(object):
     """Page-locked host arrays (cudaHostAlloc) exposed as numpy arrays; freed when the last view dies."""
 
     SMALL = 1 << 20      # below this a pageable numpy array is cheaper than cudaHostAlloc
+    MAX_PINNED = 8 << 30  # one request above this is not page-locked (a 1e5-set SAIL call with all planes asks for ~20 GB)
 
     @staticmethod
     def empty(shape, dtype=_f64, force=False):
@@ -65,7 +66,10 @@ class PinnedPool(object):
             return np.empty(shape, dtype=dtype)
         lib = capi.load()
         p = C.c_void_p()
-        capi.check(lib.prosail_host_alloc(nbytes, C.byref(p)))
+        if nbytes > PinnedPool.MAX_PINNED or lib.prosail_host_alloc(nbytes, C.byref(p)) != 0 or not p.value:
+            if force:
+                raise capi.ProsailError(-1, "cudaHostAlloc of %d bytes failed: %s" % (nbytes, (lib.prosail_last_error() or b"").decode("utf-8", "replace")))
+            return np.empty(shape, dtype=dtype)         # pageable memory: slower copies, same results
         buf = (C.c_char * nbytes).from_address(p.value)
         weakref.finalize(buf, lib.prosail_host_free, C.c_void_p(p.value))
         return np.frombuffer(buf, dtype=dtype).reshape(shape)
@@ -104,6 +108,23 @@ class DeviceArray(object):
         capi.check(self.engine.lib.prosail_memcpy_d2h(self.engine.h, _ptr(out), C.c_void_p(self.ptr), self.nbytes, stream))
         self.engine.sync(stream)
         return out
+
+    def download_rows(self, row0, nrows, stream=None):
+        """Rows [row0, row0 + nrows) of a 2-D (or higher) buffer as a host array (one D2H copy of just those rows)."""
+        row0, nrows = int(row0), int(nrows)
+        if not (0 <= row0 and row0 + nrows <= self.shape[0]):
+            raise IndexError("rows %d..%d outside a buffer of %d rows" % (row0, row0 + nrows, self.shape[0]))
+        out = np.empty((nrows,) + self.shape[1:], dtype=self.dtype)
+        rowbytes = self.nbytes // max(self.shape[0], 1)
+        if nrows:
+            capi.check(self.engine.lib.prosail_memcpy_d2h(self.engine.h, _ptr(out), C.c_void_p(self.ptr + row0 * rowbytes), nrows * rowbytes, stream))
+            self.engine.sync(stream)
+        return out
+
+    @property
+    def __cuda_array_interface__(self):
+        """Zero-copy hand-over to torch / cupy (torch.as_tensor(buf, device='cuda')): the optional torch plumbing of lut / bench."""
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (int(self.ptr), False), "version": 2, "strides": None}
 
     def free(self):
         self._fin()

@@ -201,8 +201,14 @@ class BandLutInverter(object):
         """k best entries of THIS rank's shard: (global index [Q, k], cost [Q, k], {parameter name: [Q, k] values});
         fold several ranks with :func:`reduce_topk`."""
         obs = _f32c(observations)
+        if obs.ndim != 2 or obs.shape[1] != self.n_feat:
+            raise ValueError("observations must be [Q, %d]" % self.n_feat)
         eng = self.engine
         q = obs.shape[0]
+        if q == 0 or self.n_local == 0:          # empty shard (world > LUT rows) or nothing to invert: padded result, like invert_local
+            idx = np.full((q, int(k)), -1, dtype=np.int64)
+            cost = np.full((q, int(k)), np.inf, dtype=np.float32)
+            return idx, cost, {kk: np.full((q, int(k)), np.nan) for kk in self.params}
         with eng._lock:
             d_obs = eng.empty(obs.shape, np.float32).upload(obs)
             d_idx, d_cost = eng.empty((q, int(k)), np.int64), eng.empty((q, int(k)), np.float32)

@@ -90,8 +90,12 @@ def generate_band_lut(engine, params, geometry_deg, version='5', lidf_type='camp
     local, span = shard(params, rank, world)
     k = Kernel(*geometry_deg)
     planes = tuple(capi.PLANE_NAMES.index(p) for p in products)
+    if len(set(planes)) != len(planes):
+        raise ValueError("products must not repeat: %r" % (products,))
     res = engine.prosail(local["N"], local["Cab"], local["Cxc"], local["Cbr"], local["Cw"], local["Cm"], local["lai"],
                          local["hotspot"], k.iza, k.vza, k.raa, local["soil_reflectance"], local["soil_moisture"],
                          Can=local.get("Can"), version=version, lidf_type=lidf_type, a=local["lidf_a"], b=local.get("lidf_b", 0.0),
                          planes=() if windows_only else planes, mean_planes=planes, windows_only=windows_only, dtype=dtype)
-    return res["means"], span
+    # the kernel emits the mean planes in plane-id order; hand them back in the order of `products`
+    order = np.argsort(np.argsort(planes))
+    return np.ascontiguousarray(res["means"][..., order, :]), span

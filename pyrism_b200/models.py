@@ -66,13 +66,17 @@ class _SpectralModel(object):
                 delattr(self, item)
 
     def _with_windows(self, windows, fn):
+        """Run `fn` with the engine's window list swapped for `windows`.  The whole swap -> launch -> restore sequence holds
+        the engine's (re-entrant) lock, so a model constructed on another thread in between can never see the temporary
+        one-window map (it waits for the restore)."""
         eng = self._engine
-        old, old_w = eng.windows, eng._weights
-        try:
-            eng.set_windows(windows)
-            return fn()
-        finally:
-            eng.set_windows(old, old_w)
+        with eng._lock:
+            old, old_w = eng.windows, eng._weights
+            try:
+                eng.set_windows(windows)
+                return fn()
+            finally:
+                eng.set_windows(old, old_w)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -57,9 +57,12 @@ def test_tau_against_mpmath(engine):
     mp.mp.dps = 40
     want = np.array([float((1 - mp.mpf(float(v))) * mp.exp(-mp.mpf(float(v))) + mp.mpf(float(v)) ** 2 * mp.e1(mp.mpf(float(v)))) for v in k])
     got = engine.test_math(5, k)
-    assert np.max(np.abs(got - want)) < 1e-15
+    # round 2 error budget (csrc/math64.cuh, TauRow): the terms of degree >= 4 of the piecewise polynomial are evaluated in
+    # float -- |c4| <= 1.7e-6 times a few float roundings (6e-8 each) = a few 1e-13 absolute, and the same RELATIVE to the row's
+    # own magnitude (the coefficients of a row scale with tau), against a parity bar of 1e-9 on reflectance / transmittance
+    assert np.max(np.abs(got - want)) < 5e-13
     inside = k < 64
-    assert rel(got[inside], want[inside]) < 1e-12
+    assert rel(got[inside], want[inside]) < 2e-11
     # outside the tabulated range
     assert np.array_equal(engine.test_math(5, np.array([0.0, -3.0])), [1.0, 1.0])          # k <= 0 -> tau = 1
     big = np.array([64.0, 80.0, 200.0, 700.0])
@@ -73,7 +76,7 @@ def test_tau_against_scipy_expi(engine):
     from scipy.special import expi
     k = 10.0 ** rng.uniform(-6, 1.7, 20000)
     want = (1 - k) * np.exp(-k) + k ** 2 * (-expi(-k))
-    assert np.max(np.abs(engine.test_math(5, k) - want)) < 2e-15
+    assert np.max(np.abs(engine.test_math(5, k) - want)) < 5e-13      # fp32 tail of the polynomial, see test_tau_against_mpmath
 
 
 def test_table_free_tau_against_mpmath(engine):

@@ -278,7 +278,9 @@ def test_specialised_kernels_agree_bitwise_with_the_general_one(engine):
     assert np.array_equal(brf['rsot'], four['rsot']) and np.array_equal(brf['rsot'], gen['rsot'])
     for k in ('rddt', 'rsdt', 'rdot'):
         assert np.array_equal(four[k], gen[k])
-    assert np.array_equal(wo['means'], gen['means'])
+    # the band-mean-only launch runs on the PACKED window map (only in-window wavelengths exist, 32-lane tiles of that list):
+    # same values, summed in a different grouping -- equal to rounding, not bitwise
+    assert np.max(np.abs(wo['means'] - gen['means'])) <= 1e-15
     # band means = plain inclusive means of the spectrum (models.py:811-851)
     for w, (lo, hi) in enumerate(engine.windows):
         assert np.max(np.abs(gen['means'][:, 0, 0, w] - brf['rsot'][:, 0, lo - 400:hi - 400 + 1].mean(axis=1))) <= 1e-14
