@@ -72,16 +72,13 @@ __device__ __forceinline__ float expm1_over_x(float x) {
 // the float bits.  The kernel forms 1 - tau = k g(k) (relative error ~1e-7) and tau = 1 - k g(k).
 __device__ __forceinline__ float tau_fast(float k, const float* __restrict__ tab, bool& rare) {
     const int bits = __float_as_int(k);
-    const int E0 = (bits >> 23) - 127;
-    const int E = min(max(E0, TAU_EMIN), TAU_EMAX);
-    rare = E != E0;
-    const int e1 = max(E, 1);
-    const int j = (bits & 0x007FFFFF) >> (24 - TAU_SB - e1);
-    const int idx = (TAU_NA - (1 << TAU_SB)) + j + (E <= 0 ? (E << TAU_SB) : ((1 << (TAU_SB - 1)) << E));
-    const float S = __int_as_float((128 + TAU_SB - min(E, 1)) << 23);   // 2^(TAU_SB + 1 - min(E, 1))
+    const int raw = (bits >> (23 - TAU_SB)) - ((127 + TAU_EMIN) << TAU_SB);
+    const int idx = min(max(raw, 0), TAU_NROWS - 1);
+    rare = idx != raw;
+    const float mm = __int_as_float((bits & 0x007FFFFF) | ((127 + TAU_SB + 1) << 23));     // mantissa re-scaled to [2^(SB+1), 2^(SB+2))
     const float4* row = reinterpret_cast<const float4*>(tab + idx * TAU_ROW_F);
     const float4 a = row[0], b = row[1];                            // O c0 c1 c2 | c3 c4 c5 pad
-    const float u = fmaf(k, S, -a.x);
+    const float u = mm - a.x;
     float acc = fmaf(u, b.z, b.y);
     acc = fmaf(u, acc, b.x);
     acc = fmaf(u, acc, a.w);

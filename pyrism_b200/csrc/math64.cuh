@@ -219,24 +219,26 @@ __device__ __forceinline__ double exp_neg(double x, const MathTables& mt) { retu
 
 // ---- tau(k) = (1-k) e^-k + k^2 E1(k)   (reference models.py:953-957; tau = 1 for k <= 0) ----
 //
-// Fast path: branch-free table evaluation for k in [2^TAU_EMIN, 2^(TAU_EMAX+1)) = [6.1e-5, 32).  The interval index,
-// the scale S (a power of two) and the row address come from integer operations on the bits of k; the FP64 pipe
-// sees 1 FMA (local variable) + TAU_DEG FMAs (Horner).  Arguments outside the range are clamped to a valid row
+// Fast path: branch-free table evaluation for k in [2^TAU_EMIN, 2^(TAU_EMAX+1)) = [6.1e-5, 32).  The interval index and the
+// re-scaled mantissa come from integer operations on the bits of k; the FP64 pipe sees 1 subtraction (local variable) +
+// TAU_DEG Horner steps (the upper ones on the FP32 pipe, PB_TAU_F32TAIL).  Arguments outside the range are clamped to a valid row
 // (the value is then meaningless) and flagged in `rare`; the caller repairs flagged lanes with tau_rare() after
 // both evaluations of a thread have been issued.
 #if PB_TAU_F32TAIL
+// Interval scheme (tools/gen_math_tables.py): 2^TAU_SB equal sub-intervals of every binade 2^TAU_EMIN .. 2^(TAU_EMAX+1).  The row
+// index is the top 11 + TAU_SB bits of k minus a constant (one shift, one add, one clamp), and the local variable is
+// u = mm - O with mm = the mantissa of k re-scaled to [2^(TAU_SB+1), 2^(TAU_SB+2)) by ONE logic instruction on the high word
+// and O the odd integer stored in the row: a DADD with two register operands (round 1: FMA with a power-of-two scale built
+// from the exponent, three registers, ~20 integer instructions for a two-region index).
 __device__ __forceinline__ double tau_fast(double k, const TauRow* __restrict__ tab, bool& rare) {
     const int hi = __double2hiint(k);
-    const int E0 = (hi >> 20) - 1023;
-    const int E = min(max(E0, TAU_EMIN), TAU_EMAX);
-    rare = E != E0;
-    const int e1 = max(E, 1);                                      // sub-interval bits: TAU_SB below k = 2, E + TAU_SB - 1 above
-    const int j = (hi & 0x000FFFFF) >> (21 - TAU_SB - e1);
-    const int idx = (TAU_NA - (1 << TAU_SB)) + j + (E <= 0 ? (E << TAU_SB) : ((1 << (TAU_SB - 1)) << E));
-    const double S = __hiloint2double((1024 + TAU_SB - min(E, 1)) << 20, 0);   // 2^(TAU_SB + 1 - min(E, 1))
+    const int raw = (hi >> (20 - TAU_SB)) - ((1023 + TAU_EMIN) << TAU_SB);     // negative for k < 2^TAU_EMIN, k <= 0 (sign bit) and NaN payloads
+    const int idx = min(max(raw, 0), TAU_NROWS - 1);
+    rare = idx != raw;
+    const double mm = __hiloint2double((hi & 0x000FFFFF) | ((1023 + TAU_SB + 1) << 20), __double2loint(k));
     const uint4* row = reinterpret_cast<const uint4*>(tab + idx);
     const uint4 q0 = row[0], q3 = row[3], q2 = row[2], q1 = row[1];
-    const double u = fma(k, S, -__hiloint2double((int)q0.y, (int)q0.x));
+    const double u = mm - __hiloint2double((int)q0.y, (int)q0.x);
     const float uf = (float)u;                                     // F2F.F32.F64 (SFU pipe)
     float t = fmaf(uf, __uint_as_float(q3.z), __uint_as_float(q3.y));          // f7 + u f8
     t = fmaf(uf, t, __uint_as_float(q3.x));                        // f6
@@ -250,16 +252,13 @@ __device__ __forceinline__ double tau_fast(double k, const TauRow* __restrict__ 
 #else
 __device__ __forceinline__ double tau_fast(double k, const double* __restrict__ tab, bool& rare) {
     const int hi = __double2hiint(k);
-    const int E0 = (hi >> 20) - 1023;
-    const int E = min(max(E0, TAU_EMIN), TAU_EMAX);
-    rare = E != E0;
-    const int e1 = max(E, 1);                                      // sub-interval bits: TAU_SB below k = 2, E + TAU_SB - 1 above
-    const int j = (hi & 0x000FFFFF) >> (21 - TAU_SB - e1);
-    const int idx = (TAU_NA - (1 << TAU_SB)) + j + (E <= 0 ? (E << TAU_SB) : ((1 << (TAU_SB - 1)) << E));
-    const double S = __hiloint2double((1024 + TAU_SB - min(E, 1)) << 20, 0);   // 2^(TAU_SB + 1 - min(E, 1))
+    const int raw = (hi >> (20 - TAU_SB)) - ((1023 + TAU_EMIN) << TAU_SB);
+    const int idx = min(max(raw, 0), TAU_NROWS - 1);
+    rare = idx != raw;
+    const double mm = __hiloint2double((hi & 0x000FFFFF) | ((1023 + TAU_SB + 1) << 20), __double2loint(k));
     const double2* row = reinterpret_cast<const double2*>(tab + idx * TAU_ROW);
     const double2 c01 = row[0];                                    // O, c0
-    const double u = fma(k, S, -c01.x);
+    const double u = mm - c01.x;
     static_assert(TAU_DEG % 2 == 0, "row layout assumes an even degree (TAU_ROW even)");
 #ifdef PB_TAU_EVENODD
     // even / odd split: two Horner chains in u^2 (depth 7 instead of 10, one extra multiply)

@@ -1047,14 +1047,13 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         nocanopy = hi_word(sr[S_NOCANOPY]) != 0;                 // the flag is 0 or 1: an integer test on its high word, once per set
                         fresh = false;
                     }
-                    if (__builtin_expect(nocanopy, 0)) {                         // lai <= 0: models.py:609-634
-                        emit<PLANES, MEANS, O_RSOT>(e, rs); emit<PLANES, MEANS, O_RDDT>(e, rs);
-                        emit<PLANES, MEANS, O_RSDT>(e, rs); emit<PLANES, MEANS, O_RDOT>(e, rs);
-                        emit_const<PLANES, MEANS, O_RSO>(e, zero_); emit_const<PLANES, MEANS, O_RDD>(e, zero_);
-                        emit_const<PLANES, MEANS, O_TDD>(e, one); emit_const<PLANES, MEANS, O_RSD>(e, zero_);
-                        emit_const<PLANES, MEANS, O_TSD>(e, zero_); emit_const<PLANES, MEANS, O_RDO>(e, zero_);
-                        emit_const<PLANES, MEANS, O_TDO>(e, zero_);
-                    } else {
+                    {
+                        // The canopy stage runs for EVERY item, bare soil (lai <= 0, models.py:609-634) included: with the record of
+                        // such an item (-lai -> 0, tss = too = tsstoo = 1, z = lai sumint = 0, written by the prologue) every formula
+                        // stays finite and already yields rho_surface to rounding; the exact values of the reference are patched in
+                        // afterwards under a (rare, warp-uniform) branch.  Round 1 branched BEFORE the stage: the compiler hoisted
+                        // directional-stage work above that branch and spilled five doubles per item across it (STL/LDL in the
+                        // item loop of the 168-register instance), and the loop body lost one of its large basic blocks.
                         Canopy<T> o[NU];
                         if constexpr (PACKED) {
                             Canopy<f2> op;
@@ -1081,6 +1080,14 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         }
                         if constexpr (PACKED) {      // the diffuse planes come from the packed state
                             d[0].rdd = dp.rdd.x; d[1].rdd = dp.rdd.y; d[0].tdd = dp.tdd.x; d[1].tdd = dp.tdd.y;
+                        }
+                        if (__builtin_expect(nocanopy, 0)) {                     // lai <= 0: exactly models.py:609-634
+#pragma unroll
+                            for (int u = 0; u < NU; ++u) {
+                                o[u].rsot = o[u].rddt = o[u].rsdt = o[u].rdot = rs[u];
+                                o[u].rso = o[u].rsd = o[u].tsd = o[u].rdo = o[u].tdo = zero_;
+                                d[u].rdd = zero_; d[u].tdd = one;
+                            }
                         }
                         { PB_GATHER(v, o, .rsot); emit<PLANES, MEANS, O_RSOT>(e, v); }
                         { PB_GATHER(v, o, .rddt); emit<PLANES, MEANS, O_RDDT>(e, v); }
@@ -1434,7 +1441,7 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         store_rec<T>(a.grec, item, r);
         if (g == 0) {
             srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
-            srec[S_NEGLAI] = -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;
+            srec[S_NEGLAI] = nocanopy ? 0.0 : -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;   // bare soil: the band kernel's canopy stage runs with lai = 0
             srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
             store_rec<T>(a.srec, s, srec);
         }
@@ -1699,7 +1706,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
     store_rec<T>(a.grec, item, grec);
     if (g == 0) {
         srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
-        srec[S_NEGLAI] = -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;
+        srec[S_NEGLAI] = nocanopy ? 0.0 : -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;   // bare soil: the band kernel's canopy stage runs with lai = 0
         srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
         store_rec<T>(a.srec, s, srec);
     }

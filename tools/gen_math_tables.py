@@ -30,9 +30,8 @@ SB = int(os.environ.get("TAU_SB", "3"))
 EXP2_BITS = int(os.environ.get("EXP2_BITS", "11"))
 EMIN = -14
 EMAX = 4
-NA = (0 - EMIN + 1) * 2 ** SB
-NB = sum(2 ** (E + SB - 1) for E in range(1, EMAX + 1))
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "pyrism_b200", "csrc", "math_tables.inc")
+NROWS = (EMAX - EMIN + 1) * 2 ** SB
+OUT = os.environ.get("MATH_TABLES_OUT") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "pyrism_b200", "csrc", "math_tables.inc")
 
 
 def tau(k):
@@ -41,18 +40,15 @@ def tau(k):
 
 
 def intervals():
-    """(lo, hi, S, O) per interval in table order."""
+    """(lo, hi, S, O) per interval in table order: 2^SB equal sub-intervals of EVERY binade 2^EMIN .. 2^(EMAX+1), so that the
+    row index is just the top 11 + SB bits of k minus a constant and the local variable is the mantissa (scaled to
+    [2^(SB+1), 2^(SB+2))) minus the odd integer O = 2^(SB+1) + 2 j + 1."""
     rows = []
-    for E in range(EMIN, 1):
+    for E in range(EMIN, EMAX + 1):
         for j in range(2 ** SB):
             lo = mp.mpf(2) ** E * (1 + mp.mpf(j) / 2 ** SB)
             w = mp.mpf(2) ** (E - SB)
             rows.append((lo, lo + w, mp.mpf(2) ** (SB + 1 - E), 2 ** (SB + 1) + 2 * j + 1))
-    w = mp.mpf(2) ** (1 - SB)
-    for E in range(1, EMAX + 1):
-        for j in range(2 ** (E + SB - 1)):
-            lo = mp.mpf(2) ** E + j * w
-            rows.append((lo, lo + w, mp.mpf(2) ** SB, 2 ** (E + SB) + 2 * j + 1))
     return rows
 
 
@@ -84,7 +80,7 @@ def cheb_fit_monomial(f, lo, hi, deg):
 
 def main():
     rows = intervals()
-    assert len(rows) == NA + NB
+    assert len(rows) == NROWS
     table = np.zeros((len(rows), DEG + 2))
     worst_abs = worst_rel = 0.0
     rng = np.random.default_rng(1)
@@ -105,8 +101,10 @@ def main():
             worst_abs = max(worst_abs, float(ea))
             worst_rel = max(worst_rel, float(ea / ref))
     print("tau table: degree %d, %d intervals, worst abs err %.3e, worst rel err %.3e" % (DEG, len(rows), worst_abs, worst_rel))
-    if worst_rel > 5e-14:
-        sys.exit("tau table misses the 5e-14 relative target")
+    # what the plate formulas see is the ABSOLUTE error of tau (tau <= 1 enters r, t, Ra, Ta linearly; a tiny tau only yields a
+    # tiny transmittance): the bar is 1e-9 on reflectance / transmittance, the budget of this table 5e-15 absolute
+    if worst_abs > 5e-15 or worst_rel > 1e-7:
+        sys.exit("tau table misses the 5e-15 absolute / 1e-7 relative target")
 
     # float32 table for the fp32 mode: same intervals, degree DEG_F, rows [O, c0..c5, pad], of
     #     g(k) = (1 - tau(k))/k ,   so that   1 - tau = k g(k)   carries a RELATIVE error of ~1e-7.
@@ -145,8 +143,8 @@ def main():
         fh.write("// GENERATED by tools/gen_math_tables.py -- do not edit.\n")
         fh.write("// tau(k) = (1-k)exp(-k) + k^2 E1(k): degree-%d piecewise polynomials; worst abs %.2e, worst rel %.2e (vs mpmath).\n"
                  % (DEG, worst_abs, worst_rel))
-        fh.write("#define TAU_DEG %d\n#define TAU_ROW %d\n#define TAU_NROWS %d\n#define TAU_NA %d\n#define TAU_EMIN (%d)\n#define TAU_EMAX (%d)\n"
-                 "#define TAU_SB %d\n#define EXP2_BITS %d\n" % (DEG, DEG + 2, len(rows), NA, EMIN, EMAX, SB, EXP2_BITS))
+        fh.write("#define TAU_DEG %d\n#define TAU_ROW %d\n#define TAU_NROWS %d\n#define TAU_EMIN (%d)\n#define TAU_EMAX (%d)\n"
+                 "#define TAU_SB %d\n#define EXP2_BITS %d\n" % (DEG, DEG + 2, len(rows), EMIN, EMAX, SB, EXP2_BITS))
         fh.write("static const double h_tau_table[TAU_NROWS * TAU_ROW] = {\n")
         for r in range(len(rows)):
             fh.write("  " + ", ".join(float(v).hex() for v in table[r]) + ",\n")
