@@ -123,8 +123,10 @@ __device__ __forceinline__ double sqrt_q_raw(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double t = x * y;
-    const double e = fma(-t, y, 1.0);
-    return fma(half_of(t), e, t);
+    // e/2 = 1/2 - t (y/2): halving the SEED is one integer instruction on its high word (its low word is the zero the MUFU
+    // result already carries), halving t would need a second register pair
+    const double eh = fma(-t, half_of(y), 0.5);
+    return fma(t, eh, t);
 }
 // ---- round 2: per-site error budget ----
 // The parity bar is 1e-9 absolute; round 1 held every primitive to 4e-16.  A second-order Newton step leaves e^2 ~ 9e-13

@@ -236,6 +236,9 @@ template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS> struct
 #if PB_NU == 2 && !defined(PB_NO_NU3)
 template <> struct CfgFor<double, true, MODE_PROSAIL, 1u << O_RSOT, 0u> { typedef Cfg<3, 12> type; };
 template <> struct CfgFor<double, true, MODE_PROSPECT, (1u << O_LEAF_R) | (1u << O_LEAF_T), 0u> { typedef Cfg<3, 12> type; };
+#ifdef PB_MEANS_NU3
+template <> struct CfgFor<double, true, MODE_PROSAIL, 0u, 1u << O_RSOT> { typedef Cfg<3, 12> type; };   // band-mean LUT on the packed map
+#endif
 #endif
 
 template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS>

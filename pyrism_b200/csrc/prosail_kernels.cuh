@@ -30,6 +30,9 @@ namespace pb {
 #ifndef PB_CHUNK
 #define PB_CHUNK 8
 #endif
+#ifndef PB_KC_THREAD_MAJOR
+#define PB_KC_THREAD_MAJOR 0   /* 1: [thread][plane][u] with 128-bit loads -- measured slower (BRF -0.8%, leaf-only -11%: profiles/r2f_variants.txt) */
+#endif
 #ifndef PB_WARPS
 #define PB_WARPS 16     /* warps per CTA (one CTA per SM); warps are independent (own staging buffers), the CTA only shares the math tables */
 #endif
@@ -48,7 +51,11 @@ struct Cfg {
     static constexpr int NU = NU_;                     // bands per thread: band0 + 32 u
     static constexpr int WARPS = WARPS_;
     static constexpr int THREADS = WARPS_ * 32;
-    static constexpr int KSTRIDE = NU_ * THREADS;      // elements per plane of SailSmem::kc: [thread][u]
+#if PB_KC_THREAD_MAJOR
+    static constexpr int KSTRIDE = NU_;                // SailSmem::kc is [thread][plane][u]: plane stride = NU elements
+#else
+    static constexpr int KSTRIDE = NU_ * THREADS;      // elements per plane of SailSmem::kc: [plane][thread][u]
+#endif
     static constexpr int NGROUPS = NTILES / NU_;       // groups of NU 32-band tiles, one per warp
     static_assert(NTILES % NU_ == 0, "the 66 tiles must split evenly into groups");
 };
@@ -161,11 +168,24 @@ struct alignas(128) Stage {
 template <typename T, int MODE> __host__ __device__ constexpr bool consts_in_smem() { return !std::is_same<T, float>::value && MODE == 0 /* MODE_PROSAIL */; }
 template <typename T, int MODE> __host__ __device__ constexpr int kplanes() { return consts_in_smem<T, MODE>() ? 13 : 8; }
 
+// Thread-major layout of the once-per-item constants (PB_KC_THREAD_MAJOR, default): [thread][plane][u], so that a thread's
+// kplanes x NU values are one contiguous run read with 128-bit loads (two values per LDS: 20 loads instead of 39 per item in
+// the three-band fp64 instance).  The per-thread stride is padded to D = 2 (mod 4) elements: the 8 lanes of a quarter warp
+// then start 4 banks apart (in units of the 16-byte access) and a 128-bit (double) / 64-bit (float) load is conflict free.
+template <typename T, typename CF, int MODE> __host__ __device__ constexpr int kc_col() {
+    int d = kplanes<T, MODE>() * CF::NU;
+    while (d % 4 != 2) ++d;
+    return d;
+}
 template <typename T, typename CF, int MODE>
 struct alignas(128) SailSmem {
     typename Tables<T>::type mt;           // shared by the CTA, read-only after the prologue
     Stage<T> stage[CF::WARPS][2];          // per-warp double-buffered record staging: no CTA-wide barrier in the loop
+#if PB_KC_THREAD_MAJOR
+    T kc[kc_col<T, CF, MODE>() * CF::THREADS];   // [thread][plane][u]
+#else
     T kc[kplanes<T, MODE>() * CF::KSTRIDE];   // [plane][thread][u]: a thread's bands are adjacent (vector loads), lanes consecutive
+#endif
     uint64_t bar[CF::WARPS][2];
 };
 
@@ -771,27 +791,33 @@ __device__ __forceinline__ void mean_partials_inl(const WindowMap* __restrict__ 
         if (lane == 0) dst[slot] = sum;
     }
 }
-// The specialised band-mean instances (compile-time mean mask, plain boxcar windows): the window segments of the thread's two
-// tiles are reduced two at a time -- slot j of tile 0 and slot j of tile 1 in two interleaved butterflies, so that the shuffle
-// latency of one hides behind the other.  Unused slot entries of the map have an empty mask (their sum is discarded).
-template <typename T>
-__device__ __forceinline__ void mean_partials2_inl(const WindowMap* __restrict__ win, T v0, T v1, int tile0, int lane, T* __restrict__ dst,
+// The specialised band-mean instances (compile-time mean mask, plain boxcar windows): the window segments of the thread's NU
+// tiles are reduced NU at a time -- slot j of every tile in interleaved butterflies, so that the shuffle latency of one hides
+// behind the others.  Unused slot entries of the map have an empty mask (their sum is discarded).
+template <int NU, typename T>
+__device__ __forceinline__ void mean_partialsN_inl(const WindowMap* __restrict__ win, const T (&vin)[NU], int tile0, int lane, T* __restrict__ dst,
                                                    bool f32) {
-    if (!is_f32<T>() && f32) { v0 = (T)(float)v0; v1 = (T)(float)v1; }
-    const int tile1 = tile0 + 1;
-    const int ns0 = win->nslots[tile0], ns1 = win->nslots[tile1];
-    const int n = max(ns0, ns1);
+    T v[NU];
+    int ns[NU], n = 0;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        v[u] = (!is_f32<T>() && f32) ? (T)(float)vin[u] : vin[u];
+        ns[u] = win->nslots[tile0 + u];
+        n = max(n, ns[u]);
+    }
     for (int j = 0; j < n; ++j) {
-        T x0 = ((win->mask[tile0][j] >> lane) & 1u) ? v0 : T(0);
-        T x1 = ((win->mask[tile1][j] >> lane) & 1u) ? v1 : T(0);
+        T x[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) x[u] = ((win->mask[tile0 + u][j] >> lane) & 1u) ? v[u] : T(0);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            x0 += __shfl_xor_sync(0xffffffffu, x0, o);
-            x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+#pragma unroll
+            for (int u = 0; u < NU; ++u) x[u] += __shfl_xor_sync(0xffffffffu, x[u], o);
         }
         if (lane == 0) {
-            if (j < ns0) dst[win->slot[tile0][j]] = x0;
-            if (j < ns1) dst[win->slot[tile1][j]] = x1;
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                if (j < ns[u]) dst[win->slot[tile0 + u][j]] = x[u];
         }
     }
 }
@@ -840,8 +866,8 @@ __device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
                 if (!e.tail || e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
         }
         if ((MEANS >> PLANE) & 1u) {       // specialised instances: never launched with spectral-response weights (dispatch_bands)
-            if constexpr (NU == 2 && !is_f32<T>()) {      // double: two interleaved butterflies (+6%); float: the per-tile loop is faster (issue-bound)
-                mean_partials2_inl(e.a.win, v[0], v[1], e.tile0, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+            if constexpr (!is_f32<T>()) {      // double: NU interleaved butterflies (+6%); float: the per-tile loop is faster (issue-bound)
+                mean_partialsN_inl<NU>(e.a.win, v, e.tile0, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
             } else {
 #pragma unroll
                 for (int u = 0; u < NU; ++u) mean_partials_inl(e.a.win, (const double*)nullptr, v[u], e.tile0 + u, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
@@ -913,13 +939,18 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     BandConst<T> c[NU];
     // fused fp64 instances keep the interface constants in shared memory (register pressure); everything else in registers
     constexpr bool CSMEM = consts_in_smem<T, MODE>();
-    const T* kc = sm.kc + threadIdx.x * NU;        // this thread's NU adjacent columns of the once-per-item constants
+#if PB_KC_THREAD_MAJOR
+    constexpr int KCOL = kc_col<T, CF, MODE>();
+#else
+    constexpr int KCOL = NU;
+#endif
+    const T* kc = sm.kc + threadIdx.x * KCOL;      // this thread's block (thread-major) / NU adjacent columns of the once-per-item constants
     constexpr int KS = CF::KSTRIDE;
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         const int lane_u = live ? band0 + 32 * u : 0;                 // NBP = 66 * 32: always in range
         const T* bc = a.bandc + (a.packed ? a.win->band[lane_u] : lane_u);   // packed map: gather through the lane -> wavelength list
-        T* k = sm.kc + threadIdx.x * NU + u;                          // only this thread reads these back: no barrier needed
+        T* k = sm.kc + threadIdx.x * KCOL + u;                        // only this thread reads these back: no barrier needed
         k[KC_KAB * KS] = bc[C_KAB * NBP]; k[KC_KXC * KS] = bc[C_KXC * NBP]; k[KC_KAN * KS] = bc[C_KAN * NBP];
         k[KC_KBR * KS] = bc[C_KBR * NBP]; k[KC_KW * KS] = bc[C_KW * NBP]; k[KC_KM * KS] = bc[C_KM * NBP];
         k[KC_RS1 * KS] = bc[C_RS1 * NBP]; k[KC_RS2 * KS] = bc[C_RS2 * NBP];
