@@ -794,30 +794,49 @@ __device__ __forceinline__ void mean_partials_inl(const WindowMap* __restrict__ 
 // The specialised band-mean instances (compile-time mean mask, plain boxcar windows): the window segments of the thread's NU
 // tiles are reduced NU at a time -- slot j of every tile in interleaved butterflies, so that the shuffle latency of one hides
 // behind the others.  Unused slot entries of the map have an empty mask (their sum is discarded).
-template <int NU, typename T>
-__device__ __forceinline__ void mean_partialsN_inl(const WindowMap* __restrict__ win, const T (&vin)[NU], int tile0, int lane, T* __restrict__ dst,
-                                                   bool f32) {
-    T v[NU];
-    int ns[NU], n = 0;
+// What a warp needs of the window map is the same for every item it processes (its tile group is fixed), so it is read ONCE, before
+// the item loop: per tile of the thread, `member` = bit j set when this lane's band lies inside segment j of the tile, `myslot` =
+// the slot id of segment `lane` (lanes 0 .. nslots-1; after the xor butterfly every lane holds the sum, so lane j stores segment j),
+// `nmax` = most segments of any of the NU tiles.  No global-memory reads of the map inside the item loop.
+template <int NU>
+struct MeanPlan {
+    unsigned member[NU];
+    int myslot[NU];
+    int nmax;
+};
+template <int NU>
+__device__ __forceinline__ void mean_plan_init(const WindowMap* __restrict__ win, int tile0, int lane, MeanPlan<NU>& p) {
+    p.nmax = 0;
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
-        v[u] = (!is_f32<T>() && f32) ? (T)(float)vin[u] : vin[u];
-        ns[u] = win->nslots[tile0 + u];
-        n = max(n, ns[u]);
+        const int ns = win->nslots[tile0 + u];
+        unsigned m = 0;
+        for (int j = 0; j < ns; ++j) m |= ((win->mask[tile0 + u][j] >> lane) & 1u) << j;
+        p.member[u] = m;
+        p.myslot[u] = lane < ns ? win->slot[tile0 + u][lane] : -1;
+        p.nmax = max(p.nmax, ns);
     }
-    for (int j = 0; j < n; ++j) {
+}
+template <int NU, typename T>
+__device__ __forceinline__ void mean_partialsN_inl(const MeanPlan<NU>& p, const T (&vin)[NU], int lane, T* __restrict__ dst, bool f32) {
+    T v[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) v[u] = (!is_f32<T>() && f32) ? (T)(float)vin[u] : vin[u];
+    for (int j = 0; j < p.nmax; ++j) {
         T x[NU];
 #pragma unroll
-        for (int u = 0; u < NU; ++u) x[u] = ((win->mask[tile0 + u][j] >> lane) & 1u) ? v[u] : T(0);
+        for (int u = 0; u < NU; ++u) x[u] = ((p.member[u] >> j) & 1u) ? v[u] : T(0);
+#ifndef PB_MEANS_NOREDUCE      /* timing experiment only: what the kernel costs WITHOUT the butterflies (results are wrong) */
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
             for (int u = 0; u < NU; ++u) x[u] += __shfl_xor_sync(0xffffffffu, x[u], o);
         }
-        if (lane == 0) {
+#endif
+        if (lane == j) {
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-                if (j < ns[u]) dst[win->slot[tile0 + u][j]] = x[u];
+                if (p.myslot[u] >= 0) dst[p.myslot[u]] = x[u];
         }
     }
 }
@@ -844,6 +863,7 @@ struct EmitCtx {
     long long orow;      // item * pitch + band[0]   (band[u] = band[0] + 32 u)
     T* pdst;             // partial sums of this item
     int mi;              // running index of the mean plane
+    MeanPlan<NU> plan;   // this warp's share of the window map (specialised band-mean instances)
 };
 
 template <unsigned PLANES, unsigned MEANS, int PLANE, typename T, int NU>
@@ -867,7 +887,7 @@ __device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
         }
         if ((MEANS >> PLANE) & 1u) {       // specialised instances: never launched with spectral-response weights (dispatch_bands)
             if constexpr (!is_f32<T>()) {      // double: NU interleaved butterflies (+6%); float: the per-tile loop is faster (issue-bound)
-                mean_partialsN_inl<NU>(e.a.win, v, e.tile0, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+                mean_partialsN_inl<NU>(e.plan, v, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
             } else {
 #pragma unroll
                 for (int u = 0; u < NU; ++u) mean_partials_inl(e.a.win, (const double*)nullptr, v[u], e.tile0 + u, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
@@ -979,6 +999,9 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     const int nt = ANY_MEANS ? a.win->ntotal : 0;
     const int nmean = ANY_MEANS ? a.nmean : 0;
 
+    MeanPlan<NU> plan{};
+    if constexpr (PLANES != RUNTIME && MEANS != 0 && !is_f32<T>()) mean_plan_init<NU>(a.win, NU * grp, lane, plan);
+
     for (unsigned it = 0; chunk < nchunks; chunk += a.nranges, ++it) {
         const int buf = it & 1;
         const long long next = chunk + a.nranges;
@@ -1004,7 +1027,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             bool nocanopy = false;
             const T* sr = stage[buf].s;
             const T* gr = stage[buf].g;
-            EmitCtx<T, NU> e{a, tail, {}, NU * grp, lane, nt, i0 * a.out_pitch + band0, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0};
+            EmitCtx<T, NU> e{a, tail, {}, NU * grp, lane, nt, i0 * a.out_pitch + band0, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0, plan};
 #pragma unroll
             for (int u = 0; u < NU; ++u)      // only the last tile group has bands >= 2101: there the answer depends on the lane alone
                 e.valid[u] = !tail || lane < NB - (NTILES / NU - 1) * (32 * NU) - 32 * u;

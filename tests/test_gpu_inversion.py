@@ -132,3 +132,25 @@ def test_topk_shard_fold_and_band_lut_inverter(engine):
     assert np.array_equal(i2[:, 0], pick) and np.all(c2[:, 0] == 0) and best["lai"].shape == (50, 4) and np.allclose(best["lai"][:, 0], P["lai"][pick])
     with pytest.raises(pb._capi.ProsailError):
         inversion.invert_topk(engine, lutf, obs, 17)
+
+
+def test_inversion_pinned_to_float64_brute_force_on_reference_spectra(engine):
+    """The GPU inversion against an INDEPENDENT float64 arg-min on a LUT made of live-reference spectra
+    (tests/golden/inversion_lut.npz, generated by tests/golden/make_inversion_golden.py): same indices, costs within float32
+    rounding.  Then the same with the LUT regenerated on the GPU from the stored parameter sets: the GPU's band means agree with the
+    reference's to <= 1e-9 and the inversion picks the same entries."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inversion_lut.npz"))
+    lut32, obs32 = g["lut"].astype(np.float32), g["obs"].astype(np.float32)
+    idx, cost = inversion.invert(engine, lut32, obs32)
+    assert np.array_equal(idx, g["best"])
+    assert np.allclose(cost, g["cost"], rtol=2e-4, atol=1e-12)
+    idx5, cost5 = inversion.invert_topk(engine, lut32, obs32, 5)
+    srt = np.argsort(((g["obs"][:, None, :] - g["lut"][None, :, :]) ** 2).sum(axis=2), axis=1, kind="stable")[:, :5]
+    assert np.array_equal(idx5[:, 0], g["best"]) and np.mean(idx5 == srt) > 0.99     # deeper ranks may tie within float32 rounding
+    P = g["params"]
+    m = engine.prosail(P[:, 0], P[:, 1], P[:, 2], P[:, 3], P[:, 4], P[:, 5], P[:, 6], P[:, 7], np.radians([35.0]), np.radians([30.0]), np.radians([50.0]),
+                       P[:, 9], P[:, 10], lidf_type='campbell', a=P[:, 8], planes=(), mean_planes=(pb._capi.O_RSOT,), windows_only=True)['means'][:, 0, 0]
+    assert np.max(np.abs(m - g["lut"])) <= 1e-9
+    idx2, _ = inversion.invert(engine, m.astype(np.float32), obs32)
+    assert np.array_equal(idx2, g["best"])

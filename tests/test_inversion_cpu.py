@@ -97,3 +97,18 @@ def test_invert_sharded_over_gloo_world_size_2(tmp_path):
     z = np.load(out)
     ref_idx, ref_cost = inv.invert(lutf, obs)
     assert np.array_equal(z["idx"], ref_idx) and np.array_equal(z["cost"], ref_cost)
+
+
+def test_contract_oracle_agrees_with_float64_brute_force_on_reference_spectra():
+    """Pin of the inversion to reference DATA: tests/golden/inversion_lut.npz holds a 600-entry band-mean LUT and 100 observations
+    made from spectra of the live reference, with the arg-min of an independent float64 brute-force search
+    (tests/golden/make_inversion_golden.py).  Every margin between best and second-best cost is > 2e-3 relative, far above float32
+    rounding, so the float32 contract must pick exactly the float64 minimiser."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inversion_lut.npz"))
+    assert np.min(g["margin"] / (g["cost"] + g["margin"])) > 1e-3
+    idx, cost = inv.invert(g["lut"].astype(np.float32), g["obs"].astype(np.float32))
+    assert np.array_equal(idx, g["best"])
+    assert np.allclose(cost, g["cost"], rtol=2e-4, atol=1e-12)
+    assert np.array_equal(g["best"][50:], g["noisy_rows"])                  # the noisy LUT rows are recovered
+    assert np.all(inv.is_optimal(g["lut"], g["obs"], idx))
