@@ -774,6 +774,7 @@ static int set_windows_impl(prosail_handle_t* h, int n_windows, const int* lo_nm
     }
     m.wstart[n_windows] = slot;
     m.ntotal = slot;
+    for (int w = 0; w < n_windows; ++w) m.wend[w] = m.wstart[w + 1];
     for (int t = 0; t < NTILES; ++t)
         if (touched[t]) m.active_tile[m.ntiles_active++] = t;
     for (int nu = 2; nu <= 3; ++nu)          // groups of nu tiles touched by a window (the windows-only kernels visit only those)
@@ -797,25 +798,34 @@ static int set_windows_impl(prosail_handle_t* h, int n_windows, const int* lo_nm
         mp.nbands_packed = np;
         mp.nwindows = n_windows;
         const int ptiles = (np + 31) / 32;
-        int pslot = 0;
         have_packed = true;
-        for (int w = 0; w < n_windows && have_packed; ++w) {
-            const int lo = pidx[std::max(lo_nm[w], 400) - 400], hi = pidx[std::min(hi_nm[w], 2500) - 400];   // a window is a run of lanes
-            mp.wstart[w] = pslot;
-            mp.wcount[w] = m.wcount[w];
-            mp.wsum[w] = m.wsum[w];
-            for (int t = lo / 32; t <= hi / 32; ++t) {
-                if (mp.nslots[t] >= MAX_TILE_SLOTS || pslot >= MAX_SLOTS) { have_packed = false; break; }   // fall back to the unpacked map
-                unsigned mask = 0;
-                for (int l = 0; l < 32; ++l)
-                    if (t * 32 + l >= lo && t * 32 + l <= hi) mask |= 1u << l;
-                mp.mask[t][mp.nslots[t]] = mask;
-                mp.slot[t][mp.nslots[t]] = pslot++;
+        // pieces: cut the lane axis at every window edge and every tile edge
+        std::vector<char> cut((size_t)np + 1, 0);
+        for (int w = 0; w < n_windows; ++w) {
+            cut[pidx[std::max(lo_nm[w], 400) - 400]] = 1;
+            cut[pidx[std::min(hi_nm[w], 2500) - 400] + 1] = 1;
+        }
+        for (int l = 0; l < NBP; ++l) mp.piece[l] = -1;
+        int pid = -1;
+        for (int l = 0; l < np && have_packed; ++l) {
+            const int t = l / 32;
+            if (cut[l] || l % 32 == 0) {
+                ++pid;
+                if (pid >= MAX_SLOTS || mp.nslots[t] >= MAX_TILE_SLOTS) { have_packed = false; break; }   // fall back to the unpacked map
+                mp.slot[t][mp.nslots[t]] = pid;
                 mp.nslots[t]++;
             }
+            mp.piece[l] = pid;
+            mp.mask[t][mp.nslots[t] - 1] |= 1u << (l % 32);
         }
-        mp.wstart[n_windows] = pslot;
-        mp.ntotal = pslot;
+        for (int w = 0; w < n_windows && have_packed; ++w) {
+            mp.wstart[w] = mp.piece[pidx[std::max(lo_nm[w], 400) - 400]];
+            mp.wend[w] = mp.piece[pidx[std::min(hi_nm[w], 2500) - 400]] + 1;
+            mp.wcount[w] = m.wcount[w];
+            mp.wsum[w] = m.wsum[w];
+        }
+        mp.wstart[n_windows] = pid + 1;
+        mp.ntotal = pid + 1;
         mp.ntiles_active = ptiles;
         for (int t = 0; t < ptiles; ++t) mp.active_tile[t] = t;
         for (int nu = 2; nu <= 3; ++nu) {

@@ -98,9 +98,15 @@ struct WindowMap {                       // which band-mean windows touch which 
     // (25 tiles instead of the 38 tiles = 19 two-tile groups the unpacked map touches).  A window is still a run of
     // consecutive lanes (the list is sorted), so the segmented warp reduction is unchanged; `band` maps a packed lane back to
     // its wavelength index for the gather of the per-band constants (lanes past `nbands_packed`: band 0, in no mask).
+    // In the packed map the slots are PIECES: maximal runs of consecutive lanes of one tile that belong to the same set of
+    // windows (cut at every window edge and every tile edge).  Pieces are disjoint, so ONE segmented warp scan per tile yields
+    // all of its piece sums (5 shuffle + add steps, however many windows overlap there), and a window is the run of pieces
+    // [wstart[w], wend[w]) -- runs of different windows overlap where the windows do.
     int packed;                              // 1: tiles / masks / slots of this map are in packed-lane space
     int nbands_packed;
+    int wend[MAX_WINDOWS];                   // one past the last slot of window w (unpacked map: wstart[w + 1])
     int band[NBP];
+    int piece[NBP];                          // packed map: slot (piece) id of every lane, -1 for the padding lanes
 };
 
 template <typename T>
@@ -559,15 +565,13 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
 #endif
     }
     d.e1 = exp_neg(d.m * s[S_NEGLAI], mt);                            // :637
-    const T e2 = d.e1 * d.e1;
-    const T rinf2 = d.rinf * d.rinf;
     d.re = d.rinf * d.e1;
-    const T omr2 = one - rinf2;
-    const T den = fma(-rinf2, e2, one);
+    const T omr2 = fma(-d.rinf, d.rinf, one);                         // 1 - rinf^2
+    const T den = fma(-d.re, d.re, one);                              // 1 - rinf^2 e^2 = 1 - (rinf e)^2          :642
     if constexpr (is_f32<T>() || !(PB_QUADRATIC || PB_UNMERGE)) {
         // 1/(1 - rinf^2 e^2) (:642) and 1/(1 - rinf^2) (:678) from ONE reciprocal of their product: one MUFU less (an SFU
         // instruction next to a busy FP64 pipe costs about as much as the two multiplications that replace it, and the
-        // unmerged build measured 5% slower: profiles/r2b_variants.txt).  Both results only scale outputs: benign.
+        // unmerged build measured 5% slower: profiles/r2_variants.txt).  Both results only scale outputs: benign.
         const T r = rcp_b(den * omr2);
         d.invden = r * omr2;
         d.inv_omr2 = r * den;
@@ -577,7 +581,7 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
     }
     d.tdd = omr2 * d.e1 * d.invden;                                   // :654
     d.rinf_invden = d.rinf * d.invden;                                // shared by rdd and by T3 of the directional stage
-    d.rdd = d.rinf_invden * (one - e2);                               // :655
+    d.rdd = fma(-d.re, d.e1, d.rinf) * d.invden;                      // rinf (1 - e^2)/den = (rinf - (rinf e) e)/den   :655
     d.rsrdd = rs * d.rdd;
     T dn = one - d.rsrdd;                                             // :714-719
     dn = below_tiny(dn) ? tiny : dn;                                  // dn < 1e-36 (integer-pipe test; negatives too)
@@ -615,14 +619,18 @@ __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>
     o.rsd = fma(-d.re, Pss, Qss) * d.invden;
     o.tdo = tdo_u * d.invden;
     o.rdo = rdo_u * d.invden;
-    const T T1 = (cK * u1) * fma(-J1ks, too, g[G_Z]);                 // v2 g1 u1, g1 = (z - J1(k,m) too)/(K+m)   :668-675
-    const T T2 = (ck * v1) * fma(-J1ko, tss, g[G_Z]);                 // v1 g2 u2
-    const T T3 = fma(rdo_u, Qss, tdo_u * Pss) * d.rinf_invden;        // (rdo Qss + tdo Pss) rinf
-    const T rsod = (T1 + T2 - T3) * d.inv_omr2;                       // :678
-    o.rso = fma(w, g[G_LAISUM], rsod);                                // :706, :710
-    // soil coupling                                                                        :721-726
-    const T rsodt = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too) * d.rs_invdn;
-    o.rsot = fma(g[G_TSSTOO], rs, o.rso) + rsodt;
+    // T1 + T2 - T3 as nested FMAs (:668-678):  T1 = v2 g1 u1 with g1 = (z - J1(k,m) too)/(K+m),  T2 = v1 g2 u2,
+    // T3 = (rdo Qss + tdo Pss) rinf
+    const T T3 = fma(rdo_u, Qss, tdo_u * Pss) * d.rinf_invden;
+    const T Ts = fma(cK * u1, fma(-J1ks, too, g[G_Z]), fma(ck * v1, fma(-J1ko, tss, g[G_Z]), -T3));
+    // soil coupling (:721-726): rsodt = ((tss + tsd) tdo + (tsd + tss rs rdd) too) rs/dn
+    const T sc = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too);
+    if (need & (1u << O_RSO)) {
+        o.rso = fma(w, g[G_LAISUM], Ts * d.inv_omr2);                 // rsos + rsod                              :706, :710
+        o.rsot = fma(sc, d.rs_invdn, fma(g[G_TSSTOO], rs, o.rso));
+    } else {                                                          // rsot = rsod + rsos + tsstoo rs + rsodt, one FMA per term
+        o.rsot = fma(sc, d.rs_invdn, fma(Ts, d.inv_omr2, fma(w, g[G_LAISUM], g[G_TSSTOO] * rs)));
+    }
     if (need & (1u << O_RDDT)) o.rddt = fma(d.tdd * d.tdd, d.rs_invdn, d.rdd);
     if (need & (1u << O_RSDT)) o.rsdt = fma((o.tsd + tss) * d.tdd, d.rs_invdn, o.rsd);
     if (need & (1u << O_RDOT)) o.rdot = fma(d.tdd * (o.tdo + too), d.rs_invdn, o.rdo);
@@ -800,13 +808,31 @@ __device__ __forceinline__ void mean_partials_inl(const WindowMap* __restrict__ 
 // `nmax` = most segments of any of the NU tiles.  No global-memory reads of the map inside the item loop.
 template <int NU>
 struct MeanPlan {
-    unsigned member[NU];
-    int myslot[NU];
-    int nmax;
+    unsigned member[NU];   // unpacked map: bit j = this lane lies inside segment j of the tile
+    int myslot[NU];        // unpacked map: slot id of segment `lane`; packed map: slot id of the piece that ENDS at this lane, else -1
+    unsigned same[NU];     // packed map: bit k = lane - 2^k belongs to the same piece as this lane
+    int nmax;              // unpacked map: most segments of any of the NU tiles
 };
 template <int NU>
 __device__ __forceinline__ void mean_plan_init(const WindowMap* __restrict__ win, int tile0, int lane, MeanPlan<NU>& p) {
     p.nmax = 0;
+    if (win->packed) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int mine = win->piece[(tile0 + u) * 32 + lane];
+            unsigned sm = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int other = __shfl_up_sync(0xffffffffu, mine, 1 << k);
+                sm |= (lane >= (1 << k) && other == mine && mine >= 0) ? (1u << k) : 0u;
+            }
+            const int next = __shfl_down_sync(0xffffffffu, mine, 1);
+            p.same[u] = sm;
+            p.myslot[u] = (mine >= 0 && (lane == 31 || next != mine)) ? mine : -1;
+            p.member[u] = 0;
+        }
+        return;
+    }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         const int ns = win->nslots[tile0 + u];
@@ -814,25 +840,41 @@ __device__ __forceinline__ void mean_plan_init(const WindowMap* __restrict__ win
         for (int j = 0; j < ns; ++j) m |= ((win->mask[tile0 + u][j] >> lane) & 1u) << j;
         p.member[u] = m;
         p.myslot[u] = lane < ns ? win->slot[tile0 + u][lane] : -1;
+        p.same[u] = 0;
         p.nmax = max(p.nmax, ns);
     }
 }
 template <int NU, typename T>
-__device__ __forceinline__ void mean_partialsN_inl(const MeanPlan<NU>& p, const T (&vin)[NU], int lane, T* __restrict__ dst, bool f32) {
+__device__ __forceinline__ void mean_partialsN_inl(const MeanPlan<NU>& p, bool packed, const T (&vin)[NU], int lane, T* __restrict__ dst, bool f32) {
     T v[NU];
 #pragma unroll
     for (int u = 0; u < NU; ++u) v[u] = (!is_f32<T>() && f32) ? (T)(float)vin[u] : vin[u];
+    if (packed) {
+        // segmented inclusive scan over the disjoint pieces of each tile: after the five steps the last lane of a piece holds its sum
+#ifndef PB_MEANS_NOREDUCE      /* timing experiment only: what the kernel costs WITHOUT the reduction (results are wrong) */
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const T y = __shfl_up_sync(0xffffffffu, v[u], 1 << k);
+                if ((p.same[u] >> k) & 1u) v[u] += y;
+            }
+        }
+#endif
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+            if (p.myslot[u] >= 0) dst[p.myslot[u]] = v[u];
+        return;
+    }
     for (int j = 0; j < p.nmax; ++j) {
         T x[NU];
 #pragma unroll
         for (int u = 0; u < NU; ++u) x[u] = ((p.member[u] >> j) & 1u) ? v[u] : T(0);
-#ifndef PB_MEANS_NOREDUCE      /* timing experiment only: what the kernel costs WITHOUT the butterflies (results are wrong) */
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
             for (int u = 0; u < NU; ++u) x[u] += __shfl_xor_sync(0xffffffffu, x[u], o);
         }
-#endif
         if (lane == j) {
 #pragma unroll
             for (int u = 0; u < NU; ++u)
@@ -887,7 +929,7 @@ __device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
         }
         if ((MEANS >> PLANE) & 1u) {       // specialised instances: never launched with spectral-response weights (dispatch_bands)
             if constexpr (!is_f32<T>()) {      // double: NU interleaved butterflies (+6%); float: the per-tile loop is faster (issue-bound)
-                mean_partialsN_inl<NU>(e.plan, v, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
+                mean_partialsN_inl<NU>(e.plan, e.a.packed != 0, v, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
             } else {
 #pragma unroll
                 for (int u = 0; u < NU; ++u) mean_partials_inl(e.a.win, (const double*)nullptr, v[u], e.tile0 + u, e.lane, e.pdst + e.mi * e.nt, e.a.f32_means);
@@ -1183,7 +1225,7 @@ __global__ void k_finalize_means(const WindowMap* __restrict__ win, const T* __r
     const long long row = idx / nw;
     const int w = (int)(idx - row * nw);
     double acc = 0.0;
-    for (int sl = win->wstart[w]; sl < win->wstart[w + 1]; ++sl) acc += (double)partial[row * nt + sl];
+    for (int sl = win->wstart[w]; sl < win->wend[w]; ++sl) acc += (double)partial[row * nt + sl];
     const double mean = acc / win->wsum[w];
     if (means) means[idx] = (T)mean;
     if (means_f32) means_f32[idx] = (float)mean;
