@@ -70,7 +70,7 @@ enum { C_KAB = 0, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RS1, 
 // (C_RALF.. = 1 - talf, 1 - t12, 1 - t21: only the float image carries them, rounded once from the float64 values)
 
 // sample record (per parameter set)
-enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DDB, S_DDF, S_NEGLAI, S_LAI, S_NOCANOPY, S_THR };
+enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DDB, S_DDF, S_NEGLAI, S_LAI, S_NOCANOPY, S_THR, S_BF };
 // geometry record (per parameter set x geometry)
 enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_BF, G_SUMINT, G_ALF };
 
@@ -271,12 +271,13 @@ __device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf,
     const T Ra = fma(x, Ta, ralf);
     const T r = fma(x, t, r12);
     // Stokes: D^2 = (1+r+t)(1+r-t)(1-r+t)(1-r-t)                                             :1043
-    const T p = one + r, q = one - r;
-    const T P12 = fma(-t, t, p * p);               // (1+r+t)(1+r-t): >= 1, no cancellation in this form
+    const T q = one - r;
+    const T r2 = r * r;
+    const T A = one + fma(-t, t, r2);              // 1 + r^2 - t^2  (> 0: r^2 - t^2 > -1)
+    const T P12 = fma(T(2), r, A);                 // (1+r+t)(1+r-t) = (1+r)^2 - t^2: >= 1, no cancellation in this form
     const T qmt = q - t;                           // 1 - r - t: <= 0 flags zero absorption
     const T P34 = (q + t) * qmt;                   // the small factor keeps its product form
     const T D = sqrt_b_raw(P12 * P34);             // benign: D is itself the small quantity (a - 1/a = D/r).  P34 <= 0 only when r + t >= 1: that lane is flagged and recomputed
-    const T A = fma(T(-2), r, P12);                // 1 + r^2 - t^2
     const T hD = half_of(D);                       // D / 2 as an exponent decrement (integer pipe); D > 0 on every lane that is kept
     const T al = fma(half, A, hD);                 // a * r   (a of :1046)
     const T be = fma(-half, A, one + hD);          // b * t   (b of :1047), using 1 - r^2 + t^2 = 2 - A
@@ -288,7 +289,6 @@ __device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf,
     //                 X = al^2 bN2 - r^2 - al r^2 (bN2 - 1)      (algebraically :1052-1065, one division)
     //                   = (al^2 - r^2) + (bN2 - 1) al (al - r^2)
     const T bm1 = bN2 - one;
-    const T r2 = r * r;
     const T dal = fma(al, al, -r2);                // al^2 - r^2 = r^2 (a^2 - 1)
     const T X = fma(bm1, al * (al - r2), dal);
     const T TaI = Ta * rcp_b(X);                   // benign: scales kt and ks - Ra
@@ -534,6 +534,8 @@ template <typename T>
 struct Diffuse {
     T m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd, rinf_invden;
     T a1, a2;      // rho + tau rinf, tau + rho rinf: the leaf-dependent factors of (sf + sb rinf), (sf rinf + sb), ... (:649-652)
+                   // fused fp64 instances (AB form): a1 = Ap = (a1 + a2)/2 = (rho + tau)(1 + rinf)/2,  a2 = Am = bf (rho - tau)(1 - rinf)/2,
+                   // so that  sf + sb rinf = k Ap - Am,  sf rinf + sb = k Ap + Am  (and the same with K): one FMA each per geometry
 };
 
 // FROM_LEAF: rho, tau come from the PROSPECT stage of the same kernel.  Then 0 < rho, tau and rho + tau < 1 hold by
@@ -543,6 +545,18 @@ struct Diffuse {
 template <bool FROM_LEAF, typename T, typename MT>
 __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __restrict__ s, const MT& mt, Diffuse<T>& d) {
     const T one = T(1), tiny = T(1e-36);
+    if constexpr (FROM_LEAF && !is_f32<T>()) {
+        // With s = rho + tau, dd = rho - tau and ddb - ddf = bf (:587-588):  sigb = (s + bf dd)/2,  sigf = (s - bf dd)/2,
+        //   att - sigb = 1 - s,   att + sigb = 1 + bf dd   =>   m^2 = att^2 - sigb^2 = (1 - s)(1 + bf dd)   (:590-601, no cancellation)
+        //   rinf = sigb/(att + m) = (s + bf dd) / (2 - (s - bf dd) + 2 m)                                    (:639)
+        const T s_ = rho + tau, dd = rho - tau;
+        const T bd = s[S_BF] * dd;
+        const T oms = one - s_;
+        d.m = sqrt_b_pos(fma(oms, bd, oms));
+        d.rinf = (s_ + bd) * rcp_b(fma(T(2), d.m, T(2) - (s_ - bd)));
+        d.a1 = s_ * fma(T(0.5), d.rinf, T(0.5));                      // Ap
+        d.a2 = bd * fma(T(-0.5), d.rinf, T(0.5));                     // Am
+    } else {
     T sigb = fma(s[S_DDB], rho, s[S_DDF] * tau);                      // :590
     T sigf = fma(s[S_DDF], rho, s[S_DDB] * tau);                      // :591
     if (!FROM_LEAF) {
@@ -563,6 +577,9 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
 #else
         d.rinf = (att - d.m) * rcp_k(sigb);                           // :639
 #endif
+    }
+    d.a1 = fma(tau, d.rinf, rho);
+    d.a2 = fma(rho, d.rinf, tau);
     }
     d.e1 = exp_neg(d.m * s[S_NEGLAI], mt);                            // :637
     d.re = d.rinf * d.e1;
@@ -586,8 +603,6 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
     T dn = one - d.rsrdd;                                             // :714-719
     dn = below_tiny(dn) ? tiny : dn;                                  // dn < 1e-36 (integer-pipe test; negatives too)
     d.rs_invdn = rs * rcp_b(dn);
-    d.a1 = fma(tau, d.rinf, rho);
-    d.a2 = fma(rho, d.rinf, tau);
 }
 
 template <typename T>
@@ -598,7 +613,7 @@ struct Canopy {
 
 // common tail of the directional part once J1(k,m), J1(K,m), 1/(k+m), 1/(K+m) are known
 // (models.py:603-607, 649-678, 706-726)
-template <typename T>
+template <bool AB, typename T>
 __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>& d, const T* __restrict__ g, T J1ks, T J1ko, T inv_kp,
                                             T inv_Kp, unsigned need, Canopy<T>& o) {
     const T one = T(1);
@@ -607,8 +622,14 @@ __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>
     // a1 = rho + tau rinf and a2 = tau + rho rinf (geometry independent, computed once per parameter set):
     //   sf + sb rinf = sdf a1 + sdb a2,   sf rinf + sb = sdf a2 + sdb a1,   and the same with (dof, dob) for the view direction
     const T w = fma(g[G_FS], rho, g[G_FT] * tau);                     // :607
-    const T u1 = fma(g[G_SDF], d.a1, g[G_SDB] * d.a2), u2 = fma(g[G_SDF], d.a2, g[G_SDB] * d.a1);
-    const T v1 = fma(g[G_DOF], d.a1, g[G_DOB] * d.a2), v2 = fma(g[G_DOF], d.a2, g[G_DOB] * d.a1);
+    T u1, u2, v1, v2;
+    if constexpr (AB) {           // d.a1 = Ap, d.a2 = Am (see sail_diffuse): one FMA each
+        u1 = fma(g[G_K], d.a1, -d.a2); u2 = fma(g[G_K], d.a1, d.a2);
+        v1 = fma(g[G_KO], d.a1, -d.a2); v2 = fma(g[G_KO], d.a1, d.a2);
+    } else {
+        u1 = fma(g[G_SDF], d.a1, g[G_SDB] * d.a2); u2 = fma(g[G_SDF], d.a2, g[G_SDB] * d.a1);
+        v1 = fma(g[G_DOF], d.a1, g[G_DOB] * d.a2); v2 = fma(g[G_DOF], d.a2, g[G_DOB] * d.a1);
+    }
     // J2(k,m) = (1 - e1 tss)/(k+m), J2(K,m) = (1 - e1 too)/(K+m) (:646-647) only appear multiplied by u2 resp. v2, and so do the
     // 1/(k+m), 1/(K+m) of g2, g1 (:668-669): ck = u2/(k+m) and cK = v2/(K+m) are formed once
     const T ck = u2 * inv_kp, cK = v2 * inv_Kp;
@@ -641,7 +662,7 @@ __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>
 // caller then re-evaluates that band with sail_directional().
 // float: J1(k,m) = (e^{-m t} - e^{-k t})/(k - m) = e^{-k t} t expm1(d)/d with d = (k - m) t has no cancellation for any d,
 // so there is no series branch and the function never returns true.
-template <typename T>
+template <bool AB, typename T>
 __device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const Diffuse<T>& d, const T* __restrict__ s,
                                                       const T* __restrict__ g, int thr_hi, unsigned need, Canopy<T>& o) {
     const T k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO];
@@ -652,7 +673,7 @@ __device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const 
         const T xk = km * lai, xK = Km * lai;
         const T J1ks = fabsf(xk) < 0.25f ? (tss * lai) * expm1_over_x(xk) : (d.e1 - tss) * rcp(km);
         const T J1ko = fabsf(xK) < 0.25f ? (too * lai) * expm1_over_x(xK) : (d.e1 - too) * rcp(Km);
-        sail_couple(rho, tau, rs, d, g, J1ks, J1ko, rcp(kp), rcp(Kp), need, o);
+        sail_couple<AB>(rho, tau, rs, d, g, J1ks, J1ko, rcp(kp), rcp(Kp), need, o);
         return false;
     } else {
         // 1/(k-m) and 1/(k+m) from ONE reciprocal of (k-m)(k+m)                             :644-647, 765-789
@@ -662,7 +683,7 @@ __device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const 
         // measured SLOWER (round 2b) -- the three extra SFU instructions cost more than the three FP64 instructions saved
         const T J1ks = (d.e1 - tss) * rcp_b(km);
         const T J1ko = (d.e1 - too) * rcp_b(Km);
-        sail_couple(rho, tau, rs, d, g, J1ks, J1ko, rcp_b(kp), rcp_b(Kp), need, o);
+        sail_couple<AB>(rho, tau, rs, d, g, J1ks, J1ko, rcp_b(kp), rcp_b(Kp), need, o);
 #else
         // ... and both of those from one reciprocal of (k-m)(k+m)(K-m)(K+m)
         // all four reciprocals only scale their numerators (the difference e1 - tss is not touched): benign
@@ -671,14 +692,14 @@ __device__ __forceinline__ bool sail_directional_fast(T rho, T tau, T rs, const 
         const T ik = rr * pK, iK = rr * pk;
         const T J1ks = (d.e1 - tss) * (ik * kp);
         const T J1ko = (d.e1 - too) * (iK * Kp);
-        sail_couple(rho, tau, rs, d, g, J1ks, J1ko, ik * km, iK * Km, need, o);
+        sail_couple<AB>(rho, tau, rs, d, g, J1ks, J1ko, ik * km, iK * Km, need, o);
 #endif
         return rare;
     }
 }
 
 // geometry-dependent part of 4SAIL for one band with J1's series branch (models.py:765-785): the repair path (double)
-template <typename T>
+template <bool AB, typename T>
 __device__ __forceinline__ void sail_directional(T rho, T tau, T rs, const Diffuse<T>& d, const T* __restrict__ s,
                                                  const T* __restrict__ g, int thr_hi, unsigned need, Canopy<T>& o) {
     const T k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO], lai = s[S_LAI];
@@ -707,7 +728,7 @@ __device__ __forceinline__ void sail_directional(T rho, T tau, T rs, const Diffu
             J1ko = half * lai * (too + d.e1) * (one - del * del / T(12));
         }
     }
-    sail_couple(rho, tau, rs, d, g, J1ks, J1ko, inv_kp, inv_Kp, need, o);
+    sail_couple<AB>(rho, tau, rs, d, g, J1ks, J1ko, inv_kp, inv_Kp, need, o);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1024,6 +1045,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     }
     // fp32 mode with two bands per thread: the arithmetic of the item loop runs in packed FP32 (FFMA2 ...), both bands per instruction
     constexpr bool PACKED = std::is_same<T, float>::value && NU == 2;
+    constexpr bool AB = MODE == MODE_PROSAIL && !std::is_same<T, float>::value;   // Ap / Am form of the leaf-dependent factors (sail_diffuse)
     BandConst<f2> c2;
     if constexpr (PACKED) {
         c2.talf = F2(c[0].talf, c[1].talf); c2.ralf = F2(c[0].ralf, c[1].ralf); c2.t12 = F2(c[0].t12, c[1].t12);
@@ -1163,14 +1185,14 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
 #pragma unroll
                             for (int u = 0; u < NU; ++u) {
                                 o[u].rddt = o[u].rsdt = o[u].rdot = zero_;
-                                rare[u] = sail_directional_fast(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
+                                rare[u] = sail_directional_fast<AB>(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
                                 any_rare |= rare[u];
                             }
                             if constexpr (!std::is_same<T, float>::value) {
                                 if (__builtin_expect(any_rare, 0)) {
 #pragma unroll
                                     for (int u = 0; u < NU; ++u)
-                                        if (rare[u]) sail_directional(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
+                                        if (rare[u]) sail_directional<AB>(rho[u], tau[u], rs[u], d[u], sr, gr, thr_hi, need, o[u]);
                                 }
                             }
                         }
@@ -1539,6 +1561,7 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
             srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
             srec[S_NEGLAI] = nocanopy ? 0.0 : -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;   // bare soil: the band kernel's canopy stage runs with lai = 0
             srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
+            srec[S_BF] = bf;
             store_rec<T>(a.srec, s, srec);
         }
         if (a.geom_out) {
@@ -1804,6 +1827,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
         srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
         srec[S_NEGLAI] = nocanopy ? 0.0 : -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;   // bare soil: the band kernel's canopy stage runs with lai = 0
         srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
+        srec[S_BF] = bf;
         store_rec<T>(a.srec, s, srec);
     }
     if (a.geom_out) {
