@@ -43,8 +43,8 @@ FLOPS_LEAF, FLOPS_SAIL = 83, 151
 FLOPS_PER_BAND = FLOPS_LEAF + FLOPS_SAIL     # div/sqrt/exp/E1/pow counted as ONE flop each
 BYTES_PER_SPECTRUM = NB * 8     # one fp64 output plane
 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the config-2 kernel, per spectrum
-NCU_DRAM_BYTES_PER_SPECTRUM = (4.361098e9 + 80.665344e6) / 262144
-NCU_DRAM_SOURCE = "profiles/r1k_k_bands_prosail_brf_f64.txt (one ncu capture of 262144 sets, scaled; NOT measured in this run)"
+NCU_DRAM_BYTES_PER_SPECTRUM = (4.364201e9 + 83.544576e6) / 262144
+NCU_DRAM_SOURCE = "profiles/r2d_k_bands_prosail_brf_f64.txt (one ncu --set full capture of 262144 sets, scaled; NOT measured in this run)"
 BASE_SEED = 20261019
 SEED = BASE_SEED + 2            # config index 2
 GEOM_DEG = (35.0, 30.0, 50.0)
@@ -645,6 +645,22 @@ class BandMeanLut(Workload):
         return res
 
 
+def d2h_probe(eng, mib=512, reps=3):
+    """Plain device-to-host copy ceiling of this process (one cudaMemcpyAsync per copy into page-locked memory, through the same
+    C-ABI helper the host API uses): the denominator of the end-to-end figure, measured in the same run.  GB/s."""
+    from pyrism_b200.engine import PinnedPool
+    n = (mib << 20) // 8
+    host = PinnedPool.empty((n,), force=True)
+    dev = eng.empty((n,))
+    dev.download(out=host)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dev.download(out=host)
+    dt = time.perf_counter() - t0
+    dev.free()
+    return n * 8 * reps / dt / 1e9
+
+
 def readme_chain(args):
     """config 0: the README call chain through the drop-in classes; one 'step' = one chain."""
     import pyrism_b200 as pb
@@ -824,6 +840,17 @@ def main():
             e2e = {"value": world * r["units"] / dt, "unit": "spectra/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                    "samples_per_gpu": int(r["samples"]), "steps": args.e2e_steps, "api": r["api"],
                    "d2h_gbs": world * r["d2h"] * args.e2e_steps / dt / 1e9}
+            # the ceiling of that figure: this rank's plain D2H copy rate into pinned memory, all ranks copying at the same time
+            barrier()
+            probe = d2h_probe(eng)
+            if dist is not None:
+                t = torch.tensor([probe], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                probe = float(t.item())
+            e2e["d2h_probe_gbs"] = probe
+            e2e["d2h_frac_of_probe"] = e2e["d2h_gbs"] / probe
+            e2e["d2h_probe_note"] = ("sum over ranks of a plain cudaMemcpyAsync D2H of 512 MiB into page-locked memory, all ranks at once; "
+                                     "tools/d2h_probe.cu is the standalone form (profiles/r2g_d2h_probe_8gpu.txt)")
             if "second" in r:
                 s2 = r["second"]
                 dt2 = agg(s2["dt"])

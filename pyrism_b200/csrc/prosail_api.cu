@@ -236,6 +236,9 @@ template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS> struct
 #if PB_NU == 2 && !defined(PB_NO_NU3)
 template <> struct CfgFor<double, true, MODE_PROSAIL, 1u << O_RSOT, 0u> { typedef Cfg<3, 12> type; };
 template <> struct CfgFor<double, true, MODE_PROSPECT, (1u << O_LEAF_R) | (1u << O_LEAF_T), 0u> { typedef Cfg<3, 12> type; };
+#ifdef PB_FOUR_NU3
+template <> struct CfgFor<double, true, MODE_PROSAIL, 0xFu, 0u> { typedef Cfg<3, 12> type; };   // BRF + BHR + DHR + HDR planes
+#endif
 #ifdef PB_MEANS_NU3
 template <> struct CfgFor<double, true, MODE_PROSAIL, 0u, 1u << O_RSOT> { typedef Cfg<3, 12> type; };   // band-mean LUT on the packed map
 #endif
@@ -458,7 +461,9 @@ static int run_host(prosail_handle* h, const Job& j) {
     const size_t per_sample = out_per_item * G + in_per_sample;
     long long slab = std::max<long long>(1, (long long)((256ull << 20) / per_sample));
     slab = std::min<long long>(slab, std::max<long long>(1, (j.n + 1) / 2));      // at least two slabs to overlap copies
-    if (j.n <= 64) slab = std::max<long long>(slab, j.n);
+    // few sets: one slab (the drop-in scalar call must not pay two launches) -- as long as that slab stays within 1 GB of device
+    // workspace; few sets with very many geometries keep the split by the byte cap above
+    if (j.n <= 64 && (unsigned long long)per_sample * (unsigned long long)j.n <= (1ull << 30)) slab = std::max<long long>(slab, j.n);
 
     long long idx = 0;
     for (long long s0 = 0; s0 < j.n; s0 += slab, ++idx) {
