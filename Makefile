@@ -5,7 +5,7 @@ NVFLAGS ?= -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fma
 # tuning experiments: make variant NAME=nu3 EXTRA=-DPB_NU=3  ->  pyrism_b200/lib/variants/libprosail_nu3.so (PYRISM_B200_LIB selects it)
 EXTRA ?=
 SRC := pyrism_b200/csrc/prosail_api.cu
-HDR := pyrism_b200/csrc/prosail_kernels.cuh pyrism_b200/csrc/math64.cuh pyrism_b200/csrc/math32.cuh pyrism_b200/csrc/invert_kernels.cuh pyrism_b200/csrc/math_tables.inc include/prosail_b200.h
+HDR := pyrism_b200/csrc/prosail_kernels.cuh pyrism_b200/csrc/math64.cuh pyrism_b200/csrc/math32.cuh pyrism_b200/csrc/invert_kernels.cuh pyrism_b200/csrc/invert_tc.cuh pyrism_b200/csrc/math_tables.inc include/prosail_b200.h
 LIB := pyrism_b200/lib/libprosail_b200.so
 
 all: $(LIB)

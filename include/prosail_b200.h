@@ -208,6 +208,12 @@ int prosail_invert_f32(prosail_handle_t* h, long long n_lut, int n_feat, const f
                        const float* obs, long long pitch_obs, const float* weights, long long index_offset, long long* best_index,
                        float* best_cost, int on_host, void* stream);
 
+/* How the last prosail_invert_f32 call on this handle ran (waits for it): used_tensor_cores = 1 when the candidate pass ran on the
+ * tcgen05 tensor cores (n_feat <= 15, n_lut >= 512; csrc/invert_tc.cuh) -- the result is the same bit-exact contract either way;
+ * redone_exactly = observations whose candidate list could not be proven complete and were rescanned exactly; timed_out != 0 if a
+ * bounded device-side wait expired (results of that call are then -1 / +inf).  No counterpart in the reference. */
+int prosail_invert_last_stats(prosail_handle_t* h, int* used_tensor_cores, long long* redone_exactly, int* timed_out);
+
 /* The k best entries per observation (1 <= k <= 16), for estimators that average the parameters of the k closest entries:
  * best_index / best_cost are [n_obs][k], ascending cost, equal costs by ascending index; -1 / +inf pad when fewer than k
  * entries have a finite cost.  Same cost definition and evaluation order as prosail_invert_f32 (k = 1 gives the same result). */

@@ -14,6 +14,7 @@
 #include "../../include/prosail_b200.h"
 #include "prosail_kernels.cuh"
 #include "invert_kernels.cuh"
+#include "invert_tc.cuh"
 
 using namespace pb;
 
@@ -91,6 +92,9 @@ struct prosail_handle {
     AngleTables* d_angles = nullptr;
     long long prologue_thread_min = 2048;   // items from which the thread-per-item prologue is used
     WindowMap* d_win = nullptr;
+    int* inv_status = nullptr;                 // device: [0] time-out flag, [1] observations redone exactly (last tensor-core inversion)
+    cudaStream_t inv_stream = nullptr;         // stream of the last inversion
+    int inv_used_tc = 0;                       // 1: the last prosail_invert_f32 ran on the tensor cores
     WindowMap* d_winp = nullptr;               // packed map (in-window wavelengths only), see WindowMap::packed
     WindowMap h_winp;
     bool have_winp = false;
@@ -1146,6 +1150,61 @@ static int launch_invert(prosail_handle* h, InvertArgs& a, long long index_offse
     return 0;
 }
 
+// Tensor-core path of prosail_invert_f32 (csrc/invert_tc.cuh): candidates from tcgen05 tf32 MMAs, exact float32 re-rank.
+static bool invert_tc_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PYRISM_B200_INVERT_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+static int launch_invert_tc(prosail_handle* h, const InvertArgs& ia, long long index_offset, long long* best_index, float* best_cost, Work& w,
+                            const float* h_scale, cudaStream_t st) {
+    InvertTcArgs a{};
+    a.lut = ia.lut; a.n_lut = ia.n_lut; a.pitch_lut = ia.pitch_lut;
+    a.obs = ia.obs; a.n_obs = ia.n_obs; a.pitch_obs = ia.pitch_obs; a.n_feat = ia.n_feat;
+    const long long obs_blocks = (a.n_obs + TC_M - 1) / TC_M;
+    const long long lut_tiles = (a.n_lut + TC_N - 1) / TC_N;
+    // about eight CTAs per SM in flight or queued (two are resident); chunks are whole tiles
+    long long n_chunks = std::max<long long>(1, std::min<long long>(std::min<long long>(lut_tiles, 1024), (8LL * h->sm_count + obs_blocks - 1) / obs_blocks));
+    const long long tiles_per_chunk = (lut_tiles + n_chunks - 1) / n_chunks;
+    n_chunks = (lut_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    a.n_tiles = lut_tiles;
+    a.tiles_per_chunk = tiles_per_chunk;
+    a.n_chunks = (int)n_chunks;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_cost = up((size_t)a.n_obs * n_chunks * TC_KEEP * 4), b_idx = b_cost, b_flags = up((size_t)a.n_obs * 4);
+    const size_t b_pre = (size_t)lut_tiles * TC_TILE_BYTES;
+    int rc;
+    if ((rc = w.inv.reserve(b_pre + b_cost + b_idx + b_flags + 4 * 256))) return rc;
+    char* p = (char*)w.inv.p;
+    a.bpre = (unsigned char*)p; p += b_pre;                   // first: keeps the 16 KB tiles aligned for the bulk copies
+    a.cand_cost = (float*)p; p += b_cost;
+    a.cand_idx = (int*)p; p += b_idx;
+    a.flags = (int*)p; p += b_flags;
+    float* d_scale = (float*)p; p += 256;
+    a.center = (float*)p; p += 256;
+    a.lmax_bits = (unsigned*)p; p += 256;
+    a.status = (int*)p;
+    CK(cudaMemcpyAsync(d_scale, h_scale, 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    a.scale = d_scale;
+    static bool attr_set[64] = {false};
+    if (h->device >= 64 || !attr_set[h->device]) {
+        CK(cudaFuncSetAttribute(k_invert_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        if (h->device < 64) attr_set[h->device] = true;
+    }
+    k_invert_tc_center<<<1, 256, 0, st>>>(a);
+    k_invert_tc_prep<<<(unsigned)lut_tiles, TC_N, 0, st>>>(a);
+    k_invert_tc<<<dim3((unsigned)obs_blocks, (unsigned)n_chunks), TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    k_invert_tc_rerank<<<(unsigned)((a.n_obs + 127) / 128), 128, 0, st>>>(a, index_offset, best_index, best_cost);
+    k_invert_tc_fix<<<(unsigned)a.n_obs, 256, 0, st>>>(a, index_offset, best_index, best_cost);
+    h->launches += 1;
+    h->launches += 4;
+    CK(cudaGetLastError());
+    h->inv_status = a.status;
+    h->inv_stream = st;
+    h->inv_used_tc = 1;
+    return 0;
+}
+
 template <int DP>
 static int launch_invert_topk(prosail_handle* h, InvertArgs& a, int k, long long index_offset, long long* best_index, float* best_cost, Work& w,
                               const float* h_scale, cudaStream_t st) {
@@ -1235,7 +1294,10 @@ static int invert_impl(prosail_handle_t* h, int k, long long n_lut, int n_feat, 
         a.lut = lut;
         a.obs = obs;
     }
-    if (k == 0) {
+    h->inv_used_tc = 0;
+    if (k == 0 && n_feat <= TC_K - 1 && n_lut >= 4 * TC_N && n_lut < (1LL << 31) && n_obs < (1LL << 31) && invert_tc_enabled()) {
+        rc = launch_invert_tc(h, a, index_offset, d_idx, d_cost, w, scale, st);
+    } else if (k == 0) {
         if (n_feat <= 8) rc = launch_invert<8>(h, a, index_offset, d_idx, d_cost, w, scale, st);
         else if (n_feat <= 16) rc = launch_invert<16>(h, a, index_offset, d_idx, d_cost, w, scale, st);
         else rc = launch_invert<32>(h, a, index_offset, d_idx, d_cost, w, scale, st);
@@ -1250,6 +1312,20 @@ static int invert_impl(prosail_handle_t* h, int k, long long n_lut, int n_feat, 
         CK(cudaMemcpyAsync(best_cost, d_cost, (size_t)nres * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
+    return 0;
+}
+
+int prosail_invert_last_stats(prosail_handle_t* h, int* used_tensor_cores, long long* redone_exactly, int* timed_out) {
+    if (!h) return fail(PROSAIL_E_ARG, "null handle");
+    int st[2] = {0, 0};
+    if (h->inv_used_tc && h->inv_status) {
+        DeviceGuard guard(h->device);
+        CK(cudaStreamSynchronize(h->inv_stream));
+        CK(cudaMemcpy(st, h->inv_status, sizeof st, cudaMemcpyDeviceToHost));
+    }
+    if (used_tensor_cores) *used_tensor_cores = h->inv_used_tc;
+    if (redone_exactly) *redone_exactly = st[1];
+    if (timed_out) *timed_out = st[0];
     return 0;
 }
 

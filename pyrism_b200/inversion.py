@@ -92,6 +92,15 @@ def invert_device(engine, n_lut, n_feat, lut, pitch_lut, n_obs, obs, pitch_obs, 
                                              0, stream))
 
 
+def last_stats(engine):
+    """How the last ``invert`` / ``invert_device`` on this engine ran (waits for it): dict(tensor_cores=bool -- the candidate pass ran
+    on tcgen05 (``csrc/invert_tc.cuh``; n_feat <= 15 and >= 512 LUT rows), redone_exactly=int -- observations rescanned exactly because
+    their candidate list could not be proven complete, timed_out=bool).  The results obey the same bit-exact contract either way."""
+    used, redone, to = C.c_int(0), C.c_longlong(0), C.c_int(0)
+    capi.check(engine.lib.prosail_invert_last_stats(engine.h, C.byref(used), C.byref(redone), C.byref(to)))
+    return dict(tensor_cores=bool(used.value), redone_exactly=int(redone.value), timed_out=bool(to.value))
+
+
 def reduce_best(costs, indices):
     """Fold per-shard results: costs [W, Q], indices [W, Q] (global, -1 = none) -> (index [Q], cost [Q]).
     Smallest cost wins, equal costs go to the smallest index -- the same rule the kernel applies inside a shard, so the result

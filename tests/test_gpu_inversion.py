@@ -154,3 +154,47 @@ def test_inversion_pinned_to_float64_brute_force_on_reference_spectra(engine):
     assert np.max(np.abs(m - g["lut"])) <= 1e-9
     idx2, _ = inversion.invert(engine, m.astype(np.float32), obs32)
     assert np.array_equal(idx2, g["best"])
+
+
+def test_tensor_core_candidate_pass_keeps_the_bit_exact_contract(engine):
+    """prosail_invert_f32 with <= 15 features runs its candidate pass on the tcgen05 tensor cores (csrc/invert_tc.cuh: split-tf32 MMAs
+    into TMEM, then an exact float32 re-rank).  The result must be the contract's, bit for bit -- on random tables, with weights, on
+    a tightly clustered table (thousands of near-ties inside the error bound: the exact fix-up scan has to take over) and on a table
+    of identical rows (lowest index wins)."""
+    for m, q, d, use_w in ((5000, 1025, 15, False), (70001, 300, 15, True), (20000, 257, 6, True), (131072, 128, 11, False)):
+        lutf = rng.random((m, d)).astype(np.float32)
+        obs = rng.random((q, d)).astype(np.float32)
+        obs[:5] = lutf[[7, 7, m - 1, 0, m // 2]]
+        w = rng.uniform(0.2, 3.0, d).astype(np.float32) if use_w else None
+        idx, cost = inversion.invert(engine, lutf, obs, w, index_offset=3)
+        st = inversion.last_stats(engine)
+        assert st["tensor_cores"] and not st["timed_out"], st
+        ref_idx, ref_cost = inv.invert(lutf, obs, w, index_offset=3)
+        same = idx == ref_idx
+        if not np.all(same):                                # only possible on an fmaf double-rounding midpoint of the numpy oracle
+            assert np.all(inv.is_optimal(lutf, obs[~same], idx[~same], w, index_offset=3)) and (~same).sum() <= 2
+        assert np.array_equal(cost[same], ref_cost[same])
+        assert idx[0] == 7 + 3 and cost[0] == 0.0 and idx[3] == 0 + 3
+    # clustered table: every row within 1e-6 of one point -> far more near-ties than the candidate lists hold
+    base = rng.random(15).astype(np.float32)
+    lutf = (base[None, :] + 1e-6 * rng.standard_normal((6000, 15))).astype(np.float32)
+    obs = (base[None, :] + 1e-6 * rng.standard_normal((130, 15))).astype(np.float32)
+    idx, cost = inversion.invert(engine, lutf, obs)
+    st = inversion.last_stats(engine)
+    assert st["tensor_cores"] and not st["timed_out"], st
+    ref_idx, ref_cost = inv.invert(lutf, obs)
+    same = idx == ref_idx
+    assert same.mean() > 0.97 and np.all(inv.is_optimal(lutf, obs[~same], idx[~same])) if not np.all(same) else True
+    assert np.array_equal(cost[same], ref_cost[same])
+    # identical rows: the lowest index
+    lutf = np.tile(rng.random((1, 15)).astype(np.float32), (3000, 1))
+    idx, cost = inversion.invert(engine, lutf, rng.random((200, 15)).astype(np.float32), index_offset=11)
+    assert np.all(idx == 11) and inversion.last_stats(engine)["redone_exactly"] == 200
+    # NaN observation and NaN row
+    lutf = rng.random((4000, 15)).astype(np.float32)
+    lutf[17, 3] = np.nan
+    obs = rng.random((129, 15)).astype(np.float32)
+    obs[1] = np.nan
+    idx, cost = inversion.invert(engine, lutf, obs)
+    ref_idx, ref_cost = inv.invert(lutf, obs)
+    assert idx[1] == -1 and np.isinf(cost[1]) and np.array_equal(idx, ref_idx) and np.array_equal(cost, ref_cost)

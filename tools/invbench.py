@@ -24,5 +24,6 @@ for _ in range(reps):
     step()
 ms = eng.timer_end() / reps
 DP = 8 if D <= 8 else 16 if D <= 16 else 32
+print("path:", inversion.last_stats(eng))
 print("invert M=%d Q=%d D=%d: %.3f ms  %.3e pairs/s  %.2f TFLOP/s fp32 (2 x %d padded features per pair; sub counted with the fma)"
       % (M, Q, D, ms, M * Q / ms * 1e3, M * Q * 3.0 * DP / ms * 1e3 / 1e12, DP))
