@@ -71,8 +71,8 @@ def sass_histograms():
             continue
         op, mods, operands = m.group(2), m.group(3), m.group(4)
         key = op
-        if op == "MUFU":
-            key = op + mods.split(".")[1:2][0].join([".", ""]) if mods else op
+        if op == "MUFU" and mods:
+            key = op + "." + mods.split(".")[1]
         cur["ops"][key] += 1
         cur["n"] += 1
         if op in ("DFMA", "DMUL", "DADD"):
