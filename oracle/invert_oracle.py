@@ -3,7 +3,10 @@
 
 TEST INFRASTRUCTURE ONLY (same rule as prosail_oracle.py: nothing under pyrism_b200/ imports it).
 
-The reference (ibaris/pyrism) has no inversion: parity here is against the contract itself -- float32 features pre-scaled by
+The reference (ibaris/pyrism) has no inversion.  Pin: tests/golden/inversion_lut.npz (tests/golden/make_inversion_golden.py) holds a
+band-mean LUT and observations made from spectra of the LIVE reference together with the arg-min of an independent float64 brute-force
+search; this module and the GPU kernels must both reproduce it (tests/test_inversion_cpu.py, tests/test_gpu_inversion.py).  Beyond
+that pin, parity is against the contract itself -- float32 features pre-scaled by
 sqrtf(w_d), cost accumulated in ascending d with one fused multiply-add per feature, ties to the lowest index.  fmaf is
 reproduced in numpy as  float32(float64(diff) * float64(diff) + float64(acc)):  the product of two float32 values is exact in
 float64 and the sum is rounded once to 53 bits and once to 24 -- identical to a true fmaf except when the 53-bit sum lands
