@@ -198,3 +198,32 @@ def test_tensor_core_candidate_pass_keeps_the_bit_exact_contract(engine):
     idx, cost = inversion.invert(engine, lutf, obs)
     ref_idx, ref_cost = inv.invert(lutf, obs)
     assert idx[1] == -1 and np.isinf(cost[1]) and np.array_equal(idx, ref_idx) and np.array_equal(cost, ref_cost)
+
+
+def test_tensor_core_path_shapes_pitches_and_zero_weights(engine):
+    """Odd sizes around the tile boundaries (128 observations / 128 rows per tile), row pitches larger than the feature count
+    (device-resident call), zero weights (a feature that must not count) and a large index offset."""
+    from pyrism_b200.inversion import invert_device
+    for m, q, d in ((512, 1, 15), (513, 127, 15), (640, 129, 1), (1025, 385, 14), (33000, 1000, 15)):
+        pl, po = d + 3, d + 1                                   # padded rows: the extra columns hold garbage that must be ignored
+        lutp = rng.random((m, pl)).astype(np.float32) * 10
+        obsp = rng.random((q, po)).astype(np.float32) * 10
+        lutp[:, :d] = rng.random((m, d)).astype(np.float32)
+        obsp[:, :d] = rng.random((q, d)).astype(np.float32)
+        w = rng.uniform(0.5, 2.0, d).astype(np.float32)
+        if d > 2:
+            w[1] = 0.0
+        d_lut = engine.empty((m, pl), np.float32).upload(lutp)
+        d_obs = engine.empty((q, po), np.float32).upload(obsp)
+        d_idx, d_cost = engine.empty((q,), np.int64), engine.empty((q,), np.float32)
+        invert_device(engine, m, d, d_lut, pl, q, d_obs, po, d_idx, d_cost, w, 10 ** 12)
+        idx, cost = d_idx.download(), d_cost.download()
+        st = inversion.last_stats(engine)
+        assert st["tensor_cores"] and not st["timed_out"], (m, q, d, st)
+        ref_idx, ref_cost = inv.invert(lutp[:, :d], obsp[:, :d], w, index_offset=10 ** 12)
+        same = idx == ref_idx
+        if not np.all(same):
+            assert np.all(inv.is_optimal(lutp[:, :d], obsp[~same][:, :d], idx[~same], w, index_offset=10 ** 12)) and (~same).sum() <= 2
+        assert np.array_equal(cost[same], ref_cost[same]), (m, q, d)
+        for b in (d_lut, d_obs, d_idx, d_cost):
+            b.free()
