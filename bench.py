@@ -627,6 +627,8 @@ class BandMeanLut(Workload):
         inv()
         ms_inv = eng.timer_end()
         idx, cost = d_idx.download(), d_cost.download()
+        from pyrism_b200.inversion import last_stats
+        st_inv = last_stats(eng)
         fold_ms = 0.0
         if dist is not None:
             t0 = time.perf_counter()
@@ -645,7 +647,8 @@ class BandMeanLut(Workload):
         res["inversion"] = {"observations": Q, "lut_rows_total": int(self.world * self.n), "features": self.nw,
                             "kernel_ms_max_over_ranks": float(ms_inv), "fold_ms": float(fold_ms),
                             "pairs_per_s": float(Q * self.world * self.n / (ms_inv * 1e-3)),
-                            "median_cost": float(np.median(cost)), "all_found": bool(np.all(idx >= 0))}
+                            "median_cost": float(np.median(cost)), "all_found": bool(np.all(idx >= 0)),
+                            "path_rank0": st_inv}
         return res
 
 

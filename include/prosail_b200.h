@@ -211,8 +211,12 @@ int prosail_invert_f32(prosail_handle_t* h, long long n_lut, int n_feat, const f
 /* How the last prosail_invert_f32 call on this handle ran (waits for it): used_tensor_cores = 1 when the candidate pass ran on the
  * tcgen05 tensor cores (n_feat <= 15, n_lut >= 512; csrc/invert_tc.cuh) -- the result is the same bit-exact contract either way;
  * redone_exactly = observations whose candidate list could not be proven complete and were rescanned exactly; timed_out != 0 if a
- * bounded device-side wait expired (results of that call are then -1 / +inf).  No counterpart in the reference. */
-int prosail_invert_last_stats(prosail_handle_t* h, int* used_tensor_cores, long long* redone_exactly, int* timed_out);
+ * bounded device-side wait expired (the observations of that CTA were rescanned exactly as well).  The error model of the candidate
+ * pass is monitored in every call: error_ratio = largest measured |approximate - real| / sum_k |A_k||B_k| over all kept candidates
+ * (to be compared with the model's KAPPA = 8e-6), bound_violations = candidates found outside the model's bound (their
+ * observations were rescanned exactly; expected 0).  Any pointer may be NULL.  No counterpart in the reference. */
+int prosail_invert_last_stats(prosail_handle_t* h, int* used_tensor_cores, long long* redone_exactly, int* timed_out, double* error_ratio,
+                              long long* bound_violations);
 
 /* The k best entries per observation (1 <= k <= 16), for estimators that average the parameters of the k closest entries:
  * best_index / best_cost are [n_obs][k], ascending cost, equal costs by ascending index; -1 / +inf pad when fewer than k

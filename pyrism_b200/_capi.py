@@ -99,7 +99,8 @@ _SIGNATURES = {
     "prosail_volume_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p]),
     "prosail_invert_f32": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong,
                                      C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "prosail_invert_last_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
+    "prosail_invert_last_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_longlong)]),
     "prosail_invert_topk_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p,
                                           C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "prosail_device_pci_bus_id": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

@@ -10,22 +10,30 @@
 // -- the 15 L8/ASTER band means fill the K = 16 of two tf32 MMAs exactly.  TF32 keeps 11 significant bits, so every operand is split
 // x = hi + lo (both exactly representable in tf32, |x - hi - lo| <= 2^-22 |x|) and the product is accumulated as
 // A_hi B_hi + A_hi B_lo + A_lo B_hi in fp32 inside the tensor core: 6 tcgen05.mma (M = 128 observations, N = 128 LUT rows, K = 8) per tile.
-// The approximate bracket c^ differs from the exact one by at most eps = KAPPA * S,  S = sum_k |A_k| |B_k|  (operand representation
-// 3 * 2^-22, at most 50 fp32 accumulation steps of 2^-23 each; measured: tests/test_gpu_inversion.py), so the true minimiser of the
-// float32 contract satisfies  c^ <= c^_min + tau  with  tau = 2 eps + 2 GAMMA cost  (GAMMA = float32 rounding of the 15-term
-// contract sum).  Each thread keeps the TC_KEEP smallest c^ of its observation per LUT chunk; k_invert_tc_rerank evaluates the exact
-// contract cost of the candidates within tau and applies the tie rule.  If a chunk's list is full of candidates within tau (the
-// list may have dropped one), the observation is flagged and k_invert_tc_fix redoes it with a plain exact scan -- correctness
-// never depends on the bound being tight, only on it being a bound.
+// Error model.  With m = ||phi(o)||, n = ||phi(l)|| the approximate bracket c^ differs from the real-arithmetic bracket of the same
+// float32 operands by at most
+//     eps(o, l) = KAPPA * (2 m n + n^2) + KN * n^2 + KC * (m + n) * sqrt(cost)            (2 m n + n^2 >= sum_k |A_k| |B_k|, Cauchy-Schwarz)
+// KAPPA: operand representation (3 * 2^-22) plus the tensor core's fp32 accumulation over 6 MMAs; KN: float32 rounding and split of
+// the norm slot (computed in double, rounded once); KC: the rounding of the centring subtraction itself.  Let l^ be the row with the
+// smallest c^ and C1 its exact contract cost (one evaluation).  The contract's minimiser l* has cost <= C1, hence
+// ||phi(l*)|| <= m + sqrt(C1) =: nmax, and   c^(l*) <= c^(l^) + eps(o, l^) + eps(o, nmax) + 2 GAMMA C1 =: c^(l^) + tau
+// (GAMMA = float32 rounding of the 15-term contract sum).  The bound is PER OBSERVATION and uses only rows that can win -- a
+// global bound over the whole LUT (round-2 first version) is dominated by bright outlier rows and flagged most observations of a
+// real band-mean table.  Each thread keeps the TC_KEEP smallest c^ of its observation per LUT chunk; k_invert_tc_rerank evaluates
+// the exact contract cost of the candidates within tau and applies the tie rule.  If a chunk's list is full of candidates within
+// tau (the list may have dropped one) the observation is put on the fix-up list and k_invert_tc_fix redoes the listed observations
+// with a plain exact scan -- correctness never depends on the bound being tight, only on it being a bound.  The bound itself is
+// MONITORED in every call: the re-rank evaluates the real bracket of every kept candidate in double and records the largest
+// |c^ - c| / (sum_k |A_k||B_k|) (status[2]); a candidate outside eps counts as a violation (status[3]) and sends its
+// observation to the exact scan.  tests/test_gpu_inversion.py asserts the measured ratio stays below KAPPA / 4.
 //
-// Kernel shape (k_invert_tc): one CTA = 128 threads = 128 observations = the 128 lanes of its TMEM accumulator (128 columns, fp32).
-// Per tile of 128 LUT rows: every thread loads, centres, splits and stores ONE LUT row into the K-major core-matrix layout of the
-// B operand (SWIZZLE_NONE: 8 rows x 16 bytes per core matrix; the descriptor fields were validated element by element with
-// tools/micro/tc_probe.cu); one elected thread issues the six MMAs and a tcgen05.commit onto an mbarrier; all threads wait, read
-// their lane with tcgen05.ld (32 columns at a time) and scan: an FMNMX tree over the 32 values and one compare against the
-// current TC_KEEP-th best -- one instruction per (observation, row) pair instead of the 30 of the FP32 kernel.  There is no warp
-// specialisation inside the CTA: FOUR CTAs share an SM (4 x 128 = all 512 TMEM columns), so one CTA's epilogue and loads run
-// while another's MMAs occupy the tensor pipe.  Every wait is bounded; a time-out is reported through `status`.
+// Kernel shape (k_invert_tc): CTA = 128 observations = the 128 lanes of TMEM; 160 threads.  k_invert_tc_prep has written every
+// 128-row LUT tile as the exact shared-memory image of the B operand (hi and lo parts, K-major core matrices, SWIZZLE_NONE; the
+// descriptor fields were validated element by element with tools/micro/tc_probe.cu).  Warp 4, lane 0 streams those tiles through a
+// 3-slot ring with cp.async.bulk + mbarrier and issues the six tcgen05.mma of each tile into one of two 128-column accumulators;
+// warps 0-3 read their lane with tcgen05.ld and scan: an FMNMX tree per 8 columns and one compare against the current TC_KEEP-th
+// best -- about one instruction per (observation, row) pair instead of the 30 of the FP32 kernel.  Two CTAs share an SM.  Every
+// wait is bounded; a time-out is reported through `status` and sends the CTA's observations to the exact scan.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,7 +45,10 @@ constexpr int TC_N = 128;                  // LUT rows per tile = TMEM columns
 constexpr int TC_K = 16;                   // 15 features + the norm slot
 constexpr int TC_KEEP = 8;                 // candidates kept per (observation, LUT chunk)
 constexpr int TC_SMEM_BYTES = 80 * 1024;   // A (16 KB) + three B slots (48 KB) + barriers + candidate lists (8 KB); two CTAs per SM
-constexpr float TC_KAPPA = 8e-6f;          // |c^ - exact| <= KAPPA * sum |A_k| |B_k|
+constexpr float TC_KAPPA = 8e-6f;          // |c^ - exact| <= KAPPA * sum |A_k| |B_k|   (default; InvertTcArgs::kappa)
+constexpr float TC_KN = 4e-7f;             // norm slot: 2^-24 (double -> float) + 2^-22 (hi / lo split)
+constexpr float TC_KC = 2.4e-7f;           // centring subtraction: 2 * 2^-24 (m + n) sqrt(cost), doubled
+constexpr int TC_FIX_GROUP = 8;            // observations per CTA of the exact fix-up scan
 constexpr float TC_GAMMA = 2e-6f;          // relative float32 rounding of the contract's 15-term fmaf sum (17 * 2^-24 < 1.1e-6)
 
 struct InvertTcArgs {
@@ -54,9 +65,11 @@ struct InvertTcArgs {
     unsigned char* bpre;     // [n_tiles][2 * TC_N * TC_K * 4]: the B-operand tiles as they sit in shared memory (written by k_invert_tc_prep)
     float* cand_cost;        // [n_obs][n_chunks][TC_KEEP] approximate brackets, ascending
     int* cand_idx;           // [n_obs][n_chunks][TC_KEEP] LUT row (within this shard), -1 = empty
-    unsigned* lmax_bits;     // [2]: max_m max_d |phi(l)_d| and max_m ||phi(l)||^2 as float bits (atomicMax; both >= 0)
-    int* status;             // [0] != 0: a bounded wait expired;  [1]: observations handed to the exact fix-up scan
-    int* flags;              // [n_obs] 1 = redo with the exact scan
+    int* status;             // [0] != 0: a bounded wait expired;  [1]: observations on the fix-up list;  [2]: float bits of the largest
+                             // measured |c^ - c| / sum |A_k||B_k| over the kept candidates;  [3]: candidates outside the bound
+    int* flags;              // [n_obs] the fix-up list: observations to redo with the exact scan (status[1] entries)
+    unsigned long long* fix_best;   // [n_obs] (cost bits << 32 | row) of the exact scan, folded with atomicMin
+    float kappa;
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,50 +155,37 @@ __global__ void __launch_bounds__(256) k_invert_tc_center(const InvertTcArgs a) 
         for (int i = 0; i < 16; ++i) t += acc[i][threadIdx.x];
         a.center[threadIdx.x] = threadIdx.x < a.n_feat ? t / (float)n : 0.0f;
     }
-    if (threadIdx.x == 0) { a.lmax_bits[0] = 0u; a.lmax_bits[1] = 0u; }
     if (threadIdx.x < 16) a.status[threadIdx.x] = 0;
 }
 
 // One pass over the LUT shard: every row becomes (phi(l), ||phi(l)||^2), split into tf32 hi / lo parts and written in the EXACT
 // shared-memory image of a B-operand tile (128 rows: 8 KB of hi parts, 8 KB of lo parts, K-major core matrices).  The main
 // kernel then needs no arithmetic at all to stage a tile: one 16 KB bulk asynchronous copy (cp.async.bulk + mbarrier).  The pass is
-// amortised over all observation blocks (each re-reads every tile); it also yields the two maxima of the error bound.
+// amortised over all observation blocks (each re-reads every tile).  The norm is summed in double and rounded once (TC_KN).
 __global__ void __launch_bounds__(TC_N) k_invert_tc_prep(const InvertTcArgs a) {
     const int tid = threadIdx.x;
     const long long tile = blockIdx.x;
     const long long r = tile * TC_N + tid;
     float v[TC_K];
-    float n2 = 0.0f, lmax = 0.0f, l2max = 0.0f;
+    double n2 = 0.0;
     if (r < a.n_lut) {
         const float* lp = a.lut + r * a.pitch_lut;
 #pragma unroll
         for (int d = 0; d < TC_K - 1; ++d) {
             const float x = d < a.n_feat ? __ldg(lp + d) * a.scale[d] - a.center[d] : 0.0f;
             v[d] = x;
-            n2 = fmaf(x, x, n2);
-            lmax = fmaxf(lmax, fabsf(x) < 1e29f ? fabsf(x) : 0.0f);
+            n2 = fma((double)x, (double)x, n2);
         }
     }
-    if (r < a.n_lut && n2 < 1e29f) {                                  // (false for NaN / inf features too)
-        l2max = n2;
+    if (r < a.n_lut && n2 < 1e29) {                                   // (false for NaN / inf features too)
+        v[TC_K - 1] = (float)n2;
     } else {                                                          // rows past the shard and rows with a non-finite feature (the contract
 #pragma unroll                                                        // gives those an infinite cost): an unreachable norm, never a candidate
         for (int d = 0; d < TC_K - 1; ++d) v[d] = 0.0f;
-        n2 = 1e30f;
-        lmax = 0.0f;
+        v[TC_K - 1] = 1e30f;
     }
-    v[TC_K - 1] = n2;
     unsigned char* base = a.bpre + tile * (2 * TC_N * TC_K * 4);
     tc_store_row(base, base + TC_N * TC_K * 4, TC_N, tid, v);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        l2max = fmaxf(l2max, __shfl_xor_sync(0xffffffffu, l2max, o));
-    }
-    if ((tid & 31) == 0) {
-        atomicMax(a.lmax_bits + 0, __float_as_uint(lmax));
-        atomicMax(a.lmax_bits + 1, __float_as_uint(l2max));
-    }
 }
 
 // Main kernel.  CTA = 128 observations (TMEM lanes).  Warps 0-3: epilogue (thread = observation).  Warp 4, lane 0: control -- streams
@@ -379,87 +379,155 @@ __device__ __forceinline__ float tc_exact_cost(const float* __restrict__ o /* sc
     return acc;
 }
 
+// eps(o, l) of the header for a row of squared norm n2 (m = ||phi(o)||, sc = bound on sqrt(cost) of the rows that matter)
+__device__ __forceinline__ float tc_eps(float kappa, float m, float n2, float sc) {
+    const float n = sqrtf(n2) * 1.000001f;
+    return 1.0001f * (kappa * (2.0f * m * n + n * n) + TC_KN * n * n + TC_KC * (m + n) * sc);
+}
+
 // candidates -> exact arg-min (one thread per observation)
 __global__ void __launch_bounds__(128) k_invert_tc_rerank(const InvertTcArgs a, long long index_offset, long long* __restrict__ best_idx,
                                                           float* __restrict__ best_cost) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.n_obs) return;
-    float sc[16], o[16];
-    float on1 = 0.0f, on2 = 0.0f;
+    float sc[16], o[16], xo[16], ce[16];
+    float on2 = 0.0f;
     for (int d = 0; d < 16; ++d) {
         sc[d] = d < a.n_feat ? a.scale[d] : 0.0f;
+        ce[d] = d < a.n_feat ? a.center[d] : 0.0f;
         o[d] = d < a.n_feat ? a.obs[q * a.pitch_obs + d] * sc[d] : 0.0f;
-        const float p = d < a.n_feat ? o[d] - a.center[d] : 0.0f;
-        on1 += fabsf(p);
-        on2 = fmaf(p, p, on2);
+        xo[d] = d < a.n_feat ? o[d] - ce[d] : 0.0f;                                // phi(o) exactly as k_invert_tc forms it
+        on2 = fmaf(xo[d], xo[d], on2);
     }
-    const float Lmax = __uint_as_float(a.lmax_bits[0]), L2max = __uint_as_float(a.lmax_bits[1]);
+    const float m = sqrtf(on2) * 1.000001f;
     const float* pc = a.cand_cost + (size_t)q * a.n_chunks * TC_KEEP;
     const int* pi = a.cand_idx + (size_t)q * a.n_chunks * TC_KEEP;
     const int ncand = a.n_chunks * TC_KEEP;
     float cmin = __int_as_float(0x7f800000);
+    int imin = -1;
     for (int i = 0; i < ncand; ++i)
-        if (pi[i] >= 0) cmin = fminf(cmin, pc[i]);
-    // |c^ - exact bracket| <= eps  for every row of the LUT;  the contract's own float32 rounding is GAMMA relative
-    const float S = 2.0f * (2.0f * on1 * Lmax) + 2.0f * L2max;                // sum |A_k||B_k| <= 2 ||phi o||_1 Lmax + ||phi l||^2 (norm slot: hi and lo parts)
-    const float eps = TC_KAPPA * S + 3e-6f * L2max;                           // + float32 rounding of ||phi(l)||^2 itself
-    const float cest = fmaxf(cmin + on2, 0.0f) + eps;
-    const float tau = 2.0f * eps + 2.0f * TC_GAMMA * cest;
-    const float lim = cmin + tau;
+        if (pi[i] >= 0 && pc[i] < cmin) { cmin = pc[i]; imin = pi[i]; }
+    bool redo = imin < 0;                 // nothing kept: the CTA timed out, or no row of the shard has a finite cost (the scan settles which)
     float best = __int_as_float(0x7f800000);
     int bidx = -1;
-    bool overflow = false;
-    for (int c = 0; c < a.n_chunks; ++c) {
-        const float* cc = pc + c * TC_KEEP;
-        const int* ci = pi + c * TC_KEEP;
-        if (ci[TC_KEEP - 1] >= 0 && cc[TC_KEEP - 1] <= lim) overflow = true;  // the list is full of candidates: it may have dropped one
-        for (int k = 0; k < TC_KEEP; ++k) {
-            const int id = ci[k];
-            if (id < 0 || !(cc[k] <= lim)) continue;
-            const float ex = tc_exact_cost(o, a.lut + (long long)id * a.pitch_lut, sc, a.n_feat);
-            if (ex < best || (ex == best && id < bidx)) { best = ex; bidx = id; }
+    if (!redo) {
+        // monitor: real bracket (double) of every kept candidate against its c^; also yields ||phi(l^)||^2
+        float n2hat = 0.0f, worst = 0.0f;
+        int viol = 0;
+        for (int i = 0; i < ncand; ++i) {
+            const int id = pi[i];
+            if (id < 0 || !(pc[i] < 1e29f)) continue;
+            const float* lrow = a.lut + (long long)id * a.pitch_lut;
+            double n2 = 0.0, dot = 0.0, sabs = 0.0;
+            for (int d = 0; d < a.n_feat; ++d) {
+                const float xl = __ldg(lrow + d) * sc[d] - ce[d];
+                n2 = fma((double)xl, (double)xl, n2);
+                dot = fma((double)xo[d], (double)xl, dot);
+                sabs += fabs((double)xo[d] * (double)xl);
+            }
+            if (!(n2 < 1e29)) continue;
+            const double err = fabs((double)pc[i] - (n2 - 2.0 * dot));
+            const double S = 2.0 * sabs + n2;
+            if (S > 0.0) worst = fmaxf(worst, (float)(err / S));
+            if (err > (double)tc_eps(a.kappa, m, (float)n2, 0.0f)) ++viol;
+            if (id == imin) n2hat = (float)n2;
+        }
+        atomicMax(reinterpret_cast<unsigned*>(a.status) + 2, __float_as_uint(worst));
+        if (viol) { atomicAdd(a.status + 3, viol); redo = true; }
+        const float C1 = tc_exact_cost(o, a.lut + (long long)imin * a.pitch_lut, sc, a.n_feat);
+        if (!(C1 < 1e29f)) redo = true;
+        const float sC = sqrtf(C1) * 1.0001f;
+        const float nmax = m + sC;
+        const float tau = tc_eps(a.kappa, m, n2hat, sC) + tc_eps(a.kappa, m, nmax * nmax, sC) + 2.02f * TC_GAMMA * C1;
+        const float lim = cmin + tau;
+        for (int c = 0; c < a.n_chunks && !redo; ++c) {
+            const float* cc = pc + c * TC_KEEP;
+            const int* ci = pi + c * TC_KEEP;
+            if (ci[TC_KEEP - 1] >= 0 && cc[TC_KEEP - 1] <= lim) redo = true;      // the list is full of candidates: it may have dropped one
+            for (int k = 0; k < TC_KEEP; ++k) {
+                const int id = ci[k];
+                if (id < 0 || !(cc[k] <= lim)) continue;
+                const float ex = tc_exact_cost(o, a.lut + (long long)id * a.pitch_lut, sc, a.n_feat);
+                if (ex < best || (ex == best && id < bidx)) { best = ex; bidx = id; }
+            }
         }
     }
-    a.flags[q] = overflow ? 1 : 0;
-    if (overflow) atomicAdd(a.status + 1, 1);
+    if (redo) {
+        const int slot = atomicAdd(a.status + 1, 1);
+        a.flags[slot] = (int)q;
+        a.fix_best[q] = ~0ull;
+    }
     best_idx[q] = bidx < 0 ? -1 : (long long)bidx + index_offset;
-    best_cost[q] = best;
+    best_cost[q] = bidx < 0 ? __int_as_float(0x7f800000) : best;
 }
 
-// flagged observations: plain exact scan of the whole shard by one CTA (rare; exits at once otherwise)
-__global__ void __launch_bounds__(256) k_invert_tc_fix(const InvertTcArgs a, long long index_offset, long long* __restrict__ best_idx, float* __restrict__ best_cost) {
-    const long long q = blockIdx.x;
-    if (!a.flags[q]) return;
-    __shared__ float s_o[16], s_sc[16];
-    __shared__ float s_best[256];
-    __shared__ long long s_idx[256];
-    if (threadIdx.x < 16) {
-        s_sc[threadIdx.x] = threadIdx.x < a.n_feat ? a.scale[threadIdx.x] : 0.0f;
-        s_o[threadIdx.x] = threadIdx.x < a.n_feat ? a.obs[q * a.pitch_obs + threadIdx.x] * s_sc[threadIdx.x] : 0.0f;
-    }
-    __syncthreads();
-    float best = __int_as_float(0x7f800000);
-    long long bidx = -1;
-    for (long long r = threadIdx.x; r < a.n_lut; r += 256) {
-        const float ex = tc_exact_cost(s_o, a.lut + r * a.pitch_lut, s_sc, a.n_feat);
-        if (ex < best) { best = ex; bidx = r; }                                // r ascends per thread: strict '<' keeps the lowest index
-    }
-    s_best[threadIdx.x] = best;
-    s_idx[threadIdx.x] = bidx;
-    __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-        if (threadIdx.x < w) {
-            const float c2 = s_best[threadIdx.x + w];
-            const long long i2 = s_idx[threadIdx.x + w];
-            const float c1 = s_best[threadIdx.x];
-            const long long i1 = s_idx[threadIdx.x];
-            if (i2 >= 0 && (i1 < 0 || c2 < c1 || (c2 == c1 && i2 < i1))) { s_best[threadIdx.x] = c2; s_idx[threadIdx.x] = i2; }
+// the fix-up list: plain exact scan.  grid.x slices the shard, grid.y walks the list in groups of TC_FIX_GROUP observations, so
+// one pass over a slice serves the whole group; the per-slice results fold with a 64-bit atomicMin on (cost bits, row) -- costs are
+// non-negative floats, whose bit patterns order like the values, and the low word breaks ties towards the lowest row.
+__global__ void __launch_bounds__(256) k_invert_tc_fix(const InvertTcArgs a) {
+    const int nflag = a.status[1];
+    __shared__ float s_o[TC_FIX_GROUP][16];
+    __shared__ float s_sc[16];
+    __shared__ unsigned long long s_red[8][TC_FIX_GROUP];
+    for (int g0 = blockIdx.y * TC_FIX_GROUP; g0 < nflag; g0 += gridDim.y * TC_FIX_GROUP) {
+        __syncthreads();
+        if (threadIdx.x < 16) s_sc[threadIdx.x] = threadIdx.x < a.n_feat ? a.scale[threadIdx.x] : 0.0f;
+        if (threadIdx.x < TC_FIX_GROUP * 16) {
+            const int j = threadIdx.x >> 4, d = threadIdx.x & 15;
+            const int qi = g0 + j < nflag ? a.flags[g0 + j] : a.flags[g0];
+            s_o[j][d] = d < a.n_feat ? a.obs[(long long)qi * a.pitch_obs + d] * a.scale[d] : 0.0f;
         }
         __syncthreads();
+        unsigned long long bestp[TC_FIX_GROUP];
+#pragma unroll
+        for (int j = 0; j < TC_FIX_GROUP; ++j) bestp[j] = ~0ull;
+        for (long long r = (long long)blockIdx.x * 256 + threadIdx.x; r < a.n_lut; r += (long long)gridDim.x * 256) {
+            const float* lrow = a.lut + r * a.pitch_lut;
+            float acc[TC_FIX_GROUP];
+#pragma unroll
+            for (int j = 0; j < TC_FIX_GROUP; ++j) acc[j] = 0.0f;
+            for (int d = 0; d < a.n_feat; ++d) {
+                const float ls = __ldg(lrow + d) * s_sc[d];
+#pragma unroll
+                for (int j = 0; j < TC_FIX_GROUP; ++j) {
+                    const float df = s_o[j][d] - ls;
+                    acc[j] = fmaf(df, df, acc[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < TC_FIX_GROUP; ++j)
+                if (acc[j] < __int_as_float(0x7f800000)) {                           // finite (false for NaN)
+                    const unsigned long long pk = ((unsigned long long)__float_as_uint(acc[j]) << 32) | (unsigned long long)(unsigned)r;
+                    bestp[j] = pk < bestp[j] ? pk : bestp[j];
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < TC_FIX_GROUP; ++j) {
+            unsigned long long v = bestp[j];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, off);
+                v = w < v ? w : v;
+            }
+            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][j] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < TC_FIX_GROUP && g0 + threadIdx.x < nflag) {
+            unsigned long long v = s_red[0][threadIdx.x];
+            for (int w = 1; w < 8; ++w) v = s_red[w][threadIdx.x] < v ? s_red[w][threadIdx.x] : v;
+            if (v != ~0ull) atomicMin(a.fix_best + a.flags[g0 + threadIdx.x], v);
+        }
     }
-    if (threadIdx.x == 0) {
-        best_idx[q] = s_idx[0] < 0 ? -1 : s_idx[0] + index_offset;
-        best_cost[q] = s_best[0];
+}
+
+__global__ void __launch_bounds__(256) k_invert_tc_fix_out(const InvertTcArgs a, long long index_offset, long long* __restrict__ best_idx,
+                                                           float* __restrict__ best_cost) {
+    const int nflag = a.status[1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nflag; i += gridDim.x * blockDim.x) {
+        const int q = a.flags[i];
+        const unsigned long long v = a.fix_best[q];
+        best_idx[q] = v == ~0ull ? -1 : (long long)(unsigned)(v & 0xffffffffull) + index_offset;
+        best_cost[q] = v == ~0ull ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(v >> 32));
     }
 }
 

@@ -1156,6 +1156,17 @@ static bool invert_tc_enabled() {
     if (v < 0) { const char* e = getenv("PYRISM_B200_INVERT_TC"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
+// KAPPA of the error model (invert_tc.cuh).  PYRISM_B200_TC_KAPPA overrides it for experiments: results stay exact for ANY value --
+// a value below the hardware's real error only sends more observations to the exact scan (the monitor catches the violations).
+static float invert_tc_kappa() {
+    static float v = -1.0f;
+    if (v < 0.0f) {
+        const char* e = getenv("PYRISM_B200_TC_KAPPA");
+        const double x = e ? atof(e) : 0.0;
+        v = (x > 0.0 && x < 1e-2) ? (float)x : TC_KAPPA;
+    }
+    return v;
+}
 static int launch_invert_tc(prosail_handle* h, const InvertArgs& ia, long long index_offset, long long* best_index, float* best_cost, Work& w,
                             const float* h_scale, cudaStream_t st) {
     InvertTcArgs a{};
@@ -1172,18 +1183,20 @@ static int launch_invert_tc(prosail_handle* h, const InvertArgs& ia, long long i
     a.n_chunks = (int)n_chunks;
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_cost = up((size_t)a.n_obs * n_chunks * TC_KEEP * 4), b_idx = b_cost, b_flags = up((size_t)a.n_obs * 4);
+    const size_t b_fix = up((size_t)a.n_obs * 8);
     const size_t b_pre = (size_t)lut_tiles * TC_TILE_BYTES;
     int rc;
-    if ((rc = w.inv.reserve(b_pre + b_cost + b_idx + b_flags + 4 * 256))) return rc;
+    if ((rc = w.inv.reserve(b_pre + b_cost + b_idx + b_flags + b_fix + 3 * 256))) return rc;
     char* p = (char*)w.inv.p;
     a.bpre = (unsigned char*)p; p += b_pre;                   // first: keeps the 16 KB tiles aligned for the bulk copies
     a.cand_cost = (float*)p; p += b_cost;
     a.cand_idx = (int*)p; p += b_idx;
+    a.fix_best = (unsigned long long*)p; p += b_fix;
     a.flags = (int*)p; p += b_flags;
     float* d_scale = (float*)p; p += 256;
     a.center = (float*)p; p += 256;
-    a.lmax_bits = (unsigned*)p; p += 256;
     a.status = (int*)p;
+    a.kappa = invert_tc_kappa();
     CK(cudaMemcpyAsync(d_scale, h_scale, 16 * sizeof(float), cudaMemcpyHostToDevice, st));
     a.scale = d_scale;
     static bool attr_set[64] = {false};
@@ -1195,9 +1208,11 @@ static int launch_invert_tc(prosail_handle* h, const InvertArgs& ia, long long i
     k_invert_tc_prep<<<(unsigned)lut_tiles, TC_N, 0, st>>>(a);
     k_invert_tc<<<dim3((unsigned)obs_blocks, (unsigned)n_chunks), TC_THREADS, TC_SMEM_BYTES, st>>>(a);
     k_invert_tc_rerank<<<(unsigned)((a.n_obs + 127) / 128), 128, 0, st>>>(a, index_offset, best_index, best_cost);
-    k_invert_tc_fix<<<(unsigned)a.n_obs, 256, 0, st>>>(a, index_offset, best_index, best_cost);
-    h->launches += 1;
-    h->launches += 4;
+    const unsigned fix_groups = (unsigned)std::min<long long>(64, (a.n_obs + TC_FIX_GROUP - 1) / TC_FIX_GROUP);
+    const unsigned fix_slices = (unsigned)std::max<long long>(1, std::min<long long>(4LL * h->sm_count, (a.n_lut + 4095) / 4096));
+    k_invert_tc_fix<<<dim3(fix_slices, fix_groups), 256, 0, st>>>(a);              // leaves at once when the list is empty
+    k_invert_tc_fix_out<<<(unsigned)std::min<long long>(64, (a.n_obs + 255) / 256), 256, 0, st>>>(a, index_offset, best_index, best_cost);
+    h->launches += 6;
     CK(cudaGetLastError());
     h->inv_status = a.status;
     h->inv_stream = st;
@@ -1315,9 +1330,10 @@ static int invert_impl(prosail_handle_t* h, int k, long long n_lut, int n_feat, 
     return 0;
 }
 
-int prosail_invert_last_stats(prosail_handle_t* h, int* used_tensor_cores, long long* redone_exactly, int* timed_out) {
+int prosail_invert_last_stats(prosail_handle_t* h, int* used_tensor_cores, long long* redone_exactly, int* timed_out, double* error_ratio,
+                              long long* bound_violations) {
     if (!h) return fail(PROSAIL_E_ARG, "null handle");
-    int st[2] = {0, 0};
+    int st[4] = {0, 0, 0, 0};
     if (h->inv_used_tc && h->inv_status) {
         DeviceGuard guard(h->device);
         CK(cudaStreamSynchronize(h->inv_stream));
@@ -1326,6 +1342,8 @@ int prosail_invert_last_stats(prosail_handle_t* h, int* used_tensor_cores, long 
     if (used_tensor_cores) *used_tensor_cores = h->inv_used_tc;
     if (redone_exactly) *redone_exactly = st[1];
     if (timed_out) *timed_out = st[0];
+    if (error_ratio) { float r; memcpy(&r, &st[2], 4); *error_ratio = (double)r; }
+    if (bound_violations) *bound_violations = st[3];
     return 0;
 }
 

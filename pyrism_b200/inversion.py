@@ -95,10 +95,14 @@ def invert_device(engine, n_lut, n_feat, lut, pitch_lut, n_obs, obs, pitch_obs, 
 def last_stats(engine):
     """How the last ``invert`` / ``invert_device`` on this engine ran (waits for it): dict(tensor_cores=bool -- the candidate pass ran
     on tcgen05 (``csrc/invert_tc.cuh``; n_feat <= 15 and >= 512 LUT rows), redone_exactly=int -- observations rescanned exactly because
-    their candidate list could not be proven complete, timed_out=bool).  The results obey the same bit-exact contract either way."""
-    used, redone, to = C.c_int(0), C.c_longlong(0), C.c_int(0)
-    capi.check(engine.lib.prosail_invert_last_stats(engine.h, C.byref(used), C.byref(redone), C.byref(to)))
-    return dict(tensor_cores=bool(used.value), redone_exactly=int(redone.value), timed_out=bool(to.value))
+    their candidate list could not be proven complete, timed_out=bool, error_ratio=float -- the largest measured error of the
+    tensor-core brackets relative to sum |A_k||B_k| over the kept candidates (the model assumes 8e-6), bound_violations=int --
+    candidates outside the model's bound (expected 0; their observations were rescanned exactly)).  The results obey the same
+    bit-exact contract either way."""
+    used, redone, to, ratio, viol = C.c_int(0), C.c_longlong(0), C.c_int(0), C.c_double(0.0), C.c_longlong(0)
+    capi.check(engine.lib.prosail_invert_last_stats(engine.h, C.byref(used), C.byref(redone), C.byref(to), C.byref(ratio), C.byref(viol)))
+    return dict(tensor_cores=bool(used.value), redone_exactly=int(redone.value), timed_out=bool(to.value), error_ratio=float(ratio.value),
+                bound_violations=int(viol.value))
 
 
 def reduce_best(costs, indices):
