@@ -15,12 +15,33 @@
 
 #define PB_MAGIC 6755399441055744.0  /* 1.5 * 2^52: round-to-nearest-integer by addition */
 
+// Round 2n: algebraic reductions of the FP64 instruction count of the fused double instances (each can be switched off for A/B
+// runs: make variant NAME=x EXTRA=-DPB_...=0; profiles/r2n_variants.txt)
+#ifndef PB_STOKES_Y
+#define PB_STOKES_Y 1    /* Stokes stage divided through by a: Y = bm1 (al - r^2) + D (3 FP64 instructions less, no cancellation) */
+#endif
+#ifndef PB_RINF_P
+#define PB_RINF_P 1      /* rinf = (P - m)/(P + m), P = att + sigb = 1 + bf (rho - tau) (2 less) */
+#endif
+#ifndef PB_HALVES
+#define PB_HALVES 1      /* Ap, Am carried doubled; the powers of two are taken out of invden / inv_omr2 on the integer pipe (2 less) */
+#endif
+#ifndef PB_FSFOLD
+#define PB_FSFOLD 1      /* lai sumint folded into Fs, Ft by the prologue (1 less) */
+#endif
+#ifndef PB_EXPS
+#define PB_EXPS 1        /* exp(-m lai): the record carries -lai 2048 log2(e), the product m lai is never formed (1 less) */
+#endif
+#ifndef PB_POWS
+#define PB_POWS 1        /* b^(N-1): (N-1) log2 b is never formed, the rounding magic works in units of 2^-11 (1 less) */
+#endif
+
 namespace pb {
 
 // Polynomial / range-reduction constants live in constant memory so that DFMA takes them straight from the
 // constant bank (operand c[3][..]); as literals they would each cost two UMOV issue slots per use.
 // (Values whose low 32 bits are zero -- 0.5, 1.0, 256.0, the rounding magic -- are encodable as immediates.)
-enum { M_L2EN = 0, M_NLN2S, M_E3, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P3, M_P2, M_P1, M_COUNT };
+enum { M_L2EN = 0, M_NLN2S, M_E3, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P3, M_P2, M_P1, M_S3, M_S2, M_S1, M_COUNT };
 static_assert(EXP2_BITS == 11, "the range-reduction constants below are for a 2048-entry 2^(j/2048) table");
 __constant__ double c_m[M_COUNT] = {
     2954.6394437405970201,       // 2048 log2(e)
@@ -34,6 +55,9 @@ __constant__ double c_m[M_COUNT] = {
     0x1.c6b08d704a0c0p-5,        // ln2^3/6
     0x1.ebfbdff82c58fp-3,        // ln2^2/2
     0x1.62e42fefa39efp-1,        // ln2
+    0x1.c6b08d704a0c0p-38,       // (ln2/2048)^3/6      exp_neg_scaled: the reduced argument is in units of 1/2048 octave
+    0x1.ebfbdff82c58fp-25,       // (ln2/2048)^2/2
+    0x1.62e42fefa39efp-12,       // ln2/2048
 };
 
 // Round 2: the band kernel is bound by the FP64 pipe INCLUDING its operand reads (a DFMA with three distinct register
@@ -112,6 +136,8 @@ __device__ __forceinline__ double sqrt_pos(double x) {
 // x * 2^-1 on the integer pipe (x normal and not within one binade of the subnormals)
 __device__ __forceinline__ double half_of(double x) { return __hiloint2double(__double2hiint(x) - 0x00100000, __double2loint(x)); }
 
+__device__ __forceinline__ double quarter_of(double x) { return __hiloint2double(__double2hiint(x) - 0x00200000, __double2loint(x)); }
+
 __device__ __forceinline__ double rcp_q(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -181,6 +207,25 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ e
     return __hiloint2double(__double2hiint(v) + ((n >> EXP2_BITS) << 20), __double2loint(v));
 }
 
+// exp(-m lai) without ever forming the product (round 2n): the sample record carries c = -lai 2048 log2(e), so that
+//   t = fma(m, c, 1.5 2^52) rounds x 2048 log2(e) to the integer n,  r = fma(m, c, -n) is the remainder in units of 1/2048 octave
+// (one rounding, |r| <= 1/2), and exp = 2^(n>>11) T[n&2047] P3(r) with the cubic's coefficients scaled by powers of ln2/2048.
+// 6 FP64 instructions + one table load (exp_neg of the product: 8).  The only new error is the rounding of c (2^-53 relative,
+// i.e. |x| 1.1e-16 relative in the result -- what the product m lai had as well).  Underflow guard: ONE integer max on n
+// (exponent floor 2^-1010); the prologue keeps |c| below 2^30 (lai < 3.6e5).
+__device__ __forceinline__ double exp_neg_scaled(double m, double c, const double* __restrict__ exp2t) {
+    const double t = fma(m, c, PB_MAGIC);
+    const int n = max(__double2loint(t), -(1010 << EXP2_BITS));
+    const double nd = t - PB_MAGIC;
+    const double r = fma(m, c, -nd);
+    double p = fma(r, c_m[M_S3], c_m[M_S2]);
+    p = fma(r, p, c_m[M_S1]);
+    p = fma(r, p, 1.0);
+    const double v = exp2t[n & ((1 << EXP2_BITS) - 1)] * p;
+    return __hiloint2double(__double2hiint(v) + ((n >> EXP2_BITS) << 20), __double2loint(v));
+}
+#define PB_EXPS_SCALE 2954.6394437405970201   /* 2048 log2(e): what the double sample record multiplies -lai with (PB_EXPS) */
+
 // log2(b) for normal b > 0: b = 2^E m, m in [1,2); i = top 8 mantissa bits; r = m/c_i - 1, |r| <= 2^-9;
 // log2 b = E + log2 c_i + log2(1+r) with a degree-4 series (absolute error <= 2^-45/(5 ln 2) = 8e-15).
 // 7 FP64 ops + one 16-byte table load.
@@ -212,6 +257,25 @@ __device__ __forceinline__ double exp2_any(double y, const double* __restrict__ 
     p = fma(r, p, c_m[M_P1]);
     p = fma(r, p, 1.0);
     const double v = exp2t[n & ((1 << EXP2_BITS) - 1)] * p;
+    return __hiloint2double(__double2hiint(v) + ((n >> EXP2_BITS) << 20), __double2loint(v));
+}
+
+// b^e = 2^(e log2 b) without forming the exponent (round 2n): with the rounding magic in units of 2^-11 (1.5 2^41; its low word
+// is zero, so it is an immediate operand), t = fma(L, e, magic) rounds e L to a multiple of 1/2048, r = fma(L, e, -(t - magic))
+// is the exact remainder rounded once, and the rest is exp2_any.  14 FP64 instructions instead of 15.  The clamp of the exponent
+// at about 500 becomes an integer min of L against 500/|e| (high word, from the sample record: lmax_hi).
+__device__ __forceinline__ double pow_pos_scaled(double b, double e, int lmax_hi, const MathTables& mt) {
+    double L = log2_pos(b, mt.logt);
+    L = __hiloint2double(min(__double2hiint(L), lmax_hi), __double2loint(L));
+    const double MG = PB_MAGIC / (double)(1 << EXP2_BITS);
+    const double t = fma(L, e, MG);
+    const int n = __double2loint(t);
+    const double nd = t - MG;                      // n / 2048
+    const double r = fma(L, e, -nd);
+    double p = fma(r, c_m[M_P3], c_m[M_P2]);
+    p = fma(r, p, c_m[M_P1]);
+    p = fma(r, p, 1.0);
+    const double v = mt.exp2t[n & ((1 << EXP2_BITS) - 1)] * p;
     return __hiloint2double(__double2hiint(v) + ((n >> EXP2_BITS) << 20), __double2loint(v));
 }
 

@@ -70,9 +70,12 @@ enum { C_KAB = 0, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RS1, 
 // (C_RALF.. = 1 - talf, 1 - t12, 1 - t21: only the float image carries them, rounded once from the float64 values)
 
 // sample record (per parameter set)
-enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DDB, S_DDF, S_NEGLAI, S_LAI, S_NOCANOPY, S_THR, S_BF };
+enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DDB, S_DDF, S_NEGLAI, S_LAI, S_LMAX, S_THR, S_BF };
+// (S_NEGLAI: -lai, +0.0 for bare soil (the no-canopy flag); double records with PB_EXPS: -lai 2048 log2(e).  S_LMAX: 500/|N-1|, the
+//  clamp of log2 b in pow_pos_scaled.)
 // geometry record (per parameter set x geometry)
-enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_BF, G_SUMINT, G_ALF };
+enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_FSL, G_FTL, G_ALF };
+// (G_FSL, G_FTL: Fs lai sumint, Ft lai sumint -- the single-scattering term rsos = w lai sumint of models.py:706-710 as two FMAs on rho, tau)
 
 // output planes (bit index in out_mask / mean_mask)
 enum { O_RSOT = 0, O_RDDT, O_RSDT, O_RDOT, O_RSO, O_RDD, O_TDD, O_RSD, O_TSD, O_RDO, O_TDO, O_KE, O_LEAF_R, O_LEAF_T, O_RHO,
@@ -261,7 +264,7 @@ __device__ __forceinline__ T soil_rho(const T* __restrict__ kc, const T* __restr
 // The interface constants enter in FOLDED form (ta21 = talf t21, t1221 = t12 t21), so that Ta = ta21 tau/(1 - x^2) and
 // t = t1221 tau/(1 - x^2) cost one multiplication each.
 template <typename T, typename MT>
-__device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf, T r12, T tau, T nm1, const MT& mt, T& refl, T& tran) {
+__device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf, T r12, T tau, T nm1, int lmax_hi, const MT& mt, T& refl, T& tran) {
     const T one = T(1), half = T(0.5);
     // one layer                                                                              :1019-1025
     const T x = r21 * tau;
@@ -283,17 +286,34 @@ __device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf,
     const T be = fma(-half, A, one + hD);          // b * t   (b of :1047), using 1 - r^2 + t^2 = 2 - A
     const T b = be * rcp_k(t);                     // NOT benign: b^(2(N-1)) - 1 differences it against 1 (third-order step)
     // b^(N-1) = 2^((N-1) log2 b)                                                             :1049
+#if PB_POWS
+    const T bNm1 = pow_pos_scaled(b, nm1, lmax_hi, mt);
+#else
     const T bNm1 = pow_pos(b, nm1, mt);
+#endif
     const T bN2 = bNm1 * bNm1;
     // With a = al/r:  kt = Ta bNm1 (al^2 - r^2)/X,  ks = Ra + Ta t al r (bN2 - 1)/X,
     //                 X = al^2 bN2 - r^2 - al r^2 (bN2 - 1)      (algebraically :1052-1065, one division)
     //                   = (al^2 - r^2) + (bN2 - 1) al (al - r^2)
     const T bm1 = bN2 - one;
+#if PB_STOKES_Y
+    // Round 2n: divide the X form below by a = al/r once more.  With 1/a = (A - D)/(2r) (because A^2 - D^2 = 4 r^2):
+    //   Rsub = r bm1/(al bN2 - gl),  Tsub = bNm1 D/(al bN2 - gl),  gl = (A - D)/2,   and   1 - Rsub r = Y/(al bN2 - gl)  with
+    //   Y = al bN2 - gl - r^2 bm1 = bm1 (al - r^2) + (al - gl) = bm1 (al - r^2) + D        (al - gl = D)
+    //   =>  kt = Ta bNm1 D / Y,   ks = Ra + Ta t r bm1 / Y.
+    // Both terms of Y are positive (al - r^2 = r (a - r) > 0), so nothing cancels -- the X form differences al^2 against r^2, which
+    // loses digits as D -> 0 -- and three FP64 instructions per band and item go (12 instead of 15 after bNm1).
+    const T Y = fma(bm1, al - r2, D);
+    const T TaI = Ta * rcp_b(Y);                   // benign: scales kt and ks - Ra
+    tran = TaI * (bNm1 * D);
+    refl = fma(TaI * bm1, t * r, Ra);
+#else
     const T dal = fma(al, al, -r2);                // al^2 - r^2 = r^2 (a^2 - 1)
     const T X = fma(bm1, al * (al - r2), dal);
     const T TaI = Ta * rcp_b(X);                   // benign: scales kt and ks - Ra
     tran = TaI * (bNm1 * dal);
     refl = fma(TaI * bm1, (t * al) * r, Ra);
+#endif
     return !is_pos(qmt);                           // r + t >= 1, tested on the sign of 1 - r - t (integer pipe)
 }
 // zero-absorption case (r + t >= 1), exactly as models.py:1057-1065 with IEEE divisions (rare path)
@@ -467,6 +487,7 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
         T tau[NU];
         bool zero[NU];
         bool any_zero = false;
+        const int lmax_hi = hi_word(s[S_LMAX]);
 #pragma unroll
         for (int u = 0; u < NU; ++u) { tau[u] = tau_fast(kall[u], mt.tau, rare[u]); any_rare |= rare[u]; }   // :953-957
         if (__builtin_expect(any_rare, 0)) {
@@ -478,9 +499,9 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
         for (int u = 0; u < NU; ++u) {
             if constexpr (CSMEM)
                 zero[u] = leaf_layers_fast(kc[u + KC_R21 * KS], kc[u + KC_TA21 * KS], kc[u + KC_T1221 * KS], kc[u + KC_RALF * KS], kc[u + KC_R12 * KS],
-                                           tau[u], nm1, mt, refl[u], tran[u]);
+                                           tau[u], nm1, lmax_hi, mt, refl[u], tran[u]);
             else
-                zero[u] = leaf_layers_fast(c[u].r21, c[u].ta21, c[u].t1221, c[u].ralf, c[u].r12, tau[u], nm1, mt, refl[u], tran[u]);
+                zero[u] = leaf_layers_fast(c[u].r21, c[u].ta21, c[u].t1221, c[u].ralf, c[u].r12, tau[u], nm1, lmax_hi, mt, refl[u], tran[u]);
             any_zero |= zero[u];
         }
         if (__builtin_expect(any_zero, 0)) {
@@ -533,6 +554,7 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
 template <typename T>
 struct Diffuse {
     T m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd, rinf_invden;
+    T invden_h;    // PB_HALVES (AB form): invden/2, and inv_omr2 then holds 1/(4 (1 - rinf^2)) -- see sail_diffuse
     T a1, a2;      // rho + tau rinf, tau + rho rinf: the leaf-dependent factors of (sf + sb rinf), (sf rinf + sb), ... (:649-652)
                    // fused fp64 instances (AB form): a1 = Ap = (a1 + a2)/2 = (rho + tau)(1 + rinf)/2,  a2 = Am = bf (rho - tau)(1 - rinf)/2,
                    // so that  sf + sb rinf = k Ap - Am,  sf rinf + sb = k Ap + Am  (and the same with K): one FMA each per geometry
@@ -552,10 +574,28 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
         const T s_ = rho + tau, dd = rho - tau;
         const T bd = s[S_BF] * dd;
         const T oms = one - s_;
+#if PB_RINF_P
+        // Round 2n: with P = att + sigb = 1 + bd and Q = att - sigb = 1 - s:  m = sqrt(P Q)  and
+        //   rinf = (att - m)/sigb = (P - m)/(P + m)        [(att - m)(P + m) - sigb (P - m) = P Q - m^2 = 0]
+        // two FP64 instructions less than sigb/(att + m) spelled out in s, bd.  P - m cancels only where rinf itself is small
+        // (dark leaves): the second-order square root (3e-12 relative in m) then leaves <= 1.5e-12 ABSOLUTE in rinf.
+        const T P = one + bd;
+        d.m = sqrt_b_pos(oms * P);
+        d.rinf = (P - d.m) * rcp_b(P + d.m);
+#else
         d.m = sqrt_b_pos(fma(oms, bd, oms));
         d.rinf = (s_ + bd) * rcp_b(fma(T(2), d.m, T(2) - (s_ - bd)));
+#endif
+#if PB_HALVES
+        // 2 Ap and 2 Am: one FMA each.  Everything downstream is homogeneous in them -- tsd, rsd, tdo, rdo of degree one, T1 + T2 - T3
+        // of degree two -- so the factors 1/2 and 1/4 are taken out of invden (invden_h) and inv_omr2 below: two exponent
+        // decrements on the integer pipe instead of two FP64 instructions.
+        d.a1 = fma(s_, d.rinf, s_);
+        d.a2 = fma(-bd, d.rinf, bd);
+#else
         d.a1 = s_ * fma(T(0.5), d.rinf, T(0.5));                      // Ap
         d.a2 = bd * fma(T(-0.5), d.rinf, T(0.5));                     // Am
+#endif
     } else {
     T sigb = fma(s[S_DDB], rho, s[S_DDF] * tau);                      // :590
     T sigf = fma(s[S_DDF], rho, s[S_DDB] * tau);                      // :591
@@ -581,6 +621,10 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
     d.a1 = fma(tau, d.rinf, rho);
     d.a2 = fma(rho, d.rinf, tau);
     }
+#if PB_EXPS
+    if constexpr (!is_f32<T>()) d.e1 = exp_neg_scaled(d.m, s[S_NEGLAI], mt.exp2t);   // the double record carries -lai 2048 log2(e)      :637
+    else
+#endif
     d.e1 = exp_neg(d.m * s[S_NEGLAI], mt);                            // :637
     d.re = d.rinf * d.e1;
     const T omr2 = fma(-d.rinf, d.rinf, one);                         // 1 - rinf^2
@@ -596,6 +640,12 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
         d.invden = rcp_b(den);
         d.inv_omr2 = rcp_b(omr2);
     }
+#if PB_HALVES
+    if constexpr (FROM_LEAF && !is_f32<T>()) {                        // both are >= 1: the exponent decrements are exact
+        d.invden_h = half_of(d.invden);
+        d.inv_omr2 = quarter_of(d.inv_omr2);
+    }
+#endif
     d.tdd = omr2 * d.e1 * d.invden;                                   // :654
     d.rinf_invden = d.rinf * d.invden;                                // shared by rdd and by T3 of the directional stage
     d.rdd = fma(-d.re, d.e1, d.rinf) * d.invden;                      // rinf (1 - e^2)/den = (rinf - (rinf e) e)/den   :655
@@ -621,7 +671,6 @@ __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>
     // sb, sf, vb, vf (:603-606) only ever appear as sf + sb rinf, sf rinf + sb, vf + vb rinf, vf rinf + vb (:649-652).  With
     // a1 = rho + tau rinf and a2 = tau + rho rinf (geometry independent, computed once per parameter set):
     //   sf + sb rinf = sdf a1 + sdb a2,   sf rinf + sb = sdf a2 + sdb a1,   and the same with (dof, dob) for the view direction
-    const T w = fma(g[G_FS], rho, g[G_FT] * tau);                     // :607
     T u1, u2, v1, v2;
     if constexpr (AB) {           // d.a1 = Ap, d.a2 = Am (see sail_diffuse): one FMA each
         u1 = fma(g[G_K], d.a1, -d.a2); u2 = fma(g[G_K], d.a1, d.a2);
@@ -636,21 +685,36 @@ __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>
     const T Pss = u1 * J1ks, Qss = ck * fma(-d.e1, tss, one), Pv = v1 * J1ko, Qv = cK * fma(-d.e1, too, one);
     // tsd, rsd, tdo, rdo (:656-659) before their common factor 1/(1 - rinf^2 e^2): T3 takes it together with rinf
     const T tsd_u = fma(-d.re, Qss, Pss), tdo_u = fma(-d.re, Qv, Pv), rdo_u = fma(-d.re, Pv, Qv);
-    o.tsd = tsd_u * d.invden;
-    o.rsd = fma(-d.re, Pss, Qss) * d.invden;
-    o.tdo = tdo_u * d.invden;
-    o.rdo = rdo_u * d.invden;
+    // (PB_HALVES, AB form: u1 .. v2 are twice the reference's, the four terms take invden/2; T1 + T2 - T3 is four times too large
+    //  and inv_omr2 carries the 1/4)
+    T invden1;
+    if constexpr (AB && PB_HALVES) invden1 = d.invden_h; else invden1 = d.invden;
+    o.tsd = tsd_u * invden1;
+    o.rsd = fma(-d.re, Pss, Qss) * invden1;
+    o.tdo = tdo_u * invden1;
+    o.rdo = rdo_u * invden1;
     // T1 + T2 - T3 as nested FMAs (:668-678):  T1 = v2 g1 u1 with g1 = (z - J1(k,m) too)/(K+m),  T2 = v1 g2 u2,
     // T3 = (rdo Qss + tdo Pss) rinf
     const T T3 = fma(rdo_u, Qss, tdo_u * Pss) * d.rinf_invden;
     const T Ts = fma(cK * u1, fma(-J1ks, too, g[G_Z]), fma(ck * v1, fma(-J1ko, tss, g[G_Z]), -T3));
     // soil coupling (:721-726): rsodt = ((tss + tsd) tdo + (tsd + tss rs rdd) too) rs/dn
     const T sc = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too);
-    if (need & (1u << O_RSO)) {
-        o.rso = fma(w, g[G_LAISUM], Ts * d.inv_omr2);                 // rsos + rsod                              :706, :710
-        o.rsot = fma(sc, d.rs_invdn, fma(g[G_TSSTOO], rs, o.rso));
-    } else {                                                          // rsot = rsod + rsos + tsstoo rs + rsodt, one FMA per term
-        o.rsot = fma(sc, d.rs_invdn, fma(Ts, d.inv_omr2, fma(w, g[G_LAISUM], g[G_TSSTOO] * rs)));
+    if constexpr (AB && PB_FSFOLD) {
+        // rsos = w lai sumint with w = Fs rho + Ft tau (:607, :706): the prologue folds lai sumint into Fs, Ft (G_FSL, G_FTL)
+        if (need & (1u << O_RSO)) {
+            o.rso = fma(g[G_FSL], rho, fma(g[G_FTL], tau, Ts * d.inv_omr2));                      // rsos + rsod             :706, :710
+            o.rsot = fma(sc, d.rs_invdn, fma(g[G_TSSTOO], rs, o.rso));
+        } else {                                                      // rsot = rsod + rsos + tsstoo rs + rsodt, one FMA per term
+            o.rsot = fma(sc, d.rs_invdn, fma(Ts, d.inv_omr2, fma(g[G_FSL], rho, fma(g[G_FTL], tau, g[G_TSSTOO] * rs))));
+        }
+    } else {
+        const T w = fma(g[G_FS], rho, g[G_FT] * tau);                 // :607
+        if (need & (1u << O_RSO)) {
+            o.rso = fma(w, g[G_LAISUM], Ts * d.inv_omr2);             // rsos + rsod                              :706, :710
+            o.rsot = fma(sc, d.rs_invdn, fma(g[G_TSSTOO], rs, o.rso));
+        } else {                                                      // rsot = rsod + rsos + tsstoo rs + rsodt, one FMA per term
+            o.rsot = fma(sc, d.rs_invdn, fma(Ts, d.inv_omr2, fma(w, g[G_LAISUM], g[G_TSSTOO] * rs)));
+        }
     }
     if (need & (1u << O_RDDT)) o.rddt = fma(d.tdd * d.tdd, d.rs_invdn, d.rdd);
     if (need & (1u << O_RSDT)) o.rsdt = fma((o.tsd + tss) * d.tdd, d.rs_invdn, o.rsd);
@@ -1162,7 +1226,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         }
                         // |k - m| lai <= 1e-3  <=>  |k - m| <= 1e-3 / lai   (threshold on the high word)
                         thr_hi = hi_word(sr[S_THR]);
-                        nocanopy = hi_word(sr[S_NOCANOPY]) != 0;                 // the flag is 0 or 1: an integer test on its high word, once per set
+                        nocanopy = hi_word(sr[S_NEGLAI]) == 0;                   // bare soil: the record carries +0.0 there (any canopy: a negative number); an integer test, once per set
                         fresh = false;
                     }
                     {
@@ -1395,6 +1459,15 @@ __global__ void k_volume(int n, const double* __restrict__ iza, const double* __
     out[4 * i] = chi_s; out[4 * i + 1] = chi_o; out[4 * i + 2] = frho; out[4 * i + 3] = ftau;
 }
 
+// S_NEGLAI of a canopy: -lai; in double records (PB_EXPS) pre-multiplied with 2048 log2(e) for exp_neg_scaled, |value| < 2^30
+template <typename T>
+__device__ __forceinline__ double neglai_rec(double lai) {
+#if PB_EXPS
+    if constexpr (!std::is_same<T, float>::value) return -fmin(lai * PB_EXPS_SCALE, 1.0e9);
+#endif
+    return -lai;
+}
+
 // write one 16-element record as T (double: 128 B, float: 64 B) with 16-byte stores
 template <typename T>
 __device__ __forceinline__ void store_rec(void* base, long long idx, const double (&rec)[REC]) {
@@ -1427,6 +1500,7 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         srec[S_CAB] = a.Cab[s] / N; srec[S_CXC] = a.Cxc[s] / N; srec[S_CAN] = a.Can ? a.Can[s] / N : 0.0;
         srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
         srec[S_NM1] = N - 1.0;
+        srec[S_LMAX] = 500.0 / fabs(N - 1.0);     // clamp of log2 b in b^(N-1) (pow_pos_scaled); inf for N = 1
     }
     if (a.has_soil) {
         const double sr = a.soil_refl[s], mo = a.soil_moist[s];
@@ -1555,11 +1629,11 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         r[G_DOB] = 0.5 * (K + bf); r[G_DOF] = 0.5 * (K - bf);
         r[G_FS] = Fs; r[G_FT] = Ft;
         r[G_TSS] = tss; r[G_TOO] = too; r[G_TSSTOO] = tsstoo;
-        r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_BF] = bf; r[G_SUMINT] = sumint; r[G_ALF] = alf;
+        r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_FSL] = Fs * (lai * sumint); r[G_FTL] = Ft * (lai * sumint); r[G_ALF] = alf;
         store_rec<T>(a.grec, item, r);
         if (g == 0) {
             srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
-            srec[S_NEGLAI] = nocanopy ? 0.0 : -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;   // bare soil: the band kernel's canopy stage runs with lai = 0
+            srec[S_NEGLAI] = nocanopy ? 0.0 : neglai_rec<T>(lai); srec[S_LAI] = lai;   // bare soil (+0.0 IS the no-canopy flag): the band kernel's canopy stage runs with lai = 0
             srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
             srec[S_BF] = bf;
             store_rec<T>(a.srec, s, srec);
@@ -1727,6 +1801,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
             srec[S_CAB] = a.Cab[s] / N; srec[S_CXC] = a.Cxc[s] / N; srec[S_CAN] = a.Can ? a.Can[s] / N : 0.0;
             srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
             srec[S_NM1] = N - 1.0;
+            srec[S_LMAX] = 500.0 / fabs(N - 1.0);     // clamp of log2 b in b^(N-1) (pow_pos_scaled); inf for N = 1
         }
         if (a.has_soil) {
             const double sr = a.soil_refl[s], mo = a.soil_moist[s];
@@ -1821,11 +1896,11 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
     grec[G_DOB] = 0.5 * (K + bf); grec[G_DOF] = 0.5 * (K - bf);
     grec[G_FS] = Fs; grec[G_FT] = Ft;
     grec[G_TSS] = tss; grec[G_TOO] = too; grec[G_TSSTOO] = tsstoo;
-    grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_BF] = bf; grec[G_SUMINT] = sumint; grec[G_ALF] = alf;
+    grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_FSL] = Fs * (lai * sumint); grec[G_FTL] = Ft * (lai * sumint); grec[G_ALF] = alf;
     store_rec<T>(a.grec, item, grec);
     if (g == 0) {
         srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
-        srec[S_NEGLAI] = nocanopy ? 0.0 : -lai; srec[S_LAI] = lai; srec[S_NOCANOPY] = nocanopy ? 1.0 : 0.0;   // bare soil: the band kernel's canopy stage runs with lai = 0
+        srec[S_NEGLAI] = nocanopy ? 0.0 : neglai_rec<T>(lai); srec[S_LAI] = lai;   // bare soil (+0.0 IS the no-canopy flag): the band kernel's canopy stage runs with lai = 0
         srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
         srec[S_BF] = bf;
         store_rec<T>(a.srec, s, srec);

@@ -1,8 +1,19 @@
 #!/bin/bash
-# round 2n: final code -- smoke, full GPU test suite, bench lines
+# round 2n: A/B of the FP64-instruction reductions (base = the round-2m library) + the gpu test suite on the new library
 mkdir -p gpurun_out; O=gpurun_out/r2n.txt; : > $O
-python __graft_entry__.py smoke >> $O 2>&1
-python -m pytest tests -m gpu -q 2>&1 | tail -4 >> $O
-python bench.py > gpurun_out/r2n_bench_c2.json 2>> $O
-python bench.py --config 4 --steps 5 > gpurun_out/r2n_bench_c4.json 2>> $O
-cat $O; tail -c 1500 gpurun_out/r2n_bench_c4.json
+V=$PWD/pyrism_b200/lib/variants
+for w in "brf f64" "leaf f64" "means f64" "four f64" "brf f32"; do
+  set -- $w
+  for lib in base ""; do
+    if [ -n "$lib" ]; then export PYRISM_B200_LIB=$V/libprosail_$lib.so; else unset PYRISM_B200_LIB; fi
+    python tools/kbench.py 1000000 5 $1 $2 >> $O 2>&1
+  done
+done
+for lib in base ""; do
+  if [ -n "$lib" ]; then export PYRISM_B200_LIB=$V/libprosail_$lib.so; else unset PYRISM_B200_LIB; fi
+  python tools/kbench.py 8192 5 multi f64 >> $O 2>&1
+done
+unset PYRISM_B200_LIB
+for x in $EXTRA_VARIANTS; do PYRISM_B200_LIB=$V/libprosail_$x.so python tools/kbench.py 1000000 5 brf f64 >> $O 2>&1; done
+cat $O
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee -a $O
