@@ -41,7 +41,7 @@ namespace pb {
 // Polynomial / range-reduction constants live in constant memory so that DFMA takes them straight from the
 // constant bank (operand c[3][..]); as literals they would each cost two UMOV issue slots per use.
 // (Values whose low 32 bits are zero -- 0.5, 1.0, 256.0, the rounding magic -- are encodable as immediates.)
-enum { M_L2EN = 0, M_NLN2S, M_E3, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P3, M_P2, M_P1, M_S3, M_S2, M_S1, M_COUNT };
+enum { M_L2EN = 0, M_NLN2S, M_E3, M_L4, M_L3, M_L2, M_L1, M_EBIAS, M_P3, M_P2, M_P1, M_S3, M_S2, M_S1, M_L2E, M_P1Q, M_COUNT };
 static_assert(EXP2_BITS == 11, "the range-reduction constants below are for a 2048-entry 2^(j/2048) table");
 __constant__ double c_m[M_COUNT] = {
     2954.6394437405970201,       // 2048 log2(e)
@@ -58,6 +58,8 @@ __constant__ double c_m[M_COUNT] = {
     0x1.c6b08d704a0c0p-38,       // (ln2/2048)^3/6      exp_neg_scaled: the reduced argument is in units of 1/2048 octave
     0x1.ebfbdff82c58fp-25,       // (ln2/2048)^2/2
     0x1.62e42fefa39efp-12,       // ln2/2048
+    -0x1.715481dd5be27p-1,       // -(1/2 + h^2/4)/ln2, h = 2^-10: quadratic coefficient of the economised cubic of log2(1 + r), |r| <= h
+    0x1.62e43004f3e59p-1,        // ln2 (1 + g^2/8), g = ln2/4096: linear coefficient of the economised quadratic of 2^r, |r| <= 1/4096
 };
 
 // Round 2: the band kernel is bound by the FP64 pipe INCLUDING its operand reads (a DFMA with three distinct register
@@ -70,11 +72,11 @@ __constant__ double c_m[M_COUNT] = {
 #ifndef PB_TAU_F32TAIL
 #define PB_TAU_F32TAIL 1
 #endif
-struct alignas(16) TauRow {            // 64 bytes: four 128-bit shared-memory loads
-    double O, c0, c1, c2, c3;          // u = k S - O;  tau = c0 + u (c1 + u (c2 + u (c3 + u T4(u))))
-    float f4, f5, f6, f7, f8, pad;     // T4(u) = f4 + u (f5 + u (f6 + u (f7 + u f8))) in float
+struct alignas(16) TauRow {            // 48 bytes: three 128-bit shared-memory loads
+    double O, c0, c1, c2;              // u = k S - O;  tau = c0 + u (c1 + u (c2 + u T3(u)))
+    float f3, f4, f5, f6;              // T3(u) = f3 + u (f4 + u (f5 + u f6)) in float (|c3| <= 5.1e-6 over the table: <= 3e-13 absolute)
 };
-static_assert(sizeof(TauRow) == 64, "TauRow layout");
+static_assert(sizeof(TauRow) == 48 && TAU_DEG == 6, "TauRow layout: degree 6, 16 sub-intervals per binade (tools/gen_math_tables.py)");
 
 // ---- shared-memory image of the lookup tables (copied once per CTA) ----
 struct alignas(16) MathTables {
@@ -84,7 +86,7 @@ struct alignas(16) MathTables {
     double tau[TAU_NROWS * TAU_ROW];   // piecewise polynomials of tau(k), see tools/gen_math_tables.py
 #endif
     double exp2t[1 << EXP2_BITS];      // 2^(j/2048)
-    double logt[512];                  // pairs (1/c_i, log2 c_i), c_i = 1 + (i+.5)/256
+    double logt[2 << LOG_BITS];        // pairs (1/c_i, log2 c_i + the constant of the economised cubic), c_i = 1 + (i+.5)/512
 };
 
 // Sign/threshold tests on the high word run on the integer pipe instead of costing an FP64-pipe DSETP.
@@ -136,6 +138,9 @@ __device__ __forceinline__ double sqrt_pos(double x) {
 // x * 2^-1 on the integer pipe (x normal and not within one binade of the subnormals)
 __device__ __forceinline__ double half_of(double x) { return __hiloint2double(__double2hiint(x) - 0x00100000, __double2loint(x)); }
 
+// max(x, floor) for a positive floor whose high word is `floor_hi`, decided on the high words alone (x < 0, -0.0 included, has a
+// negative high word): one VIMNMX instead of a compare and two selects.  The result is >= floor (1 - 2^-20).
+__device__ __forceinline__ double floor_hi(double x, int floor_hi_word) { return __hiloint2double(max(__double2hiint(x), floor_hi_word), __double2loint(x)); }
 __device__ __forceinline__ double quarter_of(double x) { return __hiloint2double(__double2hiint(x) - 0x00200000, __double2loint(x)); }
 
 __device__ __forceinline__ double rcp_q(double x) {
@@ -226,20 +231,21 @@ __device__ __forceinline__ double exp_neg_scaled(double m, double c, const doubl
 }
 #define PB_EXPS_SCALE 2954.6394437405970201   /* 2048 log2(e): what the double sample record multiplies -lai with (PB_EXPS) */
 
-// log2(b) for normal b > 0: b = 2^E m, m in [1,2); i = top 8 mantissa bits; r = m/c_i - 1, |r| <= 2^-9;
-// log2 b = E + log2 c_i + log2(1+r) with a degree-4 series (absolute error <= 2^-45/(5 ln 2) = 8e-15).
-// 7 FP64 ops + one 16-byte table load.
+// log2(b) for normal b > 0: b = 2^E m, m in [1,2); i = top LOG_BITS = 9 mantissa bits; r = m/c_i - 1, |r| <= h = 2^-10;
+// log2 b = E + log2 c_i + log2(1+r) with the cubic  (r - (1/2 + h^2/4) r^2 + r^3/3 + h^4/32)/ln2  -- the Taylor quartic with r^4
+// economised to h^2 r^2 - h^4/8 (Chebyshev), its constant folded into the table's log2 c_i: absolute error <= h^4/(32 ln2) =
+// 4.1e-14 (round 1/2k: 256 entries and the degree-4 series, 8e-15; b^(2(N-1)) - 1 amplifies it by <= 100).
+// 6 FP64 ops + one 16-byte table load.
 __device__ __forceinline__ double log2_pos(double b, const double* __restrict__ logt) {
     const int hi = __double2hiint(b);
-    const int i = (hi >> 12) & 255;
+    const int i = (hi >> (20 - LOG_BITS)) & ((1 << LOG_BITS) - 1);
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(b));
     const double2 tc = *reinterpret_cast<const double2*>(logt + 2 * i);
     const double r = fma(m, tc.x, -1.0);
     // E as a double without I2F: 2^52 + 2^31 + (E biased by 2^31), minus the constant.
     const int E = (hi >> 20) - 1023;
     const double Ed = __hiloint2double(0x43300000, E ^ 0x80000000) - c_m[M_EBIAS];
-    double q = fma(r, c_m[M_L4], c_m[M_L3]);
-    q = fma(r, q, c_m[M_L2]);
+    double q = fma(r, c_m[M_L3], c_m[M_L2E]);
     q = fma(r, q, c_m[M_L1]);
     return fma(r, q, Ed + tc.y);
 }
@@ -262,7 +268,7 @@ __device__ __forceinline__ double exp2_any(double y, const double* __restrict__ 
 
 // b^e = 2^(e log2 b) without forming the exponent (round 2n): with the rounding magic in units of 2^-11 (1.5 2^41; its low word
 // is zero, so it is an immediate operand), t = fma(L, e, magic) rounds e L to a multiple of 1/2048, r = fma(L, e, -(t - magic))
-// is the exact remainder rounded once, and the rest is exp2_any.  14 FP64 instructions instead of 15.  The clamp of the exponent
+// is the exact remainder rounded once, and the rest is exp2_any with a quadratic.  12 FP64 instructions (pow_pos: 15).  The clamp of the exponent
 // at about 500 becomes an integer min of L against 500/|e| (high word, from the sample record: lmax_hi).
 __device__ __forceinline__ double pow_pos_scaled(double b, double e, int lmax_hi, const MathTables& mt) {
     double L = log2_pos(b, mt.logt);
@@ -272,8 +278,8 @@ __device__ __forceinline__ double pow_pos_scaled(double b, double e, int lmax_hi
     const int n = __double2loint(t);
     const double nd = t - MG;                      // n / 2048
     const double r = fma(L, e, -nd);
-    double p = fma(r, c_m[M_P3], c_m[M_P2]);
-    p = fma(r, p, c_m[M_P1]);
+    // economised quadratic of 2^r (r^3 ln2^3/6 ~ (g^2/8) r ln2 on |r ln2| <= g = ln2/4096): 2e-13 relative, one FMA less than the cubic
+    double p = fma(r, c_m[M_P2], c_m[M_P1Q]);
     p = fma(r, p, 1.0);
     const double v = mt.exp2t[n & ((1 << EXP2_BITS) - 1)] * p;
     return __hiloint2double(__double2hiint(v) + ((n >> EXP2_BITS) << 20), __double2loint(v));
@@ -303,15 +309,13 @@ __device__ __forceinline__ double tau_fast(double k, const TauRow* __restrict__ 
     rare = idx != raw;
     const double mm = __hiloint2double((hi & 0x000FFFFF) | ((1023 + TAU_SB + 1) << 20), __double2loint(k));
     const uint4* row = reinterpret_cast<const uint4*>(tab + idx);
-    const uint4 q0 = row[0], q3 = row[3], q2 = row[2], q1 = row[1];
+    const uint4 q0 = row[0], q2 = row[2], q1 = row[1];
     const double u = mm - __hiloint2double((int)q0.y, (int)q0.x);
     const float uf = (float)u;                                     // F2F.F32.F64 (SFU pipe)
-    float t = fmaf(uf, __uint_as_float(q3.z), __uint_as_float(q3.y));          // f7 + u f8
-    t = fmaf(uf, t, __uint_as_float(q3.x));                        // f6
-    t = fmaf(uf, t, __uint_as_float(q2.w));                        // f5
-    t = fmaf(uf, t, __uint_as_float(q2.z));                        // f4
-    double acc = fma(u, (double)t, __hiloint2double((int)q2.y, (int)q2.x));    // c3 + u T4   (F2F.F64.F32)
-    acc = fma(u, acc, __hiloint2double((int)q1.w, (int)q1.z));    // c2
+    float t = fmaf(uf, __uint_as_float(q2.w), __uint_as_float(q2.z));          // f5 + u f6
+    t = fmaf(uf, t, __uint_as_float(q2.y));                        // f4
+    t = fmaf(uf, t, __uint_as_float(q2.x));                        // f3
+    double acc = fma(u, (double)t, __hiloint2double((int)q1.w, (int)q1.z));    // c2 + u T3   (F2F.F64.F32)
     acc = fma(u, acc, __hiloint2double((int)q1.y, (int)q1.x));    // c1
     return fma(u, acc, __hiloint2double((int)q0.w, (int)q0.z));   // c0
 }

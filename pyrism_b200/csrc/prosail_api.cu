@@ -611,19 +611,19 @@ int prosail_create(int device, prosail_handle_t** out) {
         std::vector<double> img(sizeof(MathTables) / 8);
         MathTables* mt = reinterpret_cast<MathTables*>(img.data());
 #if PB_TAU_F32TAIL
-        for (int r = 0; r < TAU_NROWS; ++r) {                 // [O, c0..c8] -> O, c0..c3 in double, c4..c8 rounded to float
+        for (int r = 0; r < TAU_NROWS; ++r) {                 // [O, c0..c6] -> O, c0..c2 in double, c3..c6 rounded to float
             const double* src = h_tau_table + r * TAU_ROW;
             TauRow& t = mt->tau[r];
-            t.O = src[0]; t.c0 = src[1]; t.c1 = src[2]; t.c2 = src[3]; t.c3 = src[4];
-            t.f4 = (float)src[5]; t.f5 = (float)src[6]; t.f6 = (float)src[7]; t.f7 = (float)src[8]; t.f8 = (float)src[9];
-            t.pad = 0.0f;
+            t.O = src[0]; t.c0 = src[1]; t.c1 = src[2]; t.c2 = src[3];
+            t.f3 = (float)src[4]; t.f4 = (float)src[5]; t.f5 = (float)src[6]; t.f6 = (float)src[7];
         }
-        static_assert(TAU_DEG == 8, "TauRow holds a degree-8 polynomial");
+        static_assert(TAU_DEG == 6 && TAU_ROW == 8, "TauRow holds a degree-6 polynomial");
 #else
         memcpy(mt->tau, h_tau_table, sizeof(mt->tau));
 #endif
         memcpy(mt->exp2t, h_exp2_table, sizeof(mt->exp2t));
         memcpy(mt->logt, h_log_table, sizeof(mt->logt));
+        static_assert(sizeof(mt->logt) == sizeof(h_log_table), "log table out of sync");
         CK(cudaMalloc(&h->d_tables, sizeof(MathTables)));
         CK(cudaMemcpy(h->d_tables, img.data(), sizeof(MathTables), cudaMemcpyHostToDevice));
         static_assert(sizeof(MathTablesF) == sizeof(h_tau_table_f), "float table image out of sync");

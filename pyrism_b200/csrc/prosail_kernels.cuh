@@ -259,8 +259,10 @@ __device__ __forceinline__ T soil_rho(const T* __restrict__ kc, const T* __restr
     return fma(s[S_SOIL1], kc[KC_RS1 * KSTRIDE], s[S_SOIL2] * kc[KC_RS2 * KSTRIDE]);
 }
 
-// Branch-free plate + Stokes stage.  Returns true when r + t >= 1 (zero absorption, models.py:1057-1059); the
-// values written are then meaningless and leaf_zero_absorption() must be called for that band.
+// Branch-free plate + Stokes stage.  Returns true when 1 - r - t < 2^-17 (no or almost no absorption; r + t >= 1 is the
+// zero-absorption branch of models.py:1057-1059); the values written are then not good enough -- b^(2(N-1)) - 1 and D are tiny
+// and the second-order steps / economised polynomials of this path are amplified by 1/D -- and leaf_layers_slow() must be
+// called for that band.  Realistic leaves (k >= 1e-4) never get there.
 // The interface constants enter in FOLDED form (ta21 = talf t21, t1221 = t12 t21), so that Ta = ta21 tau/(1 - x^2) and
 // t = t1221 tau/(1 - x^2) cost one multiplication each.
 template <typename T, typename MT>
@@ -314,23 +316,42 @@ __device__ __forceinline__ bool leaf_layers_fast(T r21, T ta21, T t1221, T ralf,
     tran = TaI * (bNm1 * dal);
     refl = fma(TaI * bm1, (t * al) * r, Ra);
 #endif
-    return !is_pos(qmt);                           // r + t >= 1, tested on the sign of 1 - r - t (integer pipe)
+    return hi_word(qmt) < 0x3EE00000;              // 1 - r - t < 2^-17 (r + t >= 1 included: negative high word), tested on the integer pipe
 }
-// zero-absorption case (r + t >= 1), exactly as models.py:1057-1065 with IEEE divisions (rare path)
+// Rare path of the double kernels: no or almost no absorption (1 - r - t < 2^-17).  IEEE divisions and libm throughout.
+//   r + t >= 1: the zero-absorption case, exactly as models.py:1057-1065;
+//   otherwise:  the Stokes formulas (:1043-1065) in the cancellation-free spelling of the fast path --
+//     b - 1 = ((1 - r - t)(1 + r - t) + D)/(2t),  b^(2(N-1)) - 1 = expm1(2 (N-1) log1p(b - 1)),  Y = (b^(2(N-1)) - 1)(a r - r^2) + D --
+//     which stays accurate to ~1e-15 down to D ~ 1e-8, where the reference itself carries 1e-16/D of rounding noise in a^2 - 1.
+// (results by value -- .x = reflectance, .y = transmittance: reference parameters of a real call would force the caller's arrays into local memory)
 template <typename T>
-__device__ __forceinline__ void leaf_zero_absorption(const BandConst<T>& c, T tau, T nm1, T& refl, T& tran) {
+__device__ __noinline__ double2 leaf_layers_slow(T talf, T ralf, T t12, T r12, T t21, T r21, T tau, T nm1) {
+    T refl, tran;
     const T one = T(1);
-    const T x = c.r21 * tau;
+    const T x = r21 * tau;
     const T den1 = one - x * x;
-    const T Ta = c.talf * tau * c.t21 / den1;
-    const T Ra = c.ralf + x * Ta;
-    const T t = c.t12 * tau * c.t21 / den1;
-    const T r = c.r12 + x * t;
-    const T Tsub = t / (t + (one - t) * nm1);
-    const T Rsub = one - Tsub;
-    const T den = one - Rsub * r;
-    tran = Ta * Tsub / den;
-    refl = Ra + Ta * Rsub * t / den;
+    const T Ta = talf * tau * t21 / den1;
+    const T Ra = ralf + x * Ta;
+    const T t = t12 * tau * t21 / den1;
+    const T r = r12 + x * t;
+    if (r + t >= one) {                                               // :1057-1059
+        const T Tsub = t / (t + (one - t) * nm1);
+        const T Rsub = one - Tsub;
+        const T den = one - Rsub * r;
+        tran = Ta * Tsub / den;
+        refl = Ra + Ta * Rsub * t / den;
+        return make_double2(refl, tran);
+    }
+    const T q = one - r, qmt = q - t;
+    const T D = sqrt(((one + r + t) * (one + r - t)) * ((q + t) * qmt));      // :1043
+    const T al = T(0.5) * ((one + r * r - t * t) + D);                // a r   (:1046)
+    const T lb = log1p((qmt * (one + r - t) + D) / (t + t));          // ln b  (:1047)
+    const T bm1 = expm1((nm1 + nm1) * lb);                            // b^(2(N-1)) - 1
+    const T bNm1 = exp(nm1 * lb);                                     // :1049
+    const T Y = bm1 * (al - r * r) + D;
+    tran = Ta * bNm1 * D / Y;                                         // :1062-1065 (see leaf_layers_fast)
+    refl = Ra + Ta * t * r * bm1 / Y;
+    return make_double2(refl, tran);
 }
 
 // ---- float (fp32 mode) variants of the plate + Stokes stage ----
@@ -509,12 +530,12 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
             for (int u = 0; u < NU; ++u)
                 if (zero[u]) {
                     if constexpr (CSMEM) {       // talf = 1 - (1 - talf) etc.: within an ulp of the uploaded constants
-                        BandConst<T> cc;
-                        cc.ralf = kc[u + KC_RALF * KS]; cc.r12 = kc[u + KC_R12 * KS]; cc.r21 = kc[u + KC_R21 * KS];
-                        cc.talf = T(1) - cc.ralf; cc.t12 = T(1) - cc.r12; cc.t21 = T(1) - cc.r21;
-                        leaf_zero_absorption(cc, tau[u], nm1, refl[u], tran[u]);
+                        const T ralf = kc[u + KC_RALF * KS], r12 = kc[u + KC_R12 * KS], r21 = kc[u + KC_R21 * KS];
+                        const double2 rt = leaf_layers_slow(T(1) - ralf, ralf, T(1) - r12, r12, T(1) - r21, r21, tau[u], nm1);
+                        refl[u] = rt.x; tran[u] = rt.y;
                     } else {
-                        leaf_zero_absorption(c[u], tau[u], nm1, refl[u], tran[u]);
+                        const double2 rt = leaf_layers_slow(c[u].talf, c[u].ralf, c[u].t12, c[u].r12, c[u].t21, c[u].r21, tau[u], nm1);
+                        refl[u] = rt.x; tran[u] = rt.y;
                     }
                 }
         }
@@ -580,7 +601,10 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
         // two FP64 instructions less than sigb/(att + m) spelled out in s, bd.  P - m cancels only where rinf itself is small
         // (dark leaves): the second-order square root (3e-12 relative in m) then leaves <= 1.5e-12 ABSOLUTE in rinf.
         const T P = one + bd;
-        d.m = sqrt_b_pos(oms * P);
+        // rho + tau >= 1 (a leaf without absorption, to rounding): the reference's m is 0 or NaN there.  The argument is floored at the
+        // smallest normal number by ONE integer max on its high word (m ~ 1e-154: every later formula sees m = 0) instead of a
+        // compare and two selects on the result.
+        d.m = sqrt_b_raw(floor_hi(oms * P, 0x00100000));
         d.rinf = (P - d.m) * rcp_b(P + d.m);
 #else
         d.m = sqrt_b_pos(fma(oms, bd, oms));
@@ -651,7 +675,8 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
     d.rdd = fma(-d.re, d.e1, d.rinf) * d.invden;                      // rinf (1 - e^2)/den = (rinf - (rinf e) e)/den   :655
     d.rsrdd = rs * d.rdd;
     T dn = one - d.rsrdd;                                             // :714-719
-    dn = below_tiny(dn) ? tiny : dn;                                  // dn < 1e-36 (integer-pipe test; negatives too)
+    if constexpr (!is_f32<T>()) dn = floor_hi(dn, 0x38754484);        // dn < 1e-36, negatives too -> 1e-36 (to 2^-20 relative): one integer max on the high word
+    else dn = below_tiny(dn) ? tiny : dn;                             // dn < 1e-36 (integer-pipe test; negatives too)
     d.rs_invdn = rs * rcp_b(dn);
 }
 
@@ -1915,7 +1940,8 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
 // ---------------------------------------------------------------------------------------------
 // test / calibration kernels
 // ---------------------------------------------------------------------------------------------
-// op: 0 rcp, 1 sqrt_pos, 2 exp_neg, 3 log2_pos, 4 exp2_any, 5 tau_plate, 6 tau_full, 7 rcp_q, 8 sqrt_q_raw (x > 0)
+// op: 0 rcp, 1 sqrt_pos, 2 exp_neg, 3 log2_pos, 4 exp2_any, 5 tau_plate, 6 tau_full, 7 rcp_q, 8 sqrt_q_raw (x > 0),
+//     9 exp_neg_scaled (exp(x), x <= 0, as m = -x / 8 and the record value c = -8 * 2048 log2(e)), 10 pow_pos_scaled (x^0.75, x >= 1)
 __global__ void k_test_math(int op, long long n, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ tables) {
     extern __shared__ __align__(16) unsigned char test_smem[];              // sizeof(MathTables) bytes of dynamic shared memory
     MathTables& mt = *reinterpret_cast<MathTables*>(test_smem);
@@ -1934,6 +1960,8 @@ __global__ void k_test_math(int op, long long n, const double* __restrict__ in, 
         case 6: y = tau_full(x); break;
         case 7: y = rcp_q(x); break;
         case 8: y = sqrt_q_raw(x); break;
+        case 9: y = exp_neg_scaled(x * -0.125, -8.0 * PB_EXPS_SCALE, mt.exp2t); break;
+        case 10: y = pow_pos_scaled(x, 0.75, __double2hiint(500.0 / 0.75), mt); break;
         default: y = tau_plate(x, mt.tau); break;
     }
     out[i] = y;

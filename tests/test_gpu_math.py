@@ -42,11 +42,30 @@ def test_log2_exp2(engine):
     x = np.concatenate([rng.uniform(1.0, 4.0, 50000), 10.0 ** rng.uniform(0, 300, 20000), 1.0 + 10.0 ** rng.uniform(-12, 0, 20000)])
     got = engine.test_math(3, x)
     want = np.array([float(mp.log(mp.mpf(float(v)), 2)) for v in x[::37]])
-    # design accuracy: degree-4 series on |r| <= 2^-9 -> absolute error <= 2^-45 / (5 ln 2) = 8.2e-15 (plus rounding)
-    assert np.max(np.abs(got[::37] - want) / np.maximum(np.abs(want), 1.0)) < 1.2e-14
-    assert np.max(np.abs(got - np.log2(x)) / np.maximum(np.log2(x), 1.0)) < 1.2e-14
+    # design accuracy (round 2n): 512-entry table, economised cubic on |r| <= 2^-10 -> absolute error <= 2^-40 / (32 ln 2) = 4.1e-14
+    # (plus rounding); round 1: 256 entries and the degree-4 series, 8.2e-15
+    assert np.max(np.abs(got[::37] - want) / np.maximum(np.abs(want), 1.0)) < 4.6e-14
+    assert np.max(np.abs(got - np.log2(x)) / np.maximum(np.log2(x), 1.0)) < 4.6e-14
     y = np.concatenate([rng.uniform(-300, 500, 50000), rng.uniform(-1, 1, 20000)])
     assert rel(engine.test_math(4, y), np.exp2(y)) < 6e-16
+
+
+def test_scaled_exp_and_pow(engine):
+    """Round 2n: exp(-m lai) from the pre-scaled record value (exp_neg_scaled) and b^(N-1) without forming the exponent
+    (pow_pos_scaled: economised quadratic of 2^r, 2e-13 relative, on top of the 4.1e-14 absolute of log2)."""
+    x = -np.concatenate([rng.uniform(0, 60, 50000), 10.0 ** rng.uniform(-14, 2.8, 50000), [0.0, 700.0]])
+    got = engine.test_math(9, x)
+    want = np.exp(x)
+    # the record value carries one rounding (2^-53 relative of |x|), like the product m lai did
+    assert np.max(np.abs(got - want) / want / (6e-16 + 2.3e-16 * np.abs(x))) < 1.0
+    assert np.max(np.abs(got - want)) < 2.5e-16
+    assert np.all(engine.test_math(9, np.array([-5000.0, -1.0e5])) < 1e-300)          # exponent floor, no wrap-around
+    b = np.concatenate([1.0 + 10.0 ** rng.uniform(-8, 0, 30000), 10.0 ** rng.uniform(0, 12, 30000)])
+    got = engine.test_math(10, b)
+    want = np.array([float(mp.mpf(float(v)) ** mp.mpf(0.75)) for v in b[::29]])
+    # relative error <= 2.1e-13 (quadratic) + 0.75 ln2 * 4.1e-14 (log2) + rounding
+    assert np.max(np.abs(got[::29] - want) / want) < 2.6e-13
+    assert np.isfinite(engine.test_math(10, np.array([1e300]))).all()                  # clamped at about 2^500
 
 
 def test_tau_against_mpmath(engine):
@@ -57,11 +76,11 @@ def test_tau_against_mpmath(engine):
     mp.mp.dps = 40
     want = np.array([float((1 - mp.mpf(float(v))) * mp.exp(-mp.mpf(float(v))) + mp.mpf(float(v)) ** 2 * mp.e1(mp.mpf(float(v)))) for v in k])
     got = engine.test_math(5, k)
-    # round 2 error budget (csrc/math64.cuh, TauRow): the terms of degree >= 4 of the piecewise polynomial are evaluated in
-    # float -- |c4| <= 1.7e-6 times a few float roundings (6e-8 each) = a few 1e-13 absolute, and the same RELATIVE to the row's
+    # round 2 error budget (csrc/math64.cuh, TauRow): the terms of degree >= 3 of the piecewise polynomial (degree 6, 16 sub-intervals
+    # per binade) are evaluated in float -- |c3| <= 5.1e-6 times a few float roundings (6e-8 each) = a few 1e-13 absolute, and the same RELATIVE to the row's
     # own magnitude (the coefficients of a row scale with tau), against a parity bar of 1e-9 on reflectance / transmittance
     assert np.max(np.abs(got - want)) < 5e-13
-    # relative accuracy where tau is O(1) (k <= 2); beyond, the table (8 sub-intervals per binade up to k = 32) is built to an
+    # relative accuracy where tau is O(1) (k <= 2); beyond, the table (16 sub-intervals per binade up to k = 32) is built to an
     # ABSOLUTE target -- tau(k > 2) < 0.06 only yields a correspondingly small transmittance
     inside = k <= 2
     assert rel(got[inside], want[inside]) < 2e-11

@@ -8,10 +8,15 @@
      region A, k in [2^-14, 2):  2^SB equal sub-intervals per binade                       (15 * 2^SB intervals)
      region B, k in [2, 32):     sub-intervals of width 2^(1-SB) (2^(E+SB-1) per binade E=1..4)  (15 * 2^SB intervals)
    SB = 3 and degree 8 (240 rows of 10 doubles) replaced SB = 2 and degree 10: two three-register DFMAs less per evaluation.
+   Round 2n: SB = 4 and degree 6 (304 rows): |c3| <= 5.1e-6 over the whole table, so the terms of degree >= 3 can run in float
+   (6e-8 relative: 3e-13 absolute) -- 4 FP64 instructions per evaluation instead of 5, 3 FFMA instead of 4, and the row
+   (O, c0, c1, c2 in double + c3..c6 in float) is 48 bytes: three 128-bit loads instead of four.  The degree-6 fit is good to
+   4e-14 absolute (bar of the table 1e-13, budget of an output 1e-11).
    Row layout: [O, c0, c1, ..., cD] with u = k*S - O in [-1, 1], S a power of two, tau ~= sum c_i u^i.
    Outside (rare path of the kernel): k < 2^-14 -> series with log(k);  k >= 32 -> continued fraction of E1.
 2. EXP2 table -- 2^(j/2^EXP2_BITS), j = 0..2^EXP2_BITS - 1 (2048 entries: a cubic in the reduced argument is then exact to 4e-17).
-3. LOG table  -- for c_i = 1 + (i + 0.5)/256, i = 0..255:  1/c_i (rounded) and -log2(1/c_i) paired.
+3. LOG table  -- for c_i = 1 + (i + 0.5)/2^LOG_BITS, i = 0..2^LOG_BITS - 1:  1/c_i (rounded) and -log2(1/c_i) paired
+   (round 2n: 512 entries, |r| <= 2^-10, so that an economised cubic of log2(1 + r) is good to 4e-14: one FMA less).
 
 Coefficients are fitted with mpmath (50 digits) at Chebyshev nodes, converted to the monomial basis in u
 and rounded to double.  The script then checks the double-precision Horner evaluation against mpmath on
@@ -25,8 +30,9 @@ import mpmath as mp
 import numpy as np
 
 mp.mp.dps = 60
-DEG = int(os.environ.get("TAU_DEG", "8"))
-SB = int(os.environ.get("TAU_SB", "3"))
+DEG = int(os.environ.get("TAU_DEG", "6"))
+SB = int(os.environ.get("TAU_SB", "4"))
+LOG_BITS = int(os.environ.get("LOG_BITS", "9"))
 EXP2_BITS = int(os.environ.get("EXP2_BITS", "11"))
 EMIN = -14
 EMAX = 4
@@ -102,9 +108,10 @@ def main():
             worst_rel = max(worst_rel, float(ea / ref))
     print("tau table: degree %d, %d intervals, worst abs err %.3e, worst rel err %.3e" % (DEG, len(rows), worst_abs, worst_rel))
     # what the plate formulas see is the ABSOLUTE error of tau (tau <= 1 enters r, t, Ra, Ta linearly; a tiny tau only yields a
-    # tiny transmittance): the bar is 1e-9 on reflectance / transmittance, the budget of this table 5e-15 absolute
-    if worst_abs > 5e-15 or worst_rel > 1e-7:
-        sys.exit("tau table misses the 5e-15 absolute / 1e-7 relative target")
+    # tiny transmittance): the bar is 1e-9 on reflectance / transmittance, the budget of an output 1e-11, the
+    # budget of this table 1e-13 absolute
+    if worst_abs > 1e-13 or worst_rel > 1e-6:
+        sys.exit("tau table misses the 1e-13 absolute / 1e-6 relative target")
 
     # float32 table for the fp32 mode: same intervals, degree DEG_F, rows [O, c0..c5, pad], of
     #     g(k) = (1 - tau(k))/k ,   so that   1 - tau = k g(k)   carries a RELATIVE error of ~1e-7.
@@ -134,17 +141,18 @@ def main():
 
     exp2t = [float(mp.mpf(2) ** (mp.mpf(j) / 2 ** EXP2_BITS)) for j in range(2 ** EXP2_BITS)]
     logt = []
-    for i in range(256):
-        c = 1 + (mp.mpf(i) + mp.mpf(1) / 2) / 256
+    for i in range(2 ** LOG_BITS):
+        c = 1 + (mp.mpf(i) + mp.mpf(1) / 2) / 2 ** LOG_BITS
         inv = float(1 / c)                                  # rounded reciprocal, used as-is in the kernel
-        logt.append((inv, float(-mp.log(mp.mpf(inv), 2))))  # log2(c') for the c' = 1/inv actually used
+        # log2(c') for the c' = 1/inv actually used, plus the constant h^4/(32 ln 2) of the economised cubic (math64.cuh: log2_pos)
+        logt.append((inv, float(-mp.log(mp.mpf(inv), 2) + mp.mpf(2) ** (-4 * (LOG_BITS + 1)) / (32 * mp.log(2)))))
 
     with open(OUT, "w") as fh:
         fh.write("// GENERATED by tools/gen_math_tables.py -- do not edit.\n")
         fh.write("// tau(k) = (1-k)exp(-k) + k^2 E1(k): degree-%d piecewise polynomials; worst abs %.2e, worst rel %.2e (vs mpmath).\n"
                  % (DEG, worst_abs, worst_rel))
         fh.write("#define TAU_DEG %d\n#define TAU_ROW %d\n#define TAU_NROWS %d\n#define TAU_EMIN (%d)\n#define TAU_EMAX (%d)\n"
-                 "#define TAU_SB %d\n#define EXP2_BITS %d\n" % (DEG, DEG + 2, len(rows), EMIN, EMAX, SB, EXP2_BITS))
+                 "#define TAU_SB %d\n#define EXP2_BITS %d\n#define LOG_BITS %d\n" % (DEG, DEG + 2, len(rows), EMIN, EMAX, SB, EXP2_BITS, LOG_BITS))
         fh.write("static const double h_tau_table[TAU_NROWS * TAU_ROW] = {\n")
         for r in range(len(rows)):
             fh.write("  " + ", ".join(float(v).hex() for v in table[r]) + ",\n")
@@ -155,7 +163,7 @@ def main():
             fh.write("  " + ", ".join("%sf" % float(v).hex() for v in table_f[r]) + ",\n")
         fh.write("};\n")
         fh.write("static const double h_exp2_table[1 << EXP2_BITS] = {\n  " + ",\n  ".join(v.hex() for v in exp2t) + "\n};\n")
-        fh.write("static const double h_log_table[512] = {\n  " + ",\n  ".join("%s, %s" % (a.hex(), b.hex()) for a, b in logt) + "\n};\n")
+        fh.write("static const double h_log_table[2 << LOG_BITS] = {\n  " + ",\n  ".join("%s, %s" % (a.hex(), b.hex()) for a, b in logt) + "\n};\n")
     print("wrote", os.path.normpath(OUT))
 
 
