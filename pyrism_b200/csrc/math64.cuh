@@ -29,6 +29,9 @@
 #ifndef PB_FSFOLD
 #define PB_FSFOLD 1      /* lai sumint folded into Fs, Ft by the prologue (1 less) */
 #endif
+#ifndef PB_SOILFOLD
+#define PB_SOILFOLD 1    /* soil coupling as [A1 A2/dn + (tsstoo - tss too)] rs with A1 = tss + tsd, A2 = too + tdo (4 less) */
+#endif
 #ifndef PB_EXPS
 #define PB_EXPS 1        /* exp(-m lai): the record carries -lai 2048 log2(e), the product m lai is never formed (1 less) */
 #endif

@@ -74,8 +74,9 @@ enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DD
 // (S_NEGLAI: -lai, +0.0 for bare soil (the no-canopy flag); double records with PB_EXPS: -lai 2048 log2(e).  S_LMAX: 500/|N-1|, the
 //  clamp of log2 b in pow_pos_scaled.)
 // geometry record (per parameter set x geometry)
-enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_FSL, G_FTL, G_ALF };
-// (G_FSL, G_FTL: Fs lai sumint, Ft lai sumint -- the single-scattering term rsos = w lai sumint of models.py:706-710 as two FMAs on rho, tau)
+enum { G_K = 0, G_KO, G_SDB, G_SDF, G_DOB, G_DOF, G_FS, G_FT, G_TSS, G_TOO, G_TSSTOO, G_LAISUM, G_Z, G_FSL, G_FTL, G_DTT };
+// (G_FSL, G_FTL: Fs lai sumint, Ft lai sumint -- the single-scattering term rsos = w lai sumint of models.py:706-710 as two FMAs on rho, tau;
+//  G_DTT: tsstoo - tss too, the hotspot excess of the bidirectional gap fraction -- see the soil coupling in sail_couple)
 
 // output planes (bit index in out_mask / mean_mask)
 enum { O_RSOT = 0, O_RDDT, O_RSDT, O_RDOT, O_RSO, O_RDD, O_TDD, O_RSD, O_TSD, O_RDO, O_TDO, O_KE, O_LEAF_R, O_LEAF_T, O_RHO,
@@ -123,7 +124,9 @@ struct SailArgs {
     long long nitems;
     int G;                     // geometries per sample (item = s*G + g)
     int ngroups;               // tile groups visited (all NTILES / NU, or the active ones in windows-only mode)
-    int nranges;               // item-chunk ranges: warp gw works on group gw % ngroups, chunks gw / ngroups + i * nranges
+    int nwarps_main;           // R x ngroups warps that own one tile group each and stride over the chunks below nchunks_main (see k_bands)
+    int nwarps;                // warps that work; those past nwarps_main share the (group, chunk) pairs of the chunks from nchunks_main on
+    long long nchunks_main;
     // SAIL-only mode: leaf / soil spectra from memory, row pitch in elements (0 = one spectrum for all samples)
     const T* in_r; const T* in_t; const T* in_rho;
     long long in_pitch_r, in_pitch_t, in_pitch_rho;
@@ -575,6 +578,7 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
 template <typename T>
 struct Diffuse {
     T m, e1, rinf, re, invden, inv_omr2, tdd, rdd, rs_invdn, rsrdd, rinf_invden;
+    T invdn;       // 1/(1 - rs rdd)
     T invden_h;    // PB_HALVES (AB form): invden/2, and inv_omr2 then holds 1/(4 (1 - rinf^2)) -- see sail_diffuse
     T a1, a2;      // rho + tau rinf, tau + rho rinf: the leaf-dependent factors of (sf + sb rinf), (sf rinf + sb), ... (:649-652)
                    // fused fp64 instances (AB form): a1 = Ap = (a1 + a2)/2 = (rho + tau)(1 + rinf)/2,  a2 = Am = bf (rho - tau)(1 - rinf)/2,
@@ -677,7 +681,8 @@ __device__ __forceinline__ void sail_diffuse(T rho, T tau, T rs, const T* __rest
     T dn = one - d.rsrdd;                                             // :714-719
     if constexpr (!is_f32<T>()) dn = floor_hi(dn, 0x38754484);        // dn < 1e-36, negatives too -> 1e-36 (to 2^-20 relative): one integer max on the high word
     else dn = below_tiny(dn) ? tiny : dn;                             // dn < 1e-36 (integer-pipe test; negatives too)
-    d.rs_invdn = rs * rcp_b(dn);
+    d.invdn = rcp_b(dn);
+    d.rs_invdn = rs * d.invdn;
 }
 
 template <typename T>
@@ -722,17 +727,32 @@ __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>
     // T3 = (rdo Qss + tdo Pss) rinf
     const T T3 = fma(rdo_u, Qss, tdo_u * Pss) * d.rinf_invden;
     const T Ts = fma(cK * u1, fma(-J1ks, too, g[G_Z]), fma(ck * v1, fma(-J1ko, tss, g[G_Z]), -T3));
-    // soil coupling (:721-726): rsodt = ((tss + tsd) tdo + (tsd + tss rs rdd) too) rs/dn
-    const T sc = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too);
-    if constexpr (AB && PB_FSFOLD) {
-        // rsos = w lai sumint with w = Fs rho + Ft tau (:607, :706): the prologue folds lai sumint into Fs, Ft (G_FSL, G_FTL)
+    // rsos + rsod apart from Ts/(1 - rinf^2): w lai sumint with w = Fs rho + Ft tau (:607, :706); fused fp64 instances: the prologue
+    // folds lai sumint into Fs, Ft (G_FSL, G_FTL)
+    if constexpr (!is_f32<T>() && PB_SOILFOLD) {
+        // Soil coupling (:721-726), round 2n.  With A1 = tss + tsd and A2 = too + tdo (total down- and upward transmittances):
+        //   (tss + tsd) tdo + (tsd + tss rs rdd) too = A1 A2 - tss too (1 - rs rdd) = A1 A2 - tss too dn
+        //   =>  rsot = rsod + rsos + tsstoo rs + rsodt = rsod + rsos + [A1 A2 / dn + (tsstoo - tss too)] rs
+        // tsstoo - tss too comes from the prologue (G_DTT); A1, A2 are ONE FMA each on the unscaled numerators.  8 FP64
+        // instructions for the BRF instead of 12, all errors absolute at the 1e-16 level (the subtraction happens in the record).
+        const T A1 = fma(tsd_u, invden1, tss), A2 = fma(tdo_u, invden1, too);
+        const T cpl = fma(A1 * A2, d.invdn, g[G_DTT]);
         if (need & (1u << O_RSO)) {
-            o.rso = fma(g[G_FSL], rho, fma(g[G_FTL], tau, Ts * d.inv_omr2));                      // rsos + rsod             :706, :710
-            o.rsot = fma(sc, d.rs_invdn, fma(g[G_TSSTOO], rs, o.rso));
-        } else {                                                      // rsot = rsod + rsos + tsstoo rs + rsodt, one FMA per term
-            o.rsot = fma(sc, d.rs_invdn, fma(Ts, d.inv_omr2, fma(g[G_FSL], rho, fma(g[G_FTL], tau, g[G_TSSTOO] * rs))));
+            if constexpr (AB && PB_FSFOLD) o.rso = fma(g[G_FSL], rho, fma(g[G_FTL], tau, Ts * d.inv_omr2));     // rsos + rsod    :706, :710
+            else o.rso = fma(fma(g[G_FS], rho, g[G_FT] * tau), g[G_LAISUM], Ts * d.inv_omr2);
+            o.rsot = fma(cpl, rs, o.rso);
+        } else {
+            T ss;
+            if constexpr (AB && PB_FSFOLD) ss = fma(g[G_FSL], rho, g[G_FTL] * tau);
+            else ss = fma(g[G_FS], rho, g[G_FT] * tau) * g[G_LAISUM];
+            o.rsot = fma(cpl, rs, fma(Ts, d.inv_omr2, ss));
         }
+        if (need & (1u << O_RDDT)) o.rddt = fma(d.tdd * d.tdd, d.rs_invdn, d.rdd);
+        if (need & (1u << O_RSDT)) o.rsdt = fma(A1 * d.tdd, d.rs_invdn, o.rsd);
+        if (need & (1u << O_RDOT)) o.rdot = fma(d.tdd * A2, d.rs_invdn, o.rdo);
     } else {
+        // soil coupling (:721-726): rsodt = ((tss + tsd) tdo + (tsd + tss rs rdd) too) rs/dn
+        const T sc = fma(tss + o.tsd, o.tdo, fma(tss, d.rsrdd, o.tsd) * too);
         const T w = fma(g[G_FS], rho, g[G_FT] * tau);                 // :607
         if (need & (1u << O_RSO)) {
             o.rso = fma(w, g[G_LAISUM], Ts * d.inv_omr2);             // rsos + rsod                              :706, :710
@@ -740,10 +760,10 @@ __device__ __forceinline__ void sail_couple(T rho, T tau, T rs, const Diffuse<T>
         } else {                                                      // rsot = rsod + rsos + tsstoo rs + rsodt, one FMA per term
             o.rsot = fma(sc, d.rs_invdn, fma(Ts, d.inv_omr2, fma(w, g[G_LAISUM], g[G_TSSTOO] * rs)));
         }
+        if (need & (1u << O_RDDT)) o.rddt = fma(d.tdd * d.tdd, d.rs_invdn, d.rdd);
+        if (need & (1u << O_RSDT)) o.rsdt = fma((o.tsd + tss) * d.tdd, d.rs_invdn, o.rsd);
+        if (need & (1u << O_RDOT)) o.rdot = fma(d.tdd * (o.tdo + too), d.rs_invdn, o.rdo);
     }
-    if (need & (1u << O_RDDT)) o.rddt = fma(d.tdd * d.tdd, d.rs_invdn, d.rdd);
-    if (need & (1u << O_RSDT)) o.rsdt = fma((o.tsd + tss) * d.tdd, d.rs_invdn, o.rsd);
-    if (need & (1u << O_RDOT)) o.rdot = fma(d.tdd * (o.tdo + too), d.rs_invdn, o.rdo);
 }
 
 // Branch-free geometry-dependent part of 4SAIL (models.py:603-607, 644-678, 706-726, 765-789).
@@ -1067,8 +1087,17 @@ template <typename T> __host__ __device__ constexpr int min_ctas() { return std:
     _Pragma("unroll") for (int u = 0; u < NU; ++u) dst[u] = arr[u] field
 
 // ---------------------------------------------------------------------------------------------
-// main kernel.  1-D grid of independent warps: warp gw owns the tile group gw % ngroups (NU x 32 consecutive bands) and
-// walks the item chunks gw / ngroups, + nranges, + 2 nranges, ...  The CTA only shares the read-only math tables.
+// main kernel.  1-D grid of independent warps; a tile group = NU x 32 consecutive bands, a chunk = CHUNK items.
+//   * The first nwarps_main = R x ngroups warps (R = resident warps / ngroups, rounded down): warp gw owns the tile group
+//     gw % ngroups and walks the chunks gw / ngroups, + R, + 2 R, ... below nchunks_main -- all groups sweep the items together,
+//     so a row of an output plane is written by all of its groups at about the same time (DRAM locality; a contiguous share per
+//     warp cost the leaf-only and four-plane instances 5-10 %: profiles/r2n_variants.txt).
+//   * The E = nwarps - nwarps_main warps that this split would leave idle (1776 resident warps over 22 groups: 16 idle, 0.9 %;
+//     33 groups: 27 of 1776 or 25 of 2368) take the last E / nwarps of the chunks, [nchunks_main, nchunks), as contiguous shares
+//     of its (group, chunk) list in group-major order; such a share spans several groups and the per-group state (band
+//     constants in shared memory, window plan) is rebuilt when the group changes.  Every warp gets the same number of units.
+//   * Launches with fewer (group, chunk) pairs than resident warps: one pair per warp (nwarps_main = 0).
+// The CTA only shares the read-only math tables.
 // ---------------------------------------------------------------------------------------------
 // G1 = true: one geometry per parameter set (the LUT shape) -- every item starts a new parameter set, so nothing
 // is carried between loop iterations and the register allocator sees purely loop-local state.
@@ -1083,12 +1112,6 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     // the per-warp staging buffers and of everything derived from the tile group)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int gw = blockIdx.x * CF::WARPS + warp;                     // global warp id
-    const int range = gw / a.ngroups;
-    const int tslot = gw - range * a.ngroups;
-    const bool live = range < a.nranges;
-    const int grp = !live ? 0 : (a.only_active_tiles ? a.win->active_group[NU - 2][tslot] : tslot);
-    const int band0 = grp * (32 * NU) + lane;      // this thread's bands (packed map: lanes): band0 + 32 u
-    const bool tail = !a.packed && (grp + 1) * (32 * NU) > NB;    // warp-uniform; the packed map has no out-of-range stores (no planes)
     Stage<T>* const stage = sm.stage[warp];
     uint64_t* const bar = sm.bar[warp];
 
@@ -1105,9 +1128,29 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     __syncthreads();       // the only CTA-wide barrier: tables and barriers are ready
 
     const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
-    long long chunk = live ? range : nchunks;
-    if (lane == 0 && chunk < nchunks) stage_issue(a, &stage[0], &bar[0], chunk);
+    // this warp's walk over (group slot, chunk) pairs: `remaining` of them, starting at (tslot, chunk); the next chunk is chunk + step,
+    // wrapping from wrap_hi to wrap_lo with a change of group
+    long long remaining = 0, chunk = 0, step = 1, wrap_lo = 0, wrap_hi = nchunks;
+    int tslot = 0;
+    if (gw < a.nwarps_main) {
+        const int R = a.nwarps_main / a.ngroups;
+        const int range = gw / a.ngroups;
+        tslot = gw - range * a.ngroups;
+        chunk = range; step = R; wrap_hi = a.nchunks_main;
+        remaining = chunk < wrap_hi ? (wrap_hi - chunk + R - 1) / R : 0;
+    } else if (gw < a.nwarps) {
+        const long long e = gw - a.nwarps_main, E = a.nwarps - a.nwarps_main, nx = nchunks - a.nchunks_main;
+        const long long nunits = (long long)a.ngroups * nx;
+        const long long t0 = nunits * e / E, t1 = nunits * (e + 1) / E;
+        tslot = (int)(t0 / nx);
+        wrap_lo = a.nchunks_main;
+        chunk = wrap_lo + (t0 - tslot * nx);
+        remaining = t1 - t0;
+    }
+    if (lane == 0 && remaining > 0) stage_issue(a, &stage[0], &bar[0], chunk);
 
+    int grp = 0, band0 = lane;                     // tile group and this thread's bands (packed map: lanes): band0 + 32 u
+    bool tail = false;                             // warp-uniform: the group holds bands >= 2101
     BandConst<T> c[NU];
     // fused fp64 instances keep the interface constants in shared memory (register pressure); everything else in registers
     constexpr bool CSMEM = consts_in_smem<T, MODE>();
@@ -1118,9 +1161,19 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
 #endif
     const T* kc = sm.kc + threadIdx.x * KCOL;      // this thread's block (thread-major) / NU adjacent columns of the once-per-item constants
     constexpr int KS = CF::KSTRIDE;
+    // fp32 mode with two bands per thread: the arithmetic of the item loop runs in packed FP32 (FFMA2 ...), both bands per instruction
+    constexpr bool PACKED = std::is_same<T, float>::value && NU == 2;
+    constexpr bool AB = MODE == MODE_PROSAIL && !std::is_same<T, float>::value;   // Ap / Am form of the leaf-dependent factors (sail_diffuse)
+    BandConst<f2> c2;
+    MeanPlan<NU> plan{};
+    // per-group state: the thread's band constants (shared-memory columns / registers) and its share of the window map
+    auto enter_group = [&](int slot) {
+    grp = a.only_active_tiles ? a.win->active_group[NU - 2][slot] : slot;
+    band0 = grp * (32 * NU) + lane;
+    tail = !a.packed && (grp + 1) * (32 * NU) > NB;                   // the packed map has no out-of-range stores (no planes)
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
-        const int lane_u = live ? band0 + 32 * u : 0;                 // NBP = 66 * 32: always in range
+        const int lane_u = band0 + 32 * u;                            // NBP = 66 * 32: always in range
         const T* bc = a.bandc + (a.packed ? a.win->band[lane_u] : lane_u);   // packed map: gather through the lane -> wavelength list
         T* k = sm.kc + threadIdx.x * KCOL + u;                        // only this thread reads these back: no barrier needed
         k[KC_KAB * KS] = bc[C_KAB * NBP]; k[KC_KXC * KS] = bc[C_KXC * NBP]; k[KC_KAN * KS] = bc[C_KAN * NBP];
@@ -1132,14 +1185,12 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             k[KC_R12 * KS] = c[u].r12; k[KC_R21 * KS] = c[u].r21;
         }
     }
-    // fp32 mode with two bands per thread: the arithmetic of the item loop runs in packed FP32 (FFMA2 ...), both bands per instruction
-    constexpr bool PACKED = std::is_same<T, float>::value && NU == 2;
-    constexpr bool AB = MODE == MODE_PROSAIL && !std::is_same<T, float>::value;   // Ap / Am form of the leaf-dependent factors (sail_diffuse)
-    BandConst<f2> c2;
     if constexpr (PACKED) {
         c2.talf = F2(c[0].talf, c[1].talf); c2.ralf = F2(c[0].ralf, c[1].ralf); c2.t12 = F2(c[0].t12, c[1].t12);
         c2.r12 = F2(c[0].r12, c[1].r12); c2.t21 = F2(c[0].t21, c[1].t21); c2.r21 = F2(c[0].r21, c[1].r21);
     }
+    if constexpr (PLANES != RUNTIME && MEANS != 0 && !is_f32<T>()) mean_plan_init<NU>(a.win, NU * grp, lane, plan);
+    };
     unsigned need;
     if (PLANES == RUNTIME) {
         need = a.mean_mask;
@@ -1152,13 +1203,17 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     const int nt = ANY_MEANS ? a.win->ntotal : 0;
     const int nmean = ANY_MEANS ? a.nmean : 0;
 
-    MeanPlan<NU> plan{};
-    if constexpr (PLANES != RUNTIME && MEANS != 0 && !is_f32<T>()) mean_plan_init<NU>(a.win, NU * grp, lane, plan);
-
-    for (unsigned it = 0; chunk < nchunks; chunk += a.nranges, ++it) {
+    bool new_group = true;
+    for (unsigned it = 0; remaining > 0; --remaining, ++it) {
+        if (new_group) {
+            __syncwarp();
+            enter_group(tslot);
+            new_group = false;
+        }
         const int buf = it & 1;
-        const long long next = chunk + a.nranges;
-        if (lane == 0 && next < nchunks) {
+        long long next = chunk + step;                                // the chunk after this one: the first of the next group at the end of a group
+        if (next >= wrap_hi) { next = wrap_lo; new_group = true; }
+        if (lane == 0 && remaining > 1) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             stage_issue(a, &stage[buf ^ 1], &bar[buf ^ 1], next);
         }
@@ -1322,6 +1377,8 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             }
         }
         __syncwarp();      // all lanes are done with stage[buf] before lane 0 refills it in the next iteration
+        chunk = next;
+        tslot += new_group ? 1 : 0;
     }
 }
 #undef PB_GATHER
@@ -1654,7 +1711,7 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         r[G_DOB] = 0.5 * (K + bf); r[G_DOF] = 0.5 * (K - bf);
         r[G_FS] = Fs; r[G_FT] = Ft;
         r[G_TSS] = tss; r[G_TOO] = too; r[G_TSSTOO] = tsstoo;
-        r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_FSL] = Fs * (lai * sumint); r[G_FTL] = Ft * (lai * sumint); r[G_ALF] = alf;
+        r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_FSL] = Fs * (lai * sumint); r[G_FTL] = Ft * (lai * sumint); r[G_DTT] = tsstoo - tss * too;
         store_rec<T>(a.grec, item, r);
         if (g == 0) {
             srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
@@ -1921,7 +1978,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
     grec[G_DOB] = 0.5 * (K + bf); grec[G_DOF] = 0.5 * (K - bf);
     grec[G_FS] = Fs; grec[G_FT] = Ft;
     grec[G_TSS] = tss; grec[G_TOO] = too; grec[G_TSSTOO] = tsstoo;
-    grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_FSL] = Fs * (lai * sumint); grec[G_FTL] = Ft * (lai * sumint); grec[G_ALF] = alf;
+    grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_FSL] = Fs * (lai * sumint); grec[G_FTL] = Ft * (lai * sumint); grec[G_DTT] = tsstoo - tss * too;
     store_rec<T>(a.grec, item, grec);
     if (g == 0) {
         srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
