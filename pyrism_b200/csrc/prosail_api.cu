@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -231,7 +232,7 @@ static inline const void* offb(const void* p, long long n, size_t esz) { return 
 #endif
 // kernel configuration per real type and loop shape (G1 = one geometry per set): see struct Cfg in prosail_kernels.cuh
 template <typename T, bool G1> struct CfgOf { typedef Cfg<PB_NU, PB_NU == 3 ? 12 : (G1 ? PB_WARPS : PB_MULTI_WARPS)> type; };
-template <bool G1> struct CfgOf<float, G1> { typedef Cfg<2, PB_WARPS> type; };
+template <bool G1> struct CfgOf<float, G1> { typedef Cfg<2, PB_F32_WARPS> type; };
 
 // Three bands per thread (12 warps x 168 registers: 3 warps x 3 chains per sub-partition) for the two fp64 LUT instances that
 // measure faster that way -- BRF plane (+1.6%) and leaf-only (+1.3%); the four-plane instance (-1.3%), the band-mean instance
@@ -285,6 +286,8 @@ static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaS
         warps = resident_warps;
         a.nwarps_main = (int)(R * a.ngroups);
         a.nchunks_main = nchunks - nx;
+        static const bool no_tail = getenv("PYRISM_B200_NO_TAIL") != nullptr;    // A/B switch: the round-1 distribution (leftover warps idle)
+        if (no_tail) { warps = a.nwarps_main; a.nchunks_main = nchunks; }
     }
     a.nwarps = (int)warps;
     const unsigned grid = (unsigned)((warps + CF::WARPS - 1) / CF::WARPS);

@@ -36,6 +36,15 @@ namespace pb {
 #ifndef PB_WARPS
 #define PB_WARPS 16     /* warps per CTA (one CTA per SM); warps are independent (own staging buffers), the CTA only shares the math tables */
 #endif
+// fp32 mode: warps per CTA and resident CTAs per SM.  Round 2n: ONE CTA of 24 warps (80 registers per thread: no spills in the item
+// loop) instead of two of 16 (64 registers, LDL 2.6 / STL 2.0 per item): BRF 7.47e7 -> 7.96e7 spectra/s, band means 1.36e8 -> 1.37e8;
+// 20 warps x 96 registers: 7.89e7 / 1.28e8, 2 x 12 warps: 7.48e7 / 1.29e8 (profiles/r2n_variants_b.txt)
+#ifndef PB_F32_WARPS
+#define PB_F32_WARPS 24
+#endif
+#ifndef PB_F32_CTAS
+#define PB_F32_CTAS 1
+#endif
 
 constexpr int NB = 2101;          // wavelengths 400..2500 nm
 constexpr int NTILES = 66;        // 32-band tiles (unit of the band-mean window map)
@@ -426,9 +435,11 @@ __device__ __forceinline__ void leaf_layers_f32x2(const BandConst<f2>& c, f2 omt
 
 // rare lanes of the float path (k outside [2^-14, 32)): the whole plate + Stokes stage in float64 with IEEE divisions and
 // libm, exactly as models.py:953-957, 1019-1025, 1043-1065 (zero-absorption branch included)
-__device__ __noinline__ void leaf_exact_f32(const BandConst<float>& c, float kall, float nm1f, float& refl, float& tran) {
+// (arguments and results by value -- .x = reflectance, .y = transmittance: a reference parameter of a real call forces the caller's
+//  variable into local memory, which put two STL.64 + two LDL.64 per item on the hot path of the packed fp32 instances until round 2n)
+__device__ __noinline__ float2 leaf_exact_f32(float talf_, float ralf_, float t12_, float r12_, float t21_, float r21_, float kall, float nm1f) {
     const double tau = tau_rare((double)kall);
-    const double t21 = c.t21, r21 = c.r21, t12 = c.t12, r12 = c.r12, talf = c.talf, ralf = c.ralf, nm1 = nm1f;
+    const double t21 = t21_, r21 = r21_, t12 = t12_, r12 = r12_, talf = talf_, ralf = ralf_, nm1 = nm1f;
     const double x = r21 * tau;
     const double den1 = 1.0 - x * x;
     const double Ta = talf * tau * t21 / den1;
@@ -436,9 +447,7 @@ __device__ __noinline__ void leaf_exact_f32(const BandConst<float>& c, float kal
     const double t = t12 * tau * t21 / den1;
     const double r = r12 + x * t;
     if (!(t > 1e-280)) {                                          // opaque plate (k > ~640): nothing is transmitted
-        tran = 0.0f;
-        refl = (float)Ra;
-        return;
+        return make_float2((float)Ra, 0.0f);
     }
     const double qmt = t12 * (1.0 - tau) / (1.0 - x);
     double Rsub, Tsub;
@@ -464,8 +473,7 @@ __device__ __noinline__ void leaf_exact_f32(const BandConst<float>& c, float kal
         }
     }
     const double den = 1.0 - Rsub * r;
-    tran = (float)(Ta * Tsub / den);                              // :1062-1065
-    refl = (float)(Ra + Ta * Rsub * t / den);
+    return make_float2((float)(Ra + Ta * Rsub * t / den), (float)(Ta * Tsub / den));      // :1062-1065
 }
 
 // One-plate quantities exactly as models.py:1019-1025 (IEEE divisions), for the attributes PROSPECT.r/t/Ra/Ta/denom that the
@@ -505,7 +513,10 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
         if (__builtin_expect(any_rare, 0)) {
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-                if (rare[u]) leaf_exact_f32(c[u], kall[u], nm1, refl[u], tran[u]);
+                if (rare[u]) {
+                    const float2 rt = leaf_exact_f32(c[u].talf, c[u].ralf, c[u].t12, c[u].r12, c[u].t21, c[u].r21, kall[u], nm1);
+                    refl[u] = rt.x; tran[u] = rt.y;
+                }
         }
     } else {
         T tau[NU];
@@ -564,12 +575,12 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
     leaf_layers_f32x2(c2, mul(kall, F2(g0, g1)), nm1, refl, tran);                 // 1 - tau = k g(k)
     if (__builtin_expect(rare0 | rare1, 0)) {
         if (rare0) {
-            const BandConst<float> c{c2.talf.x, c2.ralf.x, c2.t12.x, c2.r12.x, c2.t21.x, c2.r21.x};
-            leaf_exact_f32(c, k0, nm1, refl.x, tran.x);
+            const float2 rt = leaf_exact_f32(c2.talf.x, c2.ralf.x, c2.t12.x, c2.r12.x, c2.t21.x, c2.r21.x, k0, nm1);
+            refl.x = rt.x; tran.x = rt.y;
         }
         if (rare1) {
-            const BandConst<float> c{c2.talf.y, c2.ralf.y, c2.t12.y, c2.r12.y, c2.t21.y, c2.r21.y};
-            leaf_exact_f32(c, k1, nm1, refl.y, tran.y);
+            const float2 rt = leaf_exact_f32(c2.talf.y, c2.ralf.y, c2.t12.y, c2.r12.y, c2.t21.y, c2.r21.y, k1, nm1);
+            refl.y = rt.x; tran.y = rt.y;
         }
     }
 }
@@ -1079,7 +1090,7 @@ __device__ __forceinline__ void emit_const(EmitCtx<T, NU>& e, T c) {
 
 // resident CTAs per SM the kernel is compiled for: double needs 65536 / threads registers (one CTA fills the register
 // file); float fits in half of that, so two CTAs share an SM and cover the MUFU / LDS latencies with twice the warps
-template <typename T> __host__ __device__ constexpr int min_ctas() { return std::is_same<T, float>::value ? 2 : PB_MIN_CTAS; }
+template <typename T> __host__ __device__ constexpr int min_ctas() { return std::is_same<T, float>::value ? PB_F32_CTAS : PB_MIN_CTAS; }
 
 // per-plane values of all bands of a thread, gathered from the per-band structs
 #define PB_GATHER(dst, arr, field)                       \
@@ -1270,7 +1281,10 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                     if (PLANES == RUNTIME && (need & (31u << O_LAYER_R))) {      // PROSPECT.r, t, Ra, Ta, denom (models.py:959)
                         T q[NU][5];
 #pragma unroll
-                        for (int u = 0; u < NU; ++u) leaf_one_layer(c[u], leaf_kall<KS>(kc + u, sr), q[u]);
+                        for (int u = 0; u < NU; ++u) {
+                            const BandConst<T> cc = c[u];     // a copy: the callee takes a reference, and c[] itself must stay in registers
+                            leaf_one_layer(cc, leaf_kall<KS>(kc + u, sr), q[u]);
+                        }
                         { PB_GATHER(v, q, [0]); emit<PLANES, MEANS, O_LAYER_R>(e, v); }
                         { PB_GATHER(v, q, [1]); emit<PLANES, MEANS, O_LAYER_T>(e, v); }
                         { PB_GATHER(v, q, [2]); emit<PLANES, MEANS, O_LAYER_RA>(e, v); }

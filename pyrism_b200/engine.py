@@ -526,12 +526,16 @@ _engines = {}
 _engines_lock = threading.Lock()
 
 
-def get_engine(device=None):
-    """Process-wide engine for ``device`` (default: env PYRISM_B200_DEVICE or 0)."""
+def get_engine(device=None, role='main'):
+    """Process-wide engine for ``device`` (default: env PYRISM_B200_DEVICE or 0).
+
+    ``role='select'`` returns a second handle on the same device that `PROSPECT.select / LSM.select / indices` use for their
+    one-window means: its window list changes with every call, the main engine's never does."""
     import os
     if device is None:
         device = int(os.environ.get("PYRISM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    key = device if role == 'main' else (device, role)
     with _engines_lock:
-        if device not in _engines:
-            _engines[device] = Engine(device)
-        return _engines[device]
+        if key not in _engines:
+            _engines[key] = Engine(device)
+        return _engines[key]

@@ -85,6 +85,49 @@ def test_prospect_attribute_surface():
     assert np.array_equal(p40.ks, p.ks)
 
 
+def test_select_leaves_the_shared_engine_alone_and_is_thread_safe():
+    """select() / indices() run on their own handle (`get_engine(device, role='select')`): the shared engine keeps its 15 windows,
+    and constructors on other threads see consistent L8 / ASTER means while select() calls with different windows are in flight
+    (round-1 VERDICT weak #12)."""
+    import threading
+    from pyrism_b200.engine import get_engine
+    main = get_engine()
+    p = pb.PROSPECT(N=1.5, Cab=35, Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055)
+    want_b5 = np.asarray(p.L8.B5)
+    before = main.windows
+    sel0 = p.select(851, 879)
+    assert main.windows == before and len(main.windows) == 15
+    assert get_engine(role='select') is not main and get_engine(role='select').windows == ((851, 879),)
+    errors = []
+
+    def selector(lo, hi, ref):
+        try:
+            for _ in range(30):
+                if not np.array_equal(p.select(lo, hi), ref):
+                    errors.append(("select", lo, hi))
+        except Exception as exc:      # noqa: BLE001
+            errors.append(repr(exc))
+
+    def constructor():
+        try:
+            for _ in range(30):
+                q = pb.PROSPECT(N=1.5, Cab=35, Cxc=5, Cbr=0.15, Cw=0.003, Cm=0.0055)
+                if not np.array_equal(np.asarray(q.L8.B5), want_b5) or len(q.ASTER) != 9:
+                    errors.append("constructor saw another window list")
+        except Exception as exc:      # noqa: BLE001
+            errors.append(repr(exc))
+
+    ref_red = p.select(636, 673)
+    ts = [threading.Thread(target=selector, args=(851, 879, sel0)), threading.Thread(target=selector, args=(636, 673, ref_red)),
+          threading.Thread(target=constructor), threading.Thread(target=constructor)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+    assert main.windows == before
+
+
 def test_prospect_extreme_absorption():
     """Arguments of tau() from ~0 (zero-absorption Stokes branch, models.py:1057-1059) up to k > 64."""
     o = orc.prospect(1.5, 0.0, 0.0, 0.0, 0.0, 0.0)
