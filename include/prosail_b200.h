@@ -17,8 +17,11 @@
  *     zenith -> abs value and raa += pi).
  *   - spectra have PROSAIL_NBANDS = 2101 values (400..2500 nm); `pitch` is the row stride in elements
  *     (>= 2101; 2112 gives 128-byte aligned rows).
- *   - a handle is bound to one device; calls on one handle must not overlap in time (use one handle per
- *     host thread / stream).
+ *   - thread safety: the library has no global mutable state (the error text is thread-local), so any number of host
+ *     threads may call it at the same time on DIFFERENT handles, several of which may live on the same device
+ *     (each owns its constants, window list, workspace and streams: that is how the Python drop-in gives
+ *     PROSPECT.select() / LSM.select() a window list of their own without touching the shared engine's).  Calls on
+ *     ONE handle must not overlap in time: a handle carries the window list, the staged tables and one workspace.
  */
 #ifndef PROSAIL_B200_H
 #define PROSAIL_B200_H

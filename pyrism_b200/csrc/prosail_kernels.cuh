@@ -1039,8 +1039,7 @@ constexpr unsigned RUNTIME = 0x80000000u;
 template <typename T, int NU>
 struct EmitCtx {
     const SailArgs<T>& a;
-    bool tail;           // warp-uniform: this warp owns the last tile group, the only one with bands >= 2101
-    bool valid[NU];      // band u of this thread exists (< 2101); only consulted when tail
+    bool valid[NU];      // band u of this thread exists (< 2101: only the last tile group has lanes past the end); recomputed per chunk from band0
     int tile0;           // 32-band tile of band 0 (band u is in tile0 + u): index into the window map
     int lane, nt;
     long long orow;      // item * pitch + band[0]   (band[u] = band[0] + 32 u)
@@ -1055,7 +1054,7 @@ __device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
         if (e.a.out[PLANE]) {
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-                if (!e.tail || e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
+                if (e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
         }
         if (e.a.mean_mask & (1u << PLANE)) {
 #pragma unroll
@@ -1066,7 +1065,7 @@ __device__ __forceinline__ void emit(EmitCtx<T, NU>& e, const T (&v)[NU]) {
         if ((PLANES >> PLANE) & 1u) {
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-                if (!e.tail || e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
+                if (e.valid[u]) __stcs(e.a.out[PLANE] + e.orow + 32 * u, v[u]);
         }
         if ((MEANS >> PLANE) & 1u) {       // specialised instances: never launched with spectral-response weights (dispatch_bands)
             if constexpr (!is_f32<T>()) {      // double: NU interleaved butterflies (+6%); float: the per-tile loop is faster (issue-bound)
@@ -1161,7 +1160,6 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     if (lane == 0 && remaining > 0) stage_issue(a, &stage[0], &bar[0], chunk);
 
     int grp = 0, band0 = lane;                     // tile group and this thread's bands (packed map: lanes): band0 + 32 u
-    bool tail = false;                             // warp-uniform: the group holds bands >= 2101
     BandConst<T> c[NU];
     // fused fp64 instances keep the interface constants in shared memory (register pressure); everything else in registers
     constexpr bool CSMEM = consts_in_smem<T, MODE>();
@@ -1181,7 +1179,6 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     auto enter_group = [&](int slot) {
     grp = a.only_active_tiles ? a.win->active_group[NU - 2][slot] : slot;
     band0 = grp * (32 * NU) + lane;
-    tail = !a.packed && (grp + 1) * (32 * NU) > NB;                   // the packed map has no out-of-range stores (no planes)
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
         const int lane_u = band0 + 32 * u;                            // NBP = 66 * 32: always in range
@@ -1246,10 +1243,10 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             bool nocanopy = false;
             const T* sr = stage[buf].s;
             const T* gr = stage[buf].g;
-            EmitCtx<T, NU> e{a, tail, {}, NU * grp, lane, nt, i0 * a.out_pitch + band0, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0, plan};
+            EmitCtx<T, NU> e{a, {}, NU * grp, lane, nt, i0 * a.out_pitch + band0, ANY_MEANS ? a.partial + i0 * nmean * nt : nullptr, 0, plan};
 #pragma unroll
-            for (int u = 0; u < NU; ++u)      // only the last tile group has bands >= 2101: there the answer depends on the lane alone
-                e.valid[u] = !tail || lane < NB - (NTILES / NU - 1) * (32 * NU) - 32 * u;
+            for (int u = 0; u < NU; ++u)      // (the packed map stores no planes and reads no spectra: the flag is not consulted there)
+                e.valid[u] = band0 + 32 * u < NB;
             for (int j = 0; j < n; ++j) {
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {

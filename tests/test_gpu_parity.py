@@ -154,6 +154,28 @@ def test_prospect_extreme_absorption():
         assert np.max(np.abs(p.ks[ok] - o['ks'][ok])) <= TOL and np.max(np.abs(p.kt[ok] - o['kt'][ok])) <= TOL
 
 
+def test_prospect_weak_absorption_ladder():
+    """Leaves whose absorption goes from realistic down to almost nothing (all contents scaled by 1 ... 1e-9), N below, at and above 1:
+    the fast path's economised polynomials and second-order steps are amplified by 1/D there, and from 1 - r - t < 2^-17 on the exact
+    rare path takes over (csrc/prosail_kernels.cuh: leaf_layers_slow).  Both sides of that switch hold the 1e-9 bar against the oracle;
+    negative N - 1 exercises the other sign of the exponent in pow_pos_scaled."""
+    f = np.array([1.0, 0.3, 0.1, 3e-2, 1e-2, 3e-3, 1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 3e-6, 1e-6, 1e-7, 1e-8, 1e-9])
+    worst = 0.0
+    for N in (0.9, 1.0, 1.3, 2.0, 3.0):
+        p = pb.PROSPECT(N=np.full(f.size, N), Cab=40.0 * f, Cxc=8.0 * f, Cbr=0.1 * f, Cw=0.01 * f, Cm=0.009 * f)
+        for i, fi in enumerate(f):
+            o = orc.prospect(N, 40.0 * fi, 8.0 * fi, 0.1 * fi, 0.01 * fi, 0.009 * fi)
+            ok = np.isfinite(o['ks']) & np.isfinite(o['kt'])
+            assert ok.sum() > 2000
+            # the reference's own rounding noise in a^2 - 1 and b^(2(N-1)) - 1 is 1e-16 / D: 1e-12 at f = 1e-4, 1e-9 at f = 1e-9
+            tol = TOL if fi >= 1e-6 else 2e-8
+            d = max(float(np.max(np.abs(p.ks[i][ok] - o['ks'][ok]))), float(np.max(np.abs(p.kt[i][ok] - o['kt'][ok]))))
+            assert d <= tol, (N, fi, d)
+            if fi >= 1e-4:
+                worst = max(worst, d)
+    assert worst <= 1e-10, worst          # realistic and weakly absorbing leaves stay inside the round-2 error budget's test bar
+
+
 # ------------------------------------------------------------------------------------------------------------ LSM
 def test_lsm():
     r, m = rng.uniform(0.3, 1.2, 9), rng.uniform(0, 1, 9)

@@ -5,7 +5,7 @@ CUDA path, every plane of the path against the CPU oracle evaluated on all host 
 Bars: fp64 <= 1e-10 (the round-2 error budget of the kernel, ten times inside the 1e-9 parity bar; measured 6.4e-12),
 fp32 mode <= 1e-5 (north star; measured 2.1e-6).
 
-test_edge_of_domain_cases: 25 edge-of-domain inputs (lai 1e-6 .. 300, grazing angles, hotspot 1e-9 .. 10, LIDF extremes,
+test_edge_of_domain_cases: 30 edge-of-domain inputs (lai 1e-6 .. 5000, grazing angles, hotspot 1e-9 .. 10, LIDF extremes,
 pigment-free / opaque leaves, black and very bright soil) through the drop-in PROSAIL class in both precisions.
 """
 import multiprocessing as mp
@@ -86,7 +86,9 @@ CASES = [("base", {}), ("lai 50", dict(lai=50.0)), ("lai 1e-6", dict(lai=1e-6)),
          ("campbell a 89.9", dict(a=89.9)), ("verhoef -1 0", dict(lidf_type='verhoef', a=-1.0, b=0.0)), ("verhoef .99 0", dict(lidf_type='verhoef', a=0.99, b=0.0)),
          ("verhoef 0 1", dict(lidf_type='verhoef', a=0.0, b=-1.0)), ("N 1", dict(N=1.0)), ("N 6", dict(N=6.0)), ("no pigments", dict(Cab=0.0, Cxc=0.0, Cbr=0.0)),
          ("dry thin leaf", dict(Cw=1e-5, Cm=1e-4)), ("thick leaf", dict(Cw=0.2, Cm=0.1, Cab=200.0)), ("black soil", dict(sr=0.0)),
-         ("bright wet soil", dict(sr=2.5, sm=1.0)), ("dry soil", dict(sm=0.0)), ("lai 0", dict(lai=0.0))]
+         ("bright wet soil", dict(sr=2.5, sm=1.0)), ("dry soil", dict(sm=0.0)), ("lai 0", dict(lai=0.0)),
+         # round 2n: beyond the underflow floor of the scaled exp (exp(-m lai) < 1e-300), exponents of b^(N-1) of both signs
+         ("lai 5000", dict(lai=5000.0)), ("N 0.8", dict(N=0.8)), ("N 1.0001", dict(N=1.0001)), ("weak absorption", dict(Cab=0.4, Cxc=0.08, Cbr=0.001, Cw=1e-4, Cm=9e-5))]
 
 
 @pytest.mark.parametrize("name,over", CASES, ids=[c[0] for c in CASES])
