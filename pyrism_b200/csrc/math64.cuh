@@ -32,6 +32,9 @@
 #ifndef PB_SOILFOLD
 #define PB_SOILFOLD 1    /* soil coupling as [A1 A2/dn + (tsstoo - tss too)] rs with A1 = tss + tsd, A2 = too + tdo (4 less) */
 #endif
+#ifndef PB_F32_ALG
+#define PB_F32_ALG 1     /* the packed fp32 item loop with the same re-derived stages (Y form, P/Q form, A1 A2 soil coupling): ~18 packed instructions less per item */
+#endif
 #ifndef PB_EXPS
 #define PB_EXPS 1        /* exp(-m lai): the record carries -lai 2048 log2(e), the product m lai is never formed (1 less) */
 #endif

@@ -426,11 +426,19 @@ __device__ __forceinline__ void leaf_layers_f32x2(const BandConst<f2>& c, f2 omt
     const f2 bNm1 = exp2_fast(F2(fminf(lb.x, 60.0f), fminf(lb.y, 60.0f)));   // opaque plates: b^(N-1) saturates
     const f2 bN2 = mul(bNm1, bNm1);
     const f2 bm1 = add(bN2, -1.0f);
+#if PB_F32_ALG
+    // the Y form of leaf_layers_fast (round 2n): Y = bm1 (a r - r^2) + D, all terms >= 0; four packed instructions less
+    const f2 Y = fma(bm1, fma(neg(r), r, al), D);
+    const f2 TaI = mul(Ta, rcp(Y));
+    tran = mul(TaI, mul(bNm1, D));
+    refl = fma(mul(TaI, bm1), mul(t, r), Ra);
+#else
     const f2 dal = mul(da, add(al, r));                           // (a r)^2 - r^2
     const f2 X = fma(mul(al, bm1), fma(neg(r), r, al), dal);
     const f2 TaI = mul(Ta, rcp(X));
     tran = mul(TaI, mul(bNm1, dal));
     refl = fma(mul(TaI, bm1), mul(mul(t, al), r), Ra);
+#endif
 }
 
 // rare lanes of the float path (k outside [2^-14, 32)): the whole plate + Stokes stage in float64 with IEEE divisions and
@@ -857,35 +865,49 @@ __device__ __forceinline__ void sail_directional(T rho, T tau, T rs, const Diffu
 // ---------------------------------------------------------------------------------------------
 template <bool FROM_LEAF>
 __device__ __forceinline__ void sail_diffuse_f32x2(f2 rho, f2 tau, f2 rs, const float* __restrict__ s, Diffuse<f2>& d) {
-    f2 sigb = fma(s[S_DDB], rho, mul(tau, s[S_DDF]));                 // :590
-    f2 sigf = fma(s[S_DDF], rho, mul(tau, s[S_DDB]));                 // :591
-    if (!FROM_LEAF) {
-        sigb = F2(is_zero(sigb.x) ? 1e-36f : sigb.x, is_zero(sigb.y) ? 1e-36f : sigb.y);      // :594-595
-        sigf = F2(is_zero(sigf.x) ? 1e-36f : sigf.x, is_zero(sigf.y) ? 1e-36f : sigf.y);
+    if constexpr (FROM_LEAF && PB_F32_ALG) {
+        // the P / Q form of sail_diffuse (round 2n): P = att + sigb = 1 + bf (rho - tau), Q = att - sigb = 1 - rho - tau,
+        // m = sqrt(P Q), rinf = (P - m)/(P + m); a1 = 2 Ap = s (1 + rinf), a2 = Am = (bf/2)(rho - tau)(1 - rinf): the directional
+        // stage multiplies a1 with k/2, K/2 (scalars, once per item)
+        const f2 s_ = add(rho, tau), dd = sub(rho, tau);
+        const f2 oms = sub(F2(1.0f), s_);
+        const f2 P = fma(s[S_BF], dd, F2(1.0f));
+        const f2 bdh = mul(dd, 0.5f * s[S_BF]);
+        d.m = sqrt_pos(mul(oms, P));
+        d.rinf = mul(sub(P, d.m), rcp(add(P, d.m)));
+        d.a1 = fma(s_, d.rinf, s_);
+        d.a2 = fma(neg(bdh), d.rinf, bdh);
+    } else {
+        f2 sigb = fma(s[S_DDB], rho, mul(tau, s[S_DDF]));                 // :590
+        f2 sigf = fma(s[S_DDF], rho, mul(tau, s[S_DDB]));                 // :591
+        if (!FROM_LEAF) {
+            sigb = F2(is_zero(sigb.x) ? 1e-36f : sigb.x, is_zero(sigb.y) ? 1e-36f : sigb.y);      // :594-595
+            sigf = F2(is_zero(sigf.x) ? 1e-36f : sigf.x, is_zero(sigf.y) ? 1e-36f : sigf.y);
+        }
+        const f2 att = sub(F2(1.0f), sigf);                               // :600
+        d.m = sqrt_pos(mul(sub(att, sigb), add(att, sigb)));              // :601 without the cancellation
+        d.rinf = mul(sigb, rcp(add(att, d.m)));                           // :639 as sigb / (att + m)
+        d.a1 = fma(tau, d.rinf, rho);
+        d.a2 = fma(rho, d.rinf, tau);
     }
-    const f2 att = sub(F2(1.0f), sigf);                               // :600
-    d.m = sqrt_pos(mul(sub(att, sigb), add(att, sigb)));              // :601 without the cancellation
-    d.rinf = mul(sigb, rcp(add(att, d.m)));                           // :639 as sigb / (att + m)
     d.e1 = exp2_fast(mul(d.m, s[S_NEGLAI] * 1.4426950408889634f));    // :637
-    const f2 e2 = mul(d.e1, d.e1);
-    const f2 rinf2 = mul(d.rinf, d.rinf);
     d.re = mul(d.rinf, d.e1);
-    const f2 omr2 = sub(F2(1.0f), rinf2);
-    const f2 den = fma(neg(rinf2), e2, 1.0f);                         // :642
+    const f2 omr2 = fma(neg(d.rinf), d.rinf, 1.0f);                   // 1 - rinf^2
+    const f2 den = fma(neg(d.re), d.re, 1.0f);                        // 1 - (rinf e)^2                        :642
     const f2 r = rcp(mul(den, omr2));
     d.invden = mul(r, omr2);
     d.inv_omr2 = mul(r, den);
     d.tdd = mul(mul(omr2, d.e1), d.invden);                           // :654
     d.rinf_invden = mul(d.rinf, d.invden);
-    d.rdd = mul(d.rinf_invden, sub(F2(1.0f), e2));                    // :655
+    d.rdd = mul(fma(neg(d.re), d.e1, d.rinf), d.invden);              // rinf (1 - e^2)/den                    :655
     d.rsrdd = mul(rs, d.rdd);
     f2 dn = sub(F2(1.0f), d.rsrdd);                                   // :714-719
     dn = F2(below_tiny(dn.x) ? 1e-36f : dn.x, below_tiny(dn.y) ? 1e-36f : dn.y);
-    d.rs_invdn = mul(rs, rcp(dn));
-    d.a1 = fma(tau, d.rinf, rho);
-    d.a2 = fma(rho, d.rinf, tau);
+    d.invdn = rcp(dn);
+    d.rs_invdn = mul(rs, d.invdn);
 }
 
+template <bool AB>
 __device__ __forceinline__ void sail_directional_f32x2(f2 rho, f2 tau, f2 rs, const Diffuse<f2>& d, const float* __restrict__ s,
                                                        const float* __restrict__ g, unsigned need, Canopy<f2>& o) {
     const float k = g[G_K], K = g[G_KO], tss = g[G_TSS], too = g[G_TOO], lai = s[S_LAI];
@@ -900,20 +922,41 @@ __device__ __forceinline__ void sail_directional_f32x2(f2 rho, f2 tau, f2 rs, co
     const f2 J1ko = F2(fabsf(xK.x) < 0.25f ? sK.x : dK.x, fabsf(xK.y) < 0.25f ? sK.y : dK.y);
     const f2 rkK = rcp(mul(kp, Kp));                                  // 1/(k+m) and 1/(K+m) from one reciprocal (both > 0)
     const f2 inv_kp = mul(rkK, Kp), inv_Kp = mul(rkK, kp);
-    const f2 w = fma(g[G_FS], rho, mul(tau, g[G_FT]));               // :607
-    const f2 u1 = fma(g[G_SDF], d.a1, mul(d.a2, g[G_SDB])), u2 = fma(g[G_SDF], d.a2, mul(d.a1, g[G_SDB]));   // :603-606, 649-652 via a1, a2
-    const f2 v1 = fma(g[G_DOF], d.a1, mul(d.a2, g[G_DOB])), v2 = fma(g[G_DOF], d.a2, mul(d.a1, g[G_DOB]));
+    f2 u1, u2, v1, v2;
+    if constexpr (AB) {           // d.a1 = 2 Ap, d.a2 = Am (sail_diffuse_f32x2): sf + sb rinf = k Ap - Am, sf rinf + sb = k Ap + Am, same with K
+        const float kh = 0.5f * k, Kh = 0.5f * K;
+        u1 = fma(kh, d.a1, neg(d.a2)); u2 = fma(kh, d.a1, d.a2);
+        v1 = fma(Kh, d.a1, neg(d.a2)); v2 = fma(Kh, d.a1, d.a2);
+    } else {
+        u1 = fma(g[G_SDF], d.a1, mul(d.a2, g[G_SDB])); u2 = fma(g[G_SDF], d.a2, mul(d.a1, g[G_SDB]));   // :603-606, 649-652 via a1, a2
+        v1 = fma(g[G_DOF], d.a1, mul(d.a2, g[G_DOB])); v2 = fma(g[G_DOF], d.a2, mul(d.a1, g[G_DOB]));
+    }
     const f2 ck = mul(u2, inv_kp), cK = mul(v2, inv_Kp);             // u2/(k+m), v2/(K+m): shared by Q (J2, :787-789) and T2, T1
     const f2 Pss = mul(u1, J1ks), Qss = mul(ck, fma(neg(d.e1), F2(tss), 1.0f)), Pv = mul(v1, J1ko), Qv = mul(cK, fma(neg(d.e1), F2(too), 1.0f));
     const f2 nre = neg(d.re);
-    const f2 tdo_u = fma(nre, Qv, Pv), rdo_u = fma(nre, Pv, Qv);     // before the common factor 1/(1 - rinf^2 e^2)
-    o.tsd = mul(fma(nre, Qss, Pss), d.invden);                        // :656-659
+    const f2 tsd_u = fma(nre, Qss, Pss), tdo_u = fma(nre, Qv, Pv), rdo_u = fma(nre, Pv, Qv);     // before the common factor 1/(1 - rinf^2 e^2)
+    o.tsd = mul(tsd_u, d.invden);                                     // :656-659
     o.rsd = mul(fma(nre, Pss, Qss), d.invden);
     o.tdo = mul(tdo_u, d.invden);
     o.rdo = mul(rdo_u, d.invden);
+    const f2 T3 = mul(fma(rdo_u, Qss, mul(tdo_u, Pss)), d.rinf_invden);
+#if PB_F32_ALG
+    // T1 + T2 - T3 as nested FMAs (:668-678) and the soil coupling in the A1 A2 form of sail_couple (round 2n):
+    //   rsot = rsod + rsos + [A1 A2 / dn + (tsstoo - tss too)] rs,  A1 = tss + tsd, A2 = too + tdo -- every term >= 0, nothing cancels in float
+    const f2 Ts = fma(mul(cK, u1), fma(neg(J1ks), F2(too), F2(g[G_Z])), fma(mul(ck, v1), fma(neg(J1ko), F2(tss), F2(g[G_Z])), neg(T3)));
+    f2 ss;
+    if constexpr (AB) ss = fma(g[G_FSL], rho, mul(tau, g[G_FTL]));    // rsos = w lai sumint, lai sumint folded into Fs, Ft by the prologue   :607, :706
+    else ss = mul(fma(g[G_FS], rho, mul(tau, g[G_FT])), g[G_LAISUM]);
+    o.rso = fma(Ts, d.inv_omr2, ss);                                  // rsos + rsod                              :678, :706, :710
+    const f2 A1 = fma(tsd_u, d.invden, F2(tss)), A2 = fma(tdo_u, d.invden, F2(too));
+    o.rsot = fma(fma(mul(A1, A2), d.invdn, F2(g[G_DTT])), rs, o.rso);
+    if (need & (1u << O_RDDT)) o.rddt = fma(mul(d.tdd, d.tdd), d.rs_invdn, d.rdd);
+    if (need & (1u << O_RSDT)) o.rsdt = fma(mul(A1, d.tdd), d.rs_invdn, o.rsd);
+    if (need & (1u << O_RDOT)) o.rdot = fma(mul(d.tdd, A2), d.rs_invdn, o.rdo);
+#else
+    const f2 w = fma(g[G_FS], rho, mul(tau, g[G_FT]));               // :607
     const f2 T1 = mul(mul(cK, u1), fma(neg(J1ks), F2(too), F2(g[G_Z])));   // :668-675
     const f2 T2 = mul(mul(ck, v1), fma(neg(J1ko), F2(tss), F2(g[G_Z])));
-    const f2 T3 = mul(fma(rdo_u, Qss, mul(tdo_u, Pss)), d.rinf_invden);
     const f2 rsod = mul(sub(add(T1, T2), T3), d.inv_omr2);            // :678
     o.rso = fma(g[G_LAISUM], w, rsod);                                // :706, :710
     // soil coupling                                                                        :721-726
@@ -922,6 +965,7 @@ __device__ __forceinline__ void sail_directional_f32x2(f2 rho, f2 tau, f2 rs, co
     if (need & (1u << O_RDDT)) o.rddt = fma(mul(d.tdd, d.tdd), d.rs_invdn, d.rdd);
     if (need & (1u << O_RSDT)) o.rsdt = fma(mul(add(o.tsd, tss), d.tdd), d.rs_invdn, o.rsd);
     if (need & (1u << O_RDOT)) o.rdot = fma(mul(d.tdd, add(o.tdo, too)), d.rs_invdn, o.rdo);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1331,7 +1375,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         if constexpr (PACKED) {
                             Canopy<f2> op;
                             op.rddt = op.rsdt = op.rdot = F2(0.0f);
-                            sail_directional_f32x2(F2(rho[0], rho[1]), F2(tau[0], tau[1]), F2(rs[0], rs[1]), dp, sr, gr, need, op);
+                            sail_directional_f32x2<MODE == MODE_PROSAIL && PB_F32_ALG>(F2(rho[0], rho[1]), F2(tau[0], tau[1]), F2(rs[0], rs[1]), dp, sr, gr, need, op);
                             o[0] = Canopy<T>{op.rsot.x, op.rddt.x, op.rsdt.x, op.rdot.x, op.rso.x, op.rsd.x, op.tsd.x, op.rdo.x, op.tdo.x};
                             o[1] = Canopy<T>{op.rsot.y, op.rddt.y, op.rsdt.y, op.rdot.y, op.rso.y, op.rsd.y, op.tsd.y, op.rdo.y, op.tdo.y};
                         } else {
