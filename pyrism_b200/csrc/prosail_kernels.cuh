@@ -30,9 +30,6 @@ namespace pb {
 #ifndef PB_CHUNK
 #define PB_CHUNK 8
 #endif
-#ifndef PB_KC_THREAD_MAJOR
-#define PB_KC_THREAD_MAJOR 0   /* 1: [thread][plane][u] with 128-bit loads -- measured slower (BRF -0.8%, leaf-only -11%: profiles/r2f_variants.txt) */
-#endif
 #ifndef PB_WARPS
 #define PB_WARPS 16     /* warps per CTA (one CTA per SM); warps are independent (own staging buffers), the CTA only shares the math tables */
 #endif
@@ -60,11 +57,12 @@ struct Cfg {
     static constexpr int NU = NU_;                     // bands per thread: band0 + 32 u
     static constexpr int WARPS = WARPS_;
     static constexpr int THREADS = WARPS_ * 32;
-#if PB_KC_THREAD_MAJOR
-    static constexpr int KSTRIDE = NU_;                // SailSmem::kc is [thread][plane][u]: plane stride = NU elements
-#else
-    static constexpr int KSTRIDE = NU_ * THREADS;      // elements per plane of SailSmem::kc: [plane][thread][u]
-#endif
+    // SailSmem::kc is [plane pair][thread][plane of the pair][u]: the 2 NU values a thread holds of two consecutive planes are one
+    // contiguous, 16-byte aligned run (NU = 3: 48 bytes = three conflict-free 128-bit loads instead of six 64-bit ones -- a thread's
+    // stride of 48 bytes puts the 8 lanes of a quarter warp on 8 different 16-byte bank groups)
+    static constexpr int KPAIR = 2 * NU_ * THREADS;    // elements per plane pair
+    static constexpr int KCOL = 2 * NU_;               // elements per thread and pair
+    __host__ __device__ static constexpr int koff(int plane) { return (plane >> 1) * KPAIR + (plane & 1) * NU_; }   // offset of (plane, u = 0) from the thread's base
     static constexpr int NGROUPS = NTILES / NU_;       // groups of NU 32-band tiles, one per warp
     static_assert(NTILES % NU_ == 0, "the 66 tiles must split evenly into groups");
 };
@@ -189,24 +187,12 @@ struct alignas(128) Stage {
 template <typename T, int MODE> __host__ __device__ constexpr bool consts_in_smem() { return !std::is_same<T, float>::value && MODE == 0 /* MODE_PROSAIL */; }
 template <typename T, int MODE> __host__ __device__ constexpr int kplanes() { return consts_in_smem<T, MODE>() ? 13 : 8; }
 
-// Thread-major layout of the once-per-item constants (PB_KC_THREAD_MAJOR, default): [thread][plane][u], so that a thread's
-// kplanes x NU values are one contiguous run read with 128-bit loads (two values per LDS: 20 loads instead of 39 per item in
-// the three-band fp64 instance).  The per-thread stride is padded to D = 2 (mod 4) elements: the 8 lanes of a quarter warp
-// then start 4 banks apart (in units of the 16-byte access) and a 128-bit (double) / 64-bit (float) load is conflict free.
-template <typename T, typename CF, int MODE> __host__ __device__ constexpr int kc_col() {
-    int d = kplanes<T, MODE>() * CF::NU;
-    while (d % 4 != 2) ++d;
-    return d;
-}
+// (A fully thread-major layout [thread][plane][u] measured slower in round 2f: BRF -0.8 %, leaf-only -11 %, profiles/r2f_variants.txt.)
 template <typename T, typename CF, int MODE>
 struct alignas(128) SailSmem {
     typename Tables<T>::type mt;           // shared by the CTA, read-only after the prologue
     Stage<T> stage[CF::WARPS][2];          // per-warp double-buffered record staging: no CTA-wide barrier in the loop
-#if PB_KC_THREAD_MAJOR
-    T kc[kc_col<T, CF, MODE>() * CF::THREADS];   // [thread][plane][u]
-#else
-    T kc[kplanes<T, MODE>() * CF::KSTRIDE];   // [plane][thread][u]: a thread's bands are adjacent (vector loads), lanes consecutive
-#endif
+    T kc[((kplanes<T, MODE>() + 1) / 2) * CF::KPAIR];   // [plane pair][thread][plane of the pair][u], see Cfg::koff
     uint64_t bar[CF::WARPS][2];
 };
 
@@ -253,22 +239,75 @@ template <typename T> __device__ __forceinline__ constexpr bool is_f32() { retur
 
 // PROSPECT for one band and one parameter set: leaf reflectance (ks) and transmittance (kt).
 // models.py:949-959 (kall, tau), 1019-1025 (one layer), 1043-1068 (Stokes, N layers).
-template <int KSTRIDE, typename T>
+template <typename CF, typename T>
 __device__ __forceinline__ T leaf_kall(const T* __restrict__ kc, const T* __restrict__ s) {
     // kall = sum_i C_i K_i / N ; the division by N is folded into the record (C_i / N)      :950-951
-    T kall = s[S_CAB] * kc[KC_KAB * KSTRIDE];
-    kall = fma(s[S_CXC], kc[KC_KXC * KSTRIDE], kall);
+    T kall = s[S_CAB] * kc[CF::koff(KC_KAB)];
+    kall = fma(s[S_CXC], kc[CF::koff(KC_KXC)], kall);
     // PROSPECT-5 has no anthocyanin term (Kan = zeros, models.py:935): the record carries Can/N = +0.0 and the FMA is
     // predicated off by an integer test on that (warp-uniform) value -- one three-register DFMA less per band and item
-    if (!is_zero(s[S_CAN])) kall = fma(s[S_CAN], kc[KC_KAN * KSTRIDE], kall);
-    kall = fma(s[S_CBR], kc[KC_KBR * KSTRIDE], kall);
-    kall = fma(s[S_CW], kc[KC_KW * KSTRIDE], kall);
-    return fma(s[S_CM], kc[KC_KM * KSTRIDE], kall);
+    if (!is_zero(s[S_CAN])) kall = fma(s[S_CAN], kc[CF::koff(KC_KAN)], kall);
+    kall = fma(s[S_CBR], kc[CF::koff(KC_KBR)], kall);
+    kall = fma(s[S_CW], kc[CF::koff(KC_KW)], kall);
+    return fma(s[S_CM], kc[CF::koff(KC_KM)], kall);
+}
+// The 2 NU values a thread holds of the plane pair starting at the (even) plane `first`, with explicit 128-bit loads (the run is 16-byte
+// aligned, see Cfg::koff): a[u] = plane `first`, b[u] = plane `first + 1`.
+template <typename CF, typename T>
+__device__ __forceinline__ void load_pair(const T* __restrict__ kc, int first, T (&a)[CF::NU], T (&b)[CF::NU]) {
+    constexpr int NU = CF::NU;
+    T f[2 * NU];
+    const T* p = kc + CF::koff(first);
+    if constexpr (std::is_same<T, float>::value && NU == 2) {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+    } else if constexpr (!std::is_same<T, float>::value) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            const double2 q = reinterpret_cast<const double2*>(p)[i];
+            f[2 * i] = q.x; f[2 * i + 1] = q.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 2 * NU; ++i) f[i] = p[i];
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) { a[u] = f[u]; b[u] = f[NU + u]; }
+}
+// kall of all NU bands of a thread (:950-951), the six absorption tables read as three plane pairs
+template <typename CF, typename T>
+__device__ __forceinline__ void leaf_kall_all(const T* __restrict__ kc, const T* __restrict__ s, T (&kall)[CF::NU]) {
+    constexpr int NU = CF::NU;
+    static_assert(KC_KAB == 0 && KC_KXC == 1 && KC_KAN == 2 && KC_KBR == 3 && KC_KW == 4 && KC_KM == 5, "plane pairs");
+    T a[NU], b[NU];
+    load_pair<CF>(kc, KC_KAB, a, b);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CXC], b[u], s[S_CAB] * a[u]);
+    load_pair<CF>(kc, KC_KAN, a, b);
+    // PROSPECT-5 has no anthocyanin term (Kan = zeros, models.py:935): the record carries Can/N = +0.0 and the FMA is predicated
+    // off by an integer test on that (warp-uniform) value
+    if (!is_zero(s[S_CAN])) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CAN], a[u], kall[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CBR], b[u], kall[u]);
+    load_pair<CF>(kc, KC_KW, a, b);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CM], b[u], fma(s[S_CW], a[u], kall[u]));
+}
+template <typename CF, typename T>
+__device__ __forceinline__ void soil_rho_all(const T* __restrict__ kc, const T* __restrict__ s, T (&rs)[CF::NU]) {
+    static_assert(KC_RS1 == 6 && KC_RS2 == 7, "plane pairs");
+    T a[CF::NU], b[CF::NU];
+    load_pair<CF>(kc, KC_RS1, a, b);
+#pragma unroll
+    for (int u = 0; u < CF::NU; ++u) rs[u] = fma(s[S_SOIL1], a[u], s[S_SOIL2] * b[u]);
 }
 // soil reflectance of the LSM mix, models.py:1917
-template <int KSTRIDE, typename T>
+template <typename CF, typename T>
 __device__ __forceinline__ T soil_rho(const T* __restrict__ kc, const T* __restrict__ s) {
-    return fma(s[S_SOIL1], kc[KC_RS1 * KSTRIDE], s[S_SOIL2] * kc[KC_RS2 * KSTRIDE]);
+    return fma(s[S_SOIL1], kc[CF::koff(KC_RS1)], s[S_SOIL2] * kc[CF::koff(KC_RS2)]);
 }
 
 // Branch-free plate + Stokes stage.  Returns true when 1 - r - t < 2^-17 (no or almost no absorption; r + t >= 1 is the
@@ -505,13 +544,11 @@ template <typename CF, bool CSMEM, typename T, typename MT>
 __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
                                             T (&refl)[CF::NU], T (&tran)[CF::NU]) {
     constexpr int NU = CF::NU;
-    constexpr int KS = CF::KSTRIDE;
     T kall[NU];
     bool rare[NU];
     bool any_rare = false;
     const T nm1 = s[S_NM1];
-#pragma unroll
-    for (int u = 0; u < NU; ++u) kall[u] = leaf_kall<KS>(kc + u, s);
+    leaf_kall_all<CF>(kc, s, kall);
     if constexpr (std::is_same<T, float>::value) {
         float omt[NU];
 #pragma unroll
@@ -538,10 +575,16 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
             for (int u = 0; u < NU; ++u)
                 if (rare[u]) tau[u] = tau_rare(kall[u]);
         }
+        T ta21[NU], ralf[NU], t1221[NU], r12[NU];
+        if constexpr (CSMEM) {
+            static_assert(KC_TA21 == 8 && KC_RALF == 9 && KC_T1221 == 10 && KC_R12 == 11, "plane pairs");
+            load_pair<CF>(kc, KC_TA21, ta21, ralf);
+            load_pair<CF>(kc, KC_T1221, t1221, r12);
+        }
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
             if constexpr (CSMEM)
-                zero[u] = leaf_layers_fast(kc[u + KC_R21 * KS], kc[u + KC_TA21 * KS], kc[u + KC_T1221 * KS], kc[u + KC_RALF * KS], kc[u + KC_R12 * KS],
+                zero[u] = leaf_layers_fast(kc[u + CF::koff(KC_R21)], ta21[u], t1221[u], ralf[u], r12[u],
                                            tau[u], nm1, lmax_hi, mt, refl[u], tran[u]);
             else
                 zero[u] = leaf_layers_fast(c[u].r21, c[u].ta21, c[u].t1221, c[u].ralf, c[u].r12, tau[u], nm1, lmax_hi, mt, refl[u], tran[u]);
@@ -552,7 +595,7 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
             for (int u = 0; u < NU; ++u)
                 if (zero[u]) {
                     if constexpr (CSMEM) {       // talf = 1 - (1 - talf) etc.: within an ulp of the uploaded constants
-                        const T ralf = kc[u + KC_RALF * KS], r12 = kc[u + KC_R12 * KS], r21 = kc[u + KC_R21 * KS];
+                        const T ralf = kc[u + CF::koff(KC_RALF)], r12 = kc[u + CF::koff(KC_R12)], r21 = kc[u + CF::koff(KC_R21)];
                         const double2 rt = leaf_layers_slow(T(1) - ralf, ralf, T(1) - r12, r12, T(1) - r21, r21, tau[u], nm1);
                         refl[u] = rt.x; tran[u] = rt.y;
                     } else {
@@ -570,13 +613,16 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
                                                f2& refl, f2& tran) {
     static_assert(CF::NU == 2, "the packed path pairs the two bands of a thread");
     const float nm1 = s[S_NM1];
-    constexpr int KS = CF::KSTRIDE, TH = 1;        // the two bands of a thread are adjacent in SailSmem::kc: one 64-bit load per pair
-    f2 kall = mul(F2(kc[KC_KAB * KS], kc[KC_KAB * KS + TH]), s[S_CAB]);           // :950-951, both bands per instruction
-    kall = fma(s[S_CXC], F2(kc[KC_KXC * KS], kc[KC_KXC * KS + TH]), kall);
-    kall = fma(s[S_CAN], F2(kc[KC_KAN * KS], kc[KC_KAN * KS + TH]), kall);
-    kall = fma(s[S_CBR], F2(kc[KC_KBR * KS], kc[KC_KBR * KS + TH]), kall);
-    kall = fma(s[S_CW], F2(kc[KC_KW * KS], kc[KC_KW * KS + TH]), kall);
-    kall = fma(s[S_CM], F2(kc[KC_KM * KS], kc[KC_KM * KS + TH]), kall);
+    float pa[2], pb[2];
+    load_pair<CF>(kc, KC_KAB, pa, pb);                                             // one 128-bit load per pair of planes
+    f2 kall = mul(F2(pa[0], pa[1]), s[S_CAB]);                                     // :950-951, both bands per instruction
+    kall = fma(s[S_CXC], F2(pb[0], pb[1]), kall);
+    load_pair<CF>(kc, KC_KAN, pa, pb);
+    kall = fma(s[S_CAN], F2(pa[0], pa[1]), kall);
+    kall = fma(s[S_CBR], F2(pb[0], pb[1]), kall);
+    load_pair<CF>(kc, KC_KW, pa, pb);
+    kall = fma(s[S_CW], F2(pa[0], pa[1]), kall);
+    kall = fma(s[S_CM], F2(pb[0], pb[1]), kall);
     const float k0 = kall.x, k1 = kall.y;
     bool rare0, rare1;
     const float g0 = tau_fast(k0, mt.tau, rare0), g1 = tau_fast(k1, mt.tau, rare1);
@@ -1207,13 +1253,8 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
     BandConst<T> c[NU];
     // fused fp64 instances keep the interface constants in shared memory (register pressure); everything else in registers
     constexpr bool CSMEM = consts_in_smem<T, MODE>();
-#if PB_KC_THREAD_MAJOR
-    constexpr int KCOL = kc_col<T, CF, MODE>();
-#else
-    constexpr int KCOL = NU;
-#endif
-    const T* kc = sm.kc + threadIdx.x * KCOL;      // this thread's block (thread-major) / NU adjacent columns of the once-per-item constants
-    constexpr int KS = CF::KSTRIDE;
+    constexpr int KCOL = CF::KCOL;
+    const T* kc = sm.kc + threadIdx.x * KCOL;      // this thread's 2 NU adjacent values of every plane pair of the once-per-item constants
     // fp32 mode with two bands per thread: the arithmetic of the item loop runs in packed FP32 (FFMA2 ...), both bands per instruction
     constexpr bool PACKED = std::is_same<T, float>::value && NU == 2;
     constexpr bool AB = MODE == MODE_PROSAIL && !std::is_same<T, float>::value;   // Ap / Am form of the leaf-dependent factors (sail_diffuse)
@@ -1228,13 +1269,13 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
         const int lane_u = band0 + 32 * u;                            // NBP = 66 * 32: always in range
         const T* bc = a.bandc + (a.packed ? a.win->band[lane_u] : lane_u);   // packed map: gather through the lane -> wavelength list
         T* k = sm.kc + threadIdx.x * KCOL + u;                        // only this thread reads these back: no barrier needed
-        k[KC_KAB * KS] = bc[C_KAB * NBP]; k[KC_KXC * KS] = bc[C_KXC * NBP]; k[KC_KAN * KS] = bc[C_KAN * NBP];
-        k[KC_KBR * KS] = bc[C_KBR * NBP]; k[KC_KW * KS] = bc[C_KW * NBP]; k[KC_KM * KS] = bc[C_KM * NBP];
-        k[KC_RS1 * KS] = bc[C_RS1 * NBP]; k[KC_RS2 * KS] = bc[C_RS2 * NBP];
+        k[CF::koff(KC_KAB)] = bc[C_KAB * NBP]; k[CF::koff(KC_KXC)] = bc[C_KXC * NBP]; k[CF::koff(KC_KAN)] = bc[C_KAN * NBP];
+        k[CF::koff(KC_KBR)] = bc[C_KBR * NBP]; k[CF::koff(KC_KW)] = bc[C_KW * NBP]; k[CF::koff(KC_KM)] = bc[C_KM * NBP];
+        k[CF::koff(KC_RS1)] = bc[C_RS1 * NBP]; k[CF::koff(KC_RS2)] = bc[C_RS2 * NBP];
         c[u] = load_band_const(bc);
         if constexpr (CSMEM) {                               // the fast path reads the folded terms from shared memory; c[] is dead in the loop
-            k[KC_TA21 * KS] = c[u].ta21; k[KC_RALF * KS] = c[u].ralf; k[KC_T1221 * KS] = c[u].t1221;
-            k[KC_R12 * KS] = c[u].r12; k[KC_R21 * KS] = c[u].r21;
+            k[CF::koff(KC_TA21)] = c[u].ta21; k[CF::koff(KC_RALF)] = c[u].ralf; k[CF::koff(KC_T1221)] = c[u].t1221;
+            k[CF::koff(KC_R12)] = c[u].r12; k[CF::koff(KC_R21)] = c[u].r21;
         }
     }
     if constexpr (PACKED) {
@@ -1294,8 +1335,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             for (int j = 0; j < n; ++j) {
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {
-#pragma unroll
-                    for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u, sr);
+                    soil_rho_all<CF>(kc, sr, rs);
                     emit<PLANES, MEANS, O_RHO>(e, rs);
                 } else if (MODE == MODE_PROSPECT) {
                     if constexpr (PACKED) {
@@ -1324,7 +1364,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
 #pragma unroll
                         for (int u = 0; u < NU; ++u) {
                             const BandConst<T> cc = c[u];     // a copy: the callee takes a reference, and c[] itself must stay in registers
-                            leaf_one_layer(cc, leaf_kall<KS>(kc + u, sr), q[u]);
+                            leaf_one_layer(cc, leaf_kall<CF>(kc + u, sr), q[u]);
                         }
                         { PB_GATHER(v, q, [0]); emit<PLANES, MEANS, O_LAYER_R>(e, v); }
                         { PB_GATHER(v, q, [1]); emit<PLANES, MEANS, O_LAYER_T>(e, v); }
@@ -1342,8 +1382,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                             } else {
                                 leaf_optics<CF, CSMEM>(c, kc, sr, sm.mt, rho, tau);
                             }
-#pragma unroll
-                            for (int u = 0; u < NU; ++u) rs[u] = soil_rho<KS>(kc + u, sr);
+                            soil_rho_all<CF>(kc, sr, rs);
                         } else {
 #pragma unroll
                             for (int u = 0; u < NU; ++u) {
