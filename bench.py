@@ -364,7 +364,7 @@ class LutBRF(Workload):
     def e2e(self, args, barrier):
         eng, capi = self.eng, self.capi
         Se = min(args.e2e_samples, self.S)
-        Pe = {k: v[:Se].copy() for k, v in self.P.items()}
+        Pe = {k: pinned_copy(v[:Se]) for k, v in self.P.items()}      # the step's inputs live in page-locked host memory (allocated once)
         geom = self.geom
         from pyrism_b200.engine import PinnedPool
         obuf = {"rsot": PinnedPool.empty((Se, NB), force=True)}
@@ -435,7 +435,7 @@ class LeafOnly(Workload):
     def e2e(self, args, barrier):
         eng = self.eng
         Se = min(131072, self.n)
-        Pe = {k: v[:Se].copy() for k, v in self.P.items()}
+        Pe = {k: pinned_copy(v[:Se]) for k, v in self.P.items()}      # the step's inputs live in page-locked host memory (allocated once)
 
         from pyrism_b200.engine import PinnedPool
         obuf = {"ks": PinnedPool.empty((Se, NB), force=True), "kt": PinnedPool.empty((Se, NB), force=True)}   # allocated once, outside the timed region
@@ -499,7 +499,7 @@ class MultiAngle(Workload):
     def e2e(self, args, barrier):
         eng, capi = self.eng, self.capi
         Se = min(2048, self.n)
-        Pe = {k: v[:Se].copy() for k, v in self.P.items()}
+        Pe = {k: pinned_copy(v[:Se]) for k, v in self.P.items()}      # the step's inputs live in page-locked host memory (allocated once)
         gi, gv, gr = (np.deg2rad(x) for x in self.gdeg)
         from pyrism_b200.engine import PinnedPool
         obuf = {"rsot": PinnedPool.empty((Se * 64, NB), force=True)}            # allocated once, outside the timed region
@@ -560,7 +560,7 @@ class BandMeanLut(Workload):
     def e2e(self, args, barrier):
         eng, capi = self.eng, self.capi
         Se = min(1000000, self.n)
-        Pe = {k: v[:Se].copy() for k, v in self.P.items()}
+        Pe = {k: pinned_copy(v[:Se]) for k, v in self.P.items()}      # the step's inputs live in page-locked host memory (allocated once)
         geom = self.geom
         from pyrism_b200.engine import PinnedPool
         mbuf = {"means": PinnedPool.empty((Se, 1, self.nw), force=True)}              # allocated once, outside the timed region
@@ -669,6 +669,15 @@ def d2h_probe(eng, mib=512, reps=3):
     dt = time.perf_counter() - t0
     dev.free()
     return n * 8 * reps / dt / 1e9
+
+
+def pinned_copy(a):
+    """A copy of `a` in page-locked host memory (prosail_host_alloc): the end-to-end steps upload their inputs from pinned memory, as
+    the bench contract words it, so the H2D copies are asynchronous DMA transfers instead of staged pageable copies."""
+    from pyrism_b200.engine import PinnedPool
+    b = PinnedPool.empty(a.shape, a.dtype, force=True)
+    b[...] = a
+    return b
 
 
 def readme_chain(args):
