@@ -267,27 +267,23 @@ static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaS
     if (a.ngroups == 0) return 0;
     if (a.nitems >= (1LL << 31)) return fail(PROSAIL_E_ARG, "more than 2^31 items in one launch");   // the kernel indexes items of a launch in 32 bits
     const long long nchunks = (a.nitems + CHUNK - 1) / CHUNK;
-    // persistent grid, exactly one wave (work distribution: see k_bands): R x ngroups warps stride over the first chunks group by
-    // group, the E warps left over share the last E / resident of the chunks
+    // persistent grid, exactly one wave (work distribution: see k_bands)
     const long long resident_warps = (long long)occ * h->sm_count * CF::WARPS;
     const long long units = (long long)a.ngroups * nchunks;
     long long warps;
     // Instances that write ONE plane (or none) measure faster with contiguous shares for every warp (fused fp64 BRF: 25.56 vs
-    // 25.81 ms per 1e6 sets), the ones that write 2-4 planes at 2+ TB/s need the strided walk (leaf-only 11.8 vs 13.4 ms,
-    // four planes 29.8 vs 31.7 ms): profiles/r2n_variants*.txt
+    // 25.81 ms per 1e6 sets: all 1776 resident warps work), the ones that write 2-4 planes at 2+ TB/s need the strided walk for its
+    // DRAM write locality (leaf-only 11.8 vs 13.4 ms, four planes 29.8 vs 31.7 ms) and leave resident % ngroups warps idle (0.6-1.5 %;
+    // letting those share the last chunks measured neutral and was removed): profiles/r2n_variants*.txt
     constexpr bool CONTIGUOUS = MODE == MODE_PROSAIL && PLANES == (1u << O_RSOT) && MEANS == 0;
     if (CONTIGUOUS || units <= resident_warps || resident_warps < a.ngroups) {   // also: one (group, chunk) pair per warp / fewer warps than groups
         warps = std::max<long long>(1, std::min(units, resident_warps));
         a.nwarps_main = 0;
         a.nchunks_main = 0;
     } else {
-        const long long R = resident_warps / a.ngroups, E = resident_warps - R * a.ngroups;
-        const long long nx = E ? std::max<long long>(1, (nchunks * E + resident_warps / 2) / resident_warps) : 0;
-        warps = resident_warps;
-        a.nwarps_main = (int)(R * a.ngroups);
-        a.nchunks_main = nchunks - nx;
-        static const bool no_tail = getenv("PYRISM_B200_NO_TAIL") != nullptr;    // A/B switch: the round-1 distribution (leftover warps idle)
-        if (no_tail) { warps = a.nwarps_main; a.nchunks_main = nchunks; }
+        warps = (resident_warps / a.ngroups) * a.ngroups;
+        a.nwarps_main = (int)warps;
+        a.nchunks_main = nchunks;
     }
     a.nwarps = (int)warps;
     const unsigned grid = (unsigned)((warps + CF::WARPS - 1) / CF::WARPS);

@@ -1187,16 +1187,16 @@ template <typename T> __host__ __device__ constexpr int min_ctas() { return std:
     _Pragma("unroll") for (int u = 0; u < NU; ++u) dst[u] = arr[u] field
 
 // ---------------------------------------------------------------------------------------------
-// main kernel.  1-D grid of independent warps; a tile group = NU x 32 consecutive bands, a chunk = CHUNK items.
-//   * The first nwarps_main = R x ngroups warps (R = resident warps / ngroups, rounded down): warp gw owns the tile group
-//     gw % ngroups and walks the chunks gw / ngroups, + R, + 2 R, ... below nchunks_main -- all groups sweep the items together,
-//     so a row of an output plane is written by all of its groups at about the same time (DRAM locality; a contiguous share per
-//     warp cost the leaf-only and four-plane instances 5-10 %: profiles/r2n_variants.txt).
-//   * The E = nwarps - nwarps_main warps that this split would leave idle (1776 resident warps over 22 groups: 16 idle, 0.9 %;
-//     33 groups: 27 of 1776 or 25 of 2368) take the last E / nwarps of the chunks, [nchunks_main, nchunks), as contiguous shares
-//     of its (group, chunk) list in group-major order; such a share spans several groups and the per-group state (band
-//     constants in shared memory, window plan) is rebuilt when the group changes.  Every warp gets the same number of units.
-//   * Launches with fewer (group, chunk) pairs than resident warps: one pair per warp (nwarps_main = 0).
+// main kernel.  1-D grid of independent warps; a tile group = NU x 32 consecutive bands, a chunk = CHUNK items.  Two walks over the
+// (tile group, chunk) pairs, chosen per instance by the host (launch_bands_g):
+//   * strided (nwarps_main = R x ngroups, R = resident warps / ngroups rounded down): warp gw owns the tile group gw % ngroups and
+//     walks the chunks gw / ngroups, + R, + 2 R, ... -- all groups sweep the items together, so a row of an output plane is written
+//     by all of its groups at about the same time (DRAM write locality: contiguous shares cost the leaf-only and four-plane
+//     instances 7-11 %, profiles/r2n_variants*.txt).  resident % ngroups warps stay idle (16 of 1776 for 22 groups).
+//   * contiguous (nwarps_main = 0; the one-plane instances, and launches with fewer pairs than resident warps): warp gw takes the
+//     share [U gw / nwarps, U (gw + 1) / nwarps) of the U = ngroups x nchunks pairs in group-major order; a share may span several
+//     groups, the per-group state (band constants in shared memory, window plan) is rebuilt when the group changes.  Every
+//     resident warp works (+1.0 % for the fused fp64 BRF instance).
 // The CTA only shares the read-only math tables.
 // ---------------------------------------------------------------------------------------------
 // G1 = true: one geometry per parameter set (the LUT shape) -- every item starts a new parameter set, so nothing
