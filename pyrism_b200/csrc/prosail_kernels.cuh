@@ -1,7 +1,8 @@
 // sm_100a kernels for the batched PROSPECT-5/D -> 4SAIL -> band-mean path.
 //
-// Mapping (band kernel): one THREAD owns NU wavelengths (b, b + 32, ...; NU = 2 or 3, struct Cfg) and keeps their
-// interface constants in registers (absorption coefficients and soil spectra in shared memory);
+// Mapping (band kernel): one THREAD owns NU wavelengths (b, b + 32, ...; NU = 2 or 3, struct Cfg); its once-per-item constants
+// (absorption coefficients, soil spectra and -- fused fp64 instances -- the folded interface terms) live in shared memory as
+// per-thread runs of plane pairs (Cfg::koff), the other instances keep the interface terms in registers;
 // a WARP owns NU x 32 consecutive bands (66 32-band tiles cover 2101 bands, 99.5% lane efficiency) and walks
 // over the work items (parameter set x geometry).  The NU bands of a thread are independent
 // dependency chains in one instruction stream: the path is bound by the FP64 pipe (DFMA latency 8.6
