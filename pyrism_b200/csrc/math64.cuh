@@ -34,6 +34,12 @@
 #ifndef PB_SOILFOLD
 #define PB_SOILFOLD 1    /* soil coupling as [A1 A2/dn + (tsstoo - tss too)] rs with A1 = tss + tsd, A2 = too + tdo (4 less) */
 #endif
+#ifndef PB_PIPELINE
+#define PB_PIPELINE 0    /* double LUT instances: tau(kall) of the next item evaluated inside the FP64-dense block of the current one.
+                            Measured SLOWER (BRF 26.06 vs 25.18 ms, leaf-only 12.15 vs 11.92, band means 11.77 vs 11.14, four planes
+                            31.4 vs 29.2: profiles/r2n_variants_pipeline.txt) -- ptxas does merge the two stages into one basic block,
+                            but at the register cap the extra live values cost more than the filled issue slots bring: off */
+#endif
 #ifndef PB_F32_ALG
 #define PB_F32_ALG 1     /* the packed fp32 item loop with the same re-derived stages (Y form, P/Q form, A1 A2 soil coupling): ~18 packed instructions less per item */
 #endif

@@ -538,44 +538,43 @@ __device__ __noinline__ void leaf_one_layer(const BandConst<T>& c, T kall, T (&o
     out[0] = (T)r; out[1] = (T)t; out[2] = (T)Ra; out[3] = (T)Ta; out[4] = (T)denom;
 }
 
-// all NU bands of a thread: the chains are independent and written back to back so that they interleave.
-// CSMEM (double, fused PROSAIL instances): the interface constants are read from the thread's columns of SailSmem::kc instead of
-// c[] -- 20 registers less across the item loop; the rare zero-absorption path rebuilds the plain constants from the complements.
-template <typename CF, bool CSMEM, typename T, typename MT>
-__device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
-                                            T (&refl)[CF::NU], T (&tran)[CF::NU]) {
-    constexpr int NU = CF::NU;
-    T kall[NU];
-    bool rare[NU];
-    bool any_rare = false;
-    const T nm1 = s[S_NM1];
+// Stage 1 of the double leaf path: kall and the table value tau(kall) of all NU bands -- branch free; lanes outside the table range are
+// flagged (bit u of `rare`) and repaired by leaf_tau_repair() before stage 2.  Split off so that the item loop can evaluate it for the
+// NEXT item inside the canopy stage of the current one (software pipelining, PB_PIPELINE): it is the load- and integer-heavy part
+// of the leaf (25 LDS and 50 integer / conversion instructions for 30 FP64 ones), and in the same basic block as ~270 FP64
+// instructions it fills issue slots that the FP64 pipe leaves empty.
+template <typename CF, typename T, typename MT>
+__device__ __forceinline__ void leaf_tau(const T* __restrict__ kc, const T* __restrict__ s, const MT& mt, T (&tau)[CF::NU], unsigned& rare) {
+    T kall[CF::NU];
     leaf_kall_all<CF>(kc, s, kall);
-    if constexpr (std::is_same<T, float>::value) {
-        float omt[NU];
+    rare = 0;
 #pragma unroll
-        for (int u = 0; u < NU; ++u) omt[u] = kall[u] * tau_fast(kall[u], mt.tau, rare[u]);     // 1 - tau = k g(k)
+    for (int u = 0; u < CF::NU; ++u) {
+        bool r;
+        tau[u] = tau_fast(kall[u], mt.tau, r);                        // :953-957
+        rare |= r ? (1u << u) : 0u;
+    }
+}
+template <typename CF, typename T>
+__device__ __forceinline__ void leaf_tau_repair(const T* __restrict__ kc, const T* __restrict__ s, T (&tau)[CF::NU], unsigned rare) {
+    if (__builtin_expect(rare != 0, 0)) {
+        T kall[CF::NU];
+        leaf_kall_all<CF>(kc, s, kall);                               // recomputed: the rare path does not keep kall alive across the pipeline
 #pragma unroll
-        for (int u = 0; u < NU; ++u) { leaf_layers_f32(c[u], omt[u], nm1, refl[u], tran[u]); any_rare |= rare[u]; }
-        if (__builtin_expect(any_rare, 0)) {
-#pragma unroll
-            for (int u = 0; u < NU; ++u)
-                if (rare[u]) {
-                    const float2 rt = leaf_exact_f32(c[u].talf, c[u].ralf, c[u].t12, c[u].r12, c[u].t21, c[u].r21, kall[u], nm1);
-                    refl[u] = rt.x; tran[u] = rt.y;
-                }
-        }
-    } else {
-        T tau[NU];
+        for (int u = 0; u < CF::NU; ++u)
+            if ((rare >> u) & 1u) tau[u] = tau_rare(kall[u]);
+    }
+}
+// Stage 2: plate + Stokes for all NU bands from tau (double)
+template <typename CF, bool CSMEM, typename T, typename MT>
+__device__ __forceinline__ void leaf_layers_all(const BandConst<T> (&c)[CF::NU], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
+                                                const T (&tau)[CF::NU], T (&refl)[CF::NU], T (&tran)[CF::NU]) {
+    constexpr int NU = CF::NU;
+    const T nm1 = s[S_NM1];
+    {
         bool zero[NU];
         bool any_zero = false;
         const int lmax_hi = hi_word(s[S_LMAX]);
-#pragma unroll
-        for (int u = 0; u < NU; ++u) { tau[u] = tau_fast(kall[u], mt.tau, rare[u]); any_rare |= rare[u]; }   // :953-957
-        if (__builtin_expect(any_rare, 0)) {
-#pragma unroll
-            for (int u = 0; u < NU; ++u)
-                if (rare[u]) tau[u] = tau_rare(kall[u]);
-        }
         T ta21[NU], ralf[NU], t1221[NU], r12[NU];
         if constexpr (CSMEM) {
             static_assert(KC_TA21 == 8 && KC_RALF == 9 && KC_T1221 == 10 && KC_R12 == 11, "plane pairs");
@@ -605,6 +604,42 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
                     }
                 }
         }
+    }
+}
+
+// all NU bands of a thread: the chains are independent and written back to back so that they interleave.
+// CSMEM (double, fused PROSAIL instances): the interface constants are read from the thread's columns of SailSmem::kc instead of
+// c[] -- 20 registers less across the item loop; the rare zero-absorption path rebuilds the plain constants from the complements.
+template <typename CF, bool CSMEM, typename T, typename MT>
+__device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
+                                            T (&refl)[CF::NU], T (&tran)[CF::NU]) {
+    constexpr int NU = CF::NU;
+    T kall[NU];
+    bool rare[NU];
+    bool any_rare = false;
+    const T nm1 = s[S_NM1];
+    leaf_kall_all<CF>(kc, s, kall);
+    if constexpr (std::is_same<T, float>::value) {
+        float omt[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) omt[u] = kall[u] * tau_fast(kall[u], mt.tau, rare[u]);     // 1 - tau = k g(k)
+#pragma unroll
+        for (int u = 0; u < NU; ++u) { leaf_layers_f32(c[u], omt[u], nm1, refl[u], tran[u]); any_rare |= rare[u]; }
+        if (__builtin_expect(any_rare, 0)) {
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                if (rare[u]) {
+                    const float2 rt = leaf_exact_f32(c[u].talf, c[u].ralf, c[u].t12, c[u].r12, c[u].t21, c[u].r21, kall[u], nm1);
+                    refl[u] = rt.x; tran[u] = rt.y;
+                }
+        }
+    } else {
+        T tau[NU];
+        unsigned rmask = 0;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) { tau[u] = tau_fast(kall[u], mt.tau, rare[u]); rmask |= rare[u] ? (1u << u) : 0u; }   // :953-957
+        leaf_tau_repair<CF>(kc, s, tau, rmask);
+        leaf_layers_all<CF, CSMEM>(c, kc, s, mt, tau, refl, tran);
     }
 }
 
@@ -1333,6 +1368,14 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
 #pragma unroll
             for (int u = 0; u < NU; ++u)      // (the packed map stores no planes and reads no spectra: the flag is not consulted there)
                 e.valid[u] = band0 + 32 * u < NB;
+            // software pipelining of the double LUT instances (PB_PIPELINE): tau(kall) of item j + 1 is evaluated inside the big FP64 block
+            // of item j (after the plate / Stokes stage; in the fused kernels it shares a basic block with the canopy stage).  Always
+            // evaluated, also past the last item of the chunk: the record read then is whatever follows in the staging buffer
+            // (in bounds of the Stage struct; tau_fast is total on any bit pattern) and the value is dropped.
+            constexpr bool PIPE = PB_PIPELINE && G1 && !is_f32<T>() && PLANES != RUNTIME && (MODE == MODE_PROSAIL || MODE == MODE_PROSPECT);
+            T tau_n[NU];
+            unsigned rare_n = 0;
+            if constexpr (PIPE) leaf_tau<CF>(kc, sr, sm.mt, tau_n, rare_n);
             for (int j = 0; j < n; ++j) {
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {
@@ -1343,6 +1386,13 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         f2 r2, t2;
                         leaf_optics_x2<CF>(c2, kc, sr, sm.mt, r2, t2);
                         rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
+                    } else if constexpr (PIPE) {
+                        T tau_c[NU];
+#pragma unroll
+                        for (int u = 0; u < NU; ++u) tau_c[u] = tau_n[u];
+                        leaf_tau_repair<CF>(kc, sr, tau_c, rare_n);
+                        leaf_tau<CF>(kc, sr + REC, sm.mt, tau_n, rare_n);          // next item: independent work next to the Stokes stage
+                        leaf_layers_all<CF, CSMEM>(c, kc, sr, sm.mt, tau_c, rho, tau);
                     } else {
                         leaf_optics<CF, CSMEM>(c, kc, sr, sm.mt, rho, tau);
                     }
@@ -1380,6 +1430,13 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                                 f2 r2, t2;
                                 leaf_optics_x2<CF>(c2, kc, sr, sm.mt, r2, t2);
                                 rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
+                            } else if constexpr (PIPE) {
+                                T tau_c[NU];
+#pragma unroll
+                                for (int u = 0; u < NU; ++u) tau_c[u] = tau_n[u];
+                                leaf_tau_repair<CF>(kc, sr, tau_c, rare_n);
+                                leaf_layers_all<CF, CSMEM>(c, kc, sr, sm.mt, tau_c, rho, tau);
+                                leaf_tau<CF>(kc, sr + REC, sm.mt, tau_n, rare_n);  // next item: independent work next to the canopy stage
                             } else {
                                 leaf_optics<CF, CSMEM>(c, kc, sr, sm.mt, rho, tau);
                             }
