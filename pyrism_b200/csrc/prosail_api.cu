@@ -239,7 +239,10 @@ template <bool G1> struct CfgOf<float, G1> { typedef Cfg<2, PB_F32_WARPS> type; 
 // (-18%: more wavelengths outside any window are evaluated) and the multi-geometry instances (-29%: spills) keep two.
 template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS> struct CfgFor { typedef typename CfgOf<T, G1>::type type; };
 #if PB_NU == 2 && !defined(PB_NO_NU3)
-template <> struct CfgFor<double, true, MODE_PROSAIL, 1u << O_RSOT, 0u> { typedef Cfg<3, 12> type; };
+#ifndef PB_BRF_WARPS
+#define PB_BRF_WARPS 12
+#endif
+template <> struct CfgFor<double, true, MODE_PROSAIL, 1u << O_RSOT, 0u> { typedef Cfg<3, PB_BRF_WARPS> type; };
 template <> struct CfgFor<double, true, MODE_PROSPECT, (1u << O_LEAF_R) | (1u << O_LEAF_T), 0u> { typedef Cfg<3, 12> type; };
 #ifdef PB_FOUR_NU3
 template <> struct CfgFor<double, true, MODE_PROSAIL, 0xFu, 0u> { typedef Cfg<3, 12> type; };   // BRF + BHR + DHR + HDR planes
