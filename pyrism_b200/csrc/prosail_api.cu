@@ -252,11 +252,11 @@ template <> struct CfgFor<double, true, MODE_PROSAIL, 0u, 1u << O_RSOT> { typede
 #endif
 #endif
 
-template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS>
+template <typename T, bool G1, int MODE, unsigned PLANES, unsigned MEANS, bool CAN>
 static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
     typedef typename CfgFor<T, G1, MODE, PLANES, MEANS>::type CF;
     const size_t smem = sizeof(SailSmem<T, CF, MODE>);
-    auto kern = k_bands<T, CF, MODE, PLANES, MEANS, G1>;
+    auto kern = k_bands<T, CF, MODE, PLANES, MEANS, G1, CAN>;
     // shared-memory opt-in and resident CTAs per SM: once per kernel instance and device (a benign race: idempotent values)
     static int occ_of_device[64] = {0};
     int occ = h->device < 64 ? occ_of_device[h->device] : 0;
@@ -298,9 +298,14 @@ static int launch_bands_g(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaS
     CK(cudaGetLastError());
     return 0;
 }
-template <typename T, int MODE, unsigned PLANES, unsigned MEANS>
+template <typename T, int MODE, unsigned PLANES, unsigned MEANS, bool CAN = true>
 static int launch_bands(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
-    return a.G == 1 ? launch_bands_g<T, true, MODE, PLANES, MEANS>(h, j, a, st) : launch_bands_g<T, false, MODE, PLANES, MEANS>(h, j, a, st);
+    return a.G == 1 ? launch_bands_g<T, true, MODE, PLANES, MEANS, CAN>(h, j, a, st) : launch_bands_g<T, false, MODE, PLANES, MEANS, CAN>(h, j, a, st);
+}
+// the LUT shapes come in two builds: with the anthocyanin term (PROSPECT-D) and without (PROSPECT-5)
+template <typename T, int MODE, unsigned PLANES, unsigned MEANS>
+static int launch_lut(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaStream_t st) {
+    return j.version == 0 ? launch_bands<T, MODE, PLANES, MEANS, false>(h, j, a, st) : launch_bands<T, MODE, PLANES, MEANS, true>(h, j, a, st);
 }
 
 // pick the kernel instance: compile-time plane sets for the LUT shapes, run-time selection otherwise
@@ -311,16 +316,16 @@ static int dispatch_bands(prosail_handle* h, const Job& j, SailArgs<T>& a, cudaS
     constexpr unsigned BRF = 1u << O_RSOT, FOUR = 0xFu, LEAF = (1u << O_LEAF_R) | (1u << O_LEAF_T);
     switch (j.mode) {
         case MODE_PROSAIL:
-            if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, BRF, 0>(h, j, a, st);
-            if (planes == FOUR && !j.mean_mask) return launch_bands<T, MODE_PROSAIL, FOUR, 0>(h, j, a, st);
-            if (planes == 0 && j.mean_mask == BRF && !j.f32_means && !h->have_srf) return launch_bands<T, MODE_PROSAIL, 0, BRF>(h, j, a, st);
+            if (planes == BRF && !j.mean_mask) return launch_lut<T, MODE_PROSAIL, BRF, 0>(h, j, a, st);
+            if (planes == FOUR && !j.mean_mask) return launch_lut<T, MODE_PROSAIL, FOUR, 0>(h, j, a, st);
+            if (planes == 0 && j.mean_mask == BRF && !j.f32_means && !h->have_srf) return launch_lut<T, MODE_PROSAIL, 0, BRF>(h, j, a, st);
             return launch_bands<T, MODE_PROSAIL, RUNTIME, 0>(h, j, a, st);
         case MODE_SAIL:
             if (planes == BRF && !j.mean_mask) return launch_bands<T, MODE_SAIL, BRF, 0>(h, j, a, st);
             if (planes == FOUR && !j.mean_mask) return launch_bands<T, MODE_SAIL, FOUR, 0>(h, j, a, st);
             return launch_bands<T, MODE_SAIL, RUNTIME, 0>(h, j, a, st);
         case MODE_PROSPECT:
-            if (planes == LEAF && !j.mean_mask) return launch_bands<T, MODE_PROSPECT, LEAF, 0>(h, j, a, st);
+            if (planes == LEAF && !j.mean_mask) return launch_lut<T, MODE_PROSPECT, LEAF, 0>(h, j, a, st);
             return launch_bands<T, MODE_PROSPECT, RUNTIME, 0>(h, j, a, st);
         default:
             return launch_bands<T, MODE_SOIL, RUNTIME, 0>(h, j, a, st);

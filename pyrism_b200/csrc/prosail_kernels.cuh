@@ -276,7 +276,9 @@ __device__ __forceinline__ void load_pair(const T* __restrict__ kc, int first, T
     for (int u = 0; u < NU; ++u) { a[u] = f[u]; b[u] = f[NU + u]; }
 }
 // kall of all NU bands of a thread (:950-951), the six absorption tables read as three plane pairs
-template <typename CF, typename T>
+// CAN = false: instances launched for PROSPECT-5 batches only (dispatch_bands), where the anthocyanin term does not exist
+// (Kan = zeros, models.py:935): not even a predicated-off FMA is issued for it
+template <typename CF, bool CAN, typename T>
 __device__ __forceinline__ void leaf_kall_all(const T* __restrict__ kc, const T* __restrict__ s, T (&kall)[CF::NU]) {
     constexpr int NU = CF::NU;
     static_assert(KC_KAB == 0 && KC_KXC == 1 && KC_KAN == 2 && KC_KBR == 3 && KC_KW == 4 && KC_KM == 5, "plane pairs");
@@ -287,9 +289,11 @@ __device__ __forceinline__ void leaf_kall_all(const T* __restrict__ kc, const T*
     load_pair<CF>(kc, KC_KAN, a, b);
     // PROSPECT-5 has no anthocyanin term (Kan = zeros, models.py:935): the record carries Can/N = +0.0 and the FMA is predicated
     // off by an integer test on that (warp-uniform) value
-    if (!is_zero(s[S_CAN])) {
+    if constexpr (CAN) {
+        if (!is_zero(s[S_CAN])) {
 #pragma unroll
-        for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CAN], a[u], kall[u]);
+            for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CAN], a[u], kall[u]);
+        }
     }
 #pragma unroll
     for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CBR], b[u], kall[u]);
@@ -543,10 +547,10 @@ __device__ __noinline__ void leaf_one_layer(const BandConst<T>& c, T kall, T (&o
 // NEXT item inside the canopy stage of the current one (software pipelining, PB_PIPELINE): it is the load- and integer-heavy part
 // of the leaf (25 LDS and 50 integer / conversion instructions for 30 FP64 ones), and in the same basic block as ~270 FP64
 // instructions it fills issue slots that the FP64 pipe leaves empty.
-template <typename CF, typename T, typename MT>
+template <typename CF, bool CAN, typename T, typename MT>
 __device__ __forceinline__ void leaf_tau(const T* __restrict__ kc, const T* __restrict__ s, const MT& mt, T (&tau)[CF::NU], unsigned& rare) {
     T kall[CF::NU];
-    leaf_kall_all<CF>(kc, s, kall);
+    leaf_kall_all<CF, CAN>(kc, s, kall);
     rare = 0;
 #pragma unroll
     for (int u = 0; u < CF::NU; ++u) {
@@ -555,11 +559,11 @@ __device__ __forceinline__ void leaf_tau(const T* __restrict__ kc, const T* __re
         rare |= r ? (1u << u) : 0u;
     }
 }
-template <typename CF, typename T>
+template <typename CF, bool CAN, typename T>
 __device__ __forceinline__ void leaf_tau_repair(const T* __restrict__ kc, const T* __restrict__ s, T (&tau)[CF::NU], unsigned rare) {
     if (__builtin_expect(rare != 0, 0)) {
         T kall[CF::NU];
-        leaf_kall_all<CF>(kc, s, kall);                               // recomputed: the rare path does not keep kall alive across the pipeline
+        leaf_kall_all<CF, CAN>(kc, s, kall);                               // recomputed: the rare path does not keep kall alive across the pipeline
 #pragma unroll
         for (int u = 0; u < CF::NU; ++u)
             if ((rare >> u) & 1u) tau[u] = tau_rare(kall[u]);
@@ -610,7 +614,7 @@ __device__ __forceinline__ void leaf_layers_all(const BandConst<T> (&c)[CF::NU],
 // all NU bands of a thread: the chains are independent and written back to back so that they interleave.
 // CSMEM (double, fused PROSAIL instances): the interface constants are read from the thread's columns of SailSmem::kc instead of
 // c[] -- 20 registers less across the item loop; the rare zero-absorption path rebuilds the plain constants from the complements.
-template <typename CF, bool CSMEM, typename T, typename MT>
+template <typename CF, bool CSMEM, bool CAN, typename T, typename MT>
 __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
                                             T (&refl)[CF::NU], T (&tran)[CF::NU]) {
     constexpr int NU = CF::NU;
@@ -618,7 +622,7 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
     bool rare[NU];
     bool any_rare = false;
     const T nm1 = s[S_NM1];
-    leaf_kall_all<CF>(kc, s, kall);
+    leaf_kall_all<CF, CAN>(kc, s, kall);
     if constexpr (std::is_same<T, float>::value) {
         float omt[NU];
 #pragma unroll
@@ -638,13 +642,13 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
         unsigned rmask = 0;
 #pragma unroll
         for (int u = 0; u < NU; ++u) { tau[u] = tau_fast(kall[u], mt.tau, rare[u]); rmask |= rare[u] ? (1u << u) : 0u; }   // :953-957
-        leaf_tau_repair<CF>(kc, s, tau, rmask);
+        leaf_tau_repair<CF, CAN>(kc, s, tau, rmask);
         leaf_layers_all<CF, CSMEM>(c, kc, s, mt, tau, refl, tran);
     }
 }
 
 // fp32 mode, two bands per thread: kall and the table look-ups per band (scalar), plate + Stokes stage packed
-template <typename CF, typename MT>
+template <typename CF, bool CAN, typename MT>
 __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const float* __restrict__ kc, const float* __restrict__ s, const MT& mt,
                                                f2& refl, f2& tran) {
     static_assert(CF::NU == 2, "the packed path pairs the two bands of a thread");
@@ -654,7 +658,7 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
     f2 kall = mul(F2(pa[0], pa[1]), s[S_CAB]);                                     // :950-951, both bands per instruction
     kall = fma(s[S_CXC], F2(pb[0], pb[1]), kall);
     load_pair<CF>(kc, KC_KAN, pa, pb);
-    kall = fma(s[S_CAN], F2(pa[0], pa[1]), kall);
+    if constexpr (CAN) kall = fma(s[S_CAN], F2(pa[0], pa[1]), kall);
     kall = fma(s[S_CBR], F2(pb[0], pb[1]), kall);
     load_pair<CF>(kc, KC_KW, pa, pb);
     kall = fma(s[S_CW], F2(pa[0], pa[1]), kall);
@@ -1237,7 +1241,8 @@ template <typename T> __host__ __device__ constexpr int min_ctas() { return std:
 // ---------------------------------------------------------------------------------------------
 // G1 = true: one geometry per parameter set (the LUT shape) -- every item starts a new parameter set, so nothing
 // is carried between loop iterations and the register allocator sees purely loop-local state.
-template <typename T, typename CF, int MODE, unsigned PLANES, unsigned MEANS, bool G1>
+// CAN = false: the batch is PROSPECT-5 (no anthocyanin term: one FP64 instruction per band and item less in the leaf stage)
+template <typename T, typename CF, int MODE, unsigned PLANES, unsigned MEANS, bool G1, bool CAN = true>
 __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const SailArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename Tables<T>::type MT;
@@ -1375,7 +1380,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             constexpr bool PIPE = PB_PIPELINE && G1 && !is_f32<T>() && PLANES != RUNTIME && (MODE == MODE_PROSAIL || MODE == MODE_PROSPECT);
             T tau_n[NU];
             unsigned rare_n = 0;
-            if constexpr (PIPE) leaf_tau<CF>(kc, sr, sm.mt, tau_n, rare_n);
+            if constexpr (PIPE) leaf_tau<CF, CAN>(kc, sr, sm.mt, tau_n, rare_n);
             for (int j = 0; j < n; ++j) {
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {
@@ -1384,17 +1389,17 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                 } else if (MODE == MODE_PROSPECT) {
                     if constexpr (PACKED) {
                         f2 r2, t2;
-                        leaf_optics_x2<CF>(c2, kc, sr, sm.mt, r2, t2);
+                        leaf_optics_x2<CF, CAN>(c2, kc, sr, sm.mt, r2, t2);
                         rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
                     } else if constexpr (PIPE) {
                         T tau_c[NU];
 #pragma unroll
                         for (int u = 0; u < NU; ++u) tau_c[u] = tau_n[u];
-                        leaf_tau_repair<CF>(kc, sr, tau_c, rare_n);
-                        leaf_tau<CF>(kc, sr + REC, sm.mt, tau_n, rare_n);          // next item: independent work next to the Stokes stage
+                        leaf_tau_repair<CF, CAN>(kc, sr, tau_c, rare_n);
+                        leaf_tau<CF, CAN>(kc, sr + REC, sm.mt, tau_n, rare_n);          // next item: independent work next to the Stokes stage
                         leaf_layers_all<CF, CSMEM>(c, kc, sr, sm.mt, tau_c, rho, tau);
                     } else {
-                        leaf_optics<CF, CSMEM>(c, kc, sr, sm.mt, rho, tau);
+                        leaf_optics<CF, CSMEM, CAN>(c, kc, sr, sm.mt, rho, tau);
                     }
                     emit<PLANES, MEANS, O_LEAF_R>(e, rho);
                     emit<PLANES, MEANS, O_LEAF_T>(e, tau);
@@ -1428,17 +1433,17 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         if (MODE == MODE_PROSAIL) {
                             if constexpr (PACKED) {
                                 f2 r2, t2;
-                                leaf_optics_x2<CF>(c2, kc, sr, sm.mt, r2, t2);
+                                leaf_optics_x2<CF, CAN>(c2, kc, sr, sm.mt, r2, t2);
                                 rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
                             } else if constexpr (PIPE) {
                                 T tau_c[NU];
 #pragma unroll
                                 for (int u = 0; u < NU; ++u) tau_c[u] = tau_n[u];
-                                leaf_tau_repair<CF>(kc, sr, tau_c, rare_n);
+                                leaf_tau_repair<CF, CAN>(kc, sr, tau_c, rare_n);
                                 leaf_layers_all<CF, CSMEM>(c, kc, sr, sm.mt, tau_c, rho, tau);
-                                leaf_tau<CF>(kc, sr + REC, sm.mt, tau_n, rare_n);  // next item: independent work next to the canopy stage
+                                leaf_tau<CF, CAN>(kc, sr + REC, sm.mt, tau_n, rare_n);  // next item: independent work next to the canopy stage
                             } else {
-                                leaf_optics<CF, CSMEM>(c, kc, sr, sm.mt, rho, tau);
+                                leaf_optics<CF, CSMEM, CAN>(c, kc, sr, sm.mt, rho, tau);
                             }
                             soil_rho_all<CF>(kc, sr, rs);
                         } else {
