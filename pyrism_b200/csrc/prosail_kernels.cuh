@@ -278,25 +278,43 @@ __device__ __forceinline__ void load_pair(const T* __restrict__ kc, int first, T
 // kall of all NU bands of a thread (:950-951), the six absorption tables read as three plane pairs
 // CAN = false: instances launched for PROSPECT-5 batches only (dispatch_bands), where the anthocyanin term does not exist
 // (Kan = zeros, models.py:935): not even a predicated-off FMA is issued for it
+// kz (warp-uniform, set per tile group by k_bands): which pigment tables are identically zero over the group's bands --
+//   0: none;  1: Kab and Kxc (every band from 784 nm on: chlorophyll ends at 779-780 nm, carotenoids at 559-560 nm);
+//   2: Kab, Kxc, Kan and Kbr (every band from 1100 nm on: 14 of the 22 96-band groups), where kall = Cw Kw + Cm Km.
+// The skipped terms are exact zeros (a finite content times 0.0), so the result is bit for bit that of the full sum; a non-finite
+// pigment content, whose product with 0.0 would be NaN in the reference, is turned into a NaN water content by the prologue, so
+// that every band of such a set still comes out NaN.  Per band and item: 2.7 instead of 5 FP64 instructions on average (PROSPECT-5).
 template <typename CF, bool CAN, typename T>
-__device__ __forceinline__ void leaf_kall_all(const T* __restrict__ kc, const T* __restrict__ s, T (&kall)[CF::NU]) {
+__device__ __forceinline__ void leaf_kall_all(const T* __restrict__ kc, const T* __restrict__ s, int kz, T (&kall)[CF::NU]) {
     constexpr int NU = CF::NU;
     static_assert(KC_KAB == 0 && KC_KXC == 1 && KC_KAN == 2 && KC_KBR == 3 && KC_KW == 4 && KC_KM == 5, "plane pairs");
     T a[NU], b[NU];
-    load_pair<CF>(kc, KC_KAB, a, b);
+    if (kz == 2) {
+        load_pair<CF>(kc, KC_KW, a, b);
 #pragma unroll
-    for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CXC], b[u], s[S_CAB] * a[u]);
-    load_pair<CF>(kc, KC_KAN, a, b);
-    // PROSPECT-5 has no anthocyanin term (Kan = zeros, models.py:935): the record carries Can/N = +0.0 and the FMA is predicated
-    // off by an integer test on that (warp-uniform) value
+        for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CM], b[u], s[S_CW] * a[u]);
+        return;
+    }
+    if (kz == 1) {
+        load_pair<CF>(kc, KC_KAN, a, b);
+#pragma unroll
+        for (int u = 0; u < NU; ++u) kall[u] = s[S_CBR] * b[u];
+    } else {
+        load_pair<CF>(kc, KC_KAB, a, b);
+#pragma unroll
+        for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CXC], b[u], s[S_CAB] * a[u]);
+        load_pair<CF>(kc, KC_KAN, a, b);
+#pragma unroll
+        for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CBR], b[u], kall[u]);
+    }
+    // PROSPECT-5 has no anthocyanin term (Kan = zeros, models.py:935): CAN = false builds; in the PROSPECT-D builds the record of a
+    // '5' call still carries Can/N = +0.0 and the FMA is skipped on that (warp-uniform) value
     if constexpr (CAN) {
         if (!is_zero(s[S_CAN])) {
 #pragma unroll
             for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CAN], a[u], kall[u]);
         }
     }
-#pragma unroll
-    for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CBR], b[u], kall[u]);
     load_pair<CF>(kc, KC_KW, a, b);
 #pragma unroll
     for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CM], b[u], fma(s[S_CW], a[u], kall[u]));
@@ -548,9 +566,9 @@ __device__ __noinline__ void leaf_one_layer(const BandConst<T>& c, T kall, T (&o
 // of the leaf (25 LDS and 50 integer / conversion instructions for 30 FP64 ones), and in the same basic block as ~270 FP64
 // instructions it fills issue slots that the FP64 pipe leaves empty.
 template <typename CF, bool CAN, typename T, typename MT>
-__device__ __forceinline__ void leaf_tau(const T* __restrict__ kc, const T* __restrict__ s, const MT& mt, T (&tau)[CF::NU], unsigned& rare) {
+__device__ __forceinline__ void leaf_tau(const T* __restrict__ kc, const T* __restrict__ s, int kz, const MT& mt, T (&tau)[CF::NU], unsigned& rare) {
     T kall[CF::NU];
-    leaf_kall_all<CF, CAN>(kc, s, kall);
+    leaf_kall_all<CF, CAN>(kc, s, kz, kall);
     rare = 0;
 #pragma unroll
     for (int u = 0; u < CF::NU; ++u) {
@@ -560,10 +578,10 @@ __device__ __forceinline__ void leaf_tau(const T* __restrict__ kc, const T* __re
     }
 }
 template <typename CF, bool CAN, typename T>
-__device__ __forceinline__ void leaf_tau_repair(const T* __restrict__ kc, const T* __restrict__ s, T (&tau)[CF::NU], unsigned rare) {
+__device__ __forceinline__ void leaf_tau_repair(const T* __restrict__ kc, const T* __restrict__ s, int kz, T (&tau)[CF::NU], unsigned rare) {
     if (__builtin_expect(rare != 0, 0)) {
         T kall[CF::NU];
-        leaf_kall_all<CF, CAN>(kc, s, kall);                               // recomputed: the rare path does not keep kall alive across the pipeline
+        leaf_kall_all<CF, CAN>(kc, s, kz, kall);                               // recomputed: the rare path does not keep kall alive across the pipeline
 #pragma unroll
         for (int u = 0; u < CF::NU; ++u)
             if ((rare >> u) & 1u) tau[u] = tau_rare(kall[u]);
@@ -615,14 +633,14 @@ __device__ __forceinline__ void leaf_layers_all(const BandConst<T> (&c)[CF::NU],
 // CSMEM (double, fused PROSAIL instances): the interface constants are read from the thread's columns of SailSmem::kc instead of
 // c[] -- 20 registers less across the item loop; the rare zero-absorption path rebuilds the plain constants from the complements.
 template <typename CF, bool CSMEM, bool CAN, typename T, typename MT>
-__device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], const T* __restrict__ kc, const T* __restrict__ s, const MT& mt,
+__device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], const T* __restrict__ kc, const T* __restrict__ s, int kz, const MT& mt,
                                             T (&refl)[CF::NU], T (&tran)[CF::NU]) {
     constexpr int NU = CF::NU;
     T kall[NU];
     bool rare[NU];
     bool any_rare = false;
     const T nm1 = s[S_NM1];
-    leaf_kall_all<CF, CAN>(kc, s, kall);
+    leaf_kall_all<CF, CAN>(kc, s, kz, kall);
     if constexpr (std::is_same<T, float>::value) {
         float omt[NU];
 #pragma unroll
@@ -642,27 +660,36 @@ __device__ __forceinline__ void leaf_optics(const BandConst<T> (&c)[CF::NU], con
         unsigned rmask = 0;
 #pragma unroll
         for (int u = 0; u < NU; ++u) { tau[u] = tau_fast(kall[u], mt.tau, rare[u]); rmask |= rare[u] ? (1u << u) : 0u; }   // :953-957
-        leaf_tau_repair<CF, CAN>(kc, s, tau, rmask);
+        leaf_tau_repair<CF, CAN>(kc, s, kz, tau, rmask);
         leaf_layers_all<CF, CSMEM>(c, kc, s, mt, tau, refl, tran);
     }
 }
 
 // fp32 mode, two bands per thread: kall and the table look-ups per band (scalar), plate + Stokes stage packed
 template <typename CF, bool CAN, typename MT>
-__device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const float* __restrict__ kc, const float* __restrict__ s, const MT& mt,
+__device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const float* __restrict__ kc, const float* __restrict__ s, int kz, const MT& mt,
                                                f2& refl, f2& tran) {
     static_assert(CF::NU == 2, "the packed path pairs the two bands of a thread");
     const float nm1 = s[S_NM1];
     float pa[2], pb[2];
-    load_pair<CF>(kc, KC_KAB, pa, pb);                                             // one 128-bit load per pair of planes
-    f2 kall = mul(F2(pa[0], pa[1]), s[S_CAB]);                                     // :950-951, both bands per instruction
-    kall = fma(s[S_CXC], F2(pb[0], pb[1]), kall);
-    load_pair<CF>(kc, KC_KAN, pa, pb);
-    if constexpr (CAN) kall = fma(s[S_CAN], F2(pa[0], pa[1]), kall);
-    kall = fma(s[S_CBR], F2(pb[0], pb[1]), kall);
-    load_pair<CF>(kc, KC_KW, pa, pb);
-    kall = fma(s[S_CW], F2(pa[0], pa[1]), kall);
-    kall = fma(s[S_CM], F2(pb[0], pb[1]), kall);
+    f2 kall;                                                                       // :950-951, both bands per instruction; kz: see leaf_kall_all
+    if (kz == 2) {
+        load_pair<CF>(kc, KC_KW, pa, pb);
+        kall = fma(s[S_CM], F2(pb[0], pb[1]), mul(F2(pa[0], pa[1]), s[S_CW]));
+    } else {
+        if (kz == 1) {
+            load_pair<CF>(kc, KC_KAN, pa, pb);                                     // one 128-bit load per pair of planes
+            kall = mul(F2(pb[0], pb[1]), s[S_CBR]);
+        } else {
+            load_pair<CF>(kc, KC_KAB, pa, pb);
+            kall = fma(s[S_CXC], F2(pb[0], pb[1]), mul(F2(pa[0], pa[1]), s[S_CAB]));
+            load_pair<CF>(kc, KC_KAN, pa, pb);
+            kall = fma(s[S_CBR], F2(pb[0], pb[1]), kall);
+        }
+        if constexpr (CAN) kall = fma(s[S_CAN], F2(pa[0], pa[1]), kall);
+        load_pair<CF>(kc, KC_KW, pa, pb);
+        kall = fma(s[S_CM], F2(pb[0], pb[1]), fma(s[S_CW], F2(pa[0], pa[1]), kall));
+    }
     const float k0 = kall.x, k1 = kall.y;
     bool rare0, rare1;
     const float g0 = tau_fast(k0, mt.tau, rare0), g1 = tau_fast(k1, mt.tau, rare1);
@@ -1280,17 +1307,24 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
         chunk = range; step = R; wrap_hi = a.nchunks_main;
         remaining = chunk < wrap_hi ? (wrap_hi - chunk + R - 1) / R : 0;
     } else if (gw < a.nwarps) {
-        const long long e = gw - a.nwarps_main, E = a.nwarps - a.nwarps_main, nx = nchunks - a.nchunks_main;
+        // share index: with a full grid the shares of a CTA are taken a grid apart (warp w of CTA b: share w gridDim + b), so that every
+        // SM works on (almost) all tile groups at once -- the groups differ in cost (leaf_kall_all skips pigment terms from 784 /
+        // 1100 nm on), and neighbouring shares on one SM would leave whole SMs finishing early or late
+        const int sh = a.nwarps == (int)gridDim.x * CF::WARPS && a.nwarps_main == 0 ? warp * (int)gridDim.x + (int)blockIdx.x : gw;
+        const long long e = sh - a.nwarps_main, E = a.nwarps - a.nwarps_main, nx = nchunks - a.nchunks_main;
         const long long nunits = (long long)a.ngroups * nx;
         const long long t0 = nunits * e / E, t1 = nunits * (e + 1) / E;
         tslot = (int)(t0 / nx);
         wrap_lo = a.nchunks_main;
         chunk = wrap_lo + (t0 - tslot * nx);
         remaining = t1 - t0;
+        // (Shares weighted by the cost of a group -- 1000 : 984 : 973 for the three kz classes -- measured no better than equal
+        //  counts with this spread: 24.98 vs 24.84 ms, profiles/r2n_variants_kz.txt.)
     }
     if (lane == 0 && remaining > 0) stage_issue(a, &stage[0], &bar[0], chunk);
 
     int grp = 0, band0 = lane;                     // tile group and this thread's bands (packed map: lanes): band0 + 32 u
+    int kz = 0;                                    // which pigment tables vanish over the whole tile group (leaf_kall_all)
     BandConst<T> c[NU];
     // fused fp64 instances keep the interface constants in shared memory (register pressure); everything else in registers
     constexpr bool CSMEM = consts_in_smem<T, MODE>();
@@ -1324,6 +1358,18 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
         c2.r12 = F2(c[0].r12, c[1].r12); c2.t21 = F2(c[0].t21, c[1].t21); c2.r21 = F2(c[0].r21, c[1].r21);
     }
     if constexpr (PLANES != RUNTIME && MEANS != 0 && !is_f32<T>()) mean_plan_init<NU>(a.win, NU * grp, lane, plan);
+    if constexpr (MODE == MODE_PROSAIL || MODE == MODE_PROSPECT) {
+        bool z0 = true, z1 = true;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const T* k = sm.kc + threadIdx.x * KCOL + u;
+            z0 = z0 && k[CF::koff(KC_KAB)] == T(0) && k[CF::koff(KC_KXC)] == T(0);
+            z1 = z1 && k[CF::koff(KC_KAN)] == T(0) && k[CF::koff(KC_KBR)] == T(0);
+        }
+        z0 = __all_sync(0xffffffffu, z0);
+        z1 = __all_sync(0xffffffffu, z1);
+        kz = z0 ? (z1 ? 2 : 1) : 0;
+    }
     };
     unsigned need;
     if (PLANES == RUNTIME) {
@@ -1380,7 +1426,7 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
             constexpr bool PIPE = PB_PIPELINE && G1 && !is_f32<T>() && PLANES != RUNTIME && (MODE == MODE_PROSAIL || MODE == MODE_PROSPECT);
             T tau_n[NU];
             unsigned rare_n = 0;
-            if constexpr (PIPE) leaf_tau<CF, CAN>(kc, sr, sm.mt, tau_n, rare_n);
+            if constexpr (PIPE) leaf_tau<CF, CAN>(kc, sr, kz, sm.mt, tau_n, rare_n);
             for (int j = 0; j < n; ++j) {
                 e.mi = 0;
                 if (MODE == MODE_SOIL) {
@@ -1389,17 +1435,17 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                 } else if (MODE == MODE_PROSPECT) {
                     if constexpr (PACKED) {
                         f2 r2, t2;
-                        leaf_optics_x2<CF, CAN>(c2, kc, sr, sm.mt, r2, t2);
+                        leaf_optics_x2<CF, CAN>(c2, kc, sr, kz, sm.mt, r2, t2);
                         rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
                     } else if constexpr (PIPE) {
                         T tau_c[NU];
 #pragma unroll
                         for (int u = 0; u < NU; ++u) tau_c[u] = tau_n[u];
-                        leaf_tau_repair<CF, CAN>(kc, sr, tau_c, rare_n);
-                        leaf_tau<CF, CAN>(kc, sr + REC, sm.mt, tau_n, rare_n);          // next item: independent work next to the Stokes stage
+                        leaf_tau_repair<CF, CAN>(kc, sr, kz, tau_c, rare_n);
+                        leaf_tau<CF, CAN>(kc, sr + REC, kz, sm.mt, tau_n, rare_n);          // next item: independent work next to the Stokes stage
                         leaf_layers_all<CF, CSMEM>(c, kc, sr, sm.mt, tau_c, rho, tau);
                     } else {
-                        leaf_optics<CF, CSMEM, CAN>(c, kc, sr, sm.mt, rho, tau);
+                        leaf_optics<CF, CSMEM, CAN>(c, kc, sr, kz, sm.mt, rho, tau);
                     }
                     emit<PLANES, MEANS, O_LEAF_R>(e, rho);
                     emit<PLANES, MEANS, O_LEAF_T>(e, tau);
@@ -1433,17 +1479,17 @@ __global__ void __launch_bounds__(CF::THREADS, min_ctas<T>()) k_bands(const Sail
                         if (MODE == MODE_PROSAIL) {
                             if constexpr (PACKED) {
                                 f2 r2, t2;
-                                leaf_optics_x2<CF, CAN>(c2, kc, sr, sm.mt, r2, t2);
+                                leaf_optics_x2<CF, CAN>(c2, kc, sr, kz, sm.mt, r2, t2);
                                 rho[0] = r2.x; rho[1] = r2.y; tau[0] = t2.x; tau[1] = t2.y;
                             } else if constexpr (PIPE) {
                                 T tau_c[NU];
 #pragma unroll
                                 for (int u = 0; u < NU; ++u) tau_c[u] = tau_n[u];
-                                leaf_tau_repair<CF, CAN>(kc, sr, tau_c, rare_n);
+                                leaf_tau_repair<CF, CAN>(kc, sr, kz, tau_c, rare_n);
                                 leaf_layers_all<CF, CSMEM>(c, kc, sr, sm.mt, tau_c, rho, tau);
-                                leaf_tau<CF, CAN>(kc, sr + REC, sm.mt, tau_n, rare_n);  // next item: independent work next to the canopy stage
+                                leaf_tau<CF, CAN>(kc, sr + REC, kz, sm.mt, tau_n, rare_n);  // next item: independent work next to the canopy stage
                             } else {
-                                leaf_optics<CF, CSMEM, CAN>(c, kc, sr, sm.mt, rho, tau);
+                                leaf_optics<CF, CSMEM, CAN>(c, kc, sr, kz, sm.mt, rho, tau);
                             }
                             soil_rho_all<CF>(kc, sr, rs);
                         } else {
@@ -1740,6 +1786,9 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
         srec[S_NM1] = N - 1.0;
         srec[S_LMAX] = 500.0 / fabs(N - 1.0);     // clamp of log2 b in b^(N-1) (pow_pos_scaled); inf for N = 1
+        // the band kernel skips pigment terms whose table is zero over a whole tile group (leaf_kall_all); a non-finite content
+        // times 0.0 is NaN in the reference: carried by the water term, which no band skips
+        if (!(isfinite(srec[S_CAB]) && isfinite(srec[S_CXC]) && isfinite(srec[S_CAN]) && isfinite(srec[S_CBR]))) srec[S_CW] = nan("");
     }
     if (a.has_soil) {
         const double sr = a.soil_refl[s], mo = a.soil_moist[s];
@@ -2041,6 +2090,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
             srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
             srec[S_NM1] = N - 1.0;
             srec[S_LMAX] = 500.0 / fabs(N - 1.0);     // clamp of log2 b in b^(N-1) (pow_pos_scaled); inf for N = 1
+            if (!(isfinite(srec[S_CAB]) && isfinite(srec[S_CXC]) && isfinite(srec[S_CAN]) && isfinite(srec[S_CBR]))) srec[S_CW] = nan("");   // see k_prologue
         }
         if (a.has_soil) {
             const double sr = a.soil_refl[s], mo = a.soil_moist[s];
