@@ -79,6 +79,13 @@ enum { C_KAB = 0, C_KXC, C_KAN, C_KBR, C_KW, C_KM, C_TALF, C_T12, C_T21, C_RS1, 
 
 // sample record (per parameter set)
 enum { S_CAB = 0, S_CXC, S_CAN, S_CBR, S_CW, S_CM, S_NM1, S_SOIL1, S_SOIL2, S_DDB, S_DDF, S_NEGLAI, S_LAI, S_LMAX, S_THR, S_BF };
+// In records WITH a leaf (fused PROSAIL, leaf-only) the slots S_DDB, S_DDF are not needed by the kernels (the P / Q form of
+// sail_diffuse) and carry S_CWX, S_CBRX instead: copies of Cw/N and Cbr/N that are NaN when a pigment content whose term a tile group
+// skips is not finite (leaf_kall_all).
+enum { S_CWX = S_DDB, S_CBRX = S_DDF };
+#if !PB_RINF_P || !PB_F32_ALG
+#error "S_CWX / S_CBRX reuse the slots of ddb / ddf: the fused kernels must use the P / Q form of sail_diffuse (PB_RINF_P = PB_F32_ALG = 1)"
+#endif
 // (S_NEGLAI: -lai, +0.0 for bare soil (the no-canopy flag); double records with PB_EXPS: -lai 2048 log2(e).  S_LMAX: 500/|N-1|, the
 //  clamp of log2 b in pow_pos_scaled.)
 // geometry record (per parameter set x geometry)
@@ -281,9 +288,11 @@ __device__ __forceinline__ void load_pair(const T* __restrict__ kc, int first, T
 // kz (warp-uniform, set per tile group by k_bands): which pigment tables are identically zero over the group's bands --
 //   0: none;  1: Kab and Kxc (every band from 784 nm on: chlorophyll ends at 779-780 nm, carotenoids at 559-560 nm);
 //   2: Kab, Kxc, Kan and Kbr (every band from 1100 nm on: 14 of the 22 96-band groups), where kall = Cw Kw + Cm Km.
-// The skipped terms are exact zeros (a finite content times 0.0), so the result is bit for bit that of the full sum; a non-finite
-// pigment content, whose product with 0.0 would be NaN in the reference, is turned into a NaN water content by the prologue, so
-// that every band of such a set still comes out NaN.  Per band and item: 2.7 instead of 5 FP64 instructions on average (PROSPECT-5).
+// The skipped terms are exact zeros (a finite content times 0.0), so the result is bit for bit that of the full sum.  A non-finite
+// content is the exception -- NaN or inf times 0.0 is NaN, which the reference turns into tau = 1 (models.py:953: `kall > 0` is
+// False) -- so the paths that skip read the first content they do use from a copy that the prologue sets to NaN when one of the
+// skipped contents is not finite (S_CBRX for kz = 1, S_CWX for kz = 2): kall is NaN exactly where the reference's is
+// (tests/test_gpu_parity.py::test_non_finite_pigment_content...).  Per band and item: 2.7 instead of 5 FP64 instructions on average.
 template <typename CF, bool CAN, typename T>
 __device__ __forceinline__ void leaf_kall_all(const T* __restrict__ kc, const T* __restrict__ s, int kz, T (&kall)[CF::NU]) {
     constexpr int NU = CF::NU;
@@ -292,13 +301,13 @@ __device__ __forceinline__ void leaf_kall_all(const T* __restrict__ kc, const T*
     if (kz == 2) {
         load_pair<CF>(kc, KC_KW, a, b);
 #pragma unroll
-        for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CM], b[u], s[S_CW] * a[u]);
+        for (int u = 0; u < NU; ++u) kall[u] = fma(s[S_CM], b[u], s[S_CWX] * a[u]);
         return;
     }
     if (kz == 1) {
         load_pair<CF>(kc, KC_KAN, a, b);
 #pragma unroll
-        for (int u = 0; u < NU; ++u) kall[u] = s[S_CBR] * b[u];
+        for (int u = 0; u < NU; ++u) kall[u] = s[S_CBRX] * b[u];
     } else {
         load_pair<CF>(kc, KC_KAB, a, b);
 #pragma unroll
@@ -675,11 +684,11 @@ __device__ __forceinline__ void leaf_optics_x2(const BandConst<f2>& c2, const fl
     f2 kall;                                                                       // :950-951, both bands per instruction; kz: see leaf_kall_all
     if (kz == 2) {
         load_pair<CF>(kc, KC_KW, pa, pb);
-        kall = fma(s[S_CM], F2(pb[0], pb[1]), mul(F2(pa[0], pa[1]), s[S_CW]));
+        kall = fma(s[S_CM], F2(pb[0], pb[1]), mul(F2(pa[0], pa[1]), s[S_CWX]));
     } else {
         if (kz == 1) {
             load_pair<CF>(kc, KC_KAN, pa, pb);                                     // one 128-bit load per pair of planes
-            kall = mul(F2(pb[0], pb[1]), s[S_CBR]);
+            kall = mul(F2(pb[0], pb[1]), s[S_CBRX]);
         } else {
             load_pair<CF>(kc, KC_KAB, pa, pb);
             kall = fma(s[S_CXC], F2(pb[0], pb[1]), mul(F2(pa[0], pa[1]), s[S_CAB]));
@@ -1744,6 +1753,13 @@ __global__ void k_volume(int n, const double* __restrict__ iza, const double* __
     out[4 * i] = chi_s; out[4 * i + 1] = chi_o; out[4 * i + 2] = frho; out[4 * i + 3] = ftau;
 }
 
+// S_CWX, S_CBRX of a leaf record: see the S_ enum and leaf_kall_all
+__device__ __forceinline__ void leaf_poison_copies(double (&srec)[REC]) {
+    const bool ok01 = isfinite(srec[S_CAB]) && isfinite(srec[S_CXC]);
+    srec[S_CBRX] = ok01 ? srec[S_CBR] : nan("");
+    srec[S_CWX] = ok01 && isfinite(srec[S_CAN]) && isfinite(srec[S_CBR]) ? srec[S_CW] : nan("");
+}
+
 // S_NEGLAI of a canopy: -lai; in double records (PB_EXPS) pre-multiplied with 2048 log2(e) for exp_neg_scaled, |value| < 2^30
 template <typename T>
 __device__ __forceinline__ double neglai_rec(double lai) {
@@ -1786,9 +1802,7 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
         srec[S_NM1] = N - 1.0;
         srec[S_LMAX] = 500.0 / fabs(N - 1.0);     // clamp of log2 b in b^(N-1) (pow_pos_scaled); inf for N = 1
-        // the band kernel skips pigment terms whose table is zero over a whole tile group (leaf_kall_all); a non-finite content
-        // times 0.0 is NaN in the reference: carried by the water term, which no band skips
-        if (!(isfinite(srec[S_CAB]) && isfinite(srec[S_CXC]) && isfinite(srec[S_CAN]) && isfinite(srec[S_CBR]))) srec[S_CW] = nan("");
+        leaf_poison_copies(srec);
     }
     if (a.has_soil) {
         const double sr = a.soil_refl[s], mo = a.soil_moist[s];
@@ -1920,7 +1934,7 @@ __global__ void __launch_bounds__(128) k_prologue(const PrologueArgs a) {
         r[G_LAISUM] = lai * sumint; r[G_Z] = z; r[G_FSL] = Fs * (lai * sumint); r[G_FTL] = Ft * (lai * sumint); r[G_DTT] = tsstoo - tss * too;
         store_rec<T>(a.grec, item, r);
         if (g == 0) {
-            srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
+            if (!a.has_leaf) { srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf); }      // with a leaf: S_CWX, S_CBRX (set above)
             srec[S_NEGLAI] = nocanopy ? 0.0 : neglai_rec<T>(lai); srec[S_LAI] = lai;   // bare soil (+0.0 IS the no-canopy flag): the band kernel's canopy stage runs with lai = 0
             srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
             srec[S_BF] = bf;
@@ -2090,7 +2104,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
             srec[S_CBR] = a.Cbr[s] / N; srec[S_CW] = a.Cw[s] / N; srec[S_CM] = a.Cm[s] / N;
             srec[S_NM1] = N - 1.0;
             srec[S_LMAX] = 500.0 / fabs(N - 1.0);     // clamp of log2 b in b^(N-1) (pow_pos_scaled); inf for N = 1
-            if (!(isfinite(srec[S_CAB]) && isfinite(srec[S_CXC]) && isfinite(srec[S_CAN]) && isfinite(srec[S_CBR]))) srec[S_CW] = nan("");   // see k_prologue
+            leaf_poison_copies(srec);
         }
         if (a.has_soil) {
             const double sr = a.soil_refl[s], mo = a.soil_moist[s];
@@ -2188,7 +2202,7 @@ __global__ void __launch_bounds__(128) k_prologue_t(const PrologueArgs a, const 
     grec[G_LAISUM] = lai * sumint; grec[G_Z] = z; grec[G_FSL] = Fs * (lai * sumint); grec[G_FTL] = Ft * (lai * sumint); grec[G_DTT] = tsstoo - tss * too;
     store_rec<T>(a.grec, item, grec);
     if (g == 0) {
-        srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf);
+        if (!a.has_leaf) { srec[S_DDB] = 0.5 * (1.0 + bf); srec[S_DDF] = 0.5 * (1.0 - bf); }          // with a leaf: S_CWX, S_CBRX (set above)
         srec[S_NEGLAI] = nocanopy ? 0.0 : neglai_rec<T>(lai); srec[S_LAI] = lai;   // bare soil (+0.0 IS the no-canopy flag): the band kernel's canopy stage runs with lai = 0
         srec[S_THR] = nocanopy ? 0.0 : 1e-3 / lai;
         srec[S_BF] = bf;

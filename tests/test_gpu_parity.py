@@ -176,6 +176,34 @@ def test_prospect_weak_absorption_ladder():
     assert worst <= 1e-10, worst          # realistic and weakly absorbing leaves stay inside the round-2 error budget's test bar
 
 
+def test_non_finite_pigment_content_gives_the_reference_pattern():
+    """The leaf stage skips pigment terms whose table is zero over a whole tile group (from 784 / 1100 nm on).  That is exact for finite
+    contents; a NaN or infinite content times 0.0 is NaN, and the reference turns a NaN kall into tau = 1 (`kall > 0` is False,
+    models.py:953) while an infinite kall gives NaN spectra.  The kernels reproduce that band by band: the paths that skip a term read
+    a copy of the next content that the prologue sets to NaN when a skipped content is not finite (csrc: leaf_kall_all, S_CWX / S_CBRX)."""
+    import warnings
+    base = dict(N=1.5, Cab=35.0, Cxc=5.0, Cbr=0.15, Cw=0.003, Cm=0.0055)
+    for version, names in (('5', ('Cab', 'Cxc', 'Cbr')), ('D', ('Cab', 'Cxc', 'Cbr', 'Can'))):
+        for name in names:
+            for bad in (np.nan, np.inf):
+                kw = dict(base, version=version, **({'Can': 2.0} if version == 'D' else {}))
+                kw[name] = bad
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    o = orc.prospect(**kw)
+                p = pb.PROSPECT(**kw)
+                for got, ref in ((p.ks, o['ks']), (p.kt, o['kt'])):
+                    assert np.array_equal(np.isnan(got), np.isnan(ref)), (version, name, bad, int(np.isnan(got).sum()), int(np.isnan(ref).sum()))
+                    ok = np.isfinite(ref)
+                    assert ok.any() and np.max(np.abs(got[ok] - ref[ok])) <= 2e-8, (version, name, bad)      # tau = 1 bands: the reference's own noise (see above)
+    # a batch: the finite sets next to such a set are untouched
+    P = {k: np.array([v, v, v]) for k, v in base.items()}
+    P['Cab'] = np.array([35.0, np.inf, 35.0])
+    p = pb.PROSPECT(**P)
+    o = orc.prospect(**base)
+    assert np.isnan(p.ks[1]).sum() == 380 and np.max(np.abs(p.ks[0] - o['ks'])) <= TOL and np.array_equal(p.ks[0], p.ks[2])
+
+
 # ------------------------------------------------------------------------------------------------------------ LSM
 def test_lsm():
     r, m = rng.uniform(0.3, 1.2, 9), rng.uniform(0, 1, 9)
