@@ -43,10 +43,10 @@ FLOPS_LEAF, FLOPS_SAIL = 83, 151
 FLOPS_PER_BAND = FLOPS_LEAF + FLOPS_SAIL     # div/sqrt/exp/E1/pow counted as ONE flop each
 BYTES_PER_SPECTRUM = NB * 8     # one fp64 output plane
 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the config-2 kernel, per spectrum
-# (round 2n: 4.49 GB written + 1.04 GB read.  The reads are the 256-B item records, staged by each of the 22 tile groups at a different
-#  time since every warp walks a contiguous share of the work list -- 4.1 KB per spectrum of L2 misses at 10 % DRAM
+# (round 2n: 4.49 GB written + 1.22 GB read.  The reads are the 256-B item records, staged by each of the 22 tile groups at a different
+#  time since every warp walks a contiguous share of the work list -- 4.7 KB per spectrum of L2 misses at 10 % DRAM
 #  utilisation; the strided walk of round 1/2k read them once (83.5 MB, ratio 1.010) and was 1 % slower.)
-NCU_DRAM_BYTES_PER_SPECTRUM = (4.494074e9 + 1.039972e9) / 262144
+NCU_DRAM_BYTES_PER_SPECTRUM = (4.491783e9 + 1.220478e9) / 262144
 NCU_DRAM_SOURCE = "profiles/r2n_k_bands_brf_f64.txt (one ncu --set full capture of 262144 sets, scaled; NOT measured in this run)"
 BASE_SEED = 20261019
 SEED = BASE_SEED + 2            # config index 2
