@@ -1,5 +1,7 @@
 #!/bin/bash
 # round 2n: A/B of the FP64-instruction reductions (base = the round-2m library) + the gpu test suite on the new library
+# (base: `git worktree add /tmp/base 5859ab0 && make -C /tmp/base && cp /tmp/base/pyrism_b200/lib/libprosail_b200.so pyrism_b200/lib/variants/libprosail_base.so`;
+#  the variants directory is git-ignored and was removed again after the round)
 mkdir -p gpurun_out; O=gpurun_out/r2n.txt; : > $O
 V=$PWD/pyrism_b200/lib/variants
 for w in "brf f64" "leaf f64" "means f64" "four f64" "brf f32"; do
